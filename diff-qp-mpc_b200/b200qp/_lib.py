@@ -1,0 +1,72 @@
+"""ctypes binding of libb200qp.so (the C ABI in include/b200qp.h).
+
+The product path has NO CPU fallback: if the shared library is missing, or a CUDA tensor is not
+supplied, the call fails loudly.  Build with `python -c "import __graft_entry__ as g; g.build()"`
+(or `make -C diff-qp-mpc_b200/csrc`).
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libb200qp.so")
+
+F64, F32 = 0, 1
+STATUS_DOUBLES = 8
+ST_NITER, ST_BEST_MAX, ST_Q_FAIL, ST_AQA_FAIL, ST_LAUNCHES = 0, 1, 2, 3, 4
+MAX_ITER_CAP = 64
+
+EXPORTS = (
+    "b200qp_workspace_bytes", "b200qp_forward", "b200qp_backward", "b200qp_kkt_solve",
+    "b200qp_solve_host", "b200qp_last_cuda_error", "b200qp_version",
+)
+
+
+class Problem(ctypes.Structure):
+    """b200qp_problem_t"""
+    _fields_ = [
+        ("nb", ctypes.c_int32), ("nz", ctypes.c_int32), ("nineq", ctypes.c_int32), ("neq", ctypes.c_int32),
+        ("dtype", ctypes.c_int32), ("max_iter", ctypes.c_int32), ("not_improved_lim", ctypes.c_int32),
+        ("reserved", ctypes.c_int32), ("eps", ctypes.c_double),
+        ("sQ", ctypes.c_int64), ("sp", ctypes.c_int64), ("sG", ctypes.c_int64), ("sh", ctypes.c_int64),
+        ("sA", ctypes.c_int64), ("sb", ctypes.c_int64),
+    ]
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            f"{LIB_PATH} is missing: the CUDA library has not been built. Run "
+            "`python -c 'import __graft_entry__ as g; g.build()'` at the repo root. "
+            "There is no CPU fallback for this path.")
+    L = ctypes.CDLL(LIB_PATH)
+    vp, pp = ctypes.c_void_p, ctypes.POINTER(Problem)
+    L.b200qp_workspace_bytes.restype = ctypes.c_size_t
+    L.b200qp_workspace_bytes.argtypes = [pp]
+    L.b200qp_forward.restype = ctypes.c_int
+    L.b200qp_forward.argtypes = [pp] + [vp] * 13
+    L.b200qp_backward.restype = ctypes.c_int
+    L.b200qp_backward.argtypes = [pp] + [vp] * 13
+    L.b200qp_kkt_solve.restype = ctypes.c_int
+    L.b200qp_kkt_solve.argtypes = [pp, ctypes.c_int] + [vp] * 14
+    L.b200qp_solve_host.restype = ctypes.c_int
+    L.b200qp_solve_host.argtypes = [pp] + [vp] * 18
+    L.b200qp_last_cuda_error.restype = ctypes.c_char_p
+    L.b200qp_version.restype = ctypes.c_char_p
+    _lib = L
+    return L
+
+
+def check(rc, what):
+    if rc == 0:
+        return
+    msg = {-1: "invalid argument", -2: "CUDA error", -3: "problem too large for the kernels"}.get(rc, "error")
+    detail = lib().b200qp_last_cuda_error().decode() if rc == -2 else ""
+    raise RuntimeError(f"b200qp: {what} failed ({rc}: {msg}) {detail}")

@@ -1,0 +1,230 @@
+"""QPFunction -- drop-in for the reference's qpth/qp.py:19-184 on B200.
+
+    QPFunction(eps, verbose, notImprovedLim, maxIter, solver, check_Q_spd)(Q, p, G, h, A, b
+                                                                         [, dyn_res, cost_grad])
+
+Same factory signature, same autograd contract (gradients for the six tensors, None for the two
+callables, `.mean(0)` for parameters shared across the batch), same error strings.  The whole
+forward (pre-factorisation + Mehrotra loop with the reference's batch-global termination) and
+the adjoint backward run in hand-written sm_100a kernels behind the C ABI of include/b200qp.h;
+this file only unwraps tensors.  There is no CPU path: non-CUDA inputs raise.
+"""
+from __future__ import annotations
+
+import ctypes
+from enum import Enum
+
+import torch
+from torch.autograd import Function
+
+from . import _lib
+from .util import expandParam, extract_nBatch
+
+INACC_ERR = """
+--------
+qpth warning: Returning an inaccurate and potentially incorrect solution.
+
+Some residual is large.
+Your problem may be infeasible or difficult.
+
+You can try using the CVXPY solver to see if your problem is feasible
+and you can use the verbose option to check the convergence status of
+our solver while increasing the number of iterations.
+
+Advanced users:
+You can also try to enable iterative refinement in the solver:
+https://github.com/locuslab/qpth/issues/6
+--------
+"""
+
+
+class QPSolvers(Enum):
+    """qpth/qp.py:14-16"""
+    PDIPM_BATCHED = 1
+    CVXPY = 2
+
+
+def _dtype_code(t):
+    if t.dtype == torch.float64:
+        return _lib.F64
+    if t.dtype == torch.float32:
+        return _lib.F32
+    raise RuntimeError(f"b200qp: unsupported dtype {t.dtype} (float64 or float32)")
+
+
+def _ptr(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None and t.numel() > 0 else ctypes.c_void_p(0)
+
+
+def _stream(device):
+    return ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+def _prep(X, nBatch, nDim, ref):
+    """Contiguous tensor + batch stride (0 when the parameter is shared across the batch)."""
+    if X.device != ref.device or X.dtype != ref.dtype:
+        raise RuntimeError("b200qp: all QP parameters must share Q's device and dtype")
+    per = 1
+    for s in X.shape[-(nDim - 1):]:
+        per *= s
+    if X.ndimension() == nDim:
+        if X.size(0) != nBatch:
+            raise RuntimeError("b200qp: inconsistent batch sizes")
+        return X.contiguous(), per, False
+    return X.contiguous(), 0, True
+
+
+class _Plan:
+    """Sizes + the C problem descriptor + workspace for one call."""
+
+    def __init__(self, Q_, p_, G_, h_, A_, b_, eps, notImprovedLim, maxIter):
+        if not Q_.is_cuda:
+            raise RuntimeError("b200qp.QPFunction runs on CUDA tensors only (no CPU fallback); got " + str(Q_.device))
+        nBatch = extract_nBatch(Q_, p_, G_, h_, A_, b_)
+        neq_zero = A_.nelement() == 0
+        # shape checks exactly as the reference's expandParam would raise them
+        for X, d in ((Q_, 3), (p_, 2), (G_, 3), (h_, 2)) + (() if neq_zero else ((A_, 3), (b_, 2))):
+            expandParam(X, nBatch, d)
+        nineq, nz = G_.shape[-2], G_.shape[-1]
+        neq = 0 if neq_zero else A_.shape[-2]
+        assert neq > 0 or nineq > 0
+        if nineq == 0:
+            raise RuntimeError("b200qp: nineq == 0 is not supported (the reference's loop divides by nineq)")
+        self.nBatch, self.nz, self.nineq, self.neq = nBatch, nz, nineq, neq
+        self.Q, sQ, self.Q_e = _prep(Q_, nBatch, 3, Q_)
+        self.p, sp, self.p_e = _prep(p_, nBatch, 2, Q_)
+        self.G, sG, self.G_e = _prep(G_, nBatch, 3, Q_)
+        self.h, sh, self.h_e = _prep(h_, nBatch, 2, Q_)
+        if neq > 0:
+            self.A, sA, self.A_e = _prep(A_, nBatch, 3, Q_)
+            self.b, sb, self.b_e = _prep(b_, nBatch, 2, Q_)
+        else:
+            self.A, sA, self.A_e, self.b, sb, self.b_e = None, 0, False, None, 0, False
+        if maxIter > _lib.MAX_ITER_CAP:
+            raise RuntimeError(f"b200qp: maxIter > {_lib.MAX_ITER_CAP} is not supported")
+        self.prob = _lib.Problem(nBatch, nz, nineq, neq, _dtype_code(Q_), int(maxIter), int(notImprovedLim), 0,
+                                 float(eps), sQ, sp, sG, sh, sA, sb)
+        L = _lib.lib()
+        nbytes = L.b200qp_workspace_bytes(ctypes.byref(self.prob))
+        if nbytes == 0:
+            raise RuntimeError("b200qp: unsupported problem size")
+        self.workspace = torch.empty(nbytes, dtype=torch.uint8, device=Q_.device)
+
+
+def QPFunction(eps=1e-12, verbose=0, notImprovedLim=3,
+               maxIter=20, solver=QPSolvers.PDIPM_BATCHED,
+               check_Q_spd=True):
+    """Factory with the reference's signature (qpth/qp.py:19-21)."""
+    info = {}
+
+    class QPFunctionFn(Function):
+        @staticmethod
+        def forward(ctx, Q_, p_, G_, h_, A_, b_, dyn_res=None, cost_grad=None):
+            if solver != QPSolvers.PDIPM_BATCHED:
+                raise NotImplementedError("b200qp: only QPSolvers.PDIPM_BATCHED is implemented (CVXPY is a "
+                                          "per-instance CPU solver outside the hot path)")
+            plan = _Plan(Q_, p_, G_, h_, A_, b_, eps, notImprovedLim, maxIter)
+            _check_callbacks(plan, dyn_res, cost_grad)
+            L = _lib.lib()
+            nb, nz, nineq, neq = plan.nBatch, plan.nz, plan.nineq, plan.neq
+            opt = dict(dtype=Q_.dtype, device=Q_.device)
+            zhats = torch.empty(nb, nz, **opt)
+            lams = torch.empty(nb, nineq, **opt)
+            slacks = torch.empty(nb, nineq, **opt)
+            nus = torch.empty(nb, neq, **opt)
+            status = torch.empty(_lib.STATUS_DOUBLES, dtype=torch.float64, device=Q_.device)
+            with torch.cuda.device(Q_.device):
+                rc = L.b200qp_forward(ctypes.byref(plan.prob), _ptr(plan.Q), _ptr(plan.p), _ptr(plan.G), _ptr(plan.h),
+                                      _ptr(plan.A), _ptr(plan.b), _ptr(zhats), _ptr(lams), _ptr(nus), _ptr(slacks),
+                                      _ptr(plan.workspace), _ptr(status), _stream(Q_.device))
+            _lib.check(rc, "b200qp_forward")
+            st = status.tolist()  # one small D2H read; also surfaces asynchronous kernel faults
+            info.update(n_iter=int(st[_lib.ST_NITER]), best_resid_max=st[_lib.ST_BEST_MAX],
+                        launches=int(st[_lib.ST_LAUNCHES]))
+            if st[_lib.ST_Q_FAIL] > 0:
+                if check_Q_spd:
+                    raise RuntimeError('Q is not SPD.')
+                raise RuntimeError("qpth Error: Cannot perform LU factorization on Q. "
+                                   "Please make sure that your Q matrix is PSD and has a non-zero diagonal.")
+            if st[_lib.ST_AQA_FAIL] > 0:
+                raise RuntimeError("qpth Error: Cannot perform LU factorization on AQ^{-1}A^T. "
+                                   "Please make sure that your A matrix is full rank.")
+            if st[_lib.ST_BEST_MAX] > 1. and verbose >= 0:
+                print(INACC_ERR)
+            ctx.plan = plan
+            ctx.neq, ctx.nineq, ctx.nz = neq, nineq, nz
+            ctx.nus, ctx.lams, ctx.slacks = nus, lams, slacks
+            ctx.save_for_backward(zhats, Q_, p_, G_, h_, A_, b_)
+            return zhats
+
+        @staticmethod
+        def backward(ctx, dl_dzhat):
+            zhats = ctx.saved_tensors[0]
+            plan = ctx.plan
+            L = _lib.lib()
+            nb, nz, nineq, neq = plan.nBatch, plan.nz, plan.nineq, plan.neq
+            opt = dict(dtype=zhats.dtype, device=zhats.device)
+            gz = dl_dzhat.contiguous()
+            dQ = torch.empty(nb, nz, nz, **opt)
+            dp = torch.empty(nb, nz, **opt)
+            dG = torch.empty(nb, nineq, nz, **opt)
+            dh = torch.empty(nb, nineq, **opt)
+            dA = torch.empty(nb, neq, nz, **opt) if neq > 0 else None
+            db = torch.empty(nb, neq, **opt) if neq > 0 else None
+            with torch.cuda.device(zhats.device):
+                rc = L.b200qp_backward(ctypes.byref(plan.prob), _ptr(zhats), _ptr(ctx.lams), _ptr(ctx.nus),
+                                       _ptr(ctx.slacks), _ptr(gz), _ptr(dQ), _ptr(dp), _ptr(dG), _ptr(dh), _ptr(dA),
+                                       _ptr(db), _ptr(plan.workspace), _stream(zhats.device))
+            _lib.check(rc, "b200qp_backward")
+            # parameters shared across the batch get the MEAN over it (qpth/qp.py:160-178)
+            if plan.Q_e:
+                dQ = dQ.mean(0)
+            if plan.p_e:
+                dp = dp.mean(0)
+            if plan.G_e:
+                dG = dG.mean(0)
+            if plan.h_e:
+                dh = dh.mean(0)
+            if neq > 0:
+                if plan.A_e:
+                    dA = dA.mean(0)
+                if plan.b_e:
+                    db = db.mean(0)
+            return (dQ, dp, dG, dh, dA, db, None, None)
+
+    def apply(Q, p, G, h, A, b, dyn_res=None, cost_grad=None):
+        return QPFunctionFn.apply(Q, p, G, h, A, b, dyn_res, cost_grad)
+
+    apply.info = info
+    apply.Function = QPFunctionFn
+    return apply
+
+
+def _check_callbacks(plan, dyn_res, cost_grad):
+    """This fork evaluates `cost_grad(x)` in place of Qx+p and `dyn_res(x)` in place of Ax-b inside
+    the loop (qpth/solvers/pdipm/batch.py:93-102).  The fused kernels implement the canonical
+    linear forms, so a callback is accepted iff it IS that form (checked on a probe point)."""
+    if dyn_res is None and cost_grad is None:
+        return
+    nb, nz = plan.nBatch, plan.nz
+    g = torch.Generator(device="cpu").manual_seed(1234)
+    x = torch.randn(nb, nz, generator=g, dtype=torch.float64).to(device=plan.Q.device, dtype=plan.Q.dtype)
+    tol = 1e-9 if plan.Q.dtype == torch.float64 else 1e-4
+
+    def close(a, b):
+        return torch.allclose(a, b, rtol=tol, atol=tol * (1 + float(b.abs().max()) if b.numel() else 1.0))
+
+    if cost_grad is not None:
+        Q = plan.Q if not plan.Q_e else plan.Q.unsqueeze(0).expand(nb, nz, nz)
+        p = plan.p if not plan.p_e else plan.p.unsqueeze(0).expand(nb, nz)
+        want = torch.bmm(Q, x.unsqueeze(2)).squeeze(2) + p
+        if not close(cost_grad(x), want):
+            raise NotImplementedError("b200qp: cost_grad callbacks other than x -> Qx+p are not supported by the "
+                                      "fused kernels")
+    if dyn_res is not None and plan.neq > 0:
+        A = plan.A if not plan.A_e else plan.A.unsqueeze(0).expand(nb, plan.neq, nz)
+        b = plan.b if not plan.b_e else plan.b.unsqueeze(0).expand(nb, plan.neq)
+        want = torch.bmm(A, x.unsqueeze(2)).squeeze(2) - b
+        if not close(dyn_res(x), want):
+            raise NotImplementedError("b200qp: dyn_res callbacks other than x -> Ax-b are not supported by the "
+                                      "fused kernels")

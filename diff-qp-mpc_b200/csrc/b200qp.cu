@@ -1,0 +1,345 @@
+// b200qp.cu -- host side of libb200qp.so: workspace layout, launch sequencing, the C ABI
+// declared in include/b200qp.h.  No torch types anywhere; device pointers + a cudaStream_t.
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <mutex>
+
+#include "../../include/b200qp.h"
+#include "qp_kernels.cuh"
+
+namespace b200qp {
+
+static thread_local char g_err[512] = "";
+
+static int cuda_fail(cudaError_t e, const char* what) {
+  snprintf(g_err, sizeof(g_err), "%s: %s", what, cudaGetErrorString(e));
+  return B200QP_ECUDA;
+}
+#define CK(call)                                        \
+  do {                                                  \
+    cudaError_t e_ = (call);                            \
+    if (e_ != cudaSuccess) return cuda_fail(e_, #call); \
+  } while (0)
+
+constexpr size_t kSmemResidentLimit = 200 * 1024;  // bytes/CTA we are willing to ask for
+constexpr size_t kSmemMax = 227 * 1024;
+
+struct Layout {
+  int nb, n, m, p, ldn, ldm, ldp, nt;
+  bool smem;
+  size_t es, smem_bytes;
+  long long sQi, sBQi, sR, sV, sUA, sF, sT;
+  size_t oQi, oBQi, oR, oV, oUA, opinvA, oF, opinvF, oT, opinvT;
+  size_t ox, os, oz, oy, odx, ods, odz, ody, ormu, oflags, obest, oslots, octl, total;
+};
+
+static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+static int make_layout(const b200qp_problem_t* pr, Layout& L) {
+  if (!pr || pr->nb < 1 || pr->nz < 1 || pr->nineq < 1 || pr->neq < 0) return B200QP_EINVAL;
+  if (pr->dtype != B200QP_F64 && pr->dtype != B200QP_F32) return B200QP_EINVAL;
+  if (pr->max_iter < 1 || pr->max_iter > B200QP_MAX_ITER_CAP) return B200QP_EINVAL;
+  L.nb = pr->nb; L.n = pr->nz; L.m = pr->nineq; L.p = pr->neq;
+  L.ldn = L.n | 1; L.ldm = L.m | 1; L.ldp = (L.p > 0 ? L.p : 1) | 1;
+  L.es = pr->dtype == B200QP_F64 ? 8 : 4;
+  const int widest = (L.n > L.p + L.m) ? L.n : (L.p + L.m);
+  L.nt = widest <= 128 ? 128 : 256;
+  const size_t full = smem_elems(L.n, L.m, L.p, L.ldn, L.ldm, L.ldp, L.nt, true) * L.es;
+  const size_t vecs = smem_elems(L.n, L.m, L.p, L.ldn, L.ldm, L.ldp, L.nt, false) * L.es;
+  L.smem = full <= kSmemResidentLimit;
+  L.smem_bytes = L.smem ? full : vecs;
+  if (L.smem_bytes > kSmemMax) return B200QP_ETOOBIG;
+  const int pp = L.p > 0 ? L.p : 1;
+  L.sQi = round4(L.n * L.ldn);
+  L.sBQi = round4((L.p + L.m) * L.ldn);
+  L.sR = round4(L.m * L.ldm);
+  L.sV = round4(pp * L.ldm);
+  L.sUA = round4(pp * L.ldp);
+  L.sF = round4(L.n * L.ldn);
+  L.sT = L.smem ? 0 : round4(L.m * L.ldm);
+  size_t off = 0;
+  const size_t nb = (size_t)L.nb;
+  auto put = [&](size_t elems, size_t esz) { size_t o = off; off = align_up(off + elems * esz, 256); return o; };
+  L.oQi = put(nb * L.sQi, L.es);
+  L.oBQi = put(nb * L.sBQi, L.es);
+  L.oR = put(nb * L.sR, L.es);
+  L.oV = put(L.p > 0 ? nb * L.sV : 4, L.es);
+  L.oUA = put(L.p > 0 ? nb * L.sUA : 4, L.es);
+  L.opinvA = put(nb * round4(pp), L.es);
+  L.oF = put(nb * L.sF, L.es);
+  L.opinvF = put(nb * round4(L.n), L.es);
+  L.oT = put(L.smem ? 4 : nb * L.sT, L.es);
+  L.opinvT = put(L.smem ? 4 : nb * round4(L.m), L.es);
+  L.ox = put(nb * round4(L.n), L.es);
+  L.os = put(nb * round4(L.m), L.es);
+  L.oz = put(nb * round4(L.m), L.es);
+  L.oy = put(nb * round4(pp), L.es);
+  L.odx = put(nb * round4(L.n), L.es);
+  L.ods = put(nb * round4(L.m), L.es);
+  L.odz = put(nb * round4(L.m), L.es);
+  L.ody = put(nb * round4(pp), L.es);
+  L.ormu = put(nb * 2, L.es);
+  L.oflags = put(nb, sizeof(int));
+  L.obest = put(nb, sizeof(double));
+  L.oslots = put(B200QP_MAX_ITER_CAP, sizeof(Slot));
+  L.octl = put(1, sizeof(Control));
+  L.total = off;
+  return B200QP_OK;
+}
+
+template <typename T>
+static void fill_args(KArgs<T>& a, const b200qp_problem_t* pr, const Layout& L, void* ws) {
+  memset(&a, 0, sizeof(a));
+  char* w = static_cast<char*>(ws);
+  a.nb = L.nb; a.n = L.n; a.m = L.m; a.p = L.p; a.ldn = L.ldn; a.ldm = L.ldm; a.ldp = L.ldp;
+  a.sQ = pr->sQ; a.sp = pr->sp; a.sG = pr->sG; a.sh = pr->sh; a.sA = pr->sA; a.sb = pr->sb;
+  a.Qi = (T*)(w + L.oQi); a.BQi = (T*)(w + L.oBQi); a.R = (T*)(w + L.oR); a.V = (T*)(w + L.oV);
+  a.UA = (T*)(w + L.oUA); a.pinvA = (T*)(w + L.opinvA); a.F = (T*)(w + L.oF); a.pinvF = (T*)(w + L.opinvF);
+  a.Tscr = (T*)(w + L.oT); a.pinvTscr = (T*)(w + L.opinvT);
+  a.sQi = L.sQi; a.sBQi = L.sBQi; a.sR = L.sR; a.sV = L.sV; a.sUA = L.sUA; a.sF = L.sF; a.sT = L.sT;
+  a.x = (T*)(w + L.ox); a.s = (T*)(w + L.os); a.z = (T*)(w + L.oz); a.y = (T*)(w + L.oy);
+  a.dx = (T*)(w + L.odx); a.ds = (T*)(w + L.ods); a.dz = (T*)(w + L.odz); a.dy = (T*)(w + L.ody);
+  a.rmu = (T*)(w + L.ormu);
+  a.flags = (int*)(w + L.oflags);
+  a.best_resid = (double*)(w + L.obest);
+  a.slots = (Slot*)(w + L.oslots);
+  a.ctl = (Control*)(w + L.octl);
+  a.max_iter = pr->max_iter; a.lim = pr->not_improved_lim; a.eps = pr->eps;
+}
+
+template <typename K>
+static cudaError_t ensure_smem(K kernel, size_t bytes) {
+  // The attribute is sticky per function; raising it every call costs ~1 us and keeps this
+  // stateless (the reference's module-global cache, batch.py:431, is what we avoid).
+  if (bytes > 48 * 1024) return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemMax);
+  return cudaSuccess;
+}
+
+#define DISPATCH_KERNEL(KNAME, T, L, ...)                                                      \
+  do {                                                                                         \
+    if ((L).smem) {                                                                            \
+      if ((L).nt == 128) { auto k = KNAME<T, true, 128>; CK(ensure_smem(k, (L).smem_bytes)); k<<<(L).nb, 128, (L).smem_bytes, st>>>(__VA_ARGS__); } \
+      else { auto k = KNAME<T, true, 256>; CK(ensure_smem(k, (L).smem_bytes)); k<<<(L).nb, 256, (L).smem_bytes, st>>>(__VA_ARGS__); } \
+    } else {                                                                                   \
+      if ((L).nt == 128) { auto k = KNAME<T, false, 128>; CK(ensure_smem(k, (L).smem_bytes)); k<<<(L).nb, 128, (L).smem_bytes, st>>>(__VA_ARGS__); } \
+      else { auto k = KNAME<T, false, 256>; CK(ensure_smem(k, (L).smem_bytes)); k<<<(L).nb, 256, (L).smem_bytes, st>>>(__VA_ARGS__); } \
+    }                                                                                          \
+    CK(cudaGetLastError());                                                                    \
+  } while (0)
+
+template <typename T>
+static int run_prefactor(KArgs<T>& a, const Layout& L, cudaStream_t st) {
+  if (L.nt == 128) k_prefactor<T, 128><<<L.nb, 128, 0, st>>>(a);
+  else k_prefactor<T, 256><<<L.nb, 256, 0, st>>>(a);
+  CK(cudaGetLastError());
+  return B200QP_OK;
+}
+
+template <typename T>
+static int forward_t(const b200qp_problem_t* pr, const Layout& L, const void* Q, const void* p, const void* G,
+                     const void* h, const void* A, const void* b, void* zhat, void* lams, void* nus, void* slacks,
+                     void* ws, double* status, cudaStream_t st) {
+  KArgs<T> a;
+  fill_args(a, pr, L, ws);
+  a.Q = (const T*)Q; a.pv = (const T*)p; a.G = (const T*)G; a.h = (const T*)h;
+  a.A = (const T*)(A ? A : G); a.b = (const T*)(b ? b : h);
+  a.bx = (T*)zhat; a.bz = (T*)lams; a.bs = (T*)slacks; a.by = (T*)nus;
+  a.status = status;
+  CK(cudaMemsetAsync(a.slots, 0, sizeof(Slot) * B200QP_MAX_ITER_CAP + sizeof(Control), st));
+  int launches = 0;
+  int rc = run_prefactor(a, L, st);
+  if (rc) return rc;
+  launches++;
+  a.iter = -1;
+  DISPATCH_KERNEL(k_pdipm_iter, T, L, a);
+  launches++;
+  for (int it = 0; it < pr->max_iter; it++) {
+    a.iter = it;
+    DISPATCH_KERNEL(k_pdipm_iter, T, L, a);
+    launches++;
+  }
+  launches++;
+  k_finalize<<<1, 32, 0, st>>>(a.slots, a.ctl, status, pr->max_iter, pr->not_improved_lim, pr->eps, launches);
+  CK(cudaGetLastError());
+  return B200QP_OK;
+}
+
+template <typename T>
+static int backward_t(const b200qp_problem_t* pr, const Layout& L, const void* zhat, const void* lams, const void* nus,
+                      const void* slacks, const void* gz, void* dQ, void* dp, void* dG, void* dh, void* dA, void* db,
+                      void* ws, cudaStream_t st) {
+  KArgs<T> a;
+  fill_args(a, pr, L, ws);
+  BArgs<T> g;
+  g.zhat = (const T*)zhat; g.lams = (const T*)lams; g.nus = (const T*)(nus ? nus : zhat); g.slacks = (const T*)slacks;
+  g.gz = (const T*)gz;
+  g.dQ = (T*)dQ; g.dp = (T*)dp; g.dG = (T*)dG; g.dh = (T*)dh; g.dA = (T*)dA; g.db = (T*)db;
+  DISPATCH_KERNEL(k_backward, T, L, a, g);
+  return B200QP_OK;
+}
+
+template <typename T>
+static int kkt_solve_t(const b200qp_problem_t* pr, const Layout& L, int prefactor, const void* Q, const void* G,
+                       const void* A, const void* d, const void* rx, const void* rs, const void* rz, const void* ry,
+                       void* dx, void* ds, void* dz, void* dy, void* ws, cudaStream_t st) {
+  KArgs<T> a;
+  fill_args(a, pr, L, ws);
+  a.Q = (const T*)Q; a.G = (const T*)G; a.A = (const T*)(A ? A : G);
+  if (prefactor) {
+    CK(cudaMemsetAsync(a.slots, 0, sizeof(Slot) * B200QP_MAX_ITER_CAP + sizeof(Control), st));
+    int rc = run_prefactor(a, L, st);
+    if (rc) return rc;
+  }
+  SArgs<T> g;
+  g.d = (const T*)d; g.rx = (const T*)rx; g.rs = (const T*)rs; g.rz = (const T*)rz; g.ry = (const T*)ry;
+  g.dx = (T*)dx; g.ds = (T*)ds; g.dz = (T*)dz; g.dy = (T*)dy;
+  DISPATCH_KERNEL(k_kkt_solve, T, L, a, g);
+  return B200QP_OK;
+}
+
+// ---------------------------------------------------------------------------- host-buffer path
+struct Arena {
+  char* base = nullptr;
+  size_t cap = 0;
+  cudaStream_t stream = nullptr;
+  std::mutex mu;
+};
+static Arena g_arena;
+
+static int arena_reserve(size_t bytes) {
+  if (!g_arena.stream) CK(cudaStreamCreateWithFlags(&g_arena.stream, cudaStreamNonBlocking));
+  if (bytes <= g_arena.cap) return B200QP_OK;
+  if (g_arena.base) CK(cudaFree(g_arena.base));
+  g_arena.base = nullptr;
+  g_arena.cap = 0;
+  CK(cudaMalloc(&g_arena.base, bytes));
+  g_arena.cap = bytes;
+  return B200QP_OK;
+}
+
+}  // namespace b200qp
+
+using namespace b200qp;
+
+extern "C" {
+
+size_t b200qp_workspace_bytes(const b200qp_problem_t* prob) {
+  Layout L;
+  if (make_layout(prob, L) != B200QP_OK) return 0;
+  return L.total;
+}
+
+int b200qp_forward(const b200qp_problem_t* prob, const void* Q, const void* p, const void* G, const void* h,
+                   const void* A, const void* b, void* zhat, void* lams, void* nus, void* slacks, void* workspace,
+                   double* status, b200qp_stream_t stream) {
+  Layout L;
+  int rc = make_layout(prob, L);
+  if (rc) return rc;
+  if (!Q || !p || !G || !h || !zhat || !lams || !slacks || !workspace || !status) return B200QP_EINVAL;
+  if (prob->neq > 0 && (!A || !b || !nus)) return B200QP_EINVAL;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (prob->dtype == B200QP_F64)
+    return forward_t<double>(prob, L, Q, p, G, h, A, b, zhat, lams, nus, slacks, workspace, status, st);
+  return forward_t<float>(prob, L, Q, p, G, h, A, b, zhat, lams, nus, slacks, workspace, status, st);
+}
+
+int b200qp_backward(const b200qp_problem_t* prob, const void* zhat, const void* lams, const void* nus,
+                    const void* slacks, const void* dl_dzhat, void* dQ, void* dp, void* dG, void* dh, void* dA,
+                    void* db, void* workspace, b200qp_stream_t stream) {
+  Layout L;
+  int rc = make_layout(prob, L);
+  if (rc) return rc;
+  if (!zhat || !lams || !slacks || !dl_dzhat || !dQ || !dp || !dG || !dh || !workspace) return B200QP_EINVAL;
+  if (prob->neq > 0 && (!nus || !dA || !db)) return B200QP_EINVAL;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (prob->dtype == B200QP_F64)
+    return backward_t<double>(prob, L, zhat, lams, nus, slacks, dl_dzhat, dQ, dp, dG, dh, dA, db, workspace, st);
+  return backward_t<float>(prob, L, zhat, lams, nus, slacks, dl_dzhat, dQ, dp, dG, dh, dA, db, workspace, st);
+}
+
+int b200qp_kkt_solve(const b200qp_problem_t* prob, int prefactor, const void* Q, const void* G, const void* A,
+                     const void* d, const void* rx, const void* rs, const void* rz, const void* ry, void* dx, void* ds,
+                     void* dz, void* dy, void* workspace, b200qp_stream_t stream) {
+  Layout L;
+  int rc = make_layout(prob, L);
+  if (rc) return rc;
+  if (!d || !rx || !rs || !rz || !dx || !ds || !dz || !workspace) return B200QP_EINVAL;
+  if (prefactor && (!Q || !G)) return B200QP_EINVAL;
+  if (prob->neq > 0 && (!ry || !dy || (prefactor && !A))) return B200QP_EINVAL;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (prob->dtype == B200QP_F64)
+    return kkt_solve_t<double>(prob, L, prefactor, Q, G, A, d, rx, rs, rz, ry, dx, ds, dz, dy, workspace, st);
+  return kkt_solve_t<float>(prob, L, prefactor, Q, G, A, d, rx, rs, rz, ry, dx, ds, dz, dy, workspace, st);
+}
+
+int b200qp_solve_host(const b200qp_problem_t* prob, const void* Q, const void* p, const void* G, const void* h,
+                      const void* A, const void* b, const void* dl_dzhat, void* zhat, void* lams, void* nus,
+                      void* slacks, void* dQ, void* dp, void* dG, void* dh, void* dA, void* db, double* status) {
+  Layout L;
+  int rc = make_layout(prob, L);
+  if (rc) return rc;
+  if (!Q || !p || !G || !h || !zhat || !lams || !slacks || !status) return B200QP_EINVAL;
+  const size_t es = L.es, nb = (size_t)L.nb, n = (size_t)L.n, m = (size_t)L.m, pe = (size_t)L.p;
+  if (pe > 0 && (!A || !b || !nus)) return B200QP_EINVAL;
+  const bool bwd = dl_dzhat != nullptr;
+  if (bwd && (!dQ || !dp || !dG || !dh || (pe > 0 && (!dA || !db)))) return B200QP_EINVAL;
+  std::lock_guard<std::mutex> lock(g_arena.mu);
+  auto cnt = [&](int64_t stride, size_t per) { return (stride == 0 ? 1 : nb) * per; };
+  const size_t bQ = cnt(prob->sQ, n * n) * es, bp = cnt(prob->sp, n) * es, bG = cnt(prob->sG, m * n) * es,
+               bh = cnt(prob->sh, m) * es, bA = cnt(prob->sA, pe * n) * es, bb = cnt(prob->sb, pe) * es;
+  const size_t bz = nb * n * es, bl = nb * m * es, bn = nb * pe * es;
+  size_t off = 0;
+  auto put = [&](size_t bytes) { size_t o = off; off = align_up(off + (bytes ? bytes : 16), 256); return o; };
+  const size_t oQ = put(bQ), op = put(bp), oG = put(bG), oh = put(bh), oA = put(bA), ob = put(bb);
+  const size_t oz = put(bz), ol = put(bl), on = put(bn), os = put(bl), ost = put(8 * sizeof(double));
+  const size_t ogz = put(bwd ? bz : 0), odQ = put(bwd ? nb * n * n * es : 0), odp = put(bwd ? bz : 0),
+               odG = put(bwd ? nb * m * n * es : 0), odh = put(bwd ? bl : 0), odA = put(bwd ? nb * pe * n * es : 0),
+               odb = put(bwd ? bn : 0);
+  const size_t ows = put(L.total);
+  rc = arena_reserve(off);
+  if (rc) return rc;
+  char* d = g_arena.base;
+  cudaStream_t st = g_arena.stream;
+  CK(cudaMemcpyAsync(d + oQ, Q, bQ, cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(d + op, p, bp, cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(d + oG, G, bG, cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(d + oh, h, bh, cudaMemcpyHostToDevice, st));
+  if (pe > 0) {
+    CK(cudaMemcpyAsync(d + oA, A, bA, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(d + ob, b, bb, cudaMemcpyHostToDevice, st));
+  }
+  if (bwd) CK(cudaMemcpyAsync(d + ogz, dl_dzhat, bz, cudaMemcpyHostToDevice, st));
+  rc = b200qp_forward(prob, d + oQ, d + op, d + oG, d + oh, pe ? d + oA : nullptr, pe ? d + ob : nullptr, d + oz,
+                      d + ol, d + on, d + os, d + ows, (double*)(d + ost), st);
+  if (rc) return rc;
+  if (bwd) {
+    rc = b200qp_backward(prob, d + oz, d + ol, d + on, d + os, d + ogz, d + odQ, d + odp, d + odG, d + odh,
+                         d + odA, d + odb, d + ows, st);
+    if (rc) return rc;
+  }
+  CK(cudaMemcpyAsync(zhat, d + oz, bz, cudaMemcpyDeviceToHost, st));
+  CK(cudaMemcpyAsync(lams, d + ol, bl, cudaMemcpyDeviceToHost, st));
+  CK(cudaMemcpyAsync(slacks, d + os, bl, cudaMemcpyDeviceToHost, st));
+  if (pe > 0) CK(cudaMemcpyAsync(nus, d + on, bn, cudaMemcpyDeviceToHost, st));
+  CK(cudaMemcpyAsync(status, d + ost, 8 * sizeof(double), cudaMemcpyDeviceToHost, st));
+  if (bwd) {
+    CK(cudaMemcpyAsync(dQ, d + odQ, nb * n * n * es, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(dp, d + odp, bz, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(dG, d + odG, nb * m * n * es, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(dh, d + odh, bl, cudaMemcpyDeviceToHost, st));
+    if (pe > 0) {
+      CK(cudaMemcpyAsync(dA, d + odA, nb * pe * n * es, cudaMemcpyDeviceToHost, st));
+      CK(cudaMemcpyAsync(db, d + odb, bn, cudaMemcpyDeviceToHost, st));
+    }
+  }
+  CK(cudaStreamSynchronize(st));
+  return B200QP_OK;
+}
+
+const char* b200qp_last_cuda_error(void) { return g_err; }
+
+const char* b200qp_version(void) { return "b200qp 0.1 sm_100a"; }
+
+}  // extern "C"

@@ -1,0 +1,722 @@
+// qp_kernels.cuh -- the batched PDIPM QP kernels (one CTA per QP, sm_100a).
+//
+// Reference behaviour being re-implemented (swami1995/diff-qp-mpc, paths under /root/reference):
+//   qpth/solvers/pdipm/batch.py:377-428  pre_factor_kkt   -> k_prefactor
+//   qpth/solvers/pdipm/batch.py:46-208   forward          -> k_pdipm_iter (one launch / iteration)
+//   qpth/solvers/pdipm/batch.py:434-469  factor_kkt       -> ldlt_factor on T = R + diag(s/z)
+//   qpth/solvers/pdipm/batch.py:351-374  solve_kkt        -> kkt_solve
+//   qpth/solvers/pdipm/batch.py:211-214  get_step         -> step_pieces + deferred fill
+//   qpth/qp.py:129-183                   backward         -> k_backward
+//
+// Elimination used here (mathematically the reference's block elimination, re-ordered so the
+// only sequential work per iteration is one nineq x nineq LDL^T and two solves with it):
+//   once per call:   Qi = Q^-1,  BQi = [A;G] Qi,  [Saa Sag; Sga Sgg] = BQi [A;G]^T,
+//                    Saa = La Da La^T,  V = La^-1 Sag,  R = Sgg - V^T Da^-1 V
+//   per iteration:   T = R + diag(s/z) = L D L^T
+//   per solve:       t = Qi rx; [hy;hz] = BQi rx + [-ry; rs/d - rz]; u = La^-1 hy;
+//                    qz = T^-1 (hz - V^T Da^-1 u); qy = La^-T Da^-1 (u - V qz);
+//                    dz = -qz, dy = -qy, ds = (-rs - dz)/d, dx = -t + BQi^T [qy;qz]
+// oracle/algo_model.py is the same algebra on the CPU and is what the golden-vector tests pin.
+//
+// Batch-global couplings of the reference loop are resolved at kernel boundaries through one
+// `Slot` of device-side reductions per iteration (no host round trip, CUDA-graph capturable):
+// iteration i's kernel reads slot i-1 to (a) decide whether the reference would have returned
+// at iteration i-1, (b) obtain the get_step fill values of iteration i-1's final direction, then
+// applies that step and carries on; work done after the reference's return point is never
+// observable because best iterates are updated before it.
+#pragma once
+#include "qp_common.cuh"
+
+namespace b200qp {
+
+struct Slot {                       // zero-initialised once per forward call
+  unsigned long long best_max;      // max_b best_resid[b]          (bits of a non-negative double)
+  unsigned long long mu_min_inv;    // ~ord_key(min_b mu[b])        (so that atomicMax works)
+  unsigned long long amax_z;        // ord_key(max_b,i  -z/dz)
+  unsigned long long amax_s;        // ord_key(max_b,i  -s/ds)
+  unsigned int improved;            // any problem improved its best residual
+  unsigned int best_nan, mu_nan, az_nan, as_nan;  // NaN seen in the respective reduction
+  unsigned int pad[3];
+};
+static_assert(sizeof(Slot) == 64, "Slot must be 64 bytes");
+
+struct Control {                    // lives after the slots
+  unsigned int q_fail;              // problems whose Q factorisation failed
+  unsigned int aqa_fail;            // problems whose A Q^-1 A^T factorisation failed
+  unsigned int pad[14];
+};
+
+constexpr int FLAG_POISON = 1, FLAG_FILL_Z = 2, FLAG_FILL_S = 4;
+
+template <typename T>
+struct KArgs {
+  int nb, n, m, p;
+  int ldn, ldm, ldp;
+  // inputs (borrowed)
+  const T *Q, *pv, *G, *h, *A, *b;
+  long long sQ, sp, sG, sh, sA, sb;
+  // pre-factorisation (workspace, per-problem strides in elements)
+  T *Qi, *BQi, *R, *V, *UA, *pinvA, *F, *pinvF, *Tscr, *pinvTscr;
+  long long sQi, sBQi, sR, sV, sUA, sF, sT;
+  // iterate + direction
+  T *x, *s, *z, *y, *dx, *ds, *dz, *dy, *rmu;
+  int* flags;
+  double* best_resid;
+  // outputs (best iterate)
+  T *bx, *bs, *bz, *by;
+  Slot* slots;
+  Control* ctl;
+  double* status;
+  int iter, max_iter, lim;
+  double eps;
+  int launches;
+};
+
+// ------------------------------------------------------------------------------------------
+// Decide, from the slots of iterations < upto, whether the reference loop has returned, and at
+// which iteration.  Executed by one full warp; every lane returns the same value.
+// Returns the 0-based iteration at which the reference returned, or -1.
+__device__ __forceinline__ int eval_termination(const Slot* slots, int upto, int lim, double eps, int lane) {
+  unsigned long long mi = 0ULL, mc = 0ULL;
+  for (int base = 0; base < upto; base += 32) {
+    const int j = base + lane;
+    bool improved = false, c23 = false;
+    if (j < upto) {
+      const Slot* sl = slots + j;
+      improved = sl->improved != 0;
+      const double bmax = sl->best_nan ? __longlong_as_double(0x7ff8000000000000LL)
+                                       : __longlong_as_double((long long)sl->best_max);
+      const double mmin = sl->mu_nan ? __longlong_as_double(0x7ff8000000000000LL) : ord_unkey(~sl->mu_min_inv);
+      c23 = (bmax < eps) || (mmin > 1e32);
+    }
+    mi |= (unsigned long long)__ballot_sync(0xffffffffu, improved) << base;
+    mc |= (unsigned long long)__ballot_sync(0xffffffffu, c23) << base;
+  }
+  int stall = 0;
+  for (int j = 0; j < upto; j++) {
+    if (j > 0) stall = ((mi >> j) & 1ULL) ? 0 : stall + 1;
+    if (stall == lim || ((mc >> j) & 1ULL)) return j;
+  }
+  return -1;
+}
+
+// Shared-memory carve-up of one problem.
+template <typename T>
+struct Smem {
+  T *Tm, *pinvT, *BQi, *V, *UA, *pinvA;
+  T *x, *s, *z, *y, *d, *rx, *rz, *ry, *t, *hv, *u;
+  T *dxa, *dsa, *dza, *dya, *rsc, *dxc, *dsc, *dzc, *dyc, *part, *red;
+  int* ctrl;
+};
+
+__host__ __device__ inline int round4(int v) { return (v + 3) & ~3; }
+
+// Elements of T needed in shared memory; mats=true includes the matrices.
+__host__ __device__ inline size_t smem_elems(int n, int m, int p, int ldn, int ldm, int ldp, int nt, bool mats) {
+  size_t e = 0;
+  if (mats) {
+    e += round4(m * ldm) + round4(m) + round4((p + m) * ldn);
+    if (p > 0) e += round4(p * ldm) + round4(p * ldp) + round4(p);
+  }
+  e += (size_t)5 * round4(n) + (size_t)10 * round4(m) + (size_t)6 * round4(p > 0 ? p : 1) + round4(p + m);
+  e += round4(nt) + 4 * 32;
+  e += 8;  // ctrl ints
+  return e;
+}
+
+template <typename T, bool SMEM>
+__device__ __forceinline__ void carve(Smem<T>& S, unsigned char* raw, const KArgs<T>& a, int prob, int nt) {
+  T* q = reinterpret_cast<T*>(raw);
+  auto take = [&](int cnt) { T* r = q; q += round4(cnt); return r; };
+  const int n = a.n, m = a.m, p = a.p, pp = p > 0 ? p : 1;
+  if (SMEM) {
+    S.Tm = take(m * a.ldm);
+    S.pinvT = take(m);
+    S.BQi = take((p + m) * a.ldn);
+    if (p > 0) {
+      S.V = take(p * a.ldm);
+      S.UA = take(p * a.ldp);
+      S.pinvA = take(p);
+    } else {
+      S.V = S.UA = S.pinvA = nullptr;
+    }
+  } else {
+    S.Tm = a.Tscr + (size_t)prob * a.sT;
+    S.pinvT = a.pinvTscr + (size_t)prob * round4(m);
+    S.BQi = a.BQi + (size_t)prob * a.sBQi;
+    S.V = a.V + (size_t)prob * a.sV;
+    S.UA = a.UA + (size_t)prob * a.sUA;
+    S.pinvA = a.pinvA + (size_t)prob * round4(pp);
+  }
+  S.x = take(n); S.rx = take(n); S.t = take(n); S.dxa = take(n); S.dxc = take(n);
+  S.s = take(m); S.z = take(m); S.d = take(m); S.rz = take(m); S.dsa = take(m); S.dza = take(m);
+  S.rsc = take(m); S.dsc = take(m); S.dzc = take(m); T* spare = take(m); (void)spare;
+  S.y = take(pp); S.ry = take(pp); S.u = take(pp); S.dya = take(pp); S.dyc = take(pp); T* sp2 = take(pp); (void)sp2;
+  S.hv = take(p + m);
+  S.part = take(nt);
+  S.red = take(4 * 32);
+  S.ctrl = reinterpret_cast<int*>(q);
+}
+
+// Stage the d-independent matrices of problem `prob` into shared memory (async).
+template <typename T, bool SMEM>
+__device__ __forceinline__ void stage_mats(const Smem<T>& S, const KArgs<T>& a, int prob, int tid, int nt) {
+  if (SMEM) {
+    cp_async_block(S.Tm, a.R + (size_t)prob * a.sR, round4(a.m * a.ldm), tid, nt);
+    cp_async_block(S.BQi, a.BQi + (size_t)prob * a.sBQi, round4((a.p + a.m) * a.ldn), tid, nt);
+    if (a.p > 0) {
+      cp_async_block(S.V, a.V + (size_t)prob * a.sV, round4(a.p * a.ldm), tid, nt);
+      cp_async_block(S.UA, a.UA + (size_t)prob * a.sUA, round4(a.p * a.ldp), tid, nt);
+      cp_async_block(S.pinvA, a.pinvA + (size_t)prob * round4(a.p), round4(a.p), tid, nt);
+    }
+    cp_async_commit();
+  }
+}
+
+// T = R + diag(1/d) and its LDL^T.  Needs the staged copy of R (SMEM) or copies it (global).
+template <typename T, bool SMEM>
+__device__ __forceinline__ bool build_and_factor_T(const Smem<T>& S, const KArgs<T>& a, int prob, int tid, int nt) {
+  const int m = a.m, ldm = a.ldm;
+  if (SMEM) {
+    cp_async_wait_all();
+    __syncthreads();
+  } else {
+    const T* R = a.R + (size_t)prob * a.sR;
+    for (int i = tid; i < m * ldm; i += nt) S.Tm[i] = R[i];
+    __syncthreads();
+  }
+  for (int i = tid; i < m; i += nt) S.Tm[(size_t)i * ldm + i] += T(1) / S.d[i];
+  __syncthreads();
+  return ldlt_factor(S.Tm, ldm, m, S.pinvT, tid, nt);
+}
+
+// Block-elimination KKT solve (see file header).  rx / rz / ry may be nullptr (= zero vector).
+// All vector arguments are shared-memory arrays; outputs must not alias inputs.
+// Entry: inputs visible (caller barrier).  Exit: outputs visible (ends with a barrier).
+template <typename T>
+__device__ __forceinline__ void kkt_solve(const Smem<T>& S, const KArgs<T>& a, int prob, const T* rx, const T* rs,
+                                          const T* rz, const T* ry, T* dx, T* ds, T* dz, T* dy, int tid, int nt) {
+  const int n = a.n, m = a.m, p = a.p, ldn = a.ldn, ldm = a.ldm, ldp = a.ldp;
+  const int lane = tid & 31, warp = tid >> 5;
+  if (rx) {
+    gemv_rows_thread(S.BQi, ldn, p + m, n, rx, S.hv, tid, nt);
+    gemv_cols(a.Qi + (size_t)prob * a.sQi, ldn, n, n, rx, S.t, S.part, tid, nt);  // ends with barrier
+  }
+  for (int i = tid; i < m; i += nt) {
+    T v = rs[i] / S.d[i];
+    if (rz) v -= rz[i];
+    S.hv[p + i] = rx ? S.hv[p + i] + v : v;
+  }
+  for (int j = tid; j < p; j += nt) {
+    T v = rx ? S.hv[j] : T(0);
+    if (ry) v -= ry[j];
+    S.u[j] = v;
+  }
+  __syncthreads();
+  if (p > 0) {
+    if (warp == 0) {
+      unit_fwd_warp(S.UA, ldp, p, S.u, lane);  // u = La^-1 hy
+      for (int j = lane; j < p; j += 32) S.hv[j] = S.u[j] * S.pinvA[j];  // Da^-1 u
+    }
+    __syncthreads();
+    // hz -= V^T (Da^-1 u)
+    gemv_cols(S.V, ldm, p, m, S.hv, S.dsc /*scratch*/, S.part, tid, nt);
+    for (int i = tid; i < m; i += nt) S.hv[p + i] -= S.dsc[i];
+    __syncthreads();
+  }
+  if (warp == 0) ldlt_solve_warp(S.Tm, ldm, m, S.pinvT, S.hv + p, lane);  // qz
+  __syncthreads();
+  if (p > 0) {
+    gemv_rows_thread(S.V, ldm, p, m, S.hv + p, S.hv, tid, nt);  // V qz  -> hv[0:p]
+    __syncthreads();
+    if (warp == 0) {
+      for (int j = lane; j < p; j += 32) S.hv[j] = (S.u[j] - S.hv[j]) * S.pinvA[j];
+      __syncwarp();
+      unit_bwd_warp(S.UA, ldp, p, S.hv, lane);  // qy
+    }
+    __syncthreads();
+  }
+  // dx = -t + BQi^T q ; dz = -qz ; ds = (-rs - dz)/d ; dy = -qy
+  gemv_cols(S.BQi, ldn, p + m, n, S.hv, dx, S.part, tid, nt);
+  for (int c = tid; c < n; c += nt) dx[c] = rx ? dx[c] - S.t[c] : dx[c];
+  for (int i = tid; i < m; i += nt) {
+    const T w = -S.hv[p + i];
+    dz[i] = w;
+    ds[i] = (-rs[i] - w) / S.d[i];
+  }
+  for (int j = tid; j < p; j += nt) dy[j] = -S.hv[j];
+  __syncthreads();
+}
+
+// get_step pieces of one problem (batch.py:211-214): the min over entries the fill does NOT
+// overwrite (NaN propagating, +inf if none), whether some entry is overwritten, and the
+// NaN-propagating max of a = -v/dv over ALL entries (the batch-global fill candidate).
+template <typename T>
+__device__ __forceinline__ void step_pieces(const T* v, const T* dv, int m, int tid, int nt, T* red, T& rmu,
+                                            bool& has_fill, T& amax) {
+  T r[3] = {t_inf<T>(), T(0), -t_inf<T>()};
+  for (int i = tid; i < m; i += nt) {
+    const T dvi = dv[i];
+    const T ai = -v[i] / dvi;
+    if (dvi > T(0)) r[1] = T(1); else r[0] = nanmin(r[0], ai);
+    r[2] = nanmax(r[2], ai);
+  }
+  // three different ops: do them one at a time (tiny)
+  T a0[1] = {r[0]}, a1[1] = {r[1]}, a2[1] = {r[2]};
+  block_reduce<1>(a0, OpNanMin(), red, tid, nt);
+  block_reduce<1>(a1, OpSum(), red + 32, tid, nt);
+  block_reduce<1>(a2, OpNanMax(), red + 64, tid, nt);
+  rmu = a0[0];
+  has_fill = a1[0] > T(0);
+  amax = a2[0];
+}
+
+// ------------------------------------------------------------------------------------------
+// One PDIPM iteration (a.iter >= 0) or the initial point (a.iter == -1).
+template <typename T, bool SMEM, int NT>
+__global__ void __launch_bounds__(NT) k_pdipm_iter(const KArgs<T> a) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int prob = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int n = a.n, m = a.m, p = a.p, it = a.iter;
+  Smem<T> S;
+  carve<T, SMEM>(S, smem_raw, a, prob, NT);
+
+  T fill_z = T(1), fill_s = T(1);
+  if (it > 0) {
+    // (a) has the reference already returned?  (b) fills of iteration it-1's final get_step
+    if (warp == 0) {
+      const int term = eval_termination(a.slots, it, a.lim, a.eps, lane);
+      if (lane == 0) S.ctrl[0] = term;
+    }
+  }
+  int flags = a.flags[prob];
+  if (it < 0) flags = 0;
+  if (!(flags & FLAG_POISON)) stage_mats<T, SMEM>(S, a, prob, tid, NT);
+  if (it > 0) {
+    __syncthreads();
+    if (S.ctrl[0] >= 0) {
+      if (SMEM) cp_async_wait_all();
+      return;
+    }
+    const Slot* sl = a.slots + (it - 1);
+    const double gz = sl->az_nan ? 0.0 : ord_unkey(sl->amax_z);
+    const double gs = sl->as_nan ? 0.0 : ord_unkey(sl->amax_s);
+    fill_z = gz > 1.0 ? (T)gz : T(1);
+    fill_s = gs > 1.0 ? (T)gs : T(1);
+  }
+  Slot* slot = a.slots + (it >= 0 ? it : 0);
+
+  if (flags & FLAG_POISON) {
+    // NaN iterate: can never improve; still takes part in the batch-global reductions.
+    if (it == 0) {  // poisoned by the initial point: the reference's outputs are all NaN
+      T* bx = a.bx + (size_t)prob * n; T* bs = a.bs + (size_t)prob * m; T* bz = a.bz + (size_t)prob * m;
+      for (int c = tid; c < n; c += NT) bx[c] = t_nan<T>();
+      for (int i = tid; i < m; i += NT) { bs[i] = t_nan<T>(); bz[i] = t_nan<T>(); }
+      if (p > 0) { T* by = a.by + (size_t)prob * p; for (int j = tid; j < p; j += NT) by[j] = t_nan<T>(); }
+    }
+    if (tid == 0) {
+      double br = __longlong_as_double(0x7ff8000000000000LL);
+      if (it == 0) a.best_resid[prob] = br; else br = a.best_resid[prob];
+      if (br != br) slot->best_nan = 1; else atomic_max_key(&slot->best_max, (unsigned long long)__double_as_longlong(br));
+      slot->mu_nan = 1;
+      slot->az_nan = 1;
+      slot->as_nan = 1;
+    }
+    return;
+  }
+
+  T* gx = a.x + (size_t)prob * round4(n);
+  T* gs_ = a.s + (size_t)prob * round4(m);
+  T* gz_ = a.z + (size_t)prob * round4(m);
+  T* gy = a.y + (size_t)prob * round4(p > 0 ? p : 1);
+  T* gdx = a.dx + (size_t)prob * round4(n);
+  T* gds = a.ds + (size_t)prob * round4(m);
+  T* gdz = a.dz + (size_t)prob * round4(m);
+  T* gdy = a.dy + (size_t)prob * round4(p > 0 ? p : 1);
+  const T* Qg = a.Q + (size_t)prob * a.sQ;
+  const T* Gg = a.G + (size_t)prob * a.sG;
+  const T* Ag = a.A + (size_t)prob * a.sA;
+  const T* pg = a.pv + (size_t)prob * a.sp;
+  const T* hg = a.h + (size_t)prob * a.sh;
+  const T* bg = a.b + (size_t)prob * a.sb;
+
+  if (it < 0) {
+    // ---- initial point: d = 1, solve with (rx,rs,rz,ry) = (p, 0, -h, -b)   (batch.py:60-66)
+    for (int i = tid; i < m; i += NT) { S.d[i] = T(1); S.rsc[i] = T(0); S.rz[i] = -hg[i]; }
+    for (int c = tid; c < n; c += NT) S.rx[c] = pg[c];
+    for (int j = tid; j < p; j += NT) S.ry[j] = -bg[j];
+    __syncthreads();
+    const bool ok = build_and_factor_T<T, SMEM>(S, a, prob, tid, NT);
+    if (!ok) {
+      if (tid == 0) a.flags[prob] = FLAG_POISON;
+      return;
+    }
+    kkt_solve(S, a, prob, S.rx, S.rsc, S.rz, p > 0 ? S.ry : (const T*)nullptr, S.x, S.s, S.z, S.y, tid, NT);
+    // shift s and z so that their minimum is >= 1   (batch.py:76-86)
+    T mn[2] = {t_inf<T>(), t_inf<T>()};
+    for (int i = tid; i < m; i += NT) { mn[0] = nanmin(mn[0], S.s[i]); mn[1] = nanmin(mn[1], S.z[i]); }
+    block_reduce<2>(mn, OpNanMin(), S.red, tid, NT);
+    for (int i = tid; i < m; i += NT) {
+      T sv = S.s[i], zv = S.z[i];
+      if (mn[0] < T(0)) sv -= mn[0] - T(1);
+      if (mn[1] < T(0)) zv -= mn[1] - T(1);
+      gs_[i] = sv; gz_[i] = zv;
+    }
+    for (int c = tid; c < n; c += NT) gx[c] = S.x[c];
+    for (int j = tid; j < p; j += NT) gy[j] = S.y[j];
+    if (tid == 0) a.flags[prob] = 0;
+    return;
+  }
+
+  // ---- load the iterate; apply the previous iteration's step (batch.py:190-204)
+  {
+    T alpha = T(0);
+    if (it > 0) {
+      const T rz_ = a.rmu[(size_t)prob * 2], rs_ = a.rmu[(size_t)prob * 2 + 1];
+      const T stz = (flags & FLAG_FILL_Z) ? nanmin(rz_, fill_z) : rz_;
+      const T sts = (flags & FLAG_FILL_S) ? nanmin(rs_, fill_s) : rs_;
+      alpha = nanmin(T(0.999) * nanmin(stz, sts), T(1));
+    }
+    for (int c = tid; c < n; c += NT) { T v = gx[c]; if (it > 0) v += alpha * gdx[c]; S.x[c] = v; }
+    for (int i = tid; i < m; i += NT) {
+      T sv = gs_[i], zv = gz_[i];
+      if (it > 0) { sv += alpha * gds[i]; zv += alpha * gdz[i]; }
+      S.s[i] = sv; S.z[i] = zv;
+    }
+    for (int j = tid; j < p; j += NT) { T v = gy[j]; if (it > 0) v += alpha * gdy[j]; S.y[j] = v; }
+  }
+  __syncthreads();
+
+  // ---- residuals (batch.py:93-108)
+  // rx = Q x + p + G^T z + A^T y ; rz = G x + s - h ; ry = A x - b
+  gemv_rows_warp(Qg, n, n, n, S.x, S.rx, tid, NT);
+  gemv_rows_warp(Gg, n, m, n, S.x, S.rz, tid, NT);
+  if (p > 0) gemv_rows_warp(Ag, n, p, n, S.x, S.ry, tid, NT);
+  gemv_cols(Gg, n, m, n, S.z, S.t, S.part, tid, NT);  // G^T z -> t (barrier inside)
+  if (p > 0) gemv_cols(Ag, n, p, n, S.y, S.dxc, S.part, tid, NT);
+  T acc[4] = {T(0), T(0), T(0), T(0)};  // |rx|^2, |rz|^2, |ry|^2, s.z
+  for (int c = tid; c < n; c += NT) {
+    T v = S.rx[c] + pg[c] + S.t[c];
+    if (p > 0) v += S.dxc[c];
+    S.rx[c] = v;
+    acc[0] += v * v;
+  }
+  for (int i = tid; i < m; i += NT) {
+    const T sv = S.s[i], zv = S.z[i];
+    const T v = S.rz[i] + sv - hg[i];
+    S.rz[i] = v;
+    acc[1] += v * v;
+    acc[3] += sv * zv;
+    S.d[i] = zv / sv;
+  }
+  for (int j = tid; j < p; j += NT) {
+    const T v = S.ry[j] - bg[j];
+    S.ry[j] = v;
+    acc[2] += v * v;
+  }
+  block_reduce<4>(acc, OpSum(), S.red, tid, NT);
+  const T mu = fabs(acc[3] / T(m));
+  const T pri = (p > 0 ? sqrt(acc[2]) : T(0)) + sqrt(acc[1]);
+  const T resid = pri + sqrt(acc[0]) + T(m) * mu;
+  const T t4 = acc[3];
+
+  // ---- factor T = R + diag(s/z)   (batch.py:110-114)
+  const bool ok = build_and_factor_T<T, SMEM>(S, a, prob, tid, NT);
+
+  // ---- best-iterate bookkeeping + global reductions (batch.py:119-144)
+  {
+    const double rd = (double)resid;
+    const double prev = a.best_resid[prob];
+    const bool better = (it == 0) ? true : (rd < prev);
+    __syncthreads();  // everyone has read best_resid before thread 0 may overwrite it
+    if (better) {
+      T* bx = a.bx + (size_t)prob * n; T* bs = a.bs + (size_t)prob * m; T* bz = a.bz + (size_t)prob * m;
+      for (int c = tid; c < n; c += NT) bx[c] = S.x[c];
+      for (int i = tid; i < m; i += NT) { bs[i] = S.s[i]; bz[i] = S.z[i]; }
+      if (p > 0) { T* by = a.by + (size_t)prob * p; for (int j = tid; j < p; j += NT) by[j] = S.y[j]; }
+    }
+    if (tid == 0) {
+      const double br = better ? rd : prev;
+      if (better) a.best_resid[prob] = rd;
+      if (better && it > 0 && !slot->improved) slot->improved = 1;
+      if (br != br) slot->best_nan = 1; else atomic_max_key(&slot->best_max, (unsigned long long)__double_as_longlong(br));
+      const double mud = (double)mu;
+      if (mud != mud) slot->mu_nan = 1; else atomic_max_key(&slot->mu_min_inv, ~ord_key(mud));
+    }
+  }
+  if (!ok) {
+    if (tid == 0) {
+      a.flags[prob] = FLAG_POISON;
+      slot->az_nan = 1;
+      slot->as_nan = 1;
+    }
+    return;
+  }
+
+  // ---- affine direction (batch.py:151-152):  rs = z
+  kkt_solve(S, a, prob, S.rx, S.z, S.rz, p > 0 ? S.ry : (const T*)nullptr, S.dxa, S.dsa, S.dza, S.dya, tid, NT);
+
+  // ---- centering (batch.py:161-169); the clamp at 1 makes alpha_aff independent of the fill
+  T alpha_aff;
+  {
+    T rmz, rms, amz, ams; bool hz, hs;
+    step_pieces(S.z, S.dza, m, tid, NT, S.red, rmz, hz, amz);
+    step_pieces(S.s, S.dsa, m, tid, NT, S.red, rms, hs, ams);
+    const T stz = hz ? nanmin(rmz, T(1)) : rmz;
+    const T sts = hs ? nanmin(rms, T(1)) : rms;
+    alpha_aff = nanmin(nanmin(stz, sts), T(1));
+  }
+  T t3v[1] = {T(0)};
+  for (int i = tid; i < m; i += NT) t3v[0] += (S.s[i] + alpha_aff * S.dsa[i]) * (S.z[i] + alpha_aff * S.dza[i]);
+  block_reduce<1>(t3v, OpSum(), S.red, tid, NT);
+  const T ratio = t3v[0] / t4;
+  const T sig = ratio * ratio * ratio;
+  for (int i = tid; i < m; i += NT) S.rsc[i] = (-mu * sig + S.dsa[i] * S.dza[i]) / S.s[i];
+  __syncthreads();
+
+  // ---- corrector (batch.py:171-182): rx = rz = ry = 0
+  kkt_solve(S, a, prob, (const T*)nullptr, S.rsc, (const T*)nullptr, (const T*)nullptr, S.dxc, S.dsc, S.dzc, S.dyc, tid, NT);
+
+  // ---- combined direction; its get_step pieces; hand over to the next launch
+  for (int c = tid; c < n; c += NT) { const T v = S.dxa[c] + S.dxc[c]; gdx[c] = v; }
+  for (int i = tid; i < m; i += NT) {
+    const T vs = S.dsa[i] + S.dsc[i], vz = S.dza[i] + S.dzc[i];
+    S.dsa[i] = vs; S.dza[i] = vz;
+    gds[i] = vs; gdz[i] = vz;
+  }
+  for (int j = tid; j < p; j += NT) gdy[j] = S.dya[j] + S.dyc[j];
+  // the iterate itself is unchanged until the step is applied by the next launch
+  if (it == 0) {
+    // nothing: x,s,z,y already in global memory from the init kernel
+  } else {
+    for (int c = tid; c < n; c += NT) gx[c] = S.x[c];
+    for (int i = tid; i < m; i += NT) { gs_[i] = S.s[i]; gz_[i] = S.z[i]; }
+    for (int j = tid; j < p; j += NT) gy[j] = S.y[j];
+  }
+  __syncthreads();
+  {
+    T rmz, rms, amz, ams; bool hz, hs;
+    step_pieces(S.z, S.dza, m, tid, NT, S.red, rmz, hz, amz);
+    step_pieces(S.s, S.dsa, m, tid, NT, S.red, rms, hs, ams);
+    if (tid == 0) {
+      a.rmu[(size_t)prob * 2] = rmz;
+      a.rmu[(size_t)prob * 2 + 1] = rms;
+      a.flags[prob] = (hz ? FLAG_FILL_Z : 0) | (hs ? FLAG_FILL_S : 0);
+      const double dz_ = (double)amz, ds_ = (double)ams;
+      if (dz_ != dz_) slot->az_nan = 1; else atomic_max_key(&slot->amax_z, ord_key(dz_));
+      if (ds_ != ds_) slot->as_nan = 1; else atomic_max_key(&slot->amax_s, ord_key(ds_));
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// After the last iteration launch: iteration count and worst best-residual -> status.
+__global__ void k_finalize(const Slot* slots, const Control* ctl, double* status, int max_iter, int lim, double eps,
+                           int launches) {
+  const int lane = threadIdx.x;
+  const int term = eval_termination(slots, max_iter, lim, eps, lane);
+  if (lane == 0) {
+    const int n_iter = term >= 0 ? term + 1 : max_iter;
+    const Slot* sl = slots + (n_iter - 1);
+    status[0] = (double)n_iter;
+    status[1] = sl->best_nan ? __longlong_as_double(0x7ff8000000000000LL) : __longlong_as_double((long long)sl->best_max);
+    status[2] = (double)ctl->q_fail;
+    status[3] = (double)ctl->aqa_fail;
+    status[4] = (double)launches;
+    status[5] = status[6] = status[7] = 0.0;
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// Pre-factorisation (d-independent part).  Works in global memory (L1/L2 resident: one-off).
+template <typename T, int NT>
+__global__ void __launch_bounds__(NT) k_prefactor(const KArgs<T> a) {
+  const int prob = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int n = a.n, m = a.m, p = a.p, ldn = a.ldn, ldm = a.ldm, ldp = a.ldp;
+  const T* Qg = a.Q + (size_t)prob * a.sQ;
+  const T* Gg = a.G + (size_t)prob * a.sG;
+  const T* Ag = a.A + (size_t)prob * a.sA;
+  T* F = a.F + (size_t)prob * a.sF;
+  T* pinvF = a.pinvF + (size_t)prob * round4(n);
+  T* Qi = a.Qi + (size_t)prob * a.sQi;
+  T* BQi = a.BQi + (size_t)prob * a.sBQi;
+  T* R = a.R + (size_t)prob * a.sR;
+  T* V = a.V + (size_t)prob * a.sV;
+  T* UA = a.UA + (size_t)prob * a.sUA;
+  T* pinvA = a.pinvA + (size_t)prob * round4(p > 0 ? p : 1);
+
+  // F = Q ; LDL^T
+  for (int i = tid; i < n * n; i += NT) { const int r = i / n, c = i - r * n; F[(size_t)r * ldn + c] = Qg[i]; }
+  __syncthreads();
+  const bool okQ = ldlt_factor(F, ldn, n, pinvF, tid, NT);
+  if (!okQ && tid == 0) atomicAdd(&a.ctl->q_fail, 1u);
+  // Qi column c by thread c:  L y = e_c ; y *= pinv ; L^T x = y   (columns are independent)
+  for (int c = tid; c < n; c += NT) {
+    for (int k = 0; k < n; k++) Qi[(size_t)k * ldn + c] = (k == c) ? T(1) : T(0);
+    for (int j = c; j < n; j++) {
+      const T yj = Qi[(size_t)j * ldn + c];
+      const T* row = F + (size_t)j * ldn;
+      for (int i = j + 1; i < n; i++) Qi[(size_t)i * ldn + c] -= row[i] * yj;
+    }
+    for (int k = c; k < n; k++) Qi[(size_t)k * ldn + c] *= pinvF[k];
+    for (int j = n - 1; j > 0; j--) {
+      const T xj = Qi[(size_t)j * ldn + c];
+      for (int i = 0; i < j; i++) Qi[(size_t)i * ldn + c] -= F[(size_t)i * ldn + j] * xj;
+    }
+  }
+  __syncthreads();
+  // BQi = [A;G] Qi
+  const int pm = p + m;
+  for (int e = tid; e < pm * n; e += NT) {
+    const int r = e / n, c = e - r * n;
+    const T* brow = r < p ? Ag + (size_t)r * n : Gg + (size_t)(r - p) * n;
+    T a0 = 0, a1 = 0;
+    int k = 0;
+    for (; k + 1 < n; k += 2) { a0 += brow[k] * Qi[(size_t)k * ldn + c]; a1 += brow[k + 1] * Qi[(size_t)(k + 1) * ldn + c]; }
+    if (k < n) a0 += brow[k] * Qi[(size_t)k * ldn + c];
+    BQi[(size_t)r * ldn + c] = a0 + a1;
+  }
+  __syncthreads();
+  // M = BQi [A;G]^T  ->  Saa (UA, lower), Sag (V), Sgg (R, lower incl. diagonal)
+  for (int e = tid; e < pm * pm; e += NT) {
+    const int r = e / pm, q = e - r * pm;
+    const bool need = (r < p && q < p && q <= r) || (r < p && q >= p) || (r >= p && q >= p && q <= r);
+    if (!need) continue;
+    const T* brow = q < p ? Ag + (size_t)q * n : Gg + (size_t)(q - p) * n;
+    const T* qrow = BQi + (size_t)r * ldn;
+    T a0 = 0, a1 = 0;
+    int k = 0;
+    for (; k + 1 < n; k += 2) { a0 += qrow[k] * brow[k]; a1 += qrow[k + 1] * brow[k + 1]; }
+    if (k < n) a0 += qrow[k] * brow[k];
+    const T v = a0 + a1;
+    if (r < p && q < p) UA[(size_t)r * ldp + q] = v;
+    else if (r < p) V[(size_t)r * ldm + (q - p)] = v;
+    else R[(size_t)(r - p) * ldm + (q - p)] = v;
+  }
+  __syncthreads();
+  if (p > 0) {
+    const bool okA = ldlt_factor(UA, ldp, p, pinvA, tid, NT);
+    if (!okA && tid == 0) atomicAdd(&a.ctl->aqa_fail, 1u);
+    // V <- La^-1 Sag  (column i of V by thread i)
+    for (int i = tid; i < m; i += NT) {
+      for (int j = 0; j < p; j++) {
+        const T vj = V[(size_t)j * ldm + i];
+        const T* row = UA + (size_t)j * ldp;
+        for (int k = j + 1; k < p; k++) V[(size_t)k * ldm + i] -= row[k] * vj;
+      }
+    }
+    __syncthreads();
+    // R -= V^T Da^-1 V  (lower triangle)
+    for (int e = tid; e < m * m; e += NT) {
+      const int r = e / m, q = e - r * m;
+      if (q > r) continue;
+      T acc = 0;
+      for (int j = 0; j < p; j++) acc += V[(size_t)j * ldm + r] * pinvA[j] * V[(size_t)j * ldm + q];
+      R[(size_t)r * ldm + q] -= acc;
+    }
+  }
+  // mirror R's lower triangle so that the staged copy is symmetric (only the lower is used)
+  (void)lane; (void)warp;
+}
+
+// ------------------------------------------------------------------------------------------
+// Backward (qp.py:129-183): d = clamp(lam)/clamp(s); one factor + one solve; outer products.
+template <typename T>
+struct BArgs {
+  const T *zhat, *lams, *nus, *slacks, *gz;  // best iterate + dl/dzhat
+  T *dQ, *dp, *dG, *dh, *dA, *db;
+};
+
+template <typename T, bool SMEM, int NT>
+__global__ void __launch_bounds__(NT) k_backward(const KArgs<T> a, const BArgs<T> g) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int prob = blockIdx.x, tid = threadIdx.x;
+  const int n = a.n, m = a.m, p = a.p;
+  Smem<T> S;
+  carve<T, SMEM>(S, smem_raw, a, prob, NT);
+  stage_mats<T, SMEM>(S, a, prob, tid, NT);
+  const T* zh = g.zhat + (size_t)prob * n;
+  const T* lam = g.lams + (size_t)prob * m;
+  const T* sl = g.slacks + (size_t)prob * m;
+  const T* nu = g.nus + (size_t)prob * p;
+  const T* gz = g.gz + (size_t)prob * n;
+  for (int i = tid; i < m; i += NT) {
+    const T lv = lam[i], sv = sl[i];
+    S.z[i] = lv;  // lams
+    // torch.clamp(x, min=c): NaN stays NaN
+    const T lc = (lv < T(1e-8)) ? T(1e-8) : lv, sc = (sv < T(1e-8)) ? T(1e-8) : sv;
+    S.d[i] = lc / sc;
+    S.rsc[i] = T(0);
+  }
+  for (int c = tid; c < n; c += NT) { S.rx[c] = gz[c]; S.x[c] = zh[c]; }
+  for (int j = tid; j < p; j += NT) S.y[j] = nu[j];
+  __syncthreads();
+  const bool ok = build_and_factor_T<T, SMEM>(S, a, prob, tid, NT);
+  if (!ok) {
+    for (int i = tid; i < m * a.ldm; i += NT) S.Tm[i] = t_nan<T>();
+    for (int i = tid; i < m; i += NT) S.pinvT[i] = t_nan<T>();
+    __syncthreads();
+  }
+  kkt_solve(S, a, prob, S.rx, S.rsc, (const T*)nullptr, (const T*)nullptr, S.dxa, S.dsa, S.dza, S.dya, tid, NT);
+  // dp = dx ; dh = -dlam ; db = -dnu
+  T* dp = g.dp + (size_t)prob * n; T* dh = g.dh + (size_t)prob * m;
+  for (int c = tid; c < n; c += NT) dp[c] = S.dxa[c];
+  for (int i = tid; i < m; i += NT) dh[i] = -S.dza[i];
+  if (p > 0) { T* db = g.db + (size_t)prob * p; for (int j = tid; j < p; j += NT) db[j] = -S.dya[j]; }
+  // dQ = 0.5 (dx zhat^T + zhat dx^T)
+  T* dQ = g.dQ + (size_t)prob * n * n;
+  for (int e = tid; e < n * n; e += NT) {
+    const int r = e / n, c = e - r * n;
+    dQ[e] = T(0.5) * (S.dxa[r] * S.x[c] + S.x[r] * S.dxa[c]);
+  }
+  // dG = dlam zhat^T + lam dx^T
+  T* dG = g.dG + (size_t)prob * m * n;
+  for (int e = tid; e < m * n; e += NT) {
+    const int r = e / n, c = e - r * n;
+    dG[e] = S.dza[r] * S.x[c] + S.z[r] * S.dxa[c];
+  }
+  if (p > 0) {
+    T* dA = g.dA + (size_t)prob * p * n;
+    for (int e = tid; e < p * n; e += NT) {
+      const int r = e / n, c = e - r * n;
+      dA[e] = S.dya[r] * S.x[c] + S.y[r] * S.dxa[c];
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// Stand-alone KKT solve with caller-provided d and right-hand sides (batch.py:351-374 + :434-469).
+template <typename T>
+struct SArgs {
+  const T *d, *rx, *rs, *rz, *ry;
+  T *dx, *ds, *dz, *dy;
+};
+
+template <typename T, bool SMEM, int NT>
+__global__ void __launch_bounds__(NT) k_kkt_solve(const KArgs<T> a, const SArgs<T> g) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int prob = blockIdx.x, tid = threadIdx.x;
+  const int n = a.n, m = a.m, p = a.p;
+  Smem<T> S;
+  carve<T, SMEM>(S, smem_raw, a, prob, NT);
+  stage_mats<T, SMEM>(S, a, prob, tid, NT);
+  for (int i = tid; i < m; i += NT) {
+    S.d[i] = g.d[(size_t)prob * m + i];
+    S.rsc[i] = g.rs[(size_t)prob * m + i];
+    S.rz[i] = g.rz[(size_t)prob * m + i];
+  }
+  for (int c = tid; c < n; c += NT) S.rx[c] = g.rx[(size_t)prob * n + c];
+  for (int j = tid; j < p; j += NT) S.ry[j] = g.ry[(size_t)prob * p + j];
+  __syncthreads();
+  const bool ok = build_and_factor_T<T, SMEM>(S, a, prob, tid, NT);
+  if (!ok) {
+    for (int i = tid; i < m; i += NT) S.pinvT[i] = t_nan<T>();
+    __syncthreads();
+  }
+  kkt_solve(S, a, prob, S.rx, S.rsc, S.rz, p > 0 ? S.ry : (const T*)nullptr, S.dxa, S.dsa, S.dza, S.dya, tid, NT);
+  for (int c = tid; c < n; c += NT) g.dx[(size_t)prob * n + c] = S.dxa[c];
+  for (int i = tid; i < m; i += NT) { g.ds[(size_t)prob * m + i] = S.dsa[i]; g.dz[(size_t)prob * m + i] = S.dza[i]; }
+  for (int j = tid; j < p; j += NT) g.dy[(size_t)prob * p + j] = S.dya[j];
+}
+
+}  // namespace b200qp

@@ -1,0 +1,113 @@
+/* b200qp.h -- C ABI of the B200-native batched PDIPM QP solver (libb200qp.so).
+ *
+ * There is no FFI on this path in the reference (swami1995/diff-qp-mpc): its boundary is the
+ * Python call surface.  Each entry point below replaces the torch-op sequence of one reference
+ * function; a maintainer binds it with the ctypes stub shown in INTEGRATION.md.
+ *
+ *   b200qp_forward   replaces qpth/qp.py:74-126 (QPFunctionFn.forward) =
+ *                    qpth/solvers/pdipm/batch.py:377-428 (pre_factor_kkt)
+ *                  + qpth/solvers/pdipm/batch.py:46-208  (forward: Mehrotra loop, best-iterate
+ *                    tracking, batch-global termination) + :434-469 factor_kkt + :351-374 solve_kkt
+ *                  + :211-214 get_step
+ *   b200qp_backward  replaces qpth/qp.py:129-183 (QPFunctionFn.backward: adjoint KKT solve that
+ *                    reuses the forward pre-factorisation, outer-product gradients)
+ *   b200qp_kkt_solve replaces pre_factor_kkt + factor_kkt + solve_kkt as a stand-alone call
+ *                    (qpth/solvers/pdipm/batch.py:351-469; what test.py:222-247 exercises)
+ *   b200qp_solve_host  forward(+backward) with HOST buffers: the H2D/D2H copies are inside.
+ *
+ * Conventions: plain pointers and sizes only; all device pointers are borrowed, contiguous,
+ * on the current device; all work is enqueued on `stream` (no hidden synchronisation except in
+ * b200qp_solve_host); return 0 on success, a negative B200QP_E* code on argument/launch errors.
+ * Matrices are row-major.  Batch strides are in ELEMENTS; stride 0 = parameter shared by the
+ * whole batch (qpth/util.py:69-75 expandParam).
+ */
+#ifndef B200QP_H
+#define B200QP_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200QP_F64 0
+#define B200QP_F32 1
+
+#define B200QP_OK 0
+#define B200QP_EINVAL (-1)   /* bad sizes / null pointers / unsupported dtype            */
+#define B200QP_ECUDA (-2)    /* a CUDA runtime call failed (see b200qp_last_cuda_error)   */
+#define B200QP_ETOOBIG (-3)  /* problem does not fit the kernels' shared/global workspace */
+
+#define B200QP_MAX_ITER_CAP 64
+#define B200QP_STATUS_DOUBLES 8
+
+/* status[] layout (device buffer of B200QP_STATUS_DOUBLES doubles, written by forward) */
+#define B200QP_ST_NITER 0        /* loop bodies entered (== reference's iteration count)      */
+#define B200QP_ST_BEST_MAX 1     /* max over the batch of the best residual (NaN propagates)  */
+#define B200QP_ST_Q_FAIL 2       /* number of problems whose Q factorisation failed           */
+#define B200QP_ST_AQA_FAIL 3     /* number of problems whose A Q^-1 A^T factorisation failed  */
+#define B200QP_ST_LAUNCHES 4     /* kernels launched by the call                              */
+
+typedef void* b200qp_stream_t;   /* a cudaStream_t */
+
+typedef struct {
+  int32_t nb, nz, nineq, neq;    /* batch, variables, inequality rows, equality rows          */
+  int32_t dtype;                 /* B200QP_F64 | B200QP_F32                                   */
+  int32_t max_iter;              /* maxIter        (qpth/qp.py:19-21 default 20)              */
+  int32_t not_improved_lim;      /* notImprovedLim (default 3)                                */
+  int32_t reserved;
+  double eps;                    /* eps            (default 1e-12)                            */
+  int64_t sQ, sp, sG, sh, sA, sb; /* batch strides in elements, 0 = shared                    */
+} b200qp_problem_t;
+
+/* Bytes of device workspace forward needs; the same buffer must be handed to backward. */
+size_t b200qp_workspace_bytes(const b200qp_problem_t* prob);
+
+/* Solve the batch.  Outputs: zhat (nb,nz), lams (nb,nineq), nus (nb,neq), slacks (nb,nineq),
+ * status (device, 8 doubles).  workspace: b200qp_workspace_bytes() bytes, 16-byte aligned. */
+int b200qp_forward(const b200qp_problem_t* prob,
+                   const void* Q, const void* p, const void* G, const void* h,
+                   const void* A, const void* b,
+                   void* zhat, void* lams, void* nus, void* slacks,
+                   void* workspace, double* status, b200qp_stream_t stream);
+
+/* Adjoint solve.  Needs the forward's workspace (pre-factorisation) and outputs.
+ * Writes PER-PROBLEM gradients: dQ (nb,nz,nz) dp (nb,nz) dG (nb,nineq,nz) dh (nb,nineq)
+ * dA (nb,neq,nz) db (nb,neq); the caller averages them for shared parameters
+ * (qpth/qp.py:160-178 uses .mean(0)). */
+int b200qp_backward(const b200qp_problem_t* prob,
+                    const void* zhat, const void* lams, const void* nus, const void* slacks,
+                    const void* dl_dzhat,
+                    void* dQ, void* dp, void* dG, void* dh, void* dA, void* db,
+                    void* workspace, b200qp_stream_t stream);
+
+/* Stand-alone KKT solve: given d (nb,nineq) and right-hand sides, return the solution of
+ *   [Q 0 G' A'; 0 D I 0; G I 0 0; A 0 0 0] [dx ds dz dy]' = -[rx rs rz ry]'.
+ * prefactor != 0 recomputes the d-independent part from Q, G, A first. */
+int b200qp_kkt_solve(const b200qp_problem_t* prob, int prefactor,
+                     const void* Q, const void* G, const void* A, const void* d,
+                     const void* rx, const void* rs, const void* rz, const void* ry,
+                     void* dx, void* ds, void* dz, void* dy,
+                     void* workspace, b200qp_stream_t stream);
+
+/* Whole solve with HOST buffers (pageable or pinned): copies inputs to the device, runs
+ * forward (and backward when dl_dzhat != NULL), copies results back, synchronises.
+ * Gradient pointers may be NULL when dl_dzhat is NULL.  status: 8 host doubles. */
+int b200qp_solve_host(const b200qp_problem_t* prob,
+                      const void* Q, const void* p, const void* G, const void* h,
+                      const void* A, const void* b, const void* dl_dzhat,
+                      void* zhat, void* lams, void* nus, void* slacks,
+                      void* dQ, void* dp, void* dG, void* dh, void* dA, void* db,
+                      double* status);
+
+/* Text of the last CUDA error seen by this library on the calling thread ("" if none). */
+const char* b200qp_last_cuda_error(void);
+
+/* Library version / build tag, e.g. "b200qp 0.1 sm_100a". */
+const char* b200qp_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200QP_H */
