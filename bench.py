@@ -1,0 +1,396 @@
+#!/usr/bin/env python
+"""bench.py -- headline metric of BASELINE.json on B200: batched QP solves/s (forward+backward,
+nz=30, nineq=60, neq=0, fp64) through the QPFunction drop-in, one process per GPU.
+
+    python bench.py --gpus 1 --steps 10 --warmup 3            # our CUDA path
+    python bench.py --impl reference --steps 3 --warmup 1     # the reference's CPU algorithm
+    torchrun --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+A "step" is one QPFunction forward + backward over one batch of synthetic random QPs (recipe of
+the reference's prof-linear.py:64-75).  The batch is sharded across ranks with NO data-path
+collective (problems are independent) => weak scaling, `value` = problems
+all ranks solved / max-over-ranks device time.  Prints ONE JSON line (rank 0).
+"""
+import argparse
+import ctypes
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for _p in (ROOT, os.path.join(ROOT, "diff-qp-mpc_b200")):
+    if _p not in sys.path:
+        sys.path.insert(0, _p)
+
+import torch  # noqa: E402
+
+NZ, NINEQ, NEQ = 30, 60, 0
+METRIC = "batched QP solves/sec (fwd+bwd, nz=30, nineq=60, neq=0, fp64)"
+UNIT = "solves/s"
+
+
+def algorithmic_flops(n, m, n_iter):
+    """SURVEY.md section 8d (minimal-work, Cholesky based, neq=0)."""
+    f_pre = n ** 3 / 3 + n * n * m + n * m * m
+    f_solve = 4 * n * n + 4 * n * m + 2 * m * m
+    f_init = m ** 3 / 3 + f_solve
+    f_iter = m ** 3 / 3 + 10 * n * n + 12 * n * m + 4 * m * m
+    f_bwd = m ** 3 / 3 + f_solve + 3 * n * n + 3 * n * m
+    return dict(pre=f_pre, init=f_init, iter=f_iter, bwd=f_bwd, total=f_pre + f_init + n_iter * f_iter + f_bwd)
+
+
+def algorithmic_bytes_per_solve(n, m, es=8):
+    """read Q,p,G,h once in fwd and once in bwd; write zhat, lam, s, grads."""
+    return es * (3 * (n * n + m * n + n + m) + n + 2 * m)
+
+
+def iter_kernel_bytes(n, m, es=8):
+    """Bytes one launch of the fused iteration kernel must move per problem in THIS design (the
+    d-independent matrices are re-staged every launch because the reference's batch-global
+    termination forces a grid-wide dependency per iteration): R, BQi, Qi, Q, G + iterate/direction."""
+    ldn, ldm = n | 1, m | 1
+    mats = m * ldm + m * ldn + n * ldn + n * n + m * n
+    vecs = 2 * (2 * n + 4 * m) + (n + 2 * m)
+    return es * (mats + vecs)
+
+
+def gen_batch(nb, device, seed, dtype=torch.float64):
+    g = torch.Generator(device=device).manual_seed(seed)
+    L = torch.rand(nb, NZ, NZ, generator=g, device=device, dtype=dtype)
+    Q = torch.bmm(L, L.transpose(1, 2)) + 1e-3 * torch.eye(NZ, device=device, dtype=dtype)
+    G = torch.randn(nb, NINEQ, NZ, generator=g, device=device, dtype=dtype)
+    z0 = torch.randn(nb, NZ, generator=g, device=device, dtype=dtype)
+    s0 = torch.rand(nb, NINEQ, generator=g, device=device, dtype=dtype)
+    p = torch.randn(nb, NZ, generator=g, device=device, dtype=dtype)
+    h = torch.bmm(G, z0.unsqueeze(2)).squeeze(2) + s0
+    A = torch.zeros(nb, 0, NZ, device=device, dtype=dtype)
+    b = torch.zeros(nb, 0, device=device, dtype=dtype)
+    return Q, p, G, h, A, b
+
+
+class ClockSampler:
+    """nvidia-smi clocks/throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.proc = None
+        self.path = None
+
+    def start(self):
+        try:
+            f = tempfile.NamedTemporaryFile("w", suffix=".csv", delete=False)
+            self.path = f.name
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=f,
+                                         stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.proc is None:
+            return out
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, reasons, mx, pw = [], set(), None, []
+        try:
+            for line in open(self.path):
+                c = [x.strip() for x in line.split(",")]
+                if len(c) < 8:
+                    continue
+                try:
+                    sm.append(float(c[1])); mx = float(c[2]); pw.append(float(c[3]))
+                except ValueError:
+                    continue
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), c[4:8]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            os.unlink(self.path)
+        except Exception:
+            pass
+        if sm:
+            out.update(sm_mhz=statistics.median(sm), sm_max_mhz=mx, reasons=sorted(reasons), samples=len(sm),
+                       power_w_max=max(pw) if pw else None)
+        return out
+
+
+def cpu_oracle_rate(nb, repeats, threads):
+    """The reference's algorithm (oracle port, bit-identical to qpth on CPU) on the host cores."""
+    from oracle import qp_oracle as O
+    torch.set_num_threads(threads)
+    Q, p, G, h, A, b = gen_batch(nb, torch.device("cpu"), seed=0)
+    times = []
+    n_iter = None
+    for r in range(repeats + 1):
+        t0 = time.perf_counter()
+        fwd = O.qp_forward(Q, p, G, h, A, b)
+        O.qp_backward(fwd, Q, p, G, h, A, b, torch.ones_like(fwd["zhat"]))
+        dt = time.perf_counter() - t0
+        n_iter = fwd["n_iter"]
+        if r > 0 or repeats == 0:
+            times.append(dt)
+    return nb / statistics.median(times), n_iter, statistics.median(times)
+
+
+def run_reference(args, rank):
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    from oracle import qp_oracle as O
+    torch.set_num_threads(threads)
+    nb = args.ref_nb
+    Q, p, G, h, A, b = gen_batch(nb, torch.device("cpu"), seed=0)
+
+    def step():
+        fwd = O.qp_forward(Q, p, G, h, A, b)
+        O.qp_backward(fwd, Q, p, G, h, A, b, torch.ones_like(fwd["zhat"]))
+        return fwd["n_iter"]
+
+    for _ in range(args.warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        n_iter = step()
+    dt = time.perf_counter() - t0
+    value = nb * args.steps / dt
+    sample = f"nb={nb} random QPs per step (same generator), {n_iter} PDIPM iterations, torch CPU fp64"
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"random-QP batch nz={NZ} nineq={NINEQ} neq=0 fp64 fwd+bwd (BASELINE configs[0]/[4])",
+                   "batch_per_step": nb},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--nb", type=int, default=32768, help="QPs per GPU per step")
+    ap.add_argument("--ref-nb", type=int, default=1024, help="QPs per step of the CPU reference arm")
+    ap.add_argument("--cpu-nb", type=int, default=1024, help="bounded sample for cpu_baseline")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+
+    import torch.distributed as dist
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (the product path has no CPU fallback)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    from b200qp import _lib
+    from b200qp.qp import QPFunction
+    L = _lib.lib()
+
+    nb = args.nb
+    Q, p, G, h, A, b = gen_batch(nb, dev, seed=1000 + rank)
+    for t in (Q, p, G, h):
+        t.requires_grad_(True)
+    fn = QPFunction(verbose=-1, check_Q_spd=False)
+    ones = torch.ones(nb, NZ, device=dev, dtype=torch.float64)
+
+    def step():
+        for t in (Q, p, G, h):
+            t.grad = None
+        z = fn(Q, p, G, h, A, b)
+        z.backward(ones)
+        return z
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    # ---- timed region: device-resident inputs --------------------------------------------
+    L.b200qp_profile_enable(1)
+    ms_buf = (ctypes.c_float * 256)()
+    kind_buf = (ctypes.c_int * 256)()
+    iter_ms, all_kernel_ms, n_iters = [], [], []
+    sampler = ClockSampler(local_rank)
+    barrier()
+    sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        step()
+        n = L.b200qp_profile_read(ms_buf, kind_buf, 256)
+        ni = fn.info["n_iter"]
+        n_iters.append(ni)
+        k2 = [ms_buf[i] for i in range(n) if kind_buf[i] == 2]
+        iter_ms.extend(k2[:ni])
+        all_kernel_ms.append(sum(ms_buf[i] for i in range(n) if kind_buf[i] != 3))
+    e1.record()
+    barrier()
+    clocks = sampler.stop()
+    L.b200qp_profile_enable(0)
+    ms_total = e0.elapsed_time(e1)
+    tmax = torch.tensor([ms_total], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+    ms_total = tmax.item()
+    value = nb * world * args.steps / (ms_total * 1e-3)
+    n_iter = int(statistics.median(n_iters))
+    launches_per_step = fn.info["launches"] + 1
+
+    # ---- roofline of the dominant kernel (fused PDIPM iteration) ---------------------------
+    fl = algorithmic_flops(NZ, NINEQ, n_iter)
+    avg_iter_ms = sum(iter_ms) / max(len(iter_ms), 1)
+    peaks_fp64 = {}
+    try:
+        peaks_fp64 = json.load(open(os.path.join(ROOT, "profiles", "fp64_peaks_r01.json")))
+    except Exception:
+        pass
+    try:
+        hbm_peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]
+        hbm_src = "MEASURED_PEAKS.json"
+    except Exception:
+        hbm_peak, hbm_src = 6650.0, "fallback"
+    fp64_peak = peaks_fp64.get("dfma_tflops_sustained", 34.0)
+    ach_tf = fl["iter"] * nb / (avg_iter_ms * 1e-3) / 1e12
+    ach_gbs = iter_kernel_bytes(NZ, NINEQ) * nb / (avg_iter_ms * 1e-3) / 1e9
+    roofline = {
+        "kernel": "k_pdipm_iter<double,smem,128>", "bound": "fp64",
+        "achieved": ach_tf, "peak": fp64_peak, "unit": "TFLOP/s", "frac": ach_tf / fp64_peak,
+        "peak_source": "profiles/fp64_peaks_r01.json (DFMA microbenchmark on this pool's B200; MEASURED_PEAKS.json has no FP64 figure)",
+        "flops_per_launch": fl["iter"] * nb, "avg_launch_ms": avg_iter_ms, "launches_timed": len(iter_ms),
+        "traffic": None,
+        "hbm": {"achieved": ach_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": ach_gbs / hbm_peak,
+                "bytes_per_launch": iter_kernel_bytes(NZ, NINEQ) * nb, "peak_source": hbm_src},
+        "whole_solve": {"flops_per_solve": fl["total"], "bytes_per_solve": algorithmic_bytes_per_solve(NZ, NINEQ),
+                        "tflops": fl["total"] * value / 1e12, "frac_of_fp64_peak": fl["total"] * value / 1e12 / (fp64_peak * world),
+                        "kernel_share_of_step": sum(iter_ms) / max(sum(all_kernel_ms), 1e-9)},
+    }
+
+    # ---- end to end through the C ABI with HOST buffers ------------------------------------
+    e2e = None
+    if not args.no_e2e:
+        es = 8
+        host = {k: torch.empty(v.shape, dtype=v.dtype).pin_memory() for k, v in
+                dict(Q=Q, p=p, G=G, h=h).items()}
+        for k, v in dict(Q=Q, p=p, G=G, h=h).items():
+            host[k].copy_(v.detach())
+        gz = torch.ones(nb, NZ, dtype=torch.float64).pin_memory()
+        out = {k: torch.empty(s, dtype=torch.float64).pin_memory() for k, s in
+               dict(zhat=(nb, NZ), lams=(nb, NINEQ), slacks=(nb, NINEQ), dQ=(nb, NZ, NZ), dp=(nb, NZ),
+                    dG=(nb, NINEQ, NZ), dh=(nb, NINEQ)).items()}
+        st_host = torch.zeros(8, dtype=torch.float64)
+        prob = _lib.Problem(nb, NZ, NINEQ, 0, _lib.F64, 20, 3, 0, 1e-12, NZ * NZ, NZ, NINEQ * NZ, NINEQ, 0, 0)
+        P = lambda t: ctypes.c_void_p(t.data_ptr())
+        NULL = ctypes.c_void_p(0)
+
+        def e2e_step():
+            rc = L.b200qp_solve_host(ctypes.byref(prob), P(host["Q"]), P(host["p"]), P(host["G"]), P(host["h"]), NULL,
+                                     NULL, P(gz), P(out["zhat"]), P(out["lams"]), NULL, P(out["slacks"]), P(out["dQ"]),
+                                     P(out["dp"]), P(out["dG"]), P(out["dh"]), NULL, NULL, P(st_host))
+            _lib.check(rc, "b200qp_solve_host")
+
+        for _ in range(2):
+            e2e_step()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            e2e_step()  # synchronous: returns after the D2H copies completed
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        tm = torch.tensor([dt], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+        dt = tm.item()
+        h2d = es * nb * (NZ * NZ + NZ + NINEQ * NZ + NINEQ + NZ)
+        d2h = es * nb * (NZ + 2 * NINEQ + NZ * NZ + NZ + NINEQ * NZ + NINEQ) + 64
+        e2e = {"value": nb * world * args.steps / dt, "unit": UNIT, "h2d_bytes_per_step": h2d,
+               "d2h_bytes_per_step": d2h, "ms_per_step": 1e3 * dt / args.steps,
+               "api": "b200qp_solve_host (C ABI, pinned host buffers, copies inside the timed region)"}
+        # keep the device path honest: same answer from both entry points
+        zz = step().detach().cpu()
+        assert torch.allclose(zz, out["zhat"], rtol=0, atol=0), "host-buffer path and device path disagree"
+        del host, out
+
+    # ---- BASELINE configs[0] shape (nb=128) for reference: latency-bound -----------------------
+    small = None
+    try:
+        Qs, ps, Gs, hs, As, bs = gen_batch(128, dev, seed=0)
+        for t in (Qs, ps, Gs, hs):
+            t.requires_grad_(True)
+        o128 = torch.ones(128, NZ, device=dev, dtype=torch.float64)
+        fs = QPFunction(verbose=-1, check_Q_spd=False)
+
+        def sstep():
+            for t in (Qs, ps, Gs, hs):
+                t.grad = None
+            fs(Qs, ps, Gs, hs, As, bs).backward(o128)
+
+        for _ in range(5):
+            sstep()
+        torch.cuda.synchronize()
+        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a0.record()
+        for _ in range(20):
+            sstep()
+        a1.record()
+        torch.cuda.synchronize()
+        ms = a0.elapsed_time(a1) / 20
+        small = {"workload": "BASELINE configs[0]: nb=128 nz=30 nineq=60 fwd+bwd", "ms_per_call": ms,
+                 "solves_per_s": 128 / (ms * 1e-3), "n_iter": fs.info["n_iter"]}
+    except Exception as ex:  # pragma: no cover
+        small = {"error": repr(ex)}
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        threads = os.cpu_count() or 1
+        rate, it_cpu, sec = cpu_oracle_rate(args.cpu_nb, 2, threads)
+        cpu = {"value": rate, "unit": UNIT, "cores": threads, "kind": "port",
+               "sample": f"oracle/qp_oracle.py (bit-identical restatement of qpth on torch CPU), nb={args.cpu_nb} of the same "
+                         f"generator, fwd+bwd, {it_cpu} iterations, median of 2 after 1 warm-up ({sec:.2f} s each)"}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms_total / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"random-QP batch (prof-linear.py:64-75 recipe, torch RNG) nz={NZ} nineq={NINEQ} neq=0 "
+                                   f"fp64, QPFunction forward+backward; BASELINE configs[4] sweep point, {nb} QPs per GPU",
+                       "batch_per_gpu": nb, "global_batch": nb * world, "pdipm_iterations": n_iter,
+                       "eps": 1e-12, "maxIter": 20, "parallelism": f"batch-sharded x{world}, no data-path collective",
+                       "l2": "inputs+workspace per step exceed the 126 MB L2 (no flush needed)"},
+            "clocks": clocks, "e2e": e2e, "gpu_launches": launches_per_step * args.steps,
+            "roofline": roofline, "cpu_baseline": cpu, "cfg1_nb128": small,
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -19,7 +19,8 @@ MAX_ITER_CAP = 64
 
 EXPORTS = (
     "b200qp_workspace_bytes", "b200qp_forward", "b200qp_backward", "b200qp_kkt_solve",
-    "b200qp_solve_host", "b200qp_last_cuda_error", "b200qp_version",
+    "b200qp_solve_host", "b200qp_last_cuda_error", "b200qp_version", "b200qp_profile_enable",
+    "b200qp_profile_read",
 )
 
 
@@ -58,6 +59,10 @@ def lib():
     L.b200qp_kkt_solve.argtypes = [pp, ctypes.c_int] + [vp] * 14
     L.b200qp_solve_host.restype = ctypes.c_int
     L.b200qp_solve_host.argtypes = [pp] + [vp] * 18
+    L.b200qp_profile_enable.restype = None
+    L.b200qp_profile_enable.argtypes = [ctypes.c_int]
+    L.b200qp_profile_read.restype = ctypes.c_int
+    L.b200qp_profile_read.argtypes = [ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ctypes.c_int), ctypes.c_int]
     L.b200qp_last_cuda_error.restype = ctypes.c_char_p
     L.b200qp_version.restype = ctypes.c_char_p
     _lib = L

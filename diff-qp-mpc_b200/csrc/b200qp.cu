@@ -7,87 +7,34 @@
 #include <mutex>
 
 #include "../../include/b200qp.h"
-#include "qp_kernels.cuh"
+#include "qp_host.cuh"
 
 namespace b200qp {
 
 static thread_local char g_err[512] = "";
 
-static int cuda_fail(cudaError_t e, const char* what) {
+int cuda_fail(cudaError_t e, const char* what) {
   snprintf(g_err, sizeof(g_err), "%s: %s", what, cudaGetErrorString(e));
   return B200QP_ECUDA;
 }
-#define CK(call)                                        \
-  do {                                                  \
-    cudaError_t e_ = (call);                            \
-    if (e_ != cudaSuccess) return cuda_fail(e_, #call); \
-  } while (0)
-
-constexpr size_t kSmemResidentLimit = 200 * 1024;  // bytes/CTA we are willing to ask for
-constexpr size_t kSmemMax = 227 * 1024;
-
-struct Layout {
-  int nb, n, m, p, ldn, ldm, ldp, nt;
-  bool smem;
-  size_t es, smem_bytes;
-  long long sQi, sBQi, sR, sV, sUA, sF, sT;
-  size_t oQi, oBQi, oR, oV, oUA, opinvA, oF, opinvF, oT, opinvT;
-  size_t ox, os, oz, oy, odx, ods, odz, ody, ormu, oflags, obest, oslots, octl, total;
-};
-
-static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
-
-static int make_layout(const b200qp_problem_t* pr, Layout& L) {
-  if (!pr || pr->nb < 1 || pr->nz < 1 || pr->nineq < 1 || pr->neq < 0) return B200QP_EINVAL;
-  if (pr->dtype != B200QP_F64 && pr->dtype != B200QP_F32) return B200QP_EINVAL;
-  if (pr->max_iter < 1 || pr->max_iter > B200QP_MAX_ITER_CAP) return B200QP_EINVAL;
-  L.nb = pr->nb; L.n = pr->nz; L.m = pr->nineq; L.p = pr->neq;
-  L.ldn = L.n | 1; L.ldm = L.m | 1; L.ldp = (L.p > 0 ? L.p : 1) | 1;
-  L.es = pr->dtype == B200QP_F64 ? 8 : 4;
-  const int widest = (L.n > L.p + L.m) ? L.n : (L.p + L.m);
-  L.nt = widest <= 128 ? 128 : 256;
-  const size_t full = smem_elems(L.n, L.m, L.p, L.ldn, L.ldm, L.ldp, L.nt, true) * L.es;
-  const size_t vecs = smem_elems(L.n, L.m, L.p, L.ldn, L.ldm, L.ldp, L.nt, false) * L.es;
-  L.smem = full <= kSmemResidentLimit;
-  L.smem_bytes = L.smem ? full : vecs;
-  if (L.smem_bytes > kSmemMax) return B200QP_ETOOBIG;
-  const int pp = L.p > 0 ? L.p : 1;
-  L.sQi = round4(L.n * L.ldn);
-  L.sBQi = round4((L.p + L.m) * L.ldn);
-  L.sR = round4(L.m * L.ldm);
-  L.sV = round4(pp * L.ldm);
-  L.sUA = round4(pp * L.ldp);
-  L.sF = round4(L.n * L.ldn);
-  L.sT = L.smem ? 0 : round4(L.m * L.ldm);
-  size_t off = 0;
-  const size_t nb = (size_t)L.nb;
-  auto put = [&](size_t elems, size_t esz) { size_t o = off; off = align_up(off + elems * esz, 256); return o; };
-  L.oQi = put(nb * L.sQi, L.es);
-  L.oBQi = put(nb * L.sBQi, L.es);
-  L.oR = put(nb * L.sR, L.es);
-  L.oV = put(L.p > 0 ? nb * L.sV : 4, L.es);
-  L.oUA = put(L.p > 0 ? nb * L.sUA : 4, L.es);
-  L.opinvA = put(nb * round4(pp), L.es);
-  L.oF = put(nb * L.sF, L.es);
-  L.opinvF = put(nb * round4(L.n), L.es);
-  L.oT = put(L.smem ? 4 : nb * L.sT, L.es);
-  L.opinvT = put(L.smem ? 4 : nb * round4(L.m), L.es);
-  L.ox = put(nb * round4(L.n), L.es);
-  L.os = put(nb * round4(L.m), L.es);
-  L.oz = put(nb * round4(L.m), L.es);
-  L.oy = put(nb * round4(pp), L.es);
-  L.odx = put(nb * round4(L.n), L.es);
-  L.ods = put(nb * round4(L.m), L.es);
-  L.odz = put(nb * round4(L.m), L.es);
-  L.ody = put(nb * round4(pp), L.es);
-  L.ormu = put(nb * 2, L.es);
-  L.oflags = put(nb, sizeof(int));
-  L.obest = put(nb, sizeof(double));
-  L.oslots = put(B200QP_MAX_ITER_CAP, sizeof(Slot));
-  L.octl = put(1, sizeof(Control));
-  L.total = off;
-  return B200QP_OK;
+// ------------------------------------------------------------------------------------------
+// After the last iteration launch: iteration count and worst best-residual -> status.
+static __global__ void k_finalize(const Slot* slots, const Control* ctl, double* status, int max_iter, int lim, double eps,
+                           int launches) {
+  const int lane = threadIdx.x;
+  const int term = eval_termination(slots, max_iter, lim, eps, lane);
+  if (lane == 0) {
+    const int n_iter = term >= 0 ? term + 1 : max_iter;
+    const Slot* sl = slots + (n_iter - 1);
+    status[0] = (double)n_iter;
+    status[1] = sl->best_nan ? __longlong_as_double(0x7ff8000000000000LL) : __longlong_as_double((long long)sl->best_max);
+    status[2] = (double)ctl->q_fail;
+    status[3] = (double)ctl->aqa_fail;
+    status[4] = (double)launches;
+    status[5] = status[6] = status[7] = 0.0;
+  }
 }
+
 
 template <typename T>
 static void fill_args(KArgs<T>& a, const b200qp_problem_t* pr, const Layout& L, void* ws) {
@@ -109,33 +56,43 @@ static void fill_args(KArgs<T>& a, const b200qp_problem_t* pr, const Layout& L, 
   a.max_iter = pr->max_iter; a.lim = pr->not_improved_lim; a.eps = pr->eps;
 }
 
-template <typename K>
-static cudaError_t ensure_smem(K kernel, size_t bytes) {
-  // The attribute is sticky per function; raising it every call costs ~1 us and keeps this
-  // stateless (the reference's module-global cache, batch.py:431, is what we avoid).
-  if (bytes > 48 * 1024) return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemMax);
-  return cudaSuccess;
-}
+// ---------------------------------------------------------------------------- launch profiling
+// Optional CUDA-event bracketing of every kernel launch of forward/backward (bench.py's roofline
+// leg).  Events are recorded on the caller's stream, so they see exactly the kernels timed.
+struct Prof {
+  bool on = false;
+  int n = 0;
+  static constexpr int kCap = 256;
+  cudaEvent_t ev[kCap + 1];
+  int kind[kCap];  // 0 prefactor, 1 init, 2 iteration, 3 finalize, 4 backward
+  bool made = false;
+};
+static Prof g_prof;
 
-#define DISPATCH_KERNEL(KNAME, T, L, ...)                                                      \
-  do {                                                                                         \
-    if ((L).smem) {                                                                            \
-      if ((L).nt == 128) { auto k = KNAME<T, true, 128>; CK(ensure_smem(k, (L).smem_bytes)); k<<<(L).nb, 128, (L).smem_bytes, st>>>(__VA_ARGS__); } \
-      else { auto k = KNAME<T, true, 256>; CK(ensure_smem(k, (L).smem_bytes)); k<<<(L).nb, 256, (L).smem_bytes, st>>>(__VA_ARGS__); } \
-    } else {                                                                                   \
-      if ((L).nt == 128) { auto k = KNAME<T, false, 128>; CK(ensure_smem(k, (L).smem_bytes)); k<<<(L).nb, 128, (L).smem_bytes, st>>>(__VA_ARGS__); } \
-      else { auto k = KNAME<T, false, 256>; CK(ensure_smem(k, (L).smem_bytes)); k<<<(L).nb, 256, (L).smem_bytes, st>>>(__VA_ARGS__); } \
-    }                                                                                          \
-    CK(cudaGetLastError());                                                                    \
-  } while (0)
+static void prof_begin(cudaStream_t st) {
+  if (!g_prof.on) return;
+  if (!g_prof.made) {
+    for (int i = 0; i <= Prof::kCap; i++) cudaEventCreate(&g_prof.ev[i]);
+    g_prof.made = true;
+  }
+  g_prof.n = 0;
+  cudaEventRecord(g_prof.ev[0], st);
+}
+static void prof_mark(int kind, cudaStream_t st) {
+  if (!g_prof.on || g_prof.n >= Prof::kCap) return;
+  g_prof.kind[g_prof.n] = kind;
+  g_prof.n++;
+  cudaEventRecord(g_prof.ev[g_prof.n], st);
+}
 
 template <typename T>
-static int run_prefactor(KArgs<T>& a, const Layout& L, cudaStream_t st) {
-  if (L.nt == 128) k_prefactor<T, 128><<<L.nb, 128, 0, st>>>(a);
-  else k_prefactor<T, 256><<<L.nb, 256, 0, st>>>(a);
-  CK(cudaGetLastError());
-  return B200QP_OK;
-}
+static int run_prefactor(KArgs<T>& a, const Layout& L, cudaStream_t st) { return launch_prefactor<T>(a, L, st); }
+
+#define DISPATCH_KERNEL(FN, T, L, ...)                                   \
+  do {                                                                   \
+    int rc_ = (L).smem ? FN<T, true>(__VA_ARGS__, (L), st) : FN<T, false>(__VA_ARGS__, (L), st); \
+    if (rc_) return rc_;                                                 \
+  } while (0)
 
 template <typename T>
 static int forward_t(const b200qp_problem_t* pr, const Layout& L, const void* Q, const void* p, const void* G,
@@ -149,20 +106,25 @@ static int forward_t(const b200qp_problem_t* pr, const Layout& L, const void* Q,
   a.status = status;
   CK(cudaMemsetAsync(a.slots, 0, sizeof(Slot) * B200QP_MAX_ITER_CAP + sizeof(Control), st));
   int launches = 0;
+  prof_begin(st);
   int rc = run_prefactor(a, L, st);
   if (rc) return rc;
+  prof_mark(0, st);
   launches++;
   a.iter = -1;
-  DISPATCH_KERNEL(k_pdipm_iter, T, L, a);
+  DISPATCH_KERNEL(launch_iter, T, L, a);
+  prof_mark(1, st);
   launches++;
   for (int it = 0; it < pr->max_iter; it++) {
     a.iter = it;
-    DISPATCH_KERNEL(k_pdipm_iter, T, L, a);
+    DISPATCH_KERNEL(launch_iter, T, L, a);
+    prof_mark(2, st);
     launches++;
   }
   launches++;
   k_finalize<<<1, 32, 0, st>>>(a.slots, a.ctl, status, pr->max_iter, pr->not_improved_lim, pr->eps, launches);
   CK(cudaGetLastError());
+  prof_mark(3, st);
   return B200QP_OK;
 }
 
@@ -176,7 +138,11 @@ static int backward_t(const b200qp_problem_t* pr, const Layout& L, const void* z
   g.zhat = (const T*)zhat; g.lams = (const T*)lams; g.nus = (const T*)(nus ? nus : zhat); g.slacks = (const T*)slacks;
   g.gz = (const T*)gz;
   g.dQ = (T*)dQ; g.dp = (T*)dp; g.dG = (T*)dG; g.dh = (T*)dh; g.dA = (T*)dA; g.db = (T*)db;
-  DISPATCH_KERNEL(k_backward, T, L, a, g);
+  const bool chained = g_prof.on && g_prof.n > 0 && g_prof.kind[g_prof.n - 1] == 3;
+  if (g_prof.on && !chained) prof_begin(st);
+  if (chained) cudaEventRecord(g_prof.ev[g_prof.n], st);  // restart the bracket after host-side gaps
+  DISPATCH_KERNEL(launch_backward, T, L, a, g);
+  prof_mark(4, st);
   return B200QP_OK;
 }
 
@@ -195,7 +161,7 @@ static int kkt_solve_t(const b200qp_problem_t* pr, const Layout& L, int prefacto
   SArgs<T> g;
   g.d = (const T*)d; g.rx = (const T*)rx; g.rs = (const T*)rs; g.rz = (const T*)rz; g.ry = (const T*)ry;
   g.dx = (T*)dx; g.ds = (T*)ds; g.dz = (T*)dz; g.dy = (T*)dy;
-  DISPATCH_KERNEL(k_kkt_solve, T, L, a, g);
+  DISPATCH_KERNEL(launch_kkt_solve, T, L, a, g);
   return B200QP_OK;
 }
 
@@ -336,6 +302,21 @@ int b200qp_solve_host(const b200qp_problem_t* prob, const void* Q, const void* p
   }
   CK(cudaStreamSynchronize(st));
   return B200QP_OK;
+}
+
+void b200qp_profile_enable(int on) { g_prof.on = on != 0; g_prof.n = 0; }
+
+int b200qp_profile_read(float* ms, int* kind, int cap) {
+  if (!g_prof.on || g_prof.n == 0) return 0;
+  cudaEventSynchronize(g_prof.ev[g_prof.n]);
+  int n = g_prof.n < cap ? g_prof.n : cap;
+  for (int i = 0; i < n; i++) {
+    float t = 0.f;
+    cudaEventElapsedTime(&t, g_prof.ev[i], g_prof.ev[i + 1]);
+    ms[i] = t;
+    kind[i] = g_prof.kind[i];
+  }
+  return n;
 }
 
 const char* b200qp_last_cuda_error(void) { return g_err; }

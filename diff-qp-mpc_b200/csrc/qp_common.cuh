@@ -150,13 +150,23 @@ template <typename T>
 __device__ __forceinline__ void gemv_rows_warp(const T* __restrict__ M, int ld, int rows, int cols,
                                                const T* v, T* out, int tid, int nt) {
   const int lane = tid & 31, warp = tid >> 5, nw = nt >> 5;
-  for (int r = warp; r < rows; r += nw) {
-    const T* row = M + (size_t)r * ld;
-    T a = 0;
-    for (int c = lane; c < cols; c += 32) a += row[c] * v[c];
+  for (int r0 = warp; r0 < rows; r0 += 4 * nw) {  // 4 rows in flight per warp
+    T a[4] = {T(0), T(0), T(0), T(0)};
+    for (int c = lane; c < cols; c += 32) {
+      const T vc = v[c];
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) a += shfl_x(a, o);
-    if (lane == 0) out[r] = a;
+      for (int u = 0; u < 4; u++) {
+        const int r = r0 + u * nw;
+        if (r < rows) a[u] += M[(size_t)r * ld + c] * vc;
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 4; u++) {
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) a[u] += shfl_x(a[u], o);
+      const int r = r0 + u * nw;
+      if (lane == 0 && r < rows) out[r] = a[u];
+    }
   }
 }
 
@@ -190,6 +200,111 @@ __device__ __forceinline__ bool ldlt_factor(T* S, int ld, int m, T* pinv, int ti
       }
       if (kk == 0) S[(size_t)j * ld + i] = lij;
     }
+    __syncthreads();
+  }
+  return ok;
+}
+
+// Register-tiled variant for m <= MPAD (compile time): the trailing matrix lives in REGISTERS,
+// distributed 2-D cyclically over a TR x TC thread grid (element (i,k) -> thread (i%TR, k%TC)), so a
+// column step costs NA+NB shared-memory reads and up to NA*NB FMAs per thread instead of two
+// loads + one store per FMA.  Only the current column travels through shared memory (`colbuf`,
+// 2*MPAD elements, double buffered): one barrier per column, every thread forms 1/D_j itself.
+// Same outputs as ldlt_factor (unit upper U in S, pinv[]); S's lower triangle is left intact.
+template <typename T, int MPAD, int NT>
+__device__ __forceinline__ bool ldlt_factor_reg(T* S, int ld, int m, T* pinv, T* colbuf, int tid) {
+  constexpr int TR = 16, TC = NT / 16;
+  constexpr int NA = MPAD / TR, NB = MPAD / TC;
+  static_assert(NA >= 1 && NB >= 1, "tile too small for the thread grid");
+  const int ti = tid % TR, tk = tid / TR;
+  T A[NA][NB];
+#pragma unroll
+  for (int a = 0; a < NA; a++) {
+#pragma unroll
+    for (int b = 0; b < NB; b++) {
+      if (TC * b <= TR * a + TR - 1) {  // block touches the lower triangle (compile time)
+        const int i = ti + TR * a, k = tk + TC * b;
+        A[a][b] = (i < m && k <= i) ? S[(size_t)i * ld + k] : T(0);
+      }
+    }
+  }
+  if (tk == 0) {
+#pragma unroll
+    for (int a = 0; a < NA; a++) {
+      const int i = ti + TR * a;
+      if (i < m) colbuf[i] = A[a][0];
+    }
+  }
+  __syncthreads();
+  bool ok = true;
+  // j = jb*TC + tkk with jb unrolled: the register column index of column j (and of every block
+  // that is still alive) is then a compile-time constant.
+#pragma unroll
+  for (int jb = 0; jb < NB; jb++) {
+    for (int tkk = 0; tkk < TC; tkk++) {
+      const int j = jb * TC + tkk;
+      if (j >= m || !ok) break;  // uniform
+      const T* cb = colbuf + (j & 1) * MPAD;
+      T* cbn = colbuf + ((j + 1) & 1) * MPAD;
+      const T dj = cb[j];
+      if (!(dj > T(0))) { ok = false; break; }  // uniform (same shared word for every thread)
+      const T pj = T(1) / dj;
+      if (tid == 0) pinv[j] = pj;
+      T li[NA], ck[NB];
+#pragma unroll
+      for (int a = 0; a < NA; a++) {
+        const int i = ti + TR * a;
+        li[a] = (i > j && i < m) ? cb[i] * pj : T(0);
+      }
+#pragma unroll
+      for (int b = jb; b < NB; b++) {
+        const int k = tk + TC * b;
+        ck[b] = (k > j && k < m) ? cb[k] : T(0);
+      }
+      if (tk == tkk) {
+#pragma unroll
+        for (int a = 0; a < NA; a++) {
+          const int i = ti + TR * a;
+          if (i > j && i < m) S[(size_t)j * ld + i] = li[a];
+        }
+      }
+#pragma unroll
+      for (int a = 0; a < NA; a++) {
+        if (TR * a + TR - 1 > j) {  // uniform: block row still alive
+#pragma unroll
+          for (int b = jb; b < NB; b++) {
+            if (TC * b <= TR * a + TR - 1) A[a][b] -= li[a] * ck[b];
+          }
+        }
+      }
+      // publish column j+1 (its register column is jb, or jb+1 when j closes this block column)
+      const int jn = j + 1;
+      if (tkk < TC - 1) {
+        if (tk == tkk + 1) {
+#pragma unroll
+          for (int a = 0; a < NA; a++) {
+            if (TC * jb <= TR * a + TR - 1) {
+              const int i = ti + TR * a;
+              if (i >= jn && i < m) cbn[i] = A[a][jb];
+            }
+          }
+        }
+      } else if (jb + 1 < NB) {
+        if (tk == 0) {
+#pragma unroll
+          for (int a = 0; a < NA; a++) {
+            if (TC * (jb + 1) <= TR * a + TR - 1) {
+              const int i = ti + TR * a;
+              if (i >= jn && i < m) cbn[i] = A[a][jb + 1 < NB ? jb + 1 : jb];
+            }
+          }
+        }
+      }
+      __syncthreads();
+    }
+  }
+  if (!ok) {
+    for (int i = tid; i < m; i += NT) pinv[i] = t_nan<T>();
     __syncthreads();
   }
   return ok;

@@ -1,0 +1,90 @@
+// qp_host.cuh -- host-side workspace layout and launcher declarations shared by the translation
+// units of libb200qp.so (kernels are instantiated per (dtype, residency) in qp_inst.cu).
+#pragma once
+#include <cuda_runtime.h>
+#include "../../include/b200qp.h"
+#include "qp_kernels.cuh"
+
+namespace b200qp {
+
+int cuda_fail(cudaError_t e, const char* what);
+#define CK(call)                                        \
+  do {                                                  \
+    cudaError_t e_ = (call);                            \
+    if (e_ != cudaSuccess) return cuda_fail(e_, #call); \
+  } while (0)
+
+constexpr size_t kSmemResidentLimit = 200 * 1024;  // bytes/CTA we are willing to ask for
+constexpr size_t kSmemMax = 227 * 1024;
+
+struct Layout {
+  int nb, n, m, p, ldn, ldm, ldp, nt;
+  bool smem;
+  size_t es, smem_bytes;
+  long long sQi, sBQi, sR, sV, sUA, sF, sT;
+  size_t oQi, oBQi, oR, oV, oUA, opinvA, oF, opinvF, oT, opinvT;
+  size_t ox, os, oz, oy, odx, ods, odz, ody, ormu, oflags, obest, oslots, octl, total;
+};
+
+inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+inline int make_layout(const b200qp_problem_t* pr, Layout& L) {
+  if (!pr || pr->nb < 1 || pr->nz < 1 || pr->nineq < 1 || pr->neq < 0) return B200QP_EINVAL;
+  if (pr->dtype != B200QP_F64 && pr->dtype != B200QP_F32) return B200QP_EINVAL;
+  if (pr->max_iter < 1 || pr->max_iter > B200QP_MAX_ITER_CAP) return B200QP_EINVAL;
+  L.nb = pr->nb; L.n = pr->nz; L.m = pr->nineq; L.p = pr->neq;
+  L.ldn = L.n | 1; L.ldm = L.m | 1; L.ldp = (L.p > 0 ? L.p : 1) | 1;
+  L.es = pr->dtype == B200QP_F64 ? 8 : 4;
+  const int widest = (L.n > L.p + L.m) ? L.n : (L.p + L.m);
+  L.nt = (widest <= 128 && L.m <= 64) ? 128 : 256;
+  const size_t full = smem_elems(L.n, L.m, L.p, L.ldn, L.ldm, L.ldp, L.nt, true) * L.es;
+  const size_t vecs = smem_elems(L.n, L.m, L.p, L.ldn, L.ldm, L.ldp, L.nt, false) * L.es;
+  L.smem = full <= kSmemResidentLimit;
+  L.smem_bytes = L.smem ? full : vecs;
+  if (L.smem_bytes > kSmemMax) return B200QP_ETOOBIG;
+  const int pp = L.p > 0 ? L.p : 1;
+  L.sQi = round4(L.n * L.ldn);
+  L.sBQi = round4((L.p + L.m) * L.ldn);
+  L.sR = round4(L.m * L.ldm);
+  L.sV = round4(pp * L.ldm);
+  L.sUA = round4(pp * L.ldp);
+  L.sF = round4(L.n * L.ldn);
+  L.sT = L.smem ? 0 : round4(L.m * L.ldm);
+  size_t off = 0;
+  const size_t nb = (size_t)L.nb;
+  auto put = [&](size_t elems, size_t esz) { size_t o = off; off = align_up(off + elems * esz, 256); return o; };
+  L.oQi = put(nb * L.sQi, L.es);
+  L.oBQi = put(nb * L.sBQi, L.es);
+  L.oR = put(nb * L.sR, L.es);
+  L.oV = put(L.p > 0 ? nb * L.sV : 4, L.es);
+  L.oUA = put(L.p > 0 ? nb * L.sUA : 4, L.es);
+  L.opinvA = put(nb * round4(pp), L.es);
+  L.oF = put(nb * L.sF, L.es);
+  L.opinvF = put(nb * round4(L.n), L.es);
+  L.oT = put(L.smem ? 4 : nb * L.sT, L.es);
+  L.opinvT = put(L.smem ? 4 : nb * round4(L.m), L.es);
+  L.ox = put(nb * round4(L.n), L.es);
+  L.os = put(nb * round4(L.m), L.es);
+  L.oz = put(nb * round4(L.m), L.es);
+  L.oy = put(nb * round4(pp), L.es);
+  L.odx = put(nb * round4(L.n), L.es);
+  L.ods = put(nb * round4(L.m), L.es);
+  L.odz = put(nb * round4(L.m), L.es);
+  L.ody = put(nb * round4(pp), L.es);
+  L.ormu = put(nb * 2, L.es);
+  L.oflags = put(nb, sizeof(int));
+  L.obest = put(nb, sizeof(double));
+  L.oslots = put(B200QP_MAX_ITER_CAP, sizeof(Slot));
+  L.octl = put(1, sizeof(Control));
+  L.total = off;
+  return B200QP_OK;
+}
+
+
+// Launchers, explicitly instantiated in qp_inst.cu for T in {double,float} x SMEM in {true,false}.
+template <typename T, bool SMEM> int launch_iter(const KArgs<T>& a, const Layout& L, cudaStream_t st);
+template <typename T, bool SMEM> int launch_backward(const KArgs<T>& a, const BArgs<T>& g, const Layout& L, cudaStream_t st);
+template <typename T, bool SMEM> int launch_kkt_solve(const KArgs<T>& a, const SArgs<T>& g, const Layout& L, cudaStream_t st);
+template <typename T> int launch_prefactor(const KArgs<T>& a, const Layout& L, cudaStream_t st);
+
+}  // namespace b200qp

@@ -1,0 +1,41 @@
+// qp_inst.cu -- kernel instantiations for one (dtype, residency) pair; compiled four times:
+//   -DINST_T=double|float  -DINST_SMEM=true|false   (+ -DINST_PREFACTOR for the prefactor kernel)
+#include "qp_host.cuh"
+
+namespace b200qp {
+
+template <typename K>
+static cudaError_t ensure_smem(K kernel, size_t bytes) {
+  // The attribute is sticky per function; raising it every call costs ~1 us and keeps this
+  // stateless (the reference's module-global cache, batch.py:431, is what we avoid).
+  if (bytes > 48 * 1024) return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemMax);
+  return cudaSuccess;
+}
+
+#define LAUNCH_NT(KNAME, ...)                                                                  \
+  do {                                                                                         \
+    if (L.nt == 128) { auto k = KNAME<T, SMEM, 128>; CK(ensure_smem(k, L.smem_bytes)); k<<<L.nb, 128, L.smem_bytes, st>>>(__VA_ARGS__); } \
+    else { auto k = KNAME<T, SMEM, 256>; CK(ensure_smem(k, L.smem_bytes)); k<<<L.nb, 256, L.smem_bytes, st>>>(__VA_ARGS__); } \
+    CK(cudaGetLastError());                                                                    \
+    return B200QP_OK;                                                                          \
+  } while (0)
+
+template <typename T, bool SMEM> int launch_iter(const KArgs<T>& a, const Layout& L, cudaStream_t st) { LAUNCH_NT(k_pdipm_iter, a); }
+template <typename T, bool SMEM> int launch_backward(const KArgs<T>& a, const BArgs<T>& g, const Layout& L, cudaStream_t st) { LAUNCH_NT(k_backward, a, g); }
+template <typename T, bool SMEM> int launch_kkt_solve(const KArgs<T>& a, const SArgs<T>& g, const Layout& L, cudaStream_t st) { LAUNCH_NT(k_kkt_solve, a, g); }
+
+template int launch_iter<INST_T, INST_SMEM>(const KArgs<INST_T>&, const Layout&, cudaStream_t);
+template int launch_backward<INST_T, INST_SMEM>(const KArgs<INST_T>&, const BArgs<INST_T>&, const Layout&, cudaStream_t);
+template int launch_kkt_solve<INST_T, INST_SMEM>(const KArgs<INST_T>&, const SArgs<INST_T>&, const Layout&, cudaStream_t);
+
+#ifdef INST_PREFACTOR
+template <typename T> int launch_prefactor(const KArgs<T>& a, const Layout& L, cudaStream_t st) {
+  if (L.nt == 128) k_prefactor<T, 128><<<L.nb, 128, 0, st>>>(a);
+  else k_prefactor<T, 256><<<L.nb, 256, 0, st>>>(a);
+  CK(cudaGetLastError());
+  return B200QP_OK;
+}
+template int launch_prefactor<INST_T>(const KArgs<INST_T>&, const Layout&, cudaStream_t);
+#endif
+
+}  // namespace b200qp

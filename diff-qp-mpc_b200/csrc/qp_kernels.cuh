@@ -174,7 +174,7 @@ __device__ __forceinline__ void stage_mats(const Smem<T>& S, const KArgs<T>& a, 
 }
 
 // T = R + diag(1/d) and its LDL^T.  Needs the staged copy of R (SMEM) or copies it (global).
-template <typename T, bool SMEM>
+template <typename T, bool SMEM, int NT>
 __device__ __forceinline__ bool build_and_factor_T(const Smem<T>& S, const KArgs<T>& a, int prob, int tid, int nt) {
   const int m = a.m, ldm = a.ldm;
   if (SMEM) {
@@ -187,6 +187,14 @@ __device__ __forceinline__ bool build_and_factor_T(const Smem<T>& S, const KArgs
   }
   for (int i = tid; i < m; i += nt) S.Tm[(size_t)i * ldm + i] += T(1) / S.d[i];
   __syncthreads();
+  if (SMEM) {
+    if (NT == 128) {
+      if (m <= 32) return ldlt_factor_reg<T, 32, 128>(S.Tm, ldm, m, S.pinvT, S.part, tid);
+      if (m <= 64) return ldlt_factor_reg<T, 64, 128>(S.Tm, ldm, m, S.pinvT, S.part, tid);
+    } else {
+      if (m <= 128) return ldlt_factor_reg<T, 128, 256>(S.Tm, ldm, m, S.pinvT, S.part, tid);
+    }
+  }
   return ldlt_factor(S.Tm, ldm, m, S.pinvT, tid, nt);
 }
 
@@ -346,7 +354,7 @@ __global__ void __launch_bounds__(NT) k_pdipm_iter(const KArgs<T> a) {
     for (int c = tid; c < n; c += NT) S.rx[c] = pg[c];
     for (int j = tid; j < p; j += NT) S.ry[j] = -bg[j];
     __syncthreads();
-    const bool ok = build_and_factor_T<T, SMEM>(S, a, prob, tid, NT);
+    const bool ok = build_and_factor_T<T, SMEM, NT>(S, a, prob, tid, NT);
     if (!ok) {
       if (tid == 0) a.flags[prob] = FLAG_POISON;
       return;
@@ -421,7 +429,7 @@ __global__ void __launch_bounds__(NT) k_pdipm_iter(const KArgs<T> a) {
   const T t4 = acc[3];
 
   // ---- factor T = R + diag(s/z)   (batch.py:110-114)
-  const bool ok = build_and_factor_T<T, SMEM>(S, a, prob, tid, NT);
+  const bool ok = build_and_factor_T<T, SMEM, NT>(S, a, prob, tid, NT);
 
   // ---- best-iterate bookkeeping + global reductions (batch.py:119-144)
   {
@@ -506,24 +514,6 @@ __global__ void __launch_bounds__(NT) k_pdipm_iter(const KArgs<T> a) {
       if (dz_ != dz_) slot->az_nan = 1; else atomic_max_key(&slot->amax_z, ord_key(dz_));
       if (ds_ != ds_) slot->as_nan = 1; else atomic_max_key(&slot->amax_s, ord_key(ds_));
     }
-  }
-}
-
-// ------------------------------------------------------------------------------------------
-// After the last iteration launch: iteration count and worst best-residual -> status.
-__global__ void k_finalize(const Slot* slots, const Control* ctl, double* status, int max_iter, int lim, double eps,
-                           int launches) {
-  const int lane = threadIdx.x;
-  const int term = eval_termination(slots, max_iter, lim, eps, lane);
-  if (lane == 0) {
-    const int n_iter = term >= 0 ? term + 1 : max_iter;
-    const Slot* sl = slots + (n_iter - 1);
-    status[0] = (double)n_iter;
-    status[1] = sl->best_nan ? __longlong_as_double(0x7ff8000000000000LL) : __longlong_as_double((long long)sl->best_max);
-    status[2] = (double)ctl->q_fail;
-    status[3] = (double)ctl->aqa_fail;
-    status[4] = (double)launches;
-    status[5] = status[6] = status[7] = 0.0;
   }
 }
 
@@ -651,7 +641,7 @@ __global__ void __launch_bounds__(NT) k_backward(const KArgs<T> a, const BArgs<T
   for (int c = tid; c < n; c += NT) { S.rx[c] = gz[c]; S.x[c] = zh[c]; }
   for (int j = tid; j < p; j += NT) S.y[j] = nu[j];
   __syncthreads();
-  const bool ok = build_and_factor_T<T, SMEM>(S, a, prob, tid, NT);
+  const bool ok = build_and_factor_T<T, SMEM, NT>(S, a, prob, tid, NT);
   if (!ok) {
     for (int i = tid; i < m * a.ldm; i += NT) S.Tm[i] = t_nan<T>();
     for (int i = tid; i < m; i += NT) S.pinvT[i] = t_nan<T>();
@@ -708,7 +698,7 @@ __global__ void __launch_bounds__(NT) k_kkt_solve(const KArgs<T> a, const SArgs<
   for (int c = tid; c < n; c += NT) S.rx[c] = g.rx[(size_t)prob * n + c];
   for (int j = tid; j < p; j += NT) S.ry[j] = g.ry[(size_t)prob * p + j];
   __syncthreads();
-  const bool ok = build_and_factor_T<T, SMEM>(S, a, prob, tid, NT);
+  const bool ok = build_and_factor_T<T, SMEM, NT>(S, a, prob, tid, NT);
   if (!ok) {
     for (int i = tid; i < m; i += NT) S.pinvT[i] = t_nan<T>();
     __syncthreads();

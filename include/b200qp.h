@@ -101,6 +101,14 @@ int b200qp_solve_host(const b200qp_problem_t* prob,
                       void* dQ, void* dp, void* dG, void* dh, void* dA, void* db,
                       double* status);
 
+/* Launch profiling for bench.py's roofline leg (no reference counterpart): when enabled, every
+ * kernel launch of forward/backward is bracketed by CUDA events on the caller's stream.
+ * b200qp_profile_read synchronises on the last event and returns the number of launches n,
+ * filling ms[i] (duration) and kind[i] (0 prefactor, 1 initial point, 2 PDIPM iteration,
+ * 3 finalize, 4 backward) for i < min(n, cap). */
+void b200qp_profile_enable(int on);
+int b200qp_profile_read(float* ms, int* kind, int cap);
+
 /* Text of the last CUDA error seen by this library on the calling thread ("" if none). */
 const char* b200qp_last_cuda_error(void);
 
