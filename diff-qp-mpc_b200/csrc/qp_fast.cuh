@@ -1,0 +1,660 @@
+// qp_fast.cuh -- the shared-memory/register resident fast path of the PDIPM kernels, used when
+// nineq <= MPAD (32/64 with 128 threads, 128 with 256 threads) and nz, neq+nineq <= #threads.
+//
+// Differences from the generic kernels in qp_kernels.cuh (same algebra, same outputs):
+//   * R = G Q^-1 G^T (Schur-corrected) is stored by the pre-factorisation in REGISTER-TILE ORDER
+//     (block q, thread t -> one element), so the iteration kernel loads T = R + diag(s/z)
+//     straight into the registers of the 2-D cyclic LDL^T with perfectly coalesced loads and no
+//     shared-memory staging;
+//   * the factor is kept PACKED (strict upper triangle of U = L^T, row-major) => 14.6 KB instead
+//     of 29 KB at nineq=60, which is what lets 5-6 CTAs share an SM;
+//   * one call site for the KKT solve (predictor/corrector are two trips through the same
+//     code: smaller instruction footprint, the kernel was instruction-fetch bound), step-length
+//     pieces and centering are done by one warp with shuffles instead of CTA-wide reductions.
+#pragma once
+#include "qp_kernels.cuh"
+
+namespace b200qp {
+
+template <int MPAD, int NT>
+struct Tile {
+  static constexpr int TR = 16, TC = NT / 16, NA = MPAD / TR, NB = MPAD / TC;
+  __host__ __device__ static constexpr bool alive(int a, int b) { return TC * b <= TR * a + TR - 1; }
+  __host__ __device__ static constexpr int nblk() {
+    int c = 0;
+    for (int a = 0; a < NA; a++)
+      for (int b = 0; b < NB; b++)
+        if (alive(a, b)) c++;
+    return c;
+  }
+};
+
+// 1/x for a positive pivot: MUFU seed + two Newton steps (5 instructions instead of the ~15 of an
+// IEEE division; <= 1 ulp).  Falls back to the division outside the safe exponent range.
+__device__ __forceinline__ double pivot_rcp(double x) {
+  if (x > 1e-290 && x < 1e290) {
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+    double e = fma(-x, r, 1.0);
+    r = fma(r, e, r);
+    e = fma(-x, r, 1.0);
+    r = fma(r, e, r);
+    return r;
+  }
+  return 1.0 / x;
+}
+__device__ __forceinline__ float pivot_rcp(float x) { return 1.0f / x; }
+
+template <typename T>
+struct FS {  // shared-memory carve-up of the fast path
+  T *Up, *pinvT, *BQi, *V, *UA, *pinvA;
+  T *x, *s, *z, *y, *d, *rx, *rz, *ry, *t, *hv, *u, *dx, *ds, *dz, *dy, *rsc, *scr, *part, *red, *colbuf, *small;
+};
+
+__host__ __device__ inline size_t fast_smem_elems(int n, int m, int p, int ldn, int ldm, int ldp, int nt, int mpad) {
+  const int pp = p > 0 ? p : 1;
+  size_t e = round4(m * (m - 1) / 2 + 1) + round4(m) + round4((p + m) * ldn);
+  if (p > 0) e += round4(p * ldm) + round4(p * ldp) + round4(p);
+  e += (size_t)4 * round4(n) + (size_t)8 * round4(m) + (size_t)4 * round4(pp) + round4(p + m);
+  e += round4(nt) + 4 * 32 + 2 * mpad + 16;
+  return e;
+}
+
+template <typename T>
+__device__ __forceinline__ void fast_carve(FS<T>& S, unsigned char* raw, int n, int m, int p, int ldn, int ldm,
+                                           int ldp, int nt, int mpad) {
+  T* q = reinterpret_cast<T*>(raw);
+  auto take = [&](int cnt) { T* r = q; q += round4(cnt); return r; };
+  const int pp = p > 0 ? p : 1;
+  S.Up = take(m * (m - 1) / 2 + 1);
+  S.pinvT = take(m);
+  S.BQi = take((p + m) * ldn);
+  if (p > 0) { S.V = take(p * ldm); S.UA = take(p * ldp); S.pinvA = take(p); }
+  else { S.V = S.UA = S.pinvA = nullptr; }
+  S.x = take(n); S.rx = take(n); S.t = take(n); S.dx = take(n);
+  S.s = take(m); S.z = take(m); S.d = take(m); S.rz = take(m); S.ds = take(m); S.dz = take(m); S.rsc = take(m); S.scr = take(m);
+  S.y = take(pp); S.ry = take(pp); S.u = take(pp); S.dy = take(pp);
+  S.hv = take(p + m);
+  S.part = take(nt);
+  S.red = take(4 * 32);
+  S.colbuf = take(2 * mpad);
+  S.small = take(16);
+}
+
+template <typename T>
+__device__ __forceinline__ void fast_stage(const FS<T>& S, const KArgs<T>& a, int prob, int tid, int nt) {
+  cp_async_block(S.BQi, a.BQi + (size_t)prob * a.sBQi, round4((a.p + a.m) * a.ldn), tid, nt);
+  if (a.p > 0) {
+    cp_async_block(S.V, a.V + (size_t)prob * a.sV, round4(a.p * a.ldm), tid, nt);
+    cp_async_block(S.UA, a.UA + (size_t)prob * a.sUA, round4(a.p * a.ldp), tid, nt);
+    cp_async_block(S.pinvA, a.pinvA + (size_t)prob * round4(a.p), round4(a.p), tid, nt);
+  }
+  cp_async_commit();
+}
+
+// T = R + diag(1/d) = L D L^T with the trailing matrix in registers (see ldlt_factor_reg in
+// qp_common.cuh for the scheme); R comes from global memory in tile order, U goes to shared
+// memory packed.  Returns false (uniformly) on a non-positive / NaN pivot.
+template <typename T, int MPAD, int NT>
+__device__ __forceinline__ bool fast_factor(const T* __restrict__ Rt, const T* d, T* Up, T* pinv, T* colbuf, int m,
+                                            int tid) {
+  using TL = Tile<MPAD, NT>;
+  constexpr int TR = TL::TR, TC = TL::TC, NA = TL::NA, NB = TL::NB;
+  const int ti = tid % TR, tk = tid / TR;
+  T A[NA][NB];
+  {
+    int q = 0;
+#pragma unroll
+    for (int a = 0; a < NA; a++) {
+#pragma unroll
+      for (int b = 0; b < NB; b++) {
+        if (TL::alive(a, b)) {
+          const int i = ti + TR * a, k = tk + TC * b;
+          T v = (i < m && k <= i) ? Rt[q * NT + tid] : T(0);
+          if (i == k && i < m) v += T(1) / d[i];
+          A[a][b] = v;
+          q++;
+        }
+      }
+    }
+  }
+  if (tk == 0) {
+#pragma unroll
+    for (int a = 0; a < NA; a++) {
+      const int i = ti + TR * a;
+      if (i < m) colbuf[i] = A[a][0];
+    }
+  }
+  __syncthreads();
+  bool ok = true;
+  int base = 0;  // packed offset of row j of U
+#pragma unroll
+  for (int jb = 0; jb < NB; jb++) {
+    for (int tkk = 0; tkk < TC; tkk++) {
+      const int j = jb * TC + tkk;
+      if (j >= m || !ok) break;  // uniform
+      const T* cb = colbuf + (j & 1) * MPAD;
+      T* cbn = colbuf + ((j + 1) & 1) * MPAD;
+      const T dj = cb[j];
+      if (!(dj > T(0))) { ok = false; break; }  // uniform: same shared word for every thread
+      const T pj = pivot_rcp(dj);
+      if (tid == 0) pinv[j] = pj;
+      T li[NA], ck[NB];
+      // no predicates: rows/cols that are already eliminated (or >= m) only feed dead registers
+#pragma unroll
+      for (int a = 0; a < NA; a++) li[a] = cb[ti + TR * a] * pj;
+#pragma unroll
+      for (int b = jb; b < NB; b++) ck[b] = cb[tk + TC * b];
+      if (tk == tkk) {
+#pragma unroll
+        for (int a = 0; a < NA; a++) {
+          const int i = ti + TR * a;
+          if (i > j && i < m) Up[base + i - j - 1] = li[a];
+        }
+      }
+#pragma unroll
+      for (int a = 0; a < NA; a++) {
+        if (TR * a + TR - 1 > j) {  // uniform: block row still alive
+#pragma unroll
+          for (int b = jb; b < NB; b++) {
+            if (TL::alive(a, b)) A[a][b] -= li[a] * ck[b];
+          }
+        }
+      }
+      const int jn = j + 1;
+      if (tkk < TC - 1) {
+        if (tk == tkk + 1) {
+#pragma unroll
+          for (int a = 0; a < NA; a++) {
+            if (TL::alive(a, jb)) {
+              const int i = ti + TR * a;
+              if (i >= jn && i < m) cbn[i] = A[a][jb];
+            }
+          }
+        }
+      } else if (jb + 1 < NB) {
+        if (tk == 0) {
+#pragma unroll
+          for (int a = 0; a < NA; a++) {
+            if (TL::alive(a, jb + 1 < NB ? jb + 1 : jb)) {
+              const int i = ti + TR * a;
+              if (i >= jn && i < m) cbn[i] = A[a][jb + 1 < NB ? jb + 1 : jb];
+            }
+          }
+        }
+      }
+      base += m - 1 - j;
+      __syncthreads();
+    }
+  }
+  if (!ok) {
+    for (int i = tid; i < m; i += NT) pinv[i] = t_nan<T>();
+    for (int i = tid; i < m * (m - 1) / 2; i += NT) Up[i] = t_nan<T>();
+    __syncthreads();
+  }
+  return ok;
+}
+
+// (L D L^T) x = v with packed unit-upper U; one warp, working vector in registers.
+template <typename T, int RPL>
+__device__ __forceinline__ void fast_ldlt_solve(const T* Up, int m, const T* pinv, T* v, int lane) {
+  T r[RPL];
+  int rb[RPL];  // packed base of row i for the backward sweep
+#pragma unroll
+  for (int s = 0; s < RPL; s++) {
+    const int i = s * 32 + lane;
+    r[s] = i < m ? v[i] : T(0);
+    rb[s] = i * (m - 1) - (i * (i - 1)) / 2 - i - 1;  // + j  ->  index of U[i][j]
+  }
+  int base = 0;
+#pragma unroll
+  for (int s = 0; s < RPL; s++) {
+    const int jend = min(32, m - s * 32);
+    for (int jj = 0; jj < jend; jj++) {
+      const int j = s * 32 + jj;
+      const T yj = shfl_d(r[s], jj);
+      const T* row = Up + base - j - 1;  // row[i] = U[j][i]
+#pragma unroll
+      for (int s2 = s; s2 < RPL; s2++) {
+        const int i = s2 * 32 + lane;
+        if (i > j && i < m) r[s2] -= row[i] * yj;
+      }
+      base += m - 1 - j;
+    }
+  }
+#pragma unroll
+  for (int s = 0; s < RPL; s++) {
+    const int i = s * 32 + lane;
+    if (i < m) r[s] *= pinv[i];
+  }
+#pragma unroll
+  for (int s = RPL - 1; s >= 0; s--) {
+    const int jend = min(32, m - s * 32);
+    for (int jj = jend - 1; jj >= 0; jj--) {
+      const int j = s * 32 + jj;
+      const T xj = shfl_d(r[s], jj);
+#pragma unroll
+      for (int s2 = 0; s2 <= s; s2++) {
+        const int i = s2 * 32 + lane;
+        if (i < j) r[s2] -= Up[rb[s2] + j] * xj;
+      }
+    }
+  }
+#pragma unroll
+  for (int s = 0; s < RPL; s++) {
+    const int i = s * 32 + lane;
+    if (i < m) v[i] = r[s];
+  }
+}
+
+// Block-elimination KKT solve, fast path.  has_rx=false means rx = rz = ry = 0 (corrector).
+// accumulate=true adds the solution to dx/ds/dz/dy instead of overwriting.
+// gdx != nullptr additionally streams the final dx/ds/dz/dy to global memory.
+// Entry: inputs visible.  Exit: ds, dz, dy visible to all threads (ends with a barrier); dx[c] is
+// only guaranteed visible to the thread c that wrote it.
+template <typename T, int MPAD, int NT>
+__device__ __forceinline__ void fast_kkt_solve(const FS<T>& S, const KArgs<T>& a, int prob, bool has_rx, const T* rx,
+                                               const T* rs, const T* rz, const T* ry, bool accumulate, T* gdx, T* gds,
+                                               T* gdz, T* gdy, int tid) {
+  const int n = a.n, m = a.m, p = a.p, ldn = a.ldn, ldm = a.ldm, ldp = a.ldp;
+  const int lane = tid & 31, warp = tid >> 5;
+  const int gn = NT / n;  // column groups for the n-wide column sums (n <= NT on this path)
+  const int cc = tid % n, cg = tid / n;
+  if (has_rx) {
+    gemv_rows_thread(S.BQi, ldn, p + m, n, rx, S.hv, tid, NT);
+    // t = Qi rx  (partials; summed in the next phase)
+    const T* Qi = a.Qi + (size_t)prob * a.sQi;
+    T acc = T(0);
+    if (cg < gn) for (int r = cg; r < n; r += gn) acc += Qi[(size_t)r * ldn + cc] * rx[r];
+    S.part[tid] = acc;
+    __syncthreads();
+  }
+  for (int i = tid; i < m; i += NT) {
+    T v = rs[i] / S.d[i];
+    if (has_rx) v += S.hv[p + i] - rz[i];
+    S.hv[p + i] = v;
+  }
+  for (int j = tid; j < p; j += NT) S.u[j] = has_rx ? S.hv[j] - ry[j] : T(0);
+  if (has_rx && tid < n) {
+    T sum = S.part[tid];
+    for (int g = 1; g < gn; g++) sum += S.part[g * n + tid];
+    S.t[tid] = sum;
+  }
+  __syncthreads();
+  if (p > 0) {
+    if (warp == 0) {
+      unit_fwd_warp(S.UA, ldp, p, S.u, lane);
+      for (int j = lane; j < p; j += 32) S.hv[j] = S.u[j] * S.pinvA[j];
+    }
+    __syncthreads();
+    for (int i = tid; i < m; i += NT) {  // hz -= V^T (Da^-1 u)
+      T acc = T(0);
+      for (int j = 0; j < p; j++) acc += S.V[(size_t)j * ldm + i] * S.hv[j];
+      S.hv[p + i] -= acc;
+    }
+    __syncthreads();
+  }
+  if (warp == 0) fast_ldlt_solve<T, (MPAD + 31) / 32>(S.Up, m, S.pinvT, S.hv + p, lane);
+  __syncthreads();
+  if (p > 0) {
+    gemv_rows_thread(S.V, ldm, p, m, S.hv + p, S.hv, tid, NT);
+    __syncthreads();
+    if (warp == 0) {
+      for (int j = lane; j < p; j += 32) S.hv[j] = (S.u[j] - S.hv[j]) * S.pinvA[j];
+      __syncwarp();
+      unit_bwd_warp(S.UA, ldp, p, S.hv, lane);
+    }
+    __syncthreads();
+  }
+  {
+    T acc = T(0);
+    if (cg < gn) for (int r = cg; r < p + m; r += gn) acc += S.BQi[(size_t)r * ldn + cc] * S.hv[r];
+    S.part[tid] = acc;
+  }
+  for (int i = tid; i < m; i += NT) {
+    const T w = -S.hv[p + i];
+    const T dsv = (-rs[i] - w) / S.d[i];
+    const T nz_ = accumulate ? S.dz[i] + w : w;
+    const T ns_ = accumulate ? S.ds[i] + dsv : dsv;
+    S.dz[i] = nz_; S.ds[i] = ns_;
+    if (gdz) { gdz[i] = nz_; gds[i] = ns_; }
+  }
+  for (int j = tid; j < p; j += NT) {
+    const T v = accumulate ? S.dy[j] - S.hv[j] : -S.hv[j];
+    S.dy[j] = v;
+    if (gdy) gdy[j] = v;
+  }
+  __syncthreads();
+  if (tid < n) {
+    T sum = S.part[tid];
+    for (int g = 1; g < gn; g++) sum += S.part[g * n + tid];
+    if (has_rx) sum -= S.t[tid];
+    if (accumulate) sum += S.dx[tid];
+    S.dx[tid] = sum;
+    if (gdx) gdx[tid] = sum;
+  }
+}
+
+// get_step pieces for (z,dz) and (s,ds) at once, by ONE warp: out = {rmu_z, rmu_s, amax_z, amax_s},
+// has = bit0 (some dz > 0) | bit1 (some ds > 0).  Every lane returns the same values.
+template <typename T>
+__device__ __forceinline__ void warp_step_pieces(const T* z, const T* dz, const T* s, const T* ds, int m, int lane,
+                                                 T (&out)[4], int& has) {
+  T rz = t_inf<T>(), rs = t_inf<T>(), az = -t_inf<T>(), as = -t_inf<T>();
+  bool hz = false, hs = false;
+  for (int i = lane; i < m; i += 32) {
+    const T dzi = dz[i], dsi = ds[i];
+    const T a1 = -z[i] / dzi, a2 = -s[i] / dsi;
+    if (dzi > T(0)) hz = true; else rz = nanmin(rz, a1);
+    if (dsi > T(0)) hs = true; else rs = nanmin(rs, a2);
+    az = nanmax(az, a1);
+    as = nanmax(as, a2);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    rz = nanmin(rz, shfl_x(rz, o));
+    rs = nanmin(rs, shfl_x(rs, o));
+    az = nanmax(az, shfl_x(az, o));
+    as = nanmax(as, shfl_x(as, o));
+  }
+  has = (__any_sync(0xffffffffu, hz) ? 1 : 0) | (__any_sync(0xffffffffu, hs) ? 2 : 0);
+  out[0] = rz; out[1] = rs; out[2] = az; out[3] = as;
+}
+
+template <typename T>
+__device__ __forceinline__ T warp_sum(T v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += shfl_x(v, o);
+  return v;
+}
+
+// ------------------------------------------------------------------------------------------
+// INIT=true: initial point (batch.py:60-86).  INIT=false: PDIPM iteration a.iter (batch.py:91-204).
+template <typename T, int MPAD, int NT, bool INIT>
+__global__ void __launch_bounds__(NT, (NT == 128 ? 5 : 2)) k_fast_iter(const KArgs<T> a) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int prob = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int n = a.n, m = a.m, p = a.p, it = a.iter;
+  FS<T> S;
+  fast_carve(S, smem_raw, n, m, p, a.ldn, a.ldm, a.ldp, NT, MPAD);
+  int* ictl = reinterpret_cast<int*>(S.small);
+
+  T fill_z = T(1), fill_s = T(1);
+  int flags = 0;
+  if (!INIT) {
+    if (it > 0 && warp == 0) {
+      const int term = eval_termination(a.slots, it, a.lim, a.eps, lane);
+      if (lane == 0) ictl[0] = term;
+    }
+    flags = a.flags[prob];
+  }
+  if (!(flags & FLAG_POISON)) fast_stage(S, a, prob, tid, NT);
+  if (!INIT && it > 0) {
+    __syncthreads();
+    if (ictl[0] >= 0) { cp_async_wait_all(); return; }
+    const Slot* sl = a.slots + (it - 1);
+    const double gz = sl->az_nan ? 0.0 : ord_unkey(sl->amax_z);
+    const double gs = sl->as_nan ? 0.0 : ord_unkey(sl->amax_s);
+    fill_z = gz > 1.0 ? (T)gz : T(1);
+    fill_s = gs > 1.0 ? (T)gs : T(1);
+  }
+  Slot* slot = a.slots + (INIT ? 0 : it);
+  const int pp = p > 0 ? p : 1;
+  T* gx = a.x + (size_t)prob * round4(n);
+  T* gs_ = a.s + (size_t)prob * round4(m);
+  T* gz_ = a.z + (size_t)prob * round4(m);
+  T* gy = a.y + (size_t)prob * round4(pp);
+  T* gdx = a.dx + (size_t)prob * round4(n);
+  T* gds = a.ds + (size_t)prob * round4(m);
+  T* gdz = a.dz + (size_t)prob * round4(m);
+  T* gdy = a.dy + (size_t)prob * round4(pp);
+  const T* Rt = a.R + (size_t)prob * a.sR;
+  const T* pg = a.pv + (size_t)prob * a.sp;
+  const T* hg = a.h + (size_t)prob * a.sh;
+  const T* bg = a.b + (size_t)prob * a.sb;
+
+  if (INIT) {
+    for (int i = tid; i < m; i += NT) { S.d[i] = T(1); S.rsc[i] = T(0); S.rz[i] = -hg[i]; }
+    for (int c = tid; c < n; c += NT) S.rx[c] = pg[c];
+    for (int j = tid; j < p; j += NT) S.ry[j] = -bg[j];
+    __syncthreads();
+    const bool ok = fast_factor<T, MPAD, NT>(Rt, S.d, S.Up, S.pinvT, S.colbuf, m, tid);
+    cp_async_wait_all();
+    __syncthreads();
+    if (!ok) {
+      if (tid == 0) a.flags[prob] = FLAG_POISON;
+      return;
+    }
+    fast_kkt_solve<T, MPAD, NT>(S, a, prob, true, S.rx, S.rsc, S.rz, S.ry, false, (T*)nullptr, (T*)nullptr,
+                                (T*)nullptr, (T*)nullptr, tid);
+    T mn[2] = {t_inf<T>(), t_inf<T>()};
+    for (int i = tid; i < m; i += NT) { mn[0] = nanmin(mn[0], S.ds[i]); mn[1] = nanmin(mn[1], S.dz[i]); }
+    block_reduce<2>(mn, OpNanMin(), S.red, tid, NT);
+    for (int i = tid; i < m; i += NT) {
+      T sv = S.ds[i], zv = S.dz[i];
+      if (mn[0] < T(0)) sv -= mn[0] - T(1);
+      if (mn[1] < T(0)) zv -= mn[1] - T(1);
+      gs_[i] = sv; gz_[i] = zv;
+    }
+    if (tid < n) gx[tid] = S.dx[tid];
+    for (int j = tid; j < p; j += NT) gy[j] = S.dy[j];
+    if (tid == 0) a.flags[prob] = 0;
+    return;
+  } else {
+    if (flags & FLAG_POISON) {
+      if (it == 0) {
+        T* bx = a.bx + (size_t)prob * n; T* bs = a.bs + (size_t)prob * m; T* bz = a.bz + (size_t)prob * m;
+        for (int c = tid; c < n; c += NT) bx[c] = t_nan<T>();
+        for (int i = tid; i < m; i += NT) { bs[i] = t_nan<T>(); bz[i] = t_nan<T>(); }
+        if (p > 0) { T* by = a.by + (size_t)prob * p; for (int j = tid; j < p; j += NT) by[j] = t_nan<T>(); }
+      }
+      if (tid == 0) {
+        double br = __longlong_as_double(0x7ff8000000000000LL);
+        if (it == 0) a.best_resid[prob] = br; else br = a.best_resid[prob];
+        if (br != br) slot->best_nan = 1; else atomic_max_key(&slot->best_max, (unsigned long long)__double_as_longlong(br));
+        slot->mu_nan = 1; slot->az_nan = 1; slot->as_nan = 1;
+      }
+      return;
+    }
+    const T* Qg = a.Q + (size_t)prob * a.sQ;
+    const T* Gg = a.G + (size_t)prob * a.sG;
+    const T* Ag = a.A + (size_t)prob * a.sA;
+    // ---- iterate + previous step
+    {
+      T alpha = T(0);
+      if (it > 0) {
+        const T rz_ = a.rmu[(size_t)prob * 2], rs_ = a.rmu[(size_t)prob * 2 + 1];
+        const T stz = (flags & FLAG_FILL_Z) ? nanmin(rz_, fill_z) : rz_;
+        const T sts = (flags & FLAG_FILL_S) ? nanmin(rs_, fill_s) : rs_;
+        alpha = nanmin(T(0.999) * nanmin(stz, sts), T(1));
+      }
+      for (int c = tid; c < n; c += NT) { T v = gx[c]; if (it > 0) { v += alpha * gdx[c]; gx[c] = v; } S.x[c] = v; }
+      for (int i = tid; i < m; i += NT) {
+        T sv = gs_[i], zv = gz_[i];
+        if (it > 0) { sv += alpha * gds[i]; zv += alpha * gdz[i]; gs_[i] = sv; gz_[i] = zv; }
+        S.s[i] = sv; S.z[i] = zv;
+      }
+      for (int j = tid; j < p; j += NT) { T v = gy[j]; if (it > 0) { v += alpha * gdy[j]; gy[j] = v; } S.y[j] = v; }
+    }
+    __syncthreads();
+    // ---- residuals
+    gemv_rows_warp(Qg, n, n, n, S.x, S.rx, tid, NT);
+    gemv_rows_warp(Gg, n, m, n, S.x, S.rz, tid, NT);
+    if (p > 0) gemv_rows_warp(Ag, n, p, n, S.x, S.ry, tid, NT);
+    {
+      const int gn = NT / n, cc = tid % n, cg = tid / n;
+      T acc = T(0);
+      if (cg < gn) {
+        for (int r = cg; r < m; r += gn) acc += Gg[(size_t)r * n + cc] * S.z[r];
+        for (int r = cg; r < p; r += gn) acc += Ag[(size_t)r * n + cc] * S.y[r];
+      }
+      S.part[tid] = acc;
+    }
+    __syncthreads();
+    T acc[4] = {T(0), T(0), T(0), T(0)};
+    if (tid < n) {
+      const int gn = NT / n;
+      T sum = S.part[tid];
+      for (int g = 1; g < gn; g++) sum += S.part[g * n + tid];
+      const T v = S.rx[tid] + pg[tid] + sum;
+      S.rx[tid] = v;
+      acc[0] = v * v;
+    }
+    for (int i = tid; i < m; i += NT) {
+      const T sv = S.s[i], zv = S.z[i];
+      const T v = S.rz[i] + sv - hg[i];
+      S.rz[i] = v;
+      acc[1] += v * v;
+      acc[3] += sv * zv;
+      S.d[i] = zv / sv;
+    }
+    for (int j = tid; j < p; j += NT) {
+      const T v = S.ry[j] - bg[j];
+      S.ry[j] = v;
+      acc[2] += v * v;
+    }
+    block_reduce<4>(acc, OpSum(), S.red, tid, NT);
+    const T mu = fabs(acc[3] / T(m));
+    const T pri = (p > 0 ? sqrt(acc[2]) : T(0)) + sqrt(acc[1]);
+    const T resid = pri + sqrt(acc[0]) + T(m) * mu;
+    const T t4 = acc[3];
+
+    const bool ok = fast_factor<T, MPAD, NT>(Rt, S.d, S.Up, S.pinvT, S.colbuf, m, tid);
+
+    {
+      const double rd = (double)resid;
+      const double prev = a.best_resid[prob];
+      const bool better = (it == 0) ? true : (rd < prev);
+      __syncthreads();
+      if (better) {
+        T* bx = a.bx + (size_t)prob * n; T* bs = a.bs + (size_t)prob * m; T* bz = a.bz + (size_t)prob * m;
+        for (int c = tid; c < n; c += NT) bx[c] = S.x[c];
+        for (int i = tid; i < m; i += NT) { bs[i] = S.s[i]; bz[i] = S.z[i]; }
+        if (p > 0) { T* by = a.by + (size_t)prob * p; for (int j = tid; j < p; j += NT) by[j] = S.y[j]; }
+      }
+      if (tid == 0) {
+        const double br = better ? rd : prev;
+        if (better) a.best_resid[prob] = rd;
+        if (better && it > 0 && !slot->improved) slot->improved = 1;
+        if (br != br) slot->best_nan = 1; else atomic_max_key(&slot->best_max, (unsigned long long)__double_as_longlong(br));
+        const double mud = (double)mu;
+        if (mud != mud) slot->mu_nan = 1; else atomic_max_key(&slot->mu_min_inv, ~ord_key(mud));
+      }
+    }
+    cp_async_wait_all();
+    __syncthreads();
+    if (!ok) {
+      if (tid == 0) { a.flags[prob] = FLAG_POISON; slot->az_nan = 1; slot->as_nan = 1; }
+      return;
+    }
+    // ---- predictor (pass 0: rs = z) and corrector (pass 1: rs = rsc, zero rx/rz/ry)
+    for (int pass = 0; pass < 2; pass++) {
+      const bool aff = pass == 0;
+      fast_kkt_solve<T, MPAD, NT>(S, a, prob, aff, S.rx, aff ? S.z : S.rsc, S.rz, S.ry, !aff, aff ? (T*)nullptr : gdx,
+                                  aff ? (T*)nullptr : gds, aff ? (T*)nullptr : gdz, aff ? (T*)nullptr : gdy, tid);
+      if (warp == 0) {
+        T pc[4]; int has;
+        warp_step_pieces(S.z, S.dz, S.s, S.ds, m, lane, pc, has);
+        if (aff) {
+          // the clamp at 1 makes alpha_aff independent of the batch-global fill
+          const T stz = (has & 1) ? nanmin(pc[0], T(1)) : pc[0];
+          const T sts = (has & 2) ? nanmin(pc[1], T(1)) : pc[1];
+          const T alpha_aff = nanmin(nanmin(stz, sts), T(1));
+          T t3 = T(0);
+          for (int i = lane; i < m; i += 32) t3 += (S.s[i] + alpha_aff * S.ds[i]) * (S.z[i] + alpha_aff * S.dz[i]);
+          t3 = warp_sum(t3);
+          const T ratio = t3 / t4;
+          const T sig = ratio * ratio * ratio;
+          for (int i = lane; i < m; i += 32) S.rsc[i] = (-mu * sig + S.ds[i] * S.dz[i]) / S.s[i];
+        } else if (lane == 0) {
+          a.rmu[(size_t)prob * 2] = pc[0];
+          a.rmu[(size_t)prob * 2 + 1] = pc[1];
+          a.flags[prob] = ((has & 1) ? FLAG_FILL_Z : 0) | ((has & 2) ? FLAG_FILL_S : 0);
+          const double dz_ = (double)pc[2], ds_ = (double)pc[3];
+          if (dz_ != dz_) slot->az_nan = 1; else atomic_max_key(&slot->amax_z, ord_key(dz_));
+          if (ds_ != ds_) slot->as_nan = 1; else atomic_max_key(&slot->amax_s, ord_key(ds_));
+        }
+      }
+      if (aff) __syncthreads();
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+template <typename T, int MPAD, int NT>
+__global__ void __launch_bounds__(NT, (NT == 128 ? 5 : 2)) k_fast_backward(const KArgs<T> a, const BArgs<T> g) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int prob = blockIdx.x, tid = threadIdx.x;
+  const int n = a.n, m = a.m, p = a.p;
+  FS<T> S;
+  fast_carve(S, smem_raw, n, m, p, a.ldn, a.ldm, a.ldp, NT, MPAD);
+  fast_stage(S, a, prob, tid, NT);
+  const T* zh = g.zhat + (size_t)prob * n;
+  const T* lam = g.lams + (size_t)prob * m;
+  const T* sl = g.slacks + (size_t)prob * m;
+  const T* nu = g.nus + (size_t)prob * p;
+  const T* gz = g.gz + (size_t)prob * n;
+  for (int i = tid; i < m; i += NT) {
+    const T lv = lam[i], sv = sl[i];
+    S.z[i] = lv;
+    const T lc = (lv < T(1e-8)) ? T(1e-8) : lv, sc = (sv < T(1e-8)) ? T(1e-8) : sv;
+    S.d[i] = lc / sc;
+    S.rsc[i] = T(0);
+    S.rz[i] = T(0);
+  }
+  for (int c = tid; c < n; c += NT) { S.rx[c] = gz[c]; S.x[c] = zh[c]; }
+  for (int j = tid; j < p; j += NT) { S.y[j] = nu[j]; S.ry[j] = T(0); }
+  __syncthreads();
+  fast_factor<T, MPAD, NT>(a.R + (size_t)prob * a.sR, S.d, S.Up, S.pinvT, S.colbuf, m, tid);  // NaN factor on failure
+  cp_async_wait_all();
+  __syncthreads();
+  fast_kkt_solve<T, MPAD, NT>(S, a, prob, true, S.rx, S.rsc, S.rz, S.ry, false, (T*)nullptr, (T*)nullptr, (T*)nullptr,
+                              (T*)nullptr, tid);
+  __syncthreads();
+  T* dp = g.dp + (size_t)prob * n; T* dh = g.dh + (size_t)prob * m;
+  for (int c = tid; c < n; c += NT) dp[c] = S.dx[c];
+  for (int i = tid; i < m; i += NT) dh[i] = -S.dz[i];
+  if (p > 0) { T* db = g.db + (size_t)prob * p; for (int j = tid; j < p; j += NT) db[j] = -S.dy[j]; }
+  T* dQ = g.dQ + (size_t)prob * n * n;
+  for (int e = tid; e < n * n; e += NT) {
+    const int r = e / n, c = e - r * n;
+    dQ[e] = T(0.5) * (S.dx[r] * S.x[c] + S.x[r] * S.dx[c]);
+  }
+  T* dG = g.dG + (size_t)prob * m * n;
+  for (int e = tid; e < m * n; e += NT) {
+    const int r = e / n, c = e - r * n;
+    dG[e] = S.dz[r] * S.x[c] + S.z[r] * S.dx[c];
+  }
+  if (p > 0) {
+    T* dA = g.dA + (size_t)prob * p * n;
+    for (int e = tid; e < p * n; e += NT) {
+      const int r = e / n, c = e - r * n;
+      dA[e] = S.dy[r] * S.x[c] + S.y[r] * S.dx[c];
+    }
+  }
+}
+
+template <typename T, int MPAD, int NT>
+__global__ void __launch_bounds__(NT, (NT == 128 ? 5 : 2)) k_fast_kkt(const KArgs<T> a, const SArgs<T> g) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int prob = blockIdx.x, tid = threadIdx.x;
+  const int n = a.n, m = a.m, p = a.p;
+  FS<T> S;
+  fast_carve(S, smem_raw, n, m, p, a.ldn, a.ldm, a.ldp, NT, MPAD);
+  fast_stage(S, a, prob, tid, NT);
+  for (int i = tid; i < m; i += NT) {
+    S.d[i] = g.d[(size_t)prob * m + i];
+    S.rsc[i] = g.rs[(size_t)prob * m + i];
+    S.rz[i] = g.rz[(size_t)prob * m + i];
+  }
+  for (int c = tid; c < n; c += NT) S.rx[c] = g.rx[(size_t)prob * n + c];
+  for (int j = tid; j < p; j += NT) S.ry[j] = g.ry[(size_t)prob * p + j];
+  __syncthreads();
+  fast_factor<T, MPAD, NT>(a.R + (size_t)prob * a.sR, S.d, S.Up, S.pinvT, S.colbuf, m, tid);
+  cp_async_wait_all();
+  __syncthreads();
+  fast_kkt_solve<T, MPAD, NT>(S, a, prob, true, S.rx, S.rsc, S.rz, S.ry, false, g.dx + (size_t)prob * n,
+                              g.ds + (size_t)prob * m, g.dz + (size_t)prob * m, p > 0 ? g.dy + (size_t)prob * p : (T*)nullptr, tid);
+}
+
+}  // namespace b200qp

@@ -3,7 +3,9 @@
 #pragma once
 #include <cuda_runtime.h>
 #include "../../include/b200qp.h"
+#include <stdlib.h>
 #include "qp_kernels.cuh"
+#include "qp_fast.cuh"
 
 namespace b200qp {
 
@@ -18,8 +20,8 @@ constexpr size_t kSmemResidentLimit = 200 * 1024;  // bytes/CTA we are willing t
 constexpr size_t kSmemMax = 227 * 1024;
 
 struct Layout {
-  int nb, n, m, p, ldn, ldm, ldp, nt;
-  bool smem;
+  int nb, n, m, p, ldn, ldm, ldp, nt, mpad;
+  bool smem, fast;
   size_t es, smem_bytes;
   long long sQi, sBQi, sR, sV, sUA, sF, sT;
   size_t oQi, oBQi, oR, oV, oUA, opinvA, oF, opinvF, oT, opinvT;
@@ -41,11 +43,18 @@ inline int make_layout(const b200qp_problem_t* pr, Layout& L) {
   const size_t vecs = smem_elems(L.n, L.m, L.p, L.ldn, L.ldm, L.ldp, L.nt, false) * L.es;
   L.smem = full <= kSmemResidentLimit;
   L.smem_bytes = L.smem ? full : vecs;
+  // fast path (qp_fast.cuh): nineq <= 64 with 128 threads, <= 128 with 256 threads
+  L.mpad = L.m <= 32 ? 32 : (L.m <= 64 ? 64 : 128);
+  L.fast = L.m <= 128 && widest <= L.nt && getenv("B200QP_FORCE_GENERIC") == nullptr;
+  if (L.fast) {
+    const size_t fb = fast_smem_elems(L.n, L.m, L.p, L.ldn, L.ldm, L.ldp, L.nt, L.mpad) * L.es;
+    if (fb <= kSmemResidentLimit) { L.smem = true; L.smem_bytes = fb; } else L.fast = false;
+  }
   if (L.smem_bytes > kSmemMax) return B200QP_ETOOBIG;
   const int pp = L.p > 0 ? L.p : 1;
   L.sQi = round4(L.n * L.ldn);
   L.sBQi = round4((L.p + L.m) * L.ldn);
-  L.sR = round4(L.m * L.ldm);
+  L.sR = L.fast ? round4(rtile_elems(L.mpad, L.nt)) : round4(L.m * L.ldm);
   L.sV = round4(pp * L.ldm);
   L.sUA = round4(pp * L.ldp);
   L.sF = round4(L.n * L.ldn);

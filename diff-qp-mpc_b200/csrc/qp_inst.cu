@@ -20,9 +20,34 @@ static cudaError_t ensure_smem(K kernel, size_t bytes) {
     return B200QP_OK;                                                                          \
   } while (0)
 
-template <typename T, bool SMEM> int launch_iter(const KArgs<T>& a, const Layout& L, cudaStream_t st) { LAUNCH_NT(k_pdipm_iter, a); }
-template <typename T, bool SMEM> int launch_backward(const KArgs<T>& a, const BArgs<T>& g, const Layout& L, cudaStream_t st) { LAUNCH_NT(k_backward, a, g); }
-template <typename T, bool SMEM> int launch_kkt_solve(const KArgs<T>& a, const SArgs<T>& g, const Layout& L, cudaStream_t st) { LAUNCH_NT(k_kkt_solve, a, g); }
+#if INST_SMEM
+// fast path: (MPAD, NT) in {(32,128), (64,128), (128,256)}
+#define LAUNCH_FAST(KERNEL_EXPR_32, KERNEL_EXPR_64, KERNEL_EXPR_128, ...)                          \
+  do {                                                                                             \
+    if (L.mpad == 32) { auto k = KERNEL_EXPR_32; CK(ensure_smem(k, L.smem_bytes)); k<<<L.nb, 128, L.smem_bytes, st>>>(__VA_ARGS__); } \
+    else if (L.mpad == 64) { auto k = KERNEL_EXPR_64; CK(ensure_smem(k, L.smem_bytes)); k<<<L.nb, 128, L.smem_bytes, st>>>(__VA_ARGS__); } \
+    else { auto k = KERNEL_EXPR_128; CK(ensure_smem(k, L.smem_bytes)); k<<<L.nb, 256, L.smem_bytes, st>>>(__VA_ARGS__); } \
+    CK(cudaGetLastError());                                                                        \
+    return B200QP_OK;                                                                              \
+  } while (0)
+template <typename T> static int fast_iter(const KArgs<T>& a, const Layout& L, cudaStream_t st) {
+  if (a.iter < 0) LAUNCH_FAST((k_fast_iter<T, 32, 128, true>), (k_fast_iter<T, 64, 128, true>), (k_fast_iter<T, 128, 256, true>), a);
+  LAUNCH_FAST((k_fast_iter<T, 32, 128, false>), (k_fast_iter<T, 64, 128, false>), (k_fast_iter<T, 128, 256, false>), a);
+}
+template <typename T> static int fast_backward(const KArgs<T>& a, const BArgs<T>& g, const Layout& L, cudaStream_t st) {
+  LAUNCH_FAST((k_fast_backward<T, 32, 128>), (k_fast_backward<T, 64, 128>), (k_fast_backward<T, 128, 256>), a, g);
+}
+template <typename T> static int fast_kkt(const KArgs<T>& a, const SArgs<T>& g, const Layout& L, cudaStream_t st) {
+  LAUNCH_FAST((k_fast_kkt<T, 32, 128>), (k_fast_kkt<T, 64, 128>), (k_fast_kkt<T, 128, 256>), a, g);
+}
+#define FAST_OR(FN, ...) if (L.fast) return FN(__VA_ARGS__, L, st)
+#else
+#define FAST_OR(FN, ...)
+#endif
+
+template <typename T, bool SMEM> int launch_iter(const KArgs<T>& a, const Layout& L, cudaStream_t st) { FAST_OR(fast_iter<T>, a); LAUNCH_NT(k_pdipm_iter, a); }
+template <typename T, bool SMEM> int launch_backward(const KArgs<T>& a, const BArgs<T>& g, const Layout& L, cudaStream_t st) { FAST_OR(fast_backward<T>, a, g); LAUNCH_NT(k_backward, a, g); }
+template <typename T, bool SMEM> int launch_kkt_solve(const KArgs<T>& a, const SArgs<T>& g, const Layout& L, cudaStream_t st) { FAST_OR(fast_kkt<T>, a, g); LAUNCH_NT(k_kkt_solve, a, g); }
 
 template int launch_iter<INST_T, INST_SMEM>(const KArgs<INST_T>&, const Layout&, cudaStream_t);
 template int launch_backward<INST_T, INST_SMEM>(const KArgs<INST_T>&, const BArgs<INST_T>&, const Layout&, cudaStream_t);

@@ -46,6 +46,29 @@ struct Control {                    // lives after the slots
   unsigned int pad[14];
 };
 
+
+// Position of R[i][k] (k <= i) in register-tile order for a (mpad, nt) tiling: block q (row-major
+// over the (a,b) blocks that touch the lower triangle), thread t = (k%TC)*16 + i%16.
+__host__ __device__ inline int rtile_index(int i, int k, int mpad, int nt) {
+  const int TR = 16, TC = nt / 16, NB = mpad / TC;
+  const int a = i / TR, ti = i - a * TR, b = k / TC, tk = k - b * TC;
+  int q = b;
+  for (int aa = 0; aa < a; aa++) {
+    int c = (TR * aa + TR - 1) / TC + 1;
+    q += c < NB ? c : NB;
+  }
+  return q * nt + tk * TR + ti;
+}
+__host__ __device__ inline int rtile_elems(int mpad, int nt) {
+  const int TR = 16, TC = nt / 16, NA = mpad / TR, NB = mpad / TC;
+  int q = 0;
+  for (int aa = 0; aa < NA; aa++) {
+    int c = (TR * aa + TR - 1) / TC + 1;
+    q += c < NB ? c : NB;
+  }
+  return q * nt;
+}
+
 constexpr int FLAG_POISON = 1, FLAG_FILL_Z = 2, FLAG_FILL_S = 4;
 
 template <typename T>
@@ -70,6 +93,7 @@ struct KArgs {
   int iter, max_iter, lim;
   double eps;
   int launches;
+  int rtile_mpad, rtile_nt;  // != 0: R is stored in register-tile order (qp_fast.cuh)
 };
 
 // ------------------------------------------------------------------------------------------
@@ -581,7 +605,7 @@ __global__ void __launch_bounds__(NT) k_prefactor(const KArgs<T> a) {
     const T v = a0 + a1;
     if (r < p && q < p) UA[(size_t)r * ldp + q] = v;
     else if (r < p) V[(size_t)r * ldm + (q - p)] = v;
-    else R[(size_t)(r - p) * ldm + (q - p)] = v;
+    else R[a.rtile_mpad ? (size_t)rtile_index(r - p, q - p, a.rtile_mpad, a.rtile_nt) : (size_t)(r - p) * ldm + (q - p)] = v;
   }
   __syncthreads();
   if (p > 0) {
@@ -602,7 +626,7 @@ __global__ void __launch_bounds__(NT) k_prefactor(const KArgs<T> a) {
       if (q > r) continue;
       T acc = 0;
       for (int j = 0; j < p; j++) acc += V[(size_t)j * ldm + r] * pinvA[j] * V[(size_t)j * ldm + q];
-      R[(size_t)r * ldm + q] -= acc;
+      R[a.rtile_mpad ? (size_t)rtile_index(r, q, a.rtile_mpad, a.rtile_nt) : (size_t)r * ldm + q] -= acc;
     }
   }
   // mirror R's lower triangle so that the staged copy is symmetric (only the lower is used)
