@@ -53,6 +53,14 @@ __device__ __forceinline__ void atomic_max_key(unsigned long long* addr, unsigne
   if (*(volatile unsigned long long*)addr < key) atomicMax(addr, key);
 }
 
+// CTA-wide barrier; a one-warp CTA (warp-per-problem kernels) only needs a warp barrier.
+template <int NT> __device__ __forceinline__ void cta_sync() {
+  if (NT == 32) __syncwarp(); else __syncthreads();
+}
+__device__ __forceinline__ void cta_sync_rt(int nt) {
+  if (nt == 32) __syncwarp(); else __syncthreads();
+}
+
 // ----------------------------------------------------------------------------- block reductions
 struct OpSum { template <typename T> __device__ __forceinline__ T operator()(T a, T b) const { return a + b; } };
 struct OpNanMin { template <typename T> __device__ __forceinline__ T operator()(T a, T b) const { return nanmin(a, b); } };
@@ -69,6 +77,7 @@ __device__ __forceinline__ void block_reduce(T (&v)[K], Op op, T* scratch, int t
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v[k] = op(v[k], shfl_x(v[k], o));
   }
+  if (nt == 32) return;  // one warp: the shuffle tree already left the result in every lane
   __syncthreads();  // scratch may still be read by a previous reduction
   if (lane == 0) {
 #pragma unroll
@@ -122,6 +131,46 @@ __device__ __forceinline__ void gemv_cols(const T* __restrict__ M, int ld, int r
     }
   }
   __syncthreads();
+}
+
+// Same contract as gemv_cols with the CTA size as a template parameter: column groups when the
+// CTA has at least two threads per column, otherwise 4-way unrolled serial sums per column.
+template <typename T, int NT>
+__device__ __forceinline__ void gemv_cols_nt(const T* __restrict__ M, int ld, int rows, int cols, const T* v, T* out,
+                                             T* part, int tid) {
+  if (2 * cols <= NT) {
+    const int groups = NT / cols, c = tid % cols, g = tid / cols;
+    if (g < groups) {
+      T a0 = 0, a1 = 0;
+      int r = g;
+      for (; r + groups < rows; r += 2 * groups) {
+        a0 += M[(size_t)r * ld + c] * v[r];
+        a1 += M[(size_t)(r + groups) * ld + c] * v[r + groups];
+      }
+      if (r < rows) a0 += M[(size_t)r * ld + c] * v[r];
+      part[tid] = a0 + a1;
+    }
+    cta_sync<NT>();
+    if (tid < cols) {
+      T s = part[tid];
+      for (int gg = 1; gg < groups; gg++) s += part[gg * cols + tid];
+      out[tid] = s;
+    }
+  } else {
+    for (int c = tid; c < cols; c += NT) {
+      T a0 = 0, a1 = 0, a2 = 0, a3 = 0;
+      int r = 0;
+      for (; r + 3 < rows; r += 4) {
+        a0 += M[(size_t)r * ld + c] * v[r];
+        a1 += M[(size_t)(r + 1) * ld + c] * v[r + 1];
+        a2 += M[(size_t)(r + 2) * ld + c] * v[r + 2];
+        a3 += M[(size_t)(r + 3) * ld + c] * v[r + 3];
+      }
+      for (; r < rows; r++) a0 += M[(size_t)r * ld + c] * v[r];
+      out[c] = (a0 + a1) + (a2 + a3);
+    }
+  }
+  cta_sync<NT>();
 }
 
 // out[r] = sum_c M[r*ld + c] * v[c]  (r < rows), one thread per row: conflict free in shared

@@ -1,5 +1,7 @@
-// qp_fast.cuh -- the shared-memory/register resident fast path of the PDIPM kernels, used when
-// nineq <= MPAD (32/64 with 128 threads, 128 with 256 threads) and nz, neq+nineq <= #threads.
+// qp_fast.cuh -- the shared-memory/register resident fast path of the PDIPM kernels:
+//   nineq <= 64   ONE WARP per QP (32-thread CTA): no CTA barriers at all, the whole trailing
+//                 matrix of the LDL^T (72 doubles per lane at MPAD=64) lives in registers;
+//   nineq <= 128  256-thread CTA per QP.
 //
 // Differences from the generic kernels in qp_kernels.cuh (same algebra, same outputs):
 //   * R = G Q^-1 G^T (Schur-corrected) is stored by the pre-factorisation in REGISTER-TILE ORDER
@@ -18,7 +20,7 @@ namespace b200qp {
 
 template <int MPAD, int NT>
 struct Tile {
-  static constexpr int TR = 16, TC = NT / 16, NA = MPAD / TR, NB = MPAD / TC;
+  static constexpr int TR = NT == 32 ? 8 : 16, TC = NT / TR, NA = MPAD / TR, NB = MPAD / TC;
   __host__ __device__ static constexpr bool alive(int a, int b) { return TC * b <= TR * a + TR - 1; }
   __host__ __device__ static constexpr int nblk() {
     int c = 0;
@@ -48,14 +50,14 @@ __device__ __forceinline__ float pivot_rcp(float x) { return 1.0f / x; }
 template <typename T>
 struct FS {  // shared-memory carve-up of the fast path
   T *Up, *pinvT, *BQi, *V, *UA, *pinvA;
-  T *x, *s, *z, *y, *d, *rx, *rz, *ry, *t, *hv, *u, *dx, *ds, *dz, *dy, *rsc, *scr, *part, *red, *colbuf, *small;
+  T *x, *s, *z, *y, *d, *rx, *rz, *ry, *t, *hv, *u, *dx, *ds, *dz, *dy, *rsc, *scr, *scrn, *part, *red, *colbuf, *small;
 };
 
 __host__ __device__ inline size_t fast_smem_elems(int n, int m, int p, int ldn, int ldm, int ldp, int nt, int mpad) {
   const int pp = p > 0 ? p : 1;
   size_t e = round4(m * (m - 1) / 2 + 1) + round4(m) + round4((p + m) * ldn);
   if (p > 0) e += round4(p * ldm) + round4(p * ldp) + round4(p);
-  e += (size_t)4 * round4(n) + (size_t)8 * round4(m) + (size_t)4 * round4(pp) + round4(p + m);
+  e += (size_t)5 * round4(n) + (size_t)8 * round4(m) + (size_t)4 * round4(pp) + round4(p + m);
   e += round4(nt) + 4 * 32 + 2 * mpad + 16;
   return e;
 }
@@ -71,7 +73,7 @@ __device__ __forceinline__ void fast_carve(FS<T>& S, unsigned char* raw, int n, 
   S.BQi = take((p + m) * ldn);
   if (p > 0) { S.V = take(p * ldm); S.UA = take(p * ldp); S.pinvA = take(p); }
   else { S.V = S.UA = S.pinvA = nullptr; }
-  S.x = take(n); S.rx = take(n); S.t = take(n); S.dx = take(n);
+  S.x = take(n); S.rx = take(n); S.t = take(n); S.dx = take(n); S.scrn = take(n);
   S.s = take(m); S.z = take(m); S.d = take(m); S.rz = take(m); S.ds = take(m); S.dz = take(m); S.rsc = take(m); S.scr = take(m);
   S.y = take(pp); S.ry = take(pp); S.u = take(pp); S.dy = take(pp);
   S.hv = take(p + m);
@@ -124,8 +126,9 @@ __device__ __forceinline__ bool fast_factor(const T* __restrict__ Rt, const T* d
       const int i = ti + TR * a;
       if (i < m) colbuf[i] = A[a][0];
     }
+    if (ti == 0) pinv[0] = (A[0][0] > T(0)) ? pivot_rcp(A[0][0]) : t_nan<T>();
   }
-  __syncthreads();
+  cta_sync<NT>();
   bool ok = true;
   int base = 0;  // packed offset of row j of U
 #pragma unroll
@@ -135,10 +138,8 @@ __device__ __forceinline__ bool fast_factor(const T* __restrict__ Rt, const T* d
       if (j >= m || !ok) break;  // uniform
       const T* cb = colbuf + (j & 1) * MPAD;
       T* cbn = colbuf + ((j + 1) & 1) * MPAD;
-      const T dj = cb[j];
-      if (!(dj > T(0))) { ok = false; break; }  // uniform: same shared word for every thread
-      const T pj = pivot_rcp(dj);
-      if (tid == 0) pinv[j] = pj;
+      const T pj = pinv[j];  // published by the owner of the diagonal element one step earlier
+      if (is_nan(pj)) { ok = false; break; }  // uniform: same shared word for every thread
       T li[NA], ck[NB];
       // no predicates: rows/cols that are already eliminated (or >= m) only feed dead registers
 #pragma unroll
@@ -161,6 +162,7 @@ __device__ __forceinline__ bool fast_factor(const T* __restrict__ Rt, const T* d
           }
         }
       }
+      // publish column j+1 and the reciprocal of its pivot
       const int jn = j + 1;
       if (tkk < TC - 1) {
         if (tk == tkk + 1) {
@@ -168,7 +170,11 @@ __device__ __forceinline__ bool fast_factor(const T* __restrict__ Rt, const T* d
           for (int a = 0; a < NA; a++) {
             if (TL::alive(a, jb)) {
               const int i = ti + TR * a;
-              if (i >= jn && i < m) cbn[i] = A[a][jb];
+              if (i >= jn && i < m) {
+                const T v = A[a][jb];
+                cbn[i] = v;
+                if (i == jn) pinv[jn] = (v > T(0)) ? pivot_rcp(v) : t_nan<T>();
+              }
             }
           }
         }
@@ -178,19 +184,23 @@ __device__ __forceinline__ bool fast_factor(const T* __restrict__ Rt, const T* d
           for (int a = 0; a < NA; a++) {
             if (TL::alive(a, jb + 1 < NB ? jb + 1 : jb)) {
               const int i = ti + TR * a;
-              if (i >= jn && i < m) cbn[i] = A[a][jb + 1 < NB ? jb + 1 : jb];
+              if (i >= jn && i < m) {
+                const T v = A[a][jb + 1 < NB ? jb + 1 : jb];
+                cbn[i] = v;
+                if (i == jn) pinv[jn] = (v > T(0)) ? pivot_rcp(v) : t_nan<T>();
+              }
             }
           }
         }
       }
       base += m - 1 - j;
-      __syncthreads();
+      cta_sync<NT>();
     }
   }
   if (!ok) {
     for (int i = tid; i < m; i += NT) pinv[i] = t_nan<T>();
     for (int i = tid; i < m * (m - 1) / 2; i += NT) Up[i] = t_nan<T>();
-    __syncthreads();
+    cta_sync<NT>();
   }
   return ok;
 }
@@ -250,24 +260,16 @@ __device__ __forceinline__ void fast_ldlt_solve(const T* Up, int m, const T* pin
 // Block-elimination KKT solve, fast path.  has_rx=false means rx = rz = ry = 0 (corrector).
 // accumulate=true adds the solution to dx/ds/dz/dy instead of overwriting.
 // gdx != nullptr additionally streams the final dx/ds/dz/dy to global memory.
-// Entry: inputs visible.  Exit: ds, dz, dy visible to all threads (ends with a barrier); dx[c] is
-// only guaranteed visible to the thread c that wrote it.
+// Entry: inputs visible.  Exit: outputs visible to all threads (ends with a barrier).
 template <typename T, int MPAD, int NT>
 __device__ __forceinline__ void fast_kkt_solve(const FS<T>& S, const KArgs<T>& a, int prob, bool has_rx, const T* rx,
                                                const T* rs, const T* rz, const T* ry, bool accumulate, T* gdx, T* gds,
                                                T* gdz, T* gdy, int tid) {
   const int n = a.n, m = a.m, p = a.p, ldn = a.ldn, ldm = a.ldm, ldp = a.ldp;
   const int lane = tid & 31, warp = tid >> 5;
-  const int gn = NT / n;  // column groups for the n-wide column sums (n <= NT on this path)
-  const int cc = tid % n, cg = tid / n;
   if (has_rx) {
     gemv_rows_thread(S.BQi, ldn, p + m, n, rx, S.hv, tid, NT);
-    // t = Qi rx  (partials; summed in the next phase)
-    const T* Qi = a.Qi + (size_t)prob * a.sQi;
-    T acc = T(0);
-    if (cg < gn) for (int r = cg; r < n; r += gn) acc += Qi[(size_t)r * ldn + cc] * rx[r];
-    S.part[tid] = acc;
-    __syncthreads();
+    gemv_cols_nt<T, NT>(a.Qi + (size_t)prob * a.sQi, ldn, n, n, rx, S.t, S.part, tid);  // t = Qi rx
   }
   for (int i = tid; i < m; i += NT) {
     T v = rs[i] / S.d[i];
@@ -275,41 +277,39 @@ __device__ __forceinline__ void fast_kkt_solve(const FS<T>& S, const KArgs<T>& a
     S.hv[p + i] = v;
   }
   for (int j = tid; j < p; j += NT) S.u[j] = has_rx ? S.hv[j] - ry[j] : T(0);
-  if (has_rx && tid < n) {
-    T sum = S.part[tid];
-    for (int g = 1; g < gn; g++) sum += S.part[g * n + tid];
-    S.t[tid] = sum;
-  }
-  __syncthreads();
+  cta_sync<NT>();
   if (p > 0) {
     if (warp == 0) {
       unit_fwd_warp(S.UA, ldp, p, S.u, lane);
       for (int j = lane; j < p; j += 32) S.hv[j] = S.u[j] * S.pinvA[j];
     }
-    __syncthreads();
+    cta_sync<NT>();
     for (int i = tid; i < m; i += NT) {  // hz -= V^T (Da^-1 u)
       T acc = T(0);
       for (int j = 0; j < p; j++) acc += S.V[(size_t)j * ldm + i] * S.hv[j];
       S.hv[p + i] -= acc;
     }
-    __syncthreads();
+    cta_sync<NT>();
   }
   if (warp == 0) fast_ldlt_solve<T, (MPAD + 31) / 32>(S.Up, m, S.pinvT, S.hv + p, lane);
-  __syncthreads();
+  cta_sync<NT>();
   if (p > 0) {
     gemv_rows_thread(S.V, ldm, p, m, S.hv + p, S.hv, tid, NT);
-    __syncthreads();
+    cta_sync<NT>();
     if (warp == 0) {
       for (int j = lane; j < p; j += 32) S.hv[j] = (S.u[j] - S.hv[j]) * S.pinvA[j];
       __syncwarp();
       unit_bwd_warp(S.UA, ldp, p, S.hv, lane);
     }
-    __syncthreads();
+    cta_sync<NT>();
   }
-  {
-    T acc = T(0);
-    if (cg < gn) for (int r = cg; r < p + m; r += gn) acc += S.BQi[(size_t)r * ldn + cc] * S.hv[r];
-    S.part[tid] = acc;
+  gemv_cols_nt<T, NT>(S.BQi, ldn, p + m, n, S.hv, S.scrn, S.part, tid);  // BQi^T q
+  for (int c = tid; c < n; c += NT) {
+    T v = S.scrn[c];
+    if (has_rx) v -= S.t[c];
+    if (accumulate) v += S.dx[c];
+    S.dx[c] = v;
+    if (gdx) gdx[c] = v;
   }
   for (int i = tid; i < m; i += NT) {
     const T w = -S.hv[p + i];
@@ -324,15 +324,7 @@ __device__ __forceinline__ void fast_kkt_solve(const FS<T>& S, const KArgs<T>& a
     S.dy[j] = v;
     if (gdy) gdy[j] = v;
   }
-  __syncthreads();
-  if (tid < n) {
-    T sum = S.part[tid];
-    for (int g = 1; g < gn; g++) sum += S.part[g * n + tid];
-    if (has_rx) sum -= S.t[tid];
-    if (accumulate) sum += S.dx[tid];
-    S.dx[tid] = sum;
-    if (gdx) gdx[tid] = sum;
-  }
+  cta_sync<NT>();
 }
 
 // get_step pieces for (z,dz) and (s,ds) at once, by ONE warp: out = {rmu_z, rmu_s, amax_z, amax_s},
@@ -371,7 +363,7 @@ __device__ __forceinline__ T warp_sum(T v) {
 // ------------------------------------------------------------------------------------------
 // INIT=true: initial point (batch.py:60-86).  INIT=false: PDIPM iteration a.iter (batch.py:91-204).
 template <typename T, int MPAD, int NT, bool INIT>
-__global__ void __launch_bounds__(NT, (NT == 128 ? 5 : 2)) k_fast_iter(const KArgs<T> a) {
+__global__ void __launch_bounds__(NT) k_fast_iter(const KArgs<T> a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int prob = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int n = a.n, m = a.m, p = a.p, it = a.iter;
@@ -390,7 +382,7 @@ __global__ void __launch_bounds__(NT, (NT == 128 ? 5 : 2)) k_fast_iter(const KAr
   }
   if (!(flags & FLAG_POISON)) fast_stage(S, a, prob, tid, NT);
   if (!INIT && it > 0) {
-    __syncthreads();
+    cta_sync<NT>();
     if (ictl[0] >= 0) { cp_async_wait_all(); return; }
     const Slot* sl = a.slots + (it - 1);
     const double gz = sl->az_nan ? 0.0 : ord_unkey(sl->amax_z);
@@ -417,10 +409,10 @@ __global__ void __launch_bounds__(NT, (NT == 128 ? 5 : 2)) k_fast_iter(const KAr
     for (int i = tid; i < m; i += NT) { S.d[i] = T(1); S.rsc[i] = T(0); S.rz[i] = -hg[i]; }
     for (int c = tid; c < n; c += NT) S.rx[c] = pg[c];
     for (int j = tid; j < p; j += NT) S.ry[j] = -bg[j];
-    __syncthreads();
+    cta_sync<NT>();
     const bool ok = fast_factor<T, MPAD, NT>(Rt, S.d, S.Up, S.pinvT, S.colbuf, m, tid);
     cp_async_wait_all();
-    __syncthreads();
+    cta_sync<NT>();
     if (!ok) {
       if (tid == 0) a.flags[prob] = FLAG_POISON;
       return;
@@ -476,29 +468,19 @@ __global__ void __launch_bounds__(NT, (NT == 128 ? 5 : 2)) k_fast_iter(const KAr
       }
       for (int j = tid; j < p; j += NT) { T v = gy[j]; if (it > 0) { v += alpha * gdy[j]; gy[j] = v; } S.y[j] = v; }
     }
-    __syncthreads();
+    cta_sync<NT>();
     // ---- residuals
     gemv_rows_warp(Qg, n, n, n, S.x, S.rx, tid, NT);
     gemv_rows_warp(Gg, n, m, n, S.x, S.rz, tid, NT);
     if (p > 0) gemv_rows_warp(Ag, n, p, n, S.x, S.ry, tid, NT);
-    {
-      const int gn = NT / n, cc = tid % n, cg = tid / n;
-      T acc = T(0);
-      if (cg < gn) {
-        for (int r = cg; r < m; r += gn) acc += Gg[(size_t)r * n + cc] * S.z[r];
-        for (int r = cg; r < p; r += gn) acc += Ag[(size_t)r * n + cc] * S.y[r];
-      }
-      S.part[tid] = acc;
-    }
-    __syncthreads();
+    gemv_cols_nt<T, NT>(Gg, n, m, n, S.z, S.t, S.part, tid);  // G^T z
+    if (p > 0) gemv_cols_nt<T, NT>(Ag, n, p, n, S.y, S.scrn, S.part, tid);  // A^T y
     T acc[4] = {T(0), T(0), T(0), T(0)};
-    if (tid < n) {
-      const int gn = NT / n;
-      T sum = S.part[tid];
-      for (int g = 1; g < gn; g++) sum += S.part[g * n + tid];
-      const T v = S.rx[tid] + pg[tid] + sum;
-      S.rx[tid] = v;
-      acc[0] = v * v;
+    for (int c = tid; c < n; c += NT) {
+      T v = S.rx[c] + pg[c] + S.t[c];
+      if (p > 0) v += S.scrn[c];
+      S.rx[c] = v;
+      acc[0] += v * v;
     }
     for (int i = tid; i < m; i += NT) {
       const T sv = S.s[i], zv = S.z[i];
@@ -525,7 +507,7 @@ __global__ void __launch_bounds__(NT, (NT == 128 ? 5 : 2)) k_fast_iter(const KAr
       const double rd = (double)resid;
       const double prev = a.best_resid[prob];
       const bool better = (it == 0) ? true : (rd < prev);
-      __syncthreads();
+      cta_sync<NT>();
       if (better) {
         T* bx = a.bx + (size_t)prob * n; T* bs = a.bs + (size_t)prob * m; T* bz = a.bz + (size_t)prob * m;
         for (int c = tid; c < n; c += NT) bx[c] = S.x[c];
@@ -542,7 +524,7 @@ __global__ void __launch_bounds__(NT, (NT == 128 ? 5 : 2)) k_fast_iter(const KAr
       }
     }
     cp_async_wait_all();
-    __syncthreads();
+    cta_sync<NT>();
     if (!ok) {
       if (tid == 0) { a.flags[prob] = FLAG_POISON; slot->az_nan = 1; slot->as_nan = 1; }
       return;
@@ -575,14 +557,14 @@ __global__ void __launch_bounds__(NT, (NT == 128 ? 5 : 2)) k_fast_iter(const KAr
           if (ds_ != ds_) slot->as_nan = 1; else atomic_max_key(&slot->amax_s, ord_key(ds_));
         }
       }
-      if (aff) __syncthreads();
+      if (aff) cta_sync<NT>();
     }
   }
 }
 
 // ------------------------------------------------------------------------------------------
 template <typename T, int MPAD, int NT>
-__global__ void __launch_bounds__(NT, (NT == 128 ? 5 : 2)) k_fast_backward(const KArgs<T> a, const BArgs<T> g) {
+__global__ void __launch_bounds__(NT) k_fast_backward(const KArgs<T> a, const BArgs<T> g) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int prob = blockIdx.x, tid = threadIdx.x;
   const int n = a.n, m = a.m, p = a.p;
@@ -604,13 +586,13 @@ __global__ void __launch_bounds__(NT, (NT == 128 ? 5 : 2)) k_fast_backward(const
   }
   for (int c = tid; c < n; c += NT) { S.rx[c] = gz[c]; S.x[c] = zh[c]; }
   for (int j = tid; j < p; j += NT) { S.y[j] = nu[j]; S.ry[j] = T(0); }
-  __syncthreads();
+  cta_sync<NT>();
   fast_factor<T, MPAD, NT>(a.R + (size_t)prob * a.sR, S.d, S.Up, S.pinvT, S.colbuf, m, tid);  // NaN factor on failure
   cp_async_wait_all();
-  __syncthreads();
+  cta_sync<NT>();
   fast_kkt_solve<T, MPAD, NT>(S, a, prob, true, S.rx, S.rsc, S.rz, S.ry, false, (T*)nullptr, (T*)nullptr, (T*)nullptr,
                               (T*)nullptr, tid);
-  __syncthreads();
+  cta_sync<NT>();
   T* dp = g.dp + (size_t)prob * n; T* dh = g.dh + (size_t)prob * m;
   for (int c = tid; c < n; c += NT) dp[c] = S.dx[c];
   for (int i = tid; i < m; i += NT) dh[i] = -S.dz[i];
@@ -635,7 +617,7 @@ __global__ void __launch_bounds__(NT, (NT == 128 ? 5 : 2)) k_fast_backward(const
 }
 
 template <typename T, int MPAD, int NT>
-__global__ void __launch_bounds__(NT, (NT == 128 ? 5 : 2)) k_fast_kkt(const KArgs<T> a, const SArgs<T> g) {
+__global__ void __launch_bounds__(NT) k_fast_kkt(const KArgs<T> a, const SArgs<T> g) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int prob = blockIdx.x, tid = threadIdx.x;
   const int n = a.n, m = a.m, p = a.p;
@@ -649,10 +631,10 @@ __global__ void __launch_bounds__(NT, (NT == 128 ? 5 : 2)) k_fast_kkt(const KArg
   }
   for (int c = tid; c < n; c += NT) S.rx[c] = g.rx[(size_t)prob * n + c];
   for (int j = tid; j < p; j += NT) S.ry[j] = g.ry[(size_t)prob * p + j];
-  __syncthreads();
+  cta_sync<NT>();
   fast_factor<T, MPAD, NT>(a.R + (size_t)prob * a.sR, S.d, S.Up, S.pinvT, S.colbuf, m, tid);
   cp_async_wait_all();
-  __syncthreads();
+  cta_sync<NT>();
   fast_kkt_solve<T, MPAD, NT>(S, a, prob, true, S.rx, S.rsc, S.rz, S.ry, false, g.dx + (size_t)prob * n,
                               g.ds + (size_t)prob * m, g.dz + (size_t)prob * m, p > 0 ? g.dy + (size_t)prob * p : (T*)nullptr, tid);
 }

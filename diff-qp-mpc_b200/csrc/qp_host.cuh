@@ -45,10 +45,14 @@ inline int make_layout(const b200qp_problem_t* pr, Layout& L) {
   L.smem_bytes = L.smem ? full : vecs;
   // fast path (qp_fast.cuh): nineq <= 64 with 128 threads, <= 128 with 256 threads
   L.mpad = L.m <= 32 ? 32 : (L.m <= 64 ? 64 : 128);
-  L.fast = L.m <= 128 && widest <= L.nt && getenv("B200QP_FORCE_GENERIC") == nullptr;
+  L.fast = L.m <= 128 && (L.m <= 64 || widest <= 256) && getenv("B200QP_FORCE_GENERIC") == nullptr;
   if (L.fast) {
+    const int generic_nt = L.nt;
+    const char* fnt = getenv("B200QP_FAST_NT");  // "32": one warp per QP up to nineq = 64
+    L.nt = L.m <= 64 ? ((fnt && atoi(fnt) == 32) ? 32 : 128) : 256;
     const size_t fb = fast_smem_elems(L.n, L.m, L.p, L.ldn, L.ldm, L.ldp, L.nt, L.mpad) * L.es;
-    if (fb <= kSmemResidentLimit) { L.smem = true; L.smem_bytes = fb; } else L.fast = false;
+    if ((L.nt == 128 && widest > 128) || fb > kSmemResidentLimit) { L.fast = false; L.nt = generic_nt; }
+    else { L.smem = true; L.smem_bytes = fb; }
   }
   if (L.smem_bytes > kSmemMax) return B200QP_ETOOBIG;
   const int pp = L.p > 0 ? L.p : 1;

@@ -21,24 +21,33 @@ static cudaError_t ensure_smem(K kernel, size_t bytes) {
   } while (0)
 
 #if INST_SMEM
-// fast path: (MPAD, NT) in {(32,128), (64,128), (128,256)}
-#define LAUNCH_FAST(KERNEL_EXPR_32, KERNEL_EXPR_64, KERNEL_EXPR_128, ...)                          \
+// fast path: (MPAD, NT) in {(32,128), (64,128), (32,32), (64,32), (128,256)}; NT = 32 is the
+// one-warp-per-QP variant (B200QP_FAST_NT=32).
+#define LAUNCH_ONE(KEXPR, NTV, ...)                                                                \
+  do { auto k = KEXPR; CK(ensure_smem(k, L.smem_bytes)); k<<<L.nb, NTV, L.smem_bytes, st>>>(__VA_ARGS__); } while (0)
+#define LAUNCH_FAST(KN, TAIL, ...)                                                                 \
   do {                                                                                             \
-    if (L.mpad == 32) { auto k = KERNEL_EXPR_32; CK(ensure_smem(k, L.smem_bytes)); k<<<L.nb, 128, L.smem_bytes, st>>>(__VA_ARGS__); } \
-    else if (L.mpad == 64) { auto k = KERNEL_EXPR_64; CK(ensure_smem(k, L.smem_bytes)); k<<<L.nb, 128, L.smem_bytes, st>>>(__VA_ARGS__); } \
-    else { auto k = KERNEL_EXPR_128; CK(ensure_smem(k, L.smem_bytes)); k<<<L.nb, 256, L.smem_bytes, st>>>(__VA_ARGS__); } \
+    if (L.mpad == 128) LAUNCH_ONE((KN<T, 128, 256 TAIL>), 256, __VA_ARGS__);                       \
+    else if (L.nt == 32) {                                                                         \
+      if (L.mpad == 32) LAUNCH_ONE((KN<T, 32, 32 TAIL>), 32, __VA_ARGS__);                         \
+      else LAUNCH_ONE((KN<T, 64, 32 TAIL>), 32, __VA_ARGS__);                                      \
+    } else {                                                                                       \
+      if (L.mpad == 32) LAUNCH_ONE((KN<T, 32, 128 TAIL>), 128, __VA_ARGS__);                       \
+      else LAUNCH_ONE((KN<T, 64, 128 TAIL>), 128, __VA_ARGS__);                                    \
+    }                                                                                              \
     CK(cudaGetLastError());                                                                        \
     return B200QP_OK;                                                                              \
   } while (0)
+#define COMMA ,
 template <typename T> static int fast_iter(const KArgs<T>& a, const Layout& L, cudaStream_t st) {
-  if (a.iter < 0) LAUNCH_FAST((k_fast_iter<T, 32, 128, true>), (k_fast_iter<T, 64, 128, true>), (k_fast_iter<T, 128, 256, true>), a);
-  LAUNCH_FAST((k_fast_iter<T, 32, 128, false>), (k_fast_iter<T, 64, 128, false>), (k_fast_iter<T, 128, 256, false>), a);
+  if (a.iter < 0) LAUNCH_FAST(k_fast_iter, COMMA true, a);
+  LAUNCH_FAST(k_fast_iter, COMMA false, a);
 }
 template <typename T> static int fast_backward(const KArgs<T>& a, const BArgs<T>& g, const Layout& L, cudaStream_t st) {
-  LAUNCH_FAST((k_fast_backward<T, 32, 128>), (k_fast_backward<T, 64, 128>), (k_fast_backward<T, 128, 256>), a, g);
+  LAUNCH_FAST(k_fast_backward, , a, g);
 }
 template <typename T> static int fast_kkt(const KArgs<T>& a, const SArgs<T>& g, const Layout& L, cudaStream_t st) {
-  LAUNCH_FAST((k_fast_kkt<T, 32, 128>), (k_fast_kkt<T, 64, 128>), (k_fast_kkt<T, 128, 256>), a, g);
+  LAUNCH_FAST(k_fast_kkt, , a, g);
 }
 #define FAST_OR(FN, ...) if (L.fast) return FN(__VA_ARGS__, L, st)
 #else

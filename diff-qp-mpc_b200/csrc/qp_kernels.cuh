@@ -48,9 +48,10 @@ struct Control {                    // lives after the slots
 
 
 // Position of R[i][k] (k <= i) in register-tile order for a (mpad, nt) tiling: block q (row-major
-// over the (a,b) blocks that touch the lower triangle), thread t = (k%TC)*16 + i%16.
+// over the (a,b) blocks that touch the lower triangle), thread t = (k%TC)*TR + i%TR, with a
+// TR x TC thread grid (TR = 8 for one-warp CTAs, 16 otherwise).
 __host__ __device__ inline int rtile_index(int i, int k, int mpad, int nt) {
-  const int TR = 16, TC = nt / 16, NB = mpad / TC;
+  const int TR = nt == 32 ? 8 : 16, TC = nt / TR, NB = mpad / TC;
   const int a = i / TR, ti = i - a * TR, b = k / TC, tk = k - b * TC;
   int q = b;
   for (int aa = 0; aa < a; aa++) {
@@ -60,7 +61,7 @@ __host__ __device__ inline int rtile_index(int i, int k, int mpad, int nt) {
   return q * nt + tk * TR + ti;
 }
 __host__ __device__ inline int rtile_elems(int mpad, int nt) {
-  const int TR = 16, TC = nt / 16, NA = mpad / TR, NB = mpad / TC;
+  const int TR = nt == 32 ? 8 : 16, TC = nt / TR, NA = mpad / TR, NB = mpad / TC;
   int q = 0;
   for (int aa = 0; aa < NA; aa++) {
     int c = (TR * aa + TR - 1) / TC + 1;
