@@ -21,7 +21,30 @@ EXPORTS = (
     "b200qp_workspace_bytes", "b200qp_forward", "b200qp_backward", "b200qp_kkt_solve",
     "b200qp_solve_host", "b200qp_last_cuda_error", "b200qp_version", "b200qp_profile_enable",
     "b200qp_profile_read",
+    "b200mpc_env_dims", "b200mpc_factor_elems", "b200mpc_scratch_bytes", "b200mpc_al_solve", "b200mpc_al_backward",
+    "b200dyn_step", "b200dyn_jac",
 )
+
+ENV_PENDULUM, ENV_INTEGRATOR, ENV_PENDULUM_DX, ENV_CARTPOLE_DX = 0, 1, 2, 3
+MPC_MAX_PARAMS = 16
+
+
+class MpcProblem(ctypes.Structure):
+    """b200mpc_problem_t (include/b200mpc.h)"""
+    _fields_ = [
+        ("B", ctypes.c_int32), ("T", ctypes.c_int32), ("env", ctypes.c_int32), ("dtype", ctypes.c_int32),
+        ("al_iter", ctypes.c_int32), ("newton_steps", ctypes.c_int32), ("n_ls", ctypes.c_int32),
+        ("warm", ctypes.c_int32), ("hist_len", ctypes.c_int32), ("reserved", ctypes.c_int32),
+        ("params", ctypes.c_double * MPC_MAX_PARAMS),
+    ]
+
+
+class MpcBuffers(ctypes.Structure):
+    """b200mpc_buffers_t (include/b200mpc.h)"""
+    _fields_ = [(n, ctypes.c_void_p) for n in (
+        "x_init", "u_init", "x0", "C", "c", "u_lower", "u_upper", "lam", "rho",
+        "cost_hist_in", "lam_hist_in", "rho_hist_in", "cost_hist_out", "lam_hist_out", "rho_hist_out",
+        "xu", "x", "u", "status", "factor", "scratch")]
 
 
 class Problem(ctypes.Structure):
@@ -63,6 +86,23 @@ def lib():
     L.b200qp_profile_enable.argtypes = [ctypes.c_int]
     L.b200qp_profile_read.restype = ctypes.c_int
     L.b200qp_profile_read.argtypes = [ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ctypes.c_int), ctypes.c_int]
+    mp, bp = ctypes.POINTER(MpcProblem), ctypes.POINTER(MpcBuffers)
+    ip = ctypes.POINTER(ctypes.c_int)
+    L.b200mpc_env_dims.restype = ctypes.c_int
+    L.b200mpc_env_dims.argtypes = [ctypes.c_int, ip, ip]
+    L.b200mpc_factor_elems.restype = ctypes.c_size_t
+    L.b200mpc_factor_elems.argtypes = [mp]
+    L.b200mpc_scratch_bytes.restype = ctypes.c_size_t
+    L.b200mpc_scratch_bytes.argtypes = [mp]
+    L.b200mpc_al_solve.restype = ctypes.c_int
+    L.b200mpc_al_solve.argtypes = [mp, bp, vp]
+    L.b200mpc_al_backward.restype = ctypes.c_int
+    L.b200mpc_al_backward.argtypes = [mp] + [vp] * 6
+    dparr = ctypes.POINTER(ctypes.c_double)
+    L.b200dyn_step.restype = ctypes.c_int
+    L.b200dyn_step.argtypes = [ctypes.c_int, ctypes.c_int, dparr, vp, vp, vp, ctypes.c_int64, vp]
+    L.b200dyn_jac.restype = ctypes.c_int
+    L.b200dyn_jac.argtypes = [ctypes.c_int, ctypes.c_int, dparr, vp, vp, vp, vp, vp, ctypes.c_int64, vp]
     L.b200qp_last_cuda_error.restype = ctypes.c_char_p
     L.b200qp_version.restype = ctypes.c_char_p
     _lib = L

@@ -1,0 +1,193 @@
+"""Batched dynamics modules with the reference's class names and call signatures
+(deqmpc/envs.py:5-54,68-82,182-233; qpth/env_dx/pendulum.py:16-84; qpth/env_dx/cartpole.py:27-96),
+evaluated by the fused step / step+Jacobian kernels behind b200dyn_step / b200dyn_jac.
+
+`dyn_spec(dx)` maps a dynamics object -- one of these classes OR the reference's own module of the
+same name (also when wrapped by torch.jit.script) -- to the (env id, parameter vector) the MPC
+kernels are specialised on.  An unknown dynamics object is an error: there is no path that calls
+back into Python from the solver.
+"""
+from __future__ import annotations
+
+import ctypes
+
+import torch
+
+from . import _lib
+
+
+def _p(t):
+    return ctypes.c_void_p(t.data_ptr())
+
+
+def _params_array(params):
+    return (ctypes.c_double * _lib.MPC_MAX_PARAMS)(*(list(params) + [0.0] * (_lib.MPC_MAX_PARAMS - len(params))))
+
+
+def dyn_spec(dx):
+    """-> (env id, params, nx, nu)"""
+    name = getattr(dx, "original_name", type(dx).__name__)
+    base = name[:-4] if name.endswith("_jac") else name
+    if base == "PendulumDynamics":
+        return _lib.ENV_PENDULUM, [float(dx.dt), float(dx.g), float(dx.m), float(dx.l)], 2, 1
+    if base == "IntegratorDynamics":
+        if int(dx.nx) != 2 or int(dx.nu) != 1:
+            raise NotImplementedError("b200qp: IntegratorDynamics kernels are built for nx=2, nu=1")
+        return _lib.ENV_INTEGRATOR, [float(dx.dt)], 2, 1
+    if base == "PendulumDx":
+        if hasattr(dx, "simple") and not dx.simple:
+            raise NotImplementedError("b200qp: only the `simple` PendulumDx model is implemented")
+        g, m, l = (float(v) for v in dx.params[:3])
+        return _lib.ENV_PENDULUM_DX, [float(dx.dt), g, m, l, float(dx.max_torque)], 3, 1
+    if base == "CartpoleDx":
+        pr = torch.as_tensor(dx.params).detach().to(dtype=torch.float32, device="cpu")
+        gravity, masscart, masspole, length = pr.unbind()
+        total_mass = masspole + masscart          # float32 arithmetic, as in the reference
+        polemass_length = masspole * length
+        return (_lib.ENV_CARTPOLE_DX, [float(dx.dt), float(gravity), float(masscart), float(masspole), float(length),
+                                       float(total_mass), float(polemass_length), float(dx.force_mag)], 5, 1)
+    raise NotImplementedError(f"b200qp: no fused kernel for dynamics {name!r}; supported: PendulumDynamics, "
+                              "IntegratorDynamics, PendulumDx, CartpoleDx (and their *_jac variants)")
+
+
+def _run(spec, x, u, want_jac):
+    env, params, nx, nu = spec
+    if not x.is_cuda:
+        raise RuntimeError("b200qp dynamics run on CUDA tensors only (no CPU fallback)")
+    if x.dtype not in (torch.float64, torch.float32):
+        raise RuntimeError("b200qp dynamics: float64 or float32 states")
+    lead = x.shape[:-1]
+    xf = x.detach().reshape(-1, nx).contiguous()
+    uf = u.detach().to(x.dtype).reshape(-1, nu).contiguous()
+    N = xf.shape[0]
+    xn = torch.empty_like(xf)
+    A = torch.empty(N, nx, nx, device=x.device, dtype=x.dtype) if want_jac else None
+    Bm = torch.empty(N, nx, nu, device=x.device, dtype=x.dtype) if want_jac else None
+    L = _lib.lib()
+    code = _lib.F64 if x.dtype == torch.float64 else _lib.F32
+    st = ctypes.c_void_p(torch.cuda.current_stream(x.device).cuda_stream)
+    with torch.cuda.device(x.device):
+        if want_jac:
+            rc = L.b200dyn_jac(env, code, _params_array(params), _p(xf), _p(uf), _p(xn), _p(A), _p(Bm), N, st)
+        else:
+            rc = L.b200dyn_step(env, code, _params_array(params), _p(xf), _p(uf), _p(xn), N, st)
+    _lib.check(rc, "b200dyn")
+    return xn.reshape(*lead, nx), A, Bm
+
+
+class _Step(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, u, spec):
+        need = x.requires_grad or u.requires_grad
+        xn, A, Bm = _run(spec, x, u, need)
+        if need:
+            ctx.save_for_backward(A, Bm)
+        ctx.shapes = (x.shape, u.shape)
+        return xn
+
+    @staticmethod
+    def backward(ctx, g):
+        A, Bm = ctx.saved_tensors
+        gf = g.reshape(-1, 1, A.shape[1])
+        gx = torch.bmm(gf, A).reshape(ctx.shapes[0])
+        gu = torch.bmm(gf, Bm).reshape(ctx.shapes[1])
+        return gx, gu, None
+
+
+class _Dynamics(torch.nn.Module):
+    def spec(self):
+        return dyn_spec(self)
+
+    def forward(self, state, action):
+        return _Step.apply(state, action, self.spec())
+
+
+class _DynamicsJac(_Dynamics):
+    """forward(x (N,nx), u (N,nu)) -> (x_next (N,nx), (df/dx (N,nx,nx), df/du (N,nx,nu))), the
+    return convention of the reference's *_jac modules (deqmpc/envs.py:74-82)."""
+
+    def forward(self, x, u):
+        xn, A, Bm = _run(self.spec(), x, u, True)
+        return xn, (A, Bm)
+
+
+class PendulumDynamics(_Dynamics):
+    """deqmpc/envs.py:5-54"""
+
+    def __init__(self):
+        super().__init__()
+        self.dt, self.max_torque, self.g, self.m, self.l = 0.05, 3.0, 10.0, 1.0, 1.0
+        self.nx, self.nu = 2, 1
+
+    def action_clip(self, action):
+        return torch.clamp(action, -self.max_torque, self.max_torque)
+
+
+class PendulumDynamics_jac(_DynamicsJac, PendulumDynamics):
+    """deqmpc/envs.py:68-82"""
+
+
+class IntegratorDynamics(_Dynamics):
+    """deqmpc/envs.py:182-214"""
+
+    def __init__(self, nx=2, nu=1, dt=0.1, max_acc=1, max_vel=1):
+        super().__init__()
+        self.dt, self.max_acc, self.max_vel, self.nx, self.nu = dt, max_acc, max_vel, nx, nu
+        self.nq = int(nx / 2)
+
+    def action_clip(self, action):
+        return torch.clamp(action, -self.max_acc, self.max_acc)
+
+
+class IntegratorDynamics_jac(_DynamicsJac, IntegratorDynamics):
+    """deqmpc/envs.py:217-233"""
+
+
+class _EnvDx(_Dynamics):
+    def get_true_obj(self):
+        """qpth/env_dx/pendulum.py:122-131 / cartpole.py:145-154"""
+        q = torch.cat((self.goal_weights, self.ctrl_penalty * torch.ones(self.n_ctrl)))
+        px = -torch.sqrt(self.goal_weights) * self.goal_state
+        p = torch.cat((px, torch.zeros(self.n_ctrl)))
+        return q, p
+
+
+class PendulumDx(_EnvDx):
+    """qpth/env_dx/pendulum.py:16-84 (simple model)"""
+
+    def __init__(self, params=None, simple=True):
+        super().__init__()
+        self.simple = simple
+        self.max_torque, self.dt, self.n_state, self.n_ctrl = 2.0, 0.05, 3, 1
+        self.params = torch.tensor((10., 1., 1.)) if params is None else params
+        self.goal_state = torch.Tensor([1., 0., 0.])
+        self.goal_weights = torch.Tensor([1., 1., 0.1])
+        self.ctrl_penalty = 0.001
+        self.lower, self.upper = -2., 2.
+        self.mpc_eps, self.linesearch_decay, self.max_linesearch_iter = 1e-3, 0.2, 5
+
+
+class PendulumDx_jac(_DynamicsJac, PendulumDx):
+    """Jacobian companion the reference lacks for env_dx: same return convention as
+    deqmpc/envs.py:74-82."""
+
+
+class CartpoleDx(_EnvDx):
+    """qpth/env_dx/cartpole.py:27-96"""
+
+    def __init__(self, params=None):
+        super().__init__()
+        self.n_state, self.n_ctrl = 5, 1
+        self.params = torch.tensor((9.8, 1.0, 0.1, 0.5)) if params is None else params
+        assert len(self.params) == 4
+        self.force_mag = 100.
+        self.dt = 0.05
+        self.lower, self.upper = -self.force_mag, self.force_mag
+        self.goal_state = torch.Tensor([0., 0., 1., 0., 0.])
+        self.goal_weights = torch.Tensor([0.1, 0.1, 1., 1., 0.1])
+        self.ctrl_penalty = 0.001
+        self.mpc_eps, self.linesearch_decay, self.max_linesearch_iter = 1e-4, 0.5, 2
+
+
+class CartpoleDx_jac(_DynamicsJac, CartpoleDx):
+    """Jacobian companion (see PendulumDx_jac)."""

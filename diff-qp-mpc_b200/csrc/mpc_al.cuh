@@ -1,0 +1,499 @@
+// mpc_al.cuh -- the augmented-Lagrangian MPC solve as ONE kernel launch (sm_100a), one warp per
+// MPC problem, everything between the call's inputs and outputs resident in shared memory.
+//
+// Reference behaviour being re-implemented (swami1995/diff-qp-mpc, /root/reference):
+//   qpth/AL_mpc.py:254-321     MPC.al_solve: warm start, al_iter x NewtonAL, lambda / rho updates
+//   qpth/al_utils.py:16-34     warm_start_al
+//   qpth/al_utils.py:363-460   NewtonAL.forward: 4 Newton steps on the AL merit
+//   qpth/al_utils.py:62-102    merit_grad_hessian        (dense J (B,M,N), H = diag(C) + rho Jc^T Jc)
+//   qpth/al_utils.py:503-527   line_search_newton        (20 step sizes 2^-k, argmin of the merit)
+//   qpth/al_utils.py:37-59     merit_function
+//   qpth/al_utils.py:462-500   NewtonAL.backward         -> k_al_backward
+//
+// What is different from the reference (same numbers, different work):
+//   * H = diag(C) + rho Jc^T Jc is block TRIDIAGONAL in the knot ordering [x0 u0 x1 u1 ...]:
+//       D_t   = diag(C_t) + rho ([A_t B_t]^T [A_t B_t] + E_x + diag_u(active bounds))
+//       S_t   = H_{t+1,t} = -rho [A_t B_t ; 0]            (only the top nx rows are non-zero)
+//     so the reference's dense (N x N) Cholesky (N = T (nx+nu)) becomes T block steps of size
+//     nx+nu; J (B,M,N) and H (B,N,N) are never materialised.
+//   * dynamics Jacobians come from forward-mode dual numbers in registers (mpc_dynamics.cuh).
+//   * the 20 line-search candidates are evaluated by 20 lanes of the warp, each rolling the merit
+//     over the horizon in registers; the argmin is a warp shuffle reduction.
+#pragma once
+#include "mpc_dynamics.cuh"
+
+namespace b200mpc {
+
+template <typename R>
+struct ALArgs {
+  int B, T, al_iter, newton_steps, n_ls, warm, hist_len;
+  DynParams P;
+  const R *x_init, *u_init, *x0, *C, *c, *u_lower, *u_upper;
+  R *lam, *rho;                                        // (B,M), (B): in/out
+  const R *cost_hist_in, *lam_hist_in, *rho_hist_in;   // (K,B) (K,B,M) (K,B), oldest first
+  R *cost_hist_out, *lam_hist_out, *rho_hist_out;      // (al_iter+1, ...)
+  R *xu_out;                                           // (B,T,nx+nu) in the solver's precision
+  float *x_out, *u_out;                                // the reference returns float32 (AL_mpc.py:319-320)
+  R *status;                                           // (B) status of the last line search
+  R *factor;                                           // (B, factor_elems) block Cholesky of the last Hessian
+  R *scratch;                                          // global scratch when the problem does not fit smem
+  long long scratch_stride;
+  int use_smem;
+};
+
+__host__ __device__ inline int pad4(int v) { return (v + 3) & ~3; }
+__host__ __device__ inline int al_factor_elems(int T, int nx, int nu) {
+  const int nt = nx + nu;
+  return T * nt * nt + (T > 1 ? (T - 1) * nx * nt : 0);
+}
+__host__ __device__ inline long long al_scratch_elems(int T, int nx, int nu) {
+  const int nt = nx + nu, M = T * nx + 2 * T * nu;
+  return (long long)4 * pad4(T * nt) + pad4(M) + pad4(T * nx) + 2 * pad4(T * nu) + pad4(al_factor_elems(T, nx, nu)) +
+         pad4(nx) + 32;
+}
+
+template <typename R> __device__ __forceinline__ R r_nan();
+template <> __device__ __forceinline__ double r_nan<double>() { return __longlong_as_double(0x7ff8000000000000LL); }
+template <> __device__ __forceinline__ float r_nan<float>() { return __int_as_float(0x7fc00000); }
+template <typename R> __device__ __forceinline__ R r_inf();
+template <> __device__ __forceinline__ double r_inf<double>() { return __longlong_as_double(0x7ff0000000000000LL); }
+template <> __device__ __forceinline__ float r_inf<float>() { return __int_as_float(0x7f800000); }
+
+template <typename R> __device__ __forceinline__ R warp_sum(R v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+template <typename R, int NX, int NU>
+struct ALScratch {
+  R *xu, *C, *c, *g, *lam, *w, *ul, *uu, *D, *E, *x0, *mer;
+  __device__ __forceinline__ void carve(R* q, int T) {
+    constexpr int NT = NX + NU;
+    auto take = [&](int n) { R* r = q; q += pad4(n); return r; };
+    xu = take(T * NT); C = take(T * NT); c = take(T * NT); g = take(T * NT);
+    lam = take(T * NX + 2 * T * NU); w = take(T * NX); ul = take(T * NU); uu = take(T * NU);
+    D = take(al_factor_elems(T, NX, NU)); E = D + T * NT * NT;
+    x0 = take(NX); mer = take(32);
+  }
+};
+
+// Merit of the candidate xu + s * g (al_utils.py:37-59) rolled over the horizon by ONE lane.
+// force: first state overwritten by x0 (line_search_newton, al_utils.py:515).
+template <class Dyn, typename R>
+__device__ __forceinline__ R merit_eval(const ALScratch<R, Dyn::NX, Dyn::NU>& S, const DynParams& P, int T, R rho,
+                                        bool use_upd, R s, bool force) {
+  constexpr int NX = Dyn::NX, NU = Dyn::NU, NT = NX + NU;
+  const int neq = T * NX;
+  R cost = R(0), pen = R(0), lin = R(0);
+  R fprev[NX];
+  for (int t = 0; t < T; t++) {
+    R z[NT];
+#pragma unroll
+    for (int j = 0; j < NT; j++) {
+      z[j] = S.xu[t * NT + j];
+      if (use_upd) z[j] += s * S.g[t * NT + j];
+    }
+    if (force && t == 0) {
+#pragma unroll
+      for (int j = 0; j < NX; j++) z[j] = S.x0[j];
+    }
+    R q1 = R(0), q2 = R(0);
+#pragma unroll
+    for (int j = 0; j < NT; j++) { q1 += z[j] * S.C[t * NT + j] * z[j]; q2 += S.c[t * NT + j] * z[j]; }
+    cost += R(0.5) * q1 + q2;
+#pragma unroll
+    for (int j = 0; j < NX; j++) {
+      const R r = (t == 0) ? z[j] - S.x0[j] : z[j] - fprev[j];
+      const R l = (t == 0) ? S.lam[(T - 1) * NX + j] : S.lam[(t - 1) * NX + j];
+      pen += r * r;
+      lin += l * r;
+    }
+#pragma unroll
+    for (int j = 0; j < NU; j++) {
+      const R r1 = z[NX + j] - S.uu[t * NU + j], r2 = -z[NX + j] + S.ul[t * NU + j];
+      const R c1 = r1 > R(0) ? r1 : (r1 != r1 ? r1 : R(0)), c2 = r2 > R(0) ? r2 : (r2 != r2 ? r2 : R(0));
+      pen += c1 * c1 + c2 * c2;
+      lin += S.lam[neq + t * 2 * NU + j] * r1 + S.lam[neq + t * 2 * NU + NU + j] * r2;
+    }
+    if (t < T - 1) Dyn::template step<R>(P, z, z + NX, fprev);
+  }
+  return cost + R(0.5) * rho * pen + lin;
+}
+
+// Gradient (into S.g) and block-tridiagonal Hessian (S.D lower blocks, S.E = H_{t+1,t} top rows)
+// of the AL merit at S.xu (al_utils.py:62-102).
+template <class Dyn, typename R>
+__device__ __forceinline__ void assemble(const ALScratch<R, Dyn::NX, Dyn::NU>& S, const DynParams& P, int T, R rho, int lane) {
+  constexpr int NX = Dyn::NX, NU = Dyn::NU, NT = NX + NU;
+  const int neq = T * NX;
+  typedef Dual<R, NT> DR;
+  for (int t = lane; t < T; t += 32) {
+    if (t < T - 1) {
+      DR z[NT], f[NX];
+#pragma unroll
+      for (int j = 0; j < NT; j++) {
+        z[j] = DR(S.xu[t * NT + j]);
+        z[j].d[j] = R(1);
+      }
+      Dyn::template step<DR>(P, z, z + NX, f);
+#pragma unroll
+      for (int i = 0; i < NX; i++) {
+#pragma unroll
+        for (int j = 0; j < NT; j++) S.E[(t * NX + i) * NT + j] = f[i].d[j];
+        S.w[t * NX + i] = S.lam[t * NX + i] + rho * (S.xu[(t + 1) * NT + i] - f[i].v);
+      }
+    }
+    if (t == 0) {
+#pragma unroll
+      for (int i = 0; i < NX; i++) S.w[(T - 1) * NX + i] = S.lam[(T - 1) * NX + i] + rho * (S.xu[i] - S.x0[i]);
+    }
+  }
+  __syncwarp();
+  for (int idx = lane; idx < T * NT; idx += 32) {
+    const int t = idx / NT, j = idx - t * NT;
+    R gv = S.C[idx] * S.xu[idx] + S.c[idx];
+    if (t < T - 1) {
+      R acc = R(0);
+#pragma unroll
+      for (int i = 0; i < NX; i++) acc += S.E[(t * NX + i) * NT + j] * S.w[t * NX + i];
+      gv -= acc;
+    }
+    if (j < NX) {
+      gv += (t >= 1) ? S.w[(t - 1) * NX + j] : S.w[(T - 1) * NX + j];
+    } else {
+      const int ju = j - NX;
+      const R u = S.xu[idx];
+      const R r1 = u - S.uu[t * NU + ju], r2 = -u + S.ul[t * NU + ju];
+      const R c1 = r1 > R(0) ? r1 : (r1 != r1 ? r1 : R(0)), c2 = r2 > R(0) ? r2 : (r2 != r2 ? r2 : R(0));
+      gv += S.lam[neq + t * 2 * NU + ju] - S.lam[neq + t * 2 * NU + NU + ju] + rho * (c1 - c2);
+    }
+    S.g[idx] = gv;
+  }
+  for (int idx = lane; idx < T * NT * NT; idx += 32) {
+    const int t = idx / (NT * NT), rem = idx - t * NT * NT, j = rem / NT, k = rem - j * NT;
+    if (k > j) continue;
+    R acc = R(0);
+    if (t < T - 1) {
+#pragma unroll
+      for (int i = 0; i < NX; i++) acc += S.E[(t * NX + i) * NT + j] * S.E[(t * NX + i) * NT + k];
+    }
+    if (j == k) {
+      if (j < NX) acc += R(1);
+      else {
+        const int ju = j - NX;
+        const R u = S.xu[t * NT + j];
+        if (u - S.uu[t * NU + ju] > R(0)) acc += R(1);
+        if (-u + S.ul[t * NU + ju] > R(0)) acc += R(1);
+      }
+    }
+    S.D[idx] = (j == k ? S.C[t * NT + j] : R(0)) + rho * acc;
+  }
+  __syncwarp();
+  for (int idx = lane; idx < (T - 1) * NX * NT; idx += 32) S.E[idx] = -rho * S.E[idx];
+  __syncwarp();
+}
+
+// In-place block Cholesky: D_t <- L_tt (lower), E_t <- L_{t+1,t} top rows = S_t L_tt^-T.
+// A non-positive pivot poisons the factor with NaN (the reference's cholesky_ex would hand back
+// an unusable factor and fall back to a dense LU solve for the WHOLE batch, al_utils.py:419-427).
+template <int NX, int NU, typename R>
+__device__ __forceinline__ void block_cholesky(R* D, R* E, int T, int lane) {
+  constexpr int NT = NX + NU;
+  for (int t = 0; t < T; t++) {
+    R* Dt = D + t * NT * NT;
+    if (t > 0) {
+      const R* Ep = E + (t - 1) * NX * NT;
+      for (int idx = lane; idx < NX * NX; idx += 32) {
+        const int i = idx / NX, k = idx - i * NX;
+        if (k <= i) {
+          R acc = R(0);
+#pragma unroll
+          for (int j = 0; j < NT; j++) acc += Ep[i * NT + j] * Ep[k * NT + j];
+          Dt[i * NT + k] -= acc;
+        }
+      }
+      __syncwarp();
+    }
+#pragma unroll 1
+    for (int j = 0; j < NT; j++) {
+      const R djj = Dt[j * NT + j];
+      const R ljj = djj > R(0) ? sqrt(djj) : r_nan<R>();
+      __syncwarp();
+      if (lane >= j && lane < NT) Dt[lane * NT + j] = (lane == j) ? ljj : Dt[lane * NT + j] / ljj;
+      __syncwarp();
+      for (int idx = lane; idx < NT * NT; idx += 32) {
+        const int i = idx / NT, k = idx - i * NT;
+        if (k > j && k <= i) Dt[idx] -= Dt[i * NT + j] * Dt[k * NT + j];
+      }
+      __syncwarp();
+    }
+    if (t < T - 1) {
+      if (lane < NX) {
+        R* row = E + (t * NX + lane) * NT;
+#pragma unroll 1
+        for (int j = 0; j < NT; j++) {
+          R v = row[j];
+          for (int k = 0; k < j; k++) v -= row[k] * Dt[j * NT + k];
+          row[j] = v / Dt[j * NT + j];
+        }
+      }
+      __syncwarp();
+    }
+  }
+}
+
+// g <- H^-1 g with the block factor (two block-bidiagonal sweeps; in-block solves by shuffles).
+template <int NX, int NU, typename R>
+__device__ __forceinline__ void block_solve(const R* D, const R* E, R* g, int T, int lane) {
+  constexpr int NT = NX + NU;
+  static_assert(NT <= 32, "one lane per row of a knot block");
+  for (int t = 0; t < T; t++) {
+    const R* Dt = D + t * NT * NT;
+    R v = R(0);
+    if (lane < NT) {
+      v = g[t * NT + lane];
+      if (t > 0 && lane < NX) {
+        const R* row = E + ((t - 1) * NX + lane) * NT;
+        R acc = R(0);
+#pragma unroll
+        for (int j = 0; j < NT; j++) acc += row[j] * g[(t - 1) * NT + j];
+        v -= acc;
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < NT; j++) {
+      const R vj = __shfl_sync(0xffffffffu, v, j) / Dt[j * NT + j];
+      if (lane == j) v = vj;
+      else if (lane > j && lane < NT) v -= Dt[lane * NT + j] * vj;
+    }
+    if (lane < NT) g[t * NT + lane] = v;
+    __syncwarp();
+  }
+  for (int t = T - 1; t >= 0; t--) {
+    const R* Dt = D + t * NT * NT;
+    R v = R(0);
+    if (lane < NT) {
+      v = g[t * NT + lane];
+      if (t < T - 1) {
+        const R* Et = E + t * NX * NT;
+        R acc = R(0);
+#pragma unroll
+        for (int i = 0; i < NX; i++) acc += Et[i * NT + lane] * g[(t + 1) * NT + i];
+        v -= acc;
+      }
+    }
+#pragma unroll
+    for (int j = NT - 1; j >= 0; j--) {
+      const R vj = __shfl_sync(0xffffffffu, v, j) / Dt[j * NT + j];
+      if (lane == j) v = vj;
+      else if (lane < j) v -= Dt[j * NT + lane] * vj;
+    }
+    if (lane < NT) g[t * NT + lane] = v;
+    __syncwarp();
+  }
+}
+
+template <class Dyn, typename R>
+__global__ void __launch_bounds__(128) k_al_solve(const ALArgs<R> a) {
+  constexpr int NX = Dyn::NX, NU = Dyn::NU, NT = NX + NU;
+  extern __shared__ __align__(16) unsigned char al_smem[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int prob = blockIdx.x * (blockDim.x >> 5) + warp;
+  if (prob >= a.B) return;  // warps never meet at a CTA barrier
+  const int T = a.T, M = T * NX + 2 * T * NU, neq = T * NX;
+  ALScratch<R, NX, NU> S;
+  S.carve(a.use_smem ? reinterpret_cast<R*>(al_smem) + (size_t)warp * a.scratch_stride
+                     : a.scratch + (size_t)prob * a.scratch_stride, T);
+  const size_t B = (size_t)a.B;
+
+  // ---- load the problem
+  for (int idx = lane; idx < T * NT; idx += 32) {
+    const int t = idx / NT, j = idx - t * NT;
+    S.xu[idx] = j < NX ? a.x_init[((size_t)prob * T + t) * NX + j] : a.u_init[((size_t)prob * T + t) * NU + (j - NX)];
+    S.C[idx] = a.C[(size_t)prob * T * NT + idx];
+    S.c[idx] = a.c[(size_t)prob * T * NT + idx];
+  }
+  for (int idx = lane; idx < T * NU; idx += 32) {
+    S.ul[idx] = a.u_lower[(size_t)prob * T * NU + idx];
+    S.uu[idx] = a.u_upper[(size_t)prob * T * NU + idx];
+  }
+  for (int idx = lane; idx < M; idx += 32) S.lam[idx] = a.lam[(size_t)prob * M + idx];
+  if (lane < NX) S.x0[lane] = a.x0[(size_t)prob * NX + lane];
+  R rho = a.rho[prob];
+  __syncwarp();
+
+  // ---- cost at the start, warm start from the previous call's history (AL_mpc.py:268-278)
+  R cost_start;
+  {
+    R acc = R(0);
+    for (int idx = lane; idx < T * NT; idx += 32) acc += R(0.5) * S.xu[idx] * S.C[idx] * S.xu[idx] + S.c[idx] * S.xu[idx];
+    cost_start = warp_sum(acc);
+  }
+  if (a.warm && a.hist_len > 0) {
+    int pick = a.hist_len - 1;  // torch.max over an all-False column returns index 0 = newest
+    for (int k = a.hist_len - 1; k >= 0; k--) {
+      if (a.cost_hist_in[(size_t)k * B + prob] < cost_start) { pick = k; break; }
+    }
+    const R* lh = a.lam_hist_in + ((size_t)pick * B + prob) * M;
+    R nh = R(0), nl = R(0);
+    for (int idx = lane; idx < M; idx += 32) { nh += lh[idx] * lh[idx]; nl += S.lam[idx] * S.lam[idx]; }
+    nh = warp_sum(nh); nl = warp_sum(nl);
+    const R scale = sqrt(nh) / sqrt(nl);
+    for (int idx = lane; idx < M; idx += 32) S.lam[idx] *= scale;
+    rho = a.rho_hist_in[(size_t)pick * B + prob];
+    __syncwarp();
+  }
+  if (lane == 0) { a.cost_hist_out[prob] = cost_start; a.rho_hist_out[prob] = rho; }
+  for (int idx = lane; idx < M; idx += 32) a.lam_hist_out[(size_t)prob * M + idx] = S.lam[idx];
+
+  R status = R(0);
+  for (int ai = 0; ai < a.al_iter; ai++) {
+    // ---- NewtonAL.forward (al_utils.py:363-460)
+    R merit = merit_eval<Dyn, R>(S, a.P, T, rho, false, R(0), false);
+    for (int ns = 0; ns < a.newton_steps; ns++) {
+      assemble<Dyn, R>(S, a.P, T, rho, lane);
+      block_cholesky<NX, NU, R>(S.D, S.E, T, lane);
+      block_solve<NX, NU, R>(S.D, S.E, S.g, T, lane);
+      for (int idx = lane; idx < T * NT; idx += 32) S.g[idx] = -S.g[idx];
+      __syncwarp();
+      // line search: lane k evaluates step 2^-k (al_utils.py:503-527)
+      R mv = r_inf<R>();
+      R step = R(1);
+      for (int k = 0; k < lane; k++) step *= R(0.5);
+      if (lane < a.n_ls) mv = merit_eval<Dyn, R>(S, a.P, T, rho, true, step, true);
+      // argmin, first index on ties, NaN wins (torch.min propagates NaN)
+      R bv = mv;
+      int bi = lane;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        const R ov = __shfl_xor_sync(0xffffffffu, bv, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+        const bool bnan = bv != bv, onan = ov != ov;
+        bool take;
+        if (bnan || onan) take = onan && (!bnan || oi < bi);
+        else take = ov < bv || (ov == bv && oi < bi);
+        if (take) { bv = ov; bi = oi; }
+      }
+      const R bstep = __shfl_sync(0xffffffffu, step, bi);
+      status = (bv < merit) ? R(1) : R(0);
+      for (int idx = lane; idx < T * NT; idx += 32) {
+        const int t = idx / NT, j = idx - t * NT;
+        R xn = S.xu[idx] + bstep * S.g[idx];
+        if (t == 0 && j < NX) xn = S.x0[j];
+        S.xu[idx] = status * xn + (R(1) - status) * S.xu[idx];
+      }
+      merit = bv;
+      __syncwarp();
+    }
+    // ---- multiplier / penalty update (AL_mpc.py:298-310)
+    for (int t = lane; t < T; t += 32) {
+      if (t < T - 1) {
+        R f[NX];
+        Dyn::template step<R>(a.P, S.xu + t * NT, S.xu + t * NT + NX, f);
+#pragma unroll
+        for (int i = 0; i < NX; i++) S.lam[t * NX + i] += rho * (S.xu[(t + 1) * NT + i] - f[i]);
+      }
+      if (t == 0) {
+#pragma unroll
+        for (int i = 0; i < NX; i++) S.lam[(T - 1) * NX + i] += rho * (S.xu[i] - S.x0[i]);
+      }
+#pragma unroll
+      for (int j = 0; j < NU; j++) {
+        const R u = S.xu[t * NT + NX + j];
+        const R l1 = S.lam[neq + t * 2 * NU + j] + rho * (u - S.uu[t * NU + j]);
+        const R l2 = S.lam[neq + t * 2 * NU + NU + j] + rho * (-u + S.ul[t * NU + j]);
+        S.lam[neq + t * 2 * NU + j] = l1 < R(0) ? R(0) : l1;       // torch.clamp(min=0): NaN stays NaN
+        S.lam[neq + t * 2 * NU + NU + j] = l2 < R(0) ? R(0) : l2;
+      }
+    }
+    __syncwarp();
+    R acc = R(0);
+    for (int idx = lane; idx < T * NT; idx += 32) acc += R(0.5) * S.xu[idx] * S.C[idx] * S.xu[idx] + S.c[idx] * S.xu[idx];
+    acc = warp_sum(acc);
+    rho = rho * R(10);
+    if (lane == 0) { a.cost_hist_out[(size_t)(ai + 1) * B + prob] = acc; a.rho_hist_out[(size_t)(ai + 1) * B + prob] = rho; }
+    for (int idx = lane; idx < M; idx += 32) a.lam_hist_out[((size_t)(ai + 1) * B + prob) * M + idx] = S.lam[idx];
+  }
+
+  // ---- outputs + the state the reference keeps on the module
+  for (int idx = lane; idx < M; idx += 32) a.lam[(size_t)prob * M + idx] = S.lam[idx];
+  if (lane == 0) { a.rho[prob] = rho; a.status[prob] = status; }
+  for (int idx = lane; idx < T * NT; idx += 32) {
+    const int t = idx / NT, j = idx - t * NT;
+    const R v = S.xu[idx];
+    a.xu_out[(size_t)prob * T * NT + idx] = v;
+    if (j < NX) a.x_out[((size_t)prob * T + t) * NX + j] = (float)v;
+    else a.u_out[((size_t)prob * T + t) * NU + (j - NX)] = (float)v;
+  }
+  const int fe = al_factor_elems(T, NX, NU);
+  for (int idx = lane; idx < fe; idx += 32) a.factor[(size_t)prob * fe + idx] = S.D[idx];
+}
+
+// NewtonAL.backward (al_utils.py:462-500): ig = -H^-1 grad ; dC = ig * x_est ; dc = ig.
+template <typename R>
+struct ALBackArgs {
+  int B, T;
+  const R *factor, *xu, *grad;
+  R *dC, *dc;
+};
+
+template <int NX, int NU, typename R>
+__global__ void __launch_bounds__(128) k_al_backward(const ALBackArgs<R> a) {
+  constexpr int NT = NX + NU;
+  extern __shared__ __align__(16) unsigned char al_smem[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int prob = blockIdx.x * (blockDim.x >> 5) + warp;
+  if (prob >= a.B) return;
+  const int T = a.T;
+  R* g = reinterpret_cast<R*>(al_smem) + (size_t)warp * pad4(T * NT);
+  const int fe = al_factor_elems(T, NX, NU);
+  const R* D = a.factor + (size_t)prob * fe;
+  const R* E = D + T * NT * NT;
+  for (int idx = lane; idx < T * NT; idx += 32) g[idx] = a.grad[(size_t)prob * T * NT + idx];
+  __syncwarp();
+  block_solve<NX, NU, R>(D, E, g, T, lane);
+  for (int idx = lane; idx < T * NT; idx += 32) {
+    const R ig = -g[idx];
+    a.dc[(size_t)prob * T * NT + idx] = ig;
+    a.dC[(size_t)prob * T * NT + idx] = ig * a.xu[(size_t)prob * T * NT + idx];
+  }
+}
+
+// Stand-alone batched dynamics: step (xn) and Jacobians (A (N,nx,nx), B (N,nx,nu)), one thread per
+// knot (deqmpc/envs.py:16-31,68-82; qpth/env_dx/*.py forward).
+template <class Dyn, typename R>
+__global__ void k_dyn_step(DynParams P, const R* x, const R* u, R* xn, R* A, R* Bm, long long N) {
+  constexpr int NX = Dyn::NX, NU = Dyn::NU, NT = NX + NU;
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= N) return;
+  if (A == nullptr) {
+    R z[NT], f[NX];
+#pragma unroll
+    for (int j = 0; j < NX; j++) z[j] = x[i * NX + j];
+#pragma unroll
+    for (int j = 0; j < NU; j++) z[NX + j] = u[i * NU + j];
+    Dyn::template step<R>(P, z, z + NX, f);
+#pragma unroll
+    for (int j = 0; j < NX; j++) xn[i * NX + j] = f[j];
+  } else {
+    typedef Dual<R, NT> DR;
+    DR z[NT], f[NX];
+#pragma unroll
+    for (int j = 0; j < NT; j++) {
+      z[j] = DR(j < NX ? x[i * NX + j] : u[i * NU + (j - NX)]);
+      z[j].d[j] = R(1);
+    }
+    Dyn::template step<DR>(P, z, z + NX, f);
+#pragma unroll
+    for (int r = 0; r < NX; r++) {
+      xn[i * NX + r] = f[r].v;
+#pragma unroll
+      for (int j = 0; j < NX; j++) A[(i * NX + r) * NX + j] = f[r].d[j];
+#pragma unroll
+      for (int j = 0; j < NU; j++) Bm[(i * NX + r) * NU + j] = f[r].d[NX + j];
+    }
+  }
+}
+
+}  // namespace b200mpc

@@ -1,0 +1,139 @@
+"""GPU parity tests of the AL-MPC path: the fused kernels (through the C ABI, behind the MPC
+drop-in) against the golden vectors of the real reference and against the oracle."""
+import pytest
+import torch
+
+from tests.mpc_cases import CASES, load, oracle_dyn, rel
+
+pytestmark = pytest.mark.gpu
+
+# fp64 parity gate of BASELINE.json's north_star: 1e-6 relative on solution, state and gradients;
+# the float32 outputs are compared at float32 resolution.
+RTOL64, RTOL32 = 1e-6, 2e-6
+
+
+def _ours(case, dev):
+    from b200qp import envs
+    from b200qp.AL_mpc import MPC
+    from b200qp.al_utils import QuadCost
+    g = load(case)
+    env = CASES[case][0]
+    dx, dxj = (envs.PendulumDynamics(), envs.PendulumDynamics_jac()) if env == "pendulum" else \
+              (envs.IntegratorDynamics(), envs.IntegratorDynamics_jac())
+    B, T = g["u_init"].shape[:2]
+    nx, nu = dx.nx, dx.nu
+    ub = float(g["ub"]) * torch.ones(nu, dtype=torch.float64, device=dev)
+    x0 = g["x0"].to(dev)
+    ctrl = MPC(nx, nu, T, u_lower=-ub, u_upper=ub, exit_unconverged=False, eps=1e-5, n_batch=B, backprop=False,
+               verbose=0, u_init=g["u_init"].to(dev), solver_type="dense", dtype=torch.float64)
+    ctrl.reinitialize(x0, None)
+    ctrl.u_init = g["u_init"].to(dev)
+    outs = []
+    for k in range(int(g["n_calls"])):
+        Cfull = torch.diag_embed(g["Cd"]).to(dev).requires_grad_(True)
+        c = (-(g["Cd"] * g[f"xref{k}"])).to(dev).requires_grad_(True)
+        x, u = ctrl(x0, QuadCost(Cfull, c), dx, dxj)
+        assert x.dtype == torch.float32 and u.dtype == torch.float32
+        (x.sum() + u.sum()).backward()
+        outs.append(dict(x=x.detach().cpu(), u=u.detach().cpu(), lam=ctrl.lamda_prev.cpu(), rho=ctrl.rho_prev.cpu(),
+                         dC=Cfull.grad.diagonal(dim1=-2, dim2=-1).cpu(), dc=c.grad.cpu()))
+    return g, outs
+
+
+@pytest.mark.parametrize("case", list(CASES))
+def test_al_mpc_matches_reference_golden(case, cuda_device):
+    g, outs = _ours(case, cuda_device)
+    for k, o in enumerate(outs):
+        errs = {key: rel(o[key], g[f"out_{key}{k}"]) for key in o}
+        print(case, "call", k, {a: f"{b:.1e}" for a, b in errs.items()})
+        assert errs["x"] <= RTOL32 and errs["u"] <= RTOL32, errs
+        for key in ("lam", "rho", "dC", "dc"):
+            assert errs[key] <= RTOL64, (key, errs)
+
+
+@pytest.mark.parametrize("env", ["pendulum", "integrator", "pendulum_dx", "cartpole_dx"])
+def test_dynamics_step_and_jacobian(env, cuda_device):
+    """b200dyn_step / b200dyn_jac against a torch restatement + autograd Jacobians on the CPU."""
+    from b200qp import envs
+    from oracle import mpc_oracle as MO
+    torch.manual_seed(0)
+    N = 257
+    if env == "pendulum":
+        mod, nx, nu = envs.PendulumDynamics_jac(), 2, 1
+        ref = MO.Pendulum().step
+    elif env == "integrator":
+        mod, nx, nu = envs.IntegratorDynamics_jac(), 2, 1
+        ref = MO.Integrator().step
+    elif env == "pendulum_dx":
+        mod, nx, nu = envs.PendulumDx_jac(), 3, 1
+
+        def ref(x, u):  # qpth/env_dx/pendulum.py:49-84
+            g_, m, l, dt = 10., 1., 1., 0.05
+            uc = torch.clamp(u[:, 0], -2., 2.)
+            c, s, dth = x.unbind(1)
+            th = torch.atan2(s, c)
+            nd = dth + dt * (-3. * g_ / (2. * l) * (-s) + 3. * uc / (m * l ** 2))
+            nt = th + nd * dt
+            return torch.stack((torch.cos(nt), torch.sin(nt), nd), 1)
+    else:
+        mod, nx, nu = envs.CartpoleDx_jac(), 5, 1
+
+        def ref(state, u):  # qpth/env_dx/cartpole.py:63-96
+            gravity, masscart, masspole, length = torch.tensor((9.8, 1.0, 0.1, 0.5)).unbind()
+            total_mass = masspole + masscart
+            pml = masspole * length
+            uc = torch.clamp(u[:, 0], -100., 100.)
+            x, dx, c, s, dth = state.unbind(1)
+            th = torch.atan2(s, c)
+            cart_in = (uc + pml * dth ** 2 * s) / total_mass
+            th_acc = (gravity * s - c * cart_in) / (length * (4. / 3. - masspole * c ** 2 / total_mass))
+            xacc = cart_in - pml * th_acc * c / total_mass
+            return torch.stack((x + 0.05 * dx, dx + 0.05 * xacc, torch.cos(th + 0.05 * dth), torch.sin(th + 0.05 * dth),
+                                dth + 0.05 * th_acc), 1)
+    x = torch.randn(N, nx, dtype=torch.float64)
+    u = 1.5 * torch.randn(N, nu, dtype=torch.float64)
+    xr, ur = x.clone().requires_grad_(True), u.clone().requires_grad_(True)
+    out = ref(xr, ur)
+    A = torch.stack([torch.autograd.grad(out[:, i].sum(), xr, retain_graph=True)[0] for i in range(nx)], 1)
+    Bm = torch.stack([torch.autograd.grad(out[:, i].sum(), ur, retain_graph=True)[0] for i in range(nx)], 1)
+    xn, (Ag, Bg) = mod(x.to(cuda_device), u.to(cuda_device))
+    assert rel(xn.cpu(), out.detach()) < 1e-12
+    assert rel(Ag.cpu(), A) < 1e-12 and rel(Bg.cpu(), Bm) < 1e-12
+    # plain step entry point + autograd through it
+    base = type(mod).__mro__[2]()
+    xg, ug = x.to(cuda_device).requires_grad_(True), u.to(cuda_device).requires_grad_(True)
+    y = base(xg, ug)
+    assert rel(y.detach().cpu(), out.detach()) < 1e-12
+    y.sum().backward()
+    assert rel(xg.grad.cpu(), A.sum(1)) < 1e-12 and rel(ug.grad.cpu(), Bm.sum(1)) < 1e-12
+
+
+def test_al_mpc_vs_oracle_seeded_large_horizon(cuda_device):
+    """Fresh seeded problem (not a golden): pendulum, T=20, B=48, tight bounds; CUDA vs oracle."""
+    from b200qp import envs
+    from b200qp.AL_mpc import MPC
+    from b200qp.al_utils import QuadCost
+    from oracle import mpc_oracle as MO
+    torch.manual_seed(7)
+    B, T, nx, nu = 48, 20, 2, 1
+    dyn = MO.Pendulum()
+    x0 = torch.stack((torch.rand(B, dtype=torch.float64) * 6 - 3, torch.rand(B, dtype=torch.float64) * 2 - 1), 1)
+    u0 = torch.randn(B, T, nu, dtype=torch.float64)
+    Cd = torch.tensor([10., 1., 0.01], dtype=torch.float64).repeat(B, T, 1)
+    c = 0.1 * torch.randn(B, T, nx + nu, dtype=torch.float64)
+    ub = 2.0 * torch.ones(nu, dtype=torch.float64)
+    st = MO.ALState(B, T * nx + 2 * T * nu)
+    xs, us, ctx = MO.al_solve(MO.rollout(x0, u0, dyn), u0, x0, Cd, c, dyn, -ub, ub, st)
+    dC, dc = MO.al_backward(ctx, torch.ones(B, T, nx + nu, dtype=torch.float64))
+    dev = cuda_device
+    ctrl = MPC(nx, nu, T, u_lower=-ub.to(dev), u_upper=ub.to(dev), n_batch=B, u_init=u0.to(dev), dtype=torch.float64)
+    ctrl.reinitialize(x0.to(dev), None)
+    ctrl.u_init = u0.to(dev)
+    Cf = torch.diag_embed(Cd).to(dev).requires_grad_(True)
+    cg = c.to(dev).requires_grad_(True)
+    x, u = ctrl(x0.to(dev), QuadCost(Cf, cg), envs.PendulumDynamics(), envs.PendulumDynamics_jac())
+    (x.sum() + u.sum()).backward()
+    assert rel(x.detach().cpu(), xs.float()) < RTOL32 and rel(u.detach().cpu(), us.float()) < RTOL32
+    assert rel(ctrl.lamda_prev.cpu(), st.lam) < RTOL64
+    assert rel(Cf.grad.diagonal(dim1=-2, dim2=-1).cpu(), dC) < RTOL64 and rel(cg.grad.cpu(), dc) < RTOL64
+    assert torch.equal(ctrl.status.cpu(), ctx["status"])
