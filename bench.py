@@ -144,6 +144,94 @@ def cpu_oracle_rate(nb, repeats, threads):
     return nb / statistics.median(times), n_iter, statistics.median(times)
 
 
+def mpc_problem(B, T, device, seed=0):
+    """BASELINE configs[1] shape: pendulum (deqmpc/envs.py), T=5, bounds +-3, Q=diag(10,1,0.01)."""
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    th = (torch.rand(B, generator=g, dtype=torch.float64) * 2 - 1) * 3.141592653589793
+    thd = torch.rand(B, generator=g, dtype=torch.float64) * 2 - 1
+    x0 = torch.stack((th, thd), 1).to(device)
+    u0 = torch.randn(B, T, 1, generator=g, dtype=torch.float64).to(device)
+    Cd = torch.tensor([10.0, 1.0, 0.01], dtype=torch.float64).repeat(B, T, 1).to(device)
+    return x0, u0, Cd
+
+
+def bench_mpc(dev, B=1024, T=5, reps=20):
+    """MPC rollouts/s: al_mpc.MPC forward (AL solve) + T-step open-loop simulation of the nominal
+    controls + implicit backward of loss = x.sum() + u.sum()  (SURVEY.md section 8d)."""
+    from b200qp import envs
+    from b200qp.AL_mpc import MPC
+    from b200qp.al_utils import QuadCost
+    x0, u0, Cd = mpc_problem(B, T, dev)
+    dx, dxj = envs.PendulumDynamics(), envs.PendulumDynamics_jac()
+    ub = 3.0 * torch.ones(1, dtype=torch.float64, device=dev)
+    ctrl = MPC(2, 1, T, u_lower=-ub, u_upper=ub, n_batch=B, u_init=u0, eps=1e-5, dtype=torch.float64)
+    Cfull = torch.diag_embed(Cd).requires_grad_(True)
+    xref = torch.zeros(B, T, 3, dtype=torch.float64, device=dev, requires_grad=True)
+
+    def step():
+        ctrl.reinitialize(x0, None)
+        ctrl.u_init = u0
+        Cfull.grad = None
+        xref.grad = None
+        c = -(Cd * xref)
+        x, u = ctrl(x0, QuadCost(Cfull, c), dx, dxj)
+        sim = ctrl.rollout(x0, u.double(), dx)
+        (x.sum() + u.sum()).backward()
+        return x, sim
+
+    for _ in range(3):
+        step()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        step()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / reps
+    # kernel-only time of the fused AL solve (the rest of the step is torch glue + tiny kernels)
+    c = -(Cd * xref).detach()
+    Cdiag = Cd.clone()
+    from b200qp.al_utils import ALSolve, ALState
+    spec = envs.dyn_spec(dx)
+    xi = ctrl.rollout(x0, u0, dx)
+    ul, uu = (-ub).expand(B, T, 1).contiguous(), ub.expand(B, T, 1).contiguous()
+    k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    kms = []
+    for _ in range(5):
+        st = ALState(torch.zeros(B, T * 2 + 2 * T, dtype=torch.float64, device=dev), torch.ones(B, 1, dtype=torch.float64, device=dev))
+        torch.cuda.synchronize()
+        k0.record()
+        ALSolve.apply(Cdiag, c, xi, u0, x0, ul, uu, st, spec, 2)
+        k1.record()
+        torch.cuda.synchronize()
+        kms.append(k0.elapsed_time(k1))
+    return {"workload": f"BASELINE configs[1] shape: pendulum AL-MPC (deqmpc/envs.py dynamics) T={T} batch={B} fp64, "
+                        "forward + open-loop simulation + implicit backward",
+            "rollouts_per_s": B / (ms * 1e-3), "ms_per_call": ms, "al_solve_call_ms": min(kms),
+            "launches_per_call": 1 + (T - 1) * 2 + 1}
+
+
+def cpu_mpc_rate(B=256, T=5, threads=1):
+    """The reference's AL-MPC algorithm (oracle port) on the host cores, bounded sample."""
+    from oracle import mpc_oracle as MO
+    torch.set_num_threads(threads)
+    x0, u0, Cd = mpc_problem(B, T, torch.device("cpu"))
+    dyn = MO.Pendulum()
+    ub = 3.0 * torch.ones(1, dtype=torch.float64)
+    c = torch.zeros(B, T, 3, dtype=torch.float64)
+    times = []
+    for r in range(3):
+        t0 = time.perf_counter()
+        st = MO.ALState(B, T * 2 + 2 * T)
+        xs, us, ctx = MO.al_solve(MO.rollout(x0, u0, dyn), u0, x0, Cd, c, dyn, -ub, ub, st)
+        MO.rollout(x0, us, dyn)
+        MO.al_backward(ctx, torch.ones(B, T, 3, dtype=torch.float64))
+        times.append(time.perf_counter() - t0)
+    sec = statistics.median(times[1:])
+    return B / sec, sec
+
+
 def run_reference(args, rank):
     if rank != 0:
         return
@@ -366,6 +454,18 @@ def main():
     except Exception as ex:  # pragma: no cover
         small = {"error": repr(ex)}
 
+    mpc = None
+    if rank == 0:
+        try:
+            mpc = bench_mpc(dev)
+            if world == 1 and not args.no_cpu:
+                threads = os.cpu_count() or 1
+                rate, sec = cpu_mpc_rate(256, 5, threads)
+                mpc["cpu_baseline"] = {"value": rate, "unit": "rollouts/s", "cores": threads, "kind": "port",
+                                       "sample": f"oracle/mpc_oracle.py (dense restatement of qpth AL_mpc) B=256 T=5, median of 2 ({sec:.2f} s each)"}
+        except Exception as ex:  # pragma: no cover
+            mpc = {"error": repr(ex)}
+
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
         threads = os.cpu_count() or 1
@@ -385,7 +485,7 @@ def main():
                        "eps": 1e-12, "maxIter": 20, "parallelism": f"batch-sharded x{world}, no data-path collective",
                        "l2": "inputs+workspace per step exceed the 126 MB L2 (no flush needed)"},
             "clocks": clocks, "e2e": e2e, "gpu_launches": launches_per_step * args.steps,
-            "roofline": roofline, "cpu_baseline": cpu, "cfg1_nb128": small,
+            "roofline": roofline, "cpu_baseline": cpu, "cfg1_nb128": small, "mpc": mpc,
         }
         print(json.dumps(line))
     if world > 1:

@@ -166,6 +166,31 @@ static int kkt_solve_t(const b200qp_problem_t* pr, const Layout& L, int prefacto
   return B200QP_OK;
 }
 
+static __global__ void k_prefactor_status(const Control* ctl, double* status) {
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < B200QP_STATUS_DOUBLES; i++) status[i] = 0.0;
+    status[B200QP_ST_Q_FAIL] = (double)ctl->q_fail;
+    status[B200QP_ST_AQA_FAIL] = (double)ctl->aqa_fail;
+    status[B200QP_ST_LAUNCHES] = 2.0;
+  }
+}
+
+template <typename T>
+static int prefactor_t(const b200qp_problem_t* pr, const Layout& L, const void* Q, const void* G, const void* A, void* ws,
+                       double* status, cudaStream_t st) {
+  KArgs<T> a;
+  fill_args(a, pr, L, ws);
+  a.Q = (const T*)Q; a.G = (const T*)G; a.A = (const T*)(A ? A : G);
+  CK(cudaMemsetAsync(a.slots, 0, sizeof(Slot) * B200QP_MAX_ITER_CAP + sizeof(Control), st));
+  int rc = run_prefactor(a, L, st);
+  if (rc) return rc;
+  if (status) {
+    k_prefactor_status<<<1, 32, 0, st>>>(a.ctl, status);
+    CK(cudaGetLastError());
+  }
+  return B200QP_OK;
+}
+
 // ---------------------------------------------------------------------------- host-buffer path
 struct Arena {
   char* base = nullptr;
@@ -224,6 +249,17 @@ int b200qp_backward(const b200qp_problem_t* prob, const void* zhat, const void* 
   if (prob->dtype == B200QP_F64)
     return backward_t<double>(prob, L, zhat, lams, nus, slacks, dl_dzhat, dQ, dp, dG, dh, dA, db, workspace, st);
   return backward_t<float>(prob, L, zhat, lams, nus, slacks, dl_dzhat, dQ, dp, dG, dh, dA, db, workspace, st);
+}
+
+int b200qp_prefactor(const b200qp_problem_t* prob, const void* Q, const void* G, const void* A, void* workspace,
+                     double* status, b200qp_stream_t stream) {
+  Layout L;
+  int rc = make_layout(prob, L);
+  if (rc) return rc;
+  if (!Q || !G || !workspace || (prob->neq > 0 && !A)) return B200QP_EINVAL;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (prob->dtype == B200QP_F64) return prefactor_t<double>(prob, L, Q, G, A, workspace, status, st);
+  return prefactor_t<float>(prob, L, Q, G, A, workspace, status, st);
 }
 
 int b200qp_kkt_solve(const b200qp_problem_t* prob, int prefactor, const void* Q, const void* G, const void* A,

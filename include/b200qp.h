@@ -82,6 +82,13 @@ int b200qp_backward(const b200qp_problem_t* prob,
                     void* dQ, void* dp, void* dG, void* dh, void* dA, void* db,
                     void* workspace, b200qp_stream_t stream);
 
+/* The d-independent pre-factorisation alone (qpth/solvers/pdipm/batch.py:377-428 pre_factor_kkt):
+ * Q^-1, [A;G]Q^-1, the Schur blocks and their factor go to `workspace` for later
+ * b200qp_kkt_solve(prefactor = 0) calls.  status (device, 8 doubles, may be NULL) receives the
+ * Q / A Q^-1 A^T failure counts in slots B200QP_ST_Q_FAIL / B200QP_ST_AQA_FAIL. */
+int b200qp_prefactor(const b200qp_problem_t* prob, const void* Q, const void* G, const void* A,
+                     void* workspace, double* status, b200qp_stream_t stream);
+
 /* Stand-alone KKT solve: given d (nb,nineq) and right-hand sides, return the solution of
  *   [Q 0 G' A'; 0 D I 0; G I 0 0; A 0 0 0] [dx ds dz dy]' = -[rx rs rz ry]'.
  * prefactor != 0 recomputes the d-independent part from Q, G, A first. */

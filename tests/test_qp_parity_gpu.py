@@ -109,3 +109,35 @@ def test_kkt_residual_property_large_batch(cuda_device):
     assert (lams * slacks).abs().max().item() < 1e-6
     assert lams.min().item() > -1e-9 and slacks.min().item() > -1e-9
     assert fn.info["n_iter"] <= 20
+
+
+def test_kkt_solver_backends_agree(cuda_device):
+    """The reference's own self-consistency tests (test.py:222-247): block pre-factor + factor +
+    solve == one-shot factor_solve == iterative-refinement solve; here all three entry points of
+    b200qp.solvers.pdipm.batch against the oracle's full-KKT LU solve."""
+    from b200qp.solvers.pdipm import batch as pdipm_b
+    from oracle import qp_oracle as O
+    torch.manual_seed(0)
+    nb, n, m, p = 9, 10, 7, 3
+    Q, pp, G, h, A, b = O.random_qp(nb, n, m, p, seed=21)
+    d = torch.rand(nb, m, dtype=torch.float64) + 0.05
+    rx, rs, rz, ry = (torch.randn(nb, k, dtype=torch.float64) for k in (n, m, m, p))
+    want = O.full_kkt_solve(Q, torch.diag_embed(d), G, A, rx, rs, rz, ry)
+    dev = cuda_device
+    Qc, Gc, Ac, dc = Q.to(dev), G.to(dev), A.to(dev), d.to(dev)
+    r = [t.to(dev) for t in (rx, rs, rz, ry)]
+    got1 = pdipm_b.factor_solve_kkt(Qc, torch.diag_embed(dc), Gc, Ac, *r)
+    Q_LU, S_LU, R = pdipm_b.pre_factor_kkt(Qc, Gc, Ac)
+    pdipm_b.factor_kkt(S_LU, R, dc)
+    got2 = pdipm_b.solve_kkt(Q_LU, dc, Gc, Ac, S_LU, *r)
+    got3 = pdipm_b.solve_kkt_ir(Qc, torch.diag_embed(dc), Gc, Ac, *r, niter=1)
+    for got in (got1, got2, got3):
+        for a_, w_, name in zip(got, want, ("dx", "ds", "dz", "dy")):
+            gate(a_.cpu(), w_, 1e-8, name)
+    # solver-level forward: same best iterates as QPFunction
+    x, y, z, s = pdipm_b.forward(Qc, pp.to(dev), Gc, h.to(dev), Ac, b.to(dev))
+    fwd = O.qp_forward(Q.clone(), pp.clone(), G.clone(), h.clone(), A.clone(), b.clone())
+    gate(x.cpu(), fwd["zhat"], 1e-6, "x")
+    gate(z.cpu(), fwd["lams"], 1e-6, "z")
+    gate(s.cpu(), fwd["slacks"], 1e-6, "s")
+    gate(y.cpu(), fwd["nus"], 1e-6, "y")
