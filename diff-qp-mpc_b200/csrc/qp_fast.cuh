@@ -47,28 +47,36 @@ __device__ __forceinline__ double pivot_rcp(double x) {
 }
 __device__ __forceinline__ float pivot_rcp(float x) { return 1.0f / x; }
 
+}  // namespace b200qp
+#include "qp_dmma.cuh"
+namespace b200qp {
+
 template <typename T>
 struct FS {  // shared-memory carve-up of the fast path
   T *Up, *pinvT, *BQi, *V, *UA, *pinvA;
   T *x, *s, *z, *y, *d, *rx, *rz, *ry, *t, *hv, *u, *dx, *ds, *dz, *dy, *rsc, *scr, *scrn, *part, *red, *colbuf, *small;
 };
 
-__host__ __device__ inline size_t fast_smem_elems(int n, int m, int p, int ldn, int ldm, int ldp, int nt, int mpad) {
+// fk = 1: DMMA factorisation (qp_dmma.cuh): the packed factor carries one bordered column and the
+// column buffer becomes the [mpad][10] panel buffer (+8 panel pivots).
+__host__ __device__ inline int fast_up_elems(int m, int fk) { return fk ? (m + 1) * m / 2 + 1 : m * (m - 1) / 2 + 1; }
+__host__ __device__ inline int fast_colbuf_elems(int mpad, int fk) { return fk ? mpad * 10 + 8 : 2 * mpad; }
+__host__ __device__ inline size_t fast_smem_elems(int n, int m, int p, int ldn, int ldm, int ldp, int nt, int mpad, int fk = 0) {
   const int pp = p > 0 ? p : 1;
-  size_t e = round4(m * (m - 1) / 2 + 1) + round4(m) + round4((p + m) * ldn);
+  size_t e = round4(fast_up_elems(m, fk)) + round4(m) + round4((p + m) * ldn);
   if (p > 0) e += round4(p * ldm) + round4(p * ldp) + round4(p);
   e += (size_t)5 * round4(n) + (size_t)8 * round4(m) + (size_t)4 * round4(pp) + round4(p + m);
-  e += round4(nt) + 4 * 32 + 2 * mpad + 16;
+  e += round4(nt) + 4 * 32 + round4(fast_colbuf_elems(mpad, fk)) + 16;
   return e;
 }
 
 template <typename T>
 __device__ __forceinline__ void fast_carve(FS<T>& S, unsigned char* raw, int n, int m, int p, int ldn, int ldm,
-                                           int ldp, int nt, int mpad) {
+                                           int ldp, int nt, int mpad, int fk = 0) {
   T* q = reinterpret_cast<T*>(raw);
   auto take = [&](int cnt) { T* r = q; q += round4(cnt); return r; };
   const int pp = p > 0 ? p : 1;
-  S.Up = take(m * (m - 1) / 2 + 1);
+  S.Up = take(fast_up_elems(m, fk));
   S.pinvT = take(m);
   S.BQi = take((p + m) * ldn);
   if (p > 0) { S.V = take(p * ldm); S.UA = take(p * ldp); S.pinvA = take(p); }
@@ -79,7 +87,7 @@ __device__ __forceinline__ void fast_carve(FS<T>& S, unsigned char* raw, int n, 
   S.hv = take(p + m);
   S.part = take(nt);
   S.red = take(4 * 32);
-  S.colbuf = take(2 * mpad);
+  S.colbuf = take(fast_colbuf_elems(mpad, fk));
   S.small = take(16);
 }
 
@@ -257,14 +265,17 @@ __device__ __forceinline__ void fast_ldlt_solve(const T* Up, int m, const T* pin
   }
 }
 
-// Block-elimination KKT solve, fast path.  has_rx=false means rx = rz = ry = 0 (corrector).
-// accumulate=true adds the solution to dx/ds/dz/dy instead of overwriting.
-// gdx != nullptr additionally streams the final dx/ds/dz/dy to global memory.
-// Entry: inputs visible.  Exit: outputs visible to all threads (ends with a barrier).
-template <typename T, int MPAD, int NT>
-__device__ __forceinline__ void fast_kkt_solve(const FS<T>& S, const KArgs<T>& a, int prob, bool has_rx, const T* rx,
-                                               const T* rs, const T* rz, const T* ry, bool accumulate, T* gdx, T* gds,
-                                               T* gdz, T* gdy, int tid) {
+// Block-elimination KKT solve, fast path, in three stages so that the predictor's right-hand side
+// can ride through the factorisation (qp_dmma.cuh):
+//   fast_kkt_pre   hv[p..p+m) <- hz - V^T Da^-1 u  (ready for T^-1), u, t = Qi rx
+//   (T^-1 hv by one warp)
+//   fast_kkt_post  dz = -qz, dy = -qy, ds = (-rs - dz)/d, dx = -t + BQi^T [qy;qz]
+// has_rx=false means rx = rz = ry = 0 (corrector).  accumulate=true adds the solution to
+// dx/ds/dz/dy instead of overwriting.  gdx != nullptr additionally streams the final
+// dx/ds/dz/dy to global memory.  Each stage ends with a barrier.
+template <typename T, int NT>
+__device__ __forceinline__ void fast_kkt_pre(const FS<T>& S, const KArgs<T>& a, int prob, bool has_rx, const T* rx,
+                                             const T* rs, const T* rz, const T* ry, int tid) {
   const int n = a.n, m = a.m, p = a.p, ldn = a.ldn, ldm = a.ldm, ldp = a.ldp;
   const int lane = tid & 31, warp = tid >> 5;
   if (has_rx) {
@@ -291,8 +302,13 @@ __device__ __forceinline__ void fast_kkt_solve(const FS<T>& S, const KArgs<T>& a
     }
     cta_sync<NT>();
   }
-  if (warp == 0) fast_ldlt_solve<T, (MPAD + 31) / 32>(S.Up, m, S.pinvT, S.hv + p, lane);
-  cta_sync<NT>();
+}
+
+template <typename T, int NT>
+__device__ __forceinline__ void fast_kkt_post(const FS<T>& S, const KArgs<T>& a, int prob, bool has_rx, const T* rs,
+                                              bool accumulate, T* gdx, T* gds, T* gdz, T* gdy, int tid) {
+  const int n = a.n, m = a.m, p = a.p, ldn = a.ldn, ldm = a.ldm, ldp = a.ldp;
+  const int lane = tid & 31, warp = tid >> 5;
   if (p > 0) {
     gemv_rows_thread(S.V, ldm, p, m, S.hv + p, S.hv, tid, NT);
     cta_sync<NT>();
@@ -325,6 +341,36 @@ __device__ __forceinline__ void fast_kkt_solve(const FS<T>& S, const KArgs<T>& a
     if (gdy) gdy[j] = v;
   }
   cta_sync<NT>();
+}
+
+// Factor-kind dispatch.  FK = 0: register-tile rank-1 LDL^T (fast_factor); FK = 1: DMMA blocked
+// LDL^T (qp_dmma.cuh; double, NT = 128, m < MPAD).  hz (FK = 1 only): right-hand side carried as a
+// bordered row, see dmma_factor.
+template <typename T, int MPAD, int NT, int FK>
+__device__ __forceinline__ bool factor_any(const T* __restrict__ Rt, const FS<T>& S, const T* hz, int m, int tid,
+                                           const DmmaTiles<MPAD>* pre = nullptr) {
+  if constexpr (FK == 1) {
+    static_assert(NT == 128, "the DMMA factorisation is written for 4 warps");
+    return dmma_factor<MPAD>(Rt, S.scr, hz, S.Up, S.pinvT, S.colbuf, m, tid, pre);  // S.scr = 1/d, filled by the caller
+  } else {
+    return fast_factor<T, MPAD, NT>(Rt, S.d, S.Up, S.pinvT, S.colbuf, m, tid);
+  }
+}
+// v <- T^-1 v by ONE warp (from_border: v <- L^-T of the bordered row, FK = 1 only)
+template <typename T, int MPAD, int FK>
+__device__ __forceinline__ void tri_solve_any(const FS<T>& S, int m, T* v, bool from_border, int lane) {
+  if constexpr (FK == 1) dmma_ldlt_solve<(MPAD + 31) / 32>(S.Up, m, m + 1, S.pinvT, v, from_border, lane);
+  else fast_ldlt_solve<T, (MPAD + 31) / 32>(S.Up, m, S.pinvT, v, lane);
+}
+
+template <typename T, int MPAD, int NT, int FK = 0>
+__device__ __forceinline__ void fast_kkt_solve(const FS<T>& S, const KArgs<T>& a, int prob, bool has_rx, const T* rx,
+                                               const T* rs, const T* rz, const T* ry, bool accumulate, T* gdx, T* gds,
+                                               T* gdz, T* gdy, int tid) {
+  fast_kkt_pre<T, NT>(S, a, prob, has_rx, rx, rs, rz, ry, tid);
+  if ((tid >> 5) == 0) tri_solve_any<T, MPAD, FK>(S, a.m, S.hv + a.p, false, tid & 31);
+  cta_sync<NT>();
+  fast_kkt_post<T, NT>(S, a, prob, has_rx, rs, accumulate, gdx, gds, gdz, gdy, tid);
 }
 
 // get_step pieces for (z,dz) and (s,ds) at once, by ONE warp: out = {rmu_z, rmu_s, amax_z, amax_s},
@@ -362,13 +408,13 @@ __device__ __forceinline__ T warp_sum(T v) {
 
 // ------------------------------------------------------------------------------------------
 // INIT=true: initial point (batch.py:60-86).  INIT=false: PDIPM iteration a.iter (batch.py:91-204).
-template <typename T, int MPAD, int NT, bool INIT>
-__global__ void __launch_bounds__(NT) k_fast_iter(const KArgs<T> a) {
+template <typename T, int MPAD, int NT, bool INIT, int FK = 0>
+__global__ void __launch_bounds__(NT, (NT == 128 ? (FK == 1 ? 4 : 5) : 1)) k_fast_iter(const KArgs<T> a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int prob = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int n = a.n, m = a.m, p = a.p, it = a.iter;
   FS<T> S;
-  fast_carve(S, smem_raw, n, m, p, a.ldn, a.ldm, a.ldp, NT, MPAD);
+  fast_carve(S, smem_raw, n, m, p, a.ldn, a.ldm, a.ldp, NT, MPAD, FK);
   int* ictl = reinterpret_cast<int*>(S.small);
 
   T fill_z = T(1), fill_s = T(1);
@@ -406,18 +452,18 @@ __global__ void __launch_bounds__(NT) k_fast_iter(const KArgs<T> a) {
   const T* bg = a.b + (size_t)prob * a.sb;
 
   if (INIT) {
-    for (int i = tid; i < m; i += NT) { S.d[i] = T(1); S.rsc[i] = T(0); S.rz[i] = -hg[i]; }
+    for (int i = tid; i < m; i += NT) { S.d[i] = T(1); S.scr[i] = T(1); S.rsc[i] = T(0); S.rz[i] = -hg[i]; }
     for (int c = tid; c < n; c += NT) S.rx[c] = pg[c];
     for (int j = tid; j < p; j += NT) S.ry[j] = -bg[j];
     cta_sync<NT>();
-    const bool ok = fast_factor<T, MPAD, NT>(Rt, S.d, S.Up, S.pinvT, S.colbuf, m, tid);
+    const bool ok = factor_any<T, MPAD, NT, FK>(Rt, S, (const T*)nullptr, m, tid);
     cp_async_wait_all();
     cta_sync<NT>();
     if (!ok) {
       if (tid == 0) a.flags[prob] = FLAG_POISON;
       return;
     }
-    fast_kkt_solve<T, MPAD, NT>(S, a, prob, true, S.rx, S.rsc, S.rz, S.ry, false, (T*)nullptr, (T*)nullptr,
+    fast_kkt_solve<T, MPAD, NT, FK>(S, a, prob, true, S.rx, S.rsc, S.rz, S.ry, false, (T*)nullptr, (T*)nullptr,
                                 (T*)nullptr, (T*)nullptr, tid);
     T mn[2] = {t_inf<T>(), t_inf<T>()};
     for (int i = tid; i < m; i += NT) { mn[0] = nanmin(mn[0], S.ds[i]); mn[1] = nanmin(mn[1], S.dz[i]); }
@@ -451,6 +497,8 @@ __global__ void __launch_bounds__(NT) k_fast_iter(const KArgs<T> a) {
     const T* Qg = a.Q + (size_t)prob * a.sQ;
     const T* Gg = a.G + (size_t)prob * a.sG;
     const T* Ag = a.A + (size_t)prob * a.sA;
+    DmmaTiles<MPAD> tiles;
+    if constexpr (FK == 1) dmma_prefetch<MPAD>(Rt, tid, tiles);
     // ---- iterate + previous step
     {
       T alpha = T(0);
@@ -488,7 +536,9 @@ __global__ void __launch_bounds__(NT) k_fast_iter(const KArgs<T> a) {
       S.rz[i] = v;
       acc[1] += v * v;
       acc[3] += sv * zv;
-      S.d[i] = zv / sv;
+      const T dv = zv / sv;
+      S.d[i] = dv;
+      S.scr[i] = T(1) / dv;
     }
     for (int j = tid; j < p; j += NT) {
       const T v = S.ry[j] - bg[j];
@@ -501,7 +551,17 @@ __global__ void __launch_bounds__(NT) k_fast_iter(const KArgs<T> a) {
     const T resid = pri + sqrt(acc[0]) + T(m) * mu;
     const T t4 = acc[3];
 
-    const bool ok = fast_factor<T, MPAD, NT>(Rt, S.d, S.Up, S.pinvT, S.colbuf, m, tid);
+    bool ok;
+    if constexpr (FK == 1) {
+      // the predictor's right-hand side rides through the factorisation as a bordered row: its
+      // forward substitution is free (qp_dmma.cuh)
+      cp_async_wait_all();
+      cta_sync<NT>();
+      fast_kkt_pre<T, NT>(S, a, prob, true, S.rx, S.z, S.rz, S.ry, tid);
+      ok = factor_any<T, MPAD, NT, FK>(Rt, S, S.hv + p, m, tid, &tiles);
+    } else {
+      ok = factor_any<T, MPAD, NT, FK>(Rt, S, (const T*)nullptr, m, tid);
+    }
 
     {
       const double rd = (double)resid;
@@ -532,8 +592,12 @@ __global__ void __launch_bounds__(NT) k_fast_iter(const KArgs<T> a) {
     // ---- predictor (pass 0: rs = z) and corrector (pass 1: rs = rsc, zero rx/rz/ry)
     for (int pass = 0; pass < 2; pass++) {
       const bool aff = pass == 0;
-      fast_kkt_solve<T, MPAD, NT>(S, a, prob, aff, S.rx, aff ? S.z : S.rsc, S.rz, S.ry, !aff, aff ? (T*)nullptr : gdx,
-                                  aff ? (T*)nullptr : gds, aff ? (T*)nullptr : gdz, aff ? (T*)nullptr : gdy, tid);
+      const T* rs_ = aff ? S.z : S.rsc;
+      if (!(FK == 1 && aff)) fast_kkt_pre<T, NT>(S, a, prob, aff, S.rx, rs_, S.rz, S.ry, tid);
+      if (warp == 0) tri_solve_any<T, MPAD, FK>(S, m, S.hv + p, FK == 1 && aff, lane);
+      cta_sync<NT>();
+      fast_kkt_post<T, NT>(S, a, prob, aff, rs_, !aff, aff ? (T*)nullptr : gdx, aff ? (T*)nullptr : gds,
+                           aff ? (T*)nullptr : gdz, aff ? (T*)nullptr : gdy, tid);
       if (warp == 0) {
         T pc[4]; int has;
         warp_step_pieces(S.z, S.dz, S.s, S.ds, m, lane, pc, has);
@@ -563,13 +627,13 @@ __global__ void __launch_bounds__(NT) k_fast_iter(const KArgs<T> a) {
 }
 
 // ------------------------------------------------------------------------------------------
-template <typename T, int MPAD, int NT>
-__global__ void __launch_bounds__(NT) k_fast_backward(const KArgs<T> a, const BArgs<T> g) {
+template <typename T, int MPAD, int NT, int FK = 0>
+__global__ void __launch_bounds__(NT, (NT == 128 ? (FK == 1 ? 4 : 5) : 1)) k_fast_backward(const KArgs<T> a, const BArgs<T> g) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int prob = blockIdx.x, tid = threadIdx.x;
   const int n = a.n, m = a.m, p = a.p;
   FS<T> S;
-  fast_carve(S, smem_raw, n, m, p, a.ldn, a.ldm, a.ldp, NT, MPAD);
+  fast_carve(S, smem_raw, n, m, p, a.ldn, a.ldm, a.ldp, NT, MPAD, FK);
   fast_stage(S, a, prob, tid, NT);
   const T* zh = g.zhat + (size_t)prob * n;
   const T* lam = g.lams + (size_t)prob * m;
@@ -581,16 +645,17 @@ __global__ void __launch_bounds__(NT) k_fast_backward(const KArgs<T> a, const BA
     S.z[i] = lv;
     const T lc = (lv < T(1e-8)) ? T(1e-8) : lv, sc = (sv < T(1e-8)) ? T(1e-8) : sv;
     S.d[i] = lc / sc;
+    S.scr[i] = T(1) / (lc / sc);
     S.rsc[i] = T(0);
     S.rz[i] = T(0);
   }
   for (int c = tid; c < n; c += NT) { S.rx[c] = gz[c]; S.x[c] = zh[c]; }
   for (int j = tid; j < p; j += NT) { S.y[j] = nu[j]; S.ry[j] = T(0); }
   cta_sync<NT>();
-  fast_factor<T, MPAD, NT>(a.R + (size_t)prob * a.sR, S.d, S.Up, S.pinvT, S.colbuf, m, tid);  // NaN factor on failure
+  factor_any<T, MPAD, NT, FK>(a.R + (size_t)prob * a.sR, S, (const T*)nullptr, m, tid);  // NaN factor on failure
   cp_async_wait_all();
   cta_sync<NT>();
-  fast_kkt_solve<T, MPAD, NT>(S, a, prob, true, S.rx, S.rsc, S.rz, S.ry, false, (T*)nullptr, (T*)nullptr, (T*)nullptr,
+  fast_kkt_solve<T, MPAD, NT, FK>(S, a, prob, true, S.rx, S.rsc, S.rz, S.ry, false, (T*)nullptr, (T*)nullptr, (T*)nullptr,
                               (T*)nullptr, tid);
   cta_sync<NT>();
   T* dp = g.dp + (size_t)prob * n; T* dh = g.dh + (size_t)prob * m;
@@ -616,26 +681,27 @@ __global__ void __launch_bounds__(NT) k_fast_backward(const KArgs<T> a, const BA
   }
 }
 
-template <typename T, int MPAD, int NT>
-__global__ void __launch_bounds__(NT) k_fast_kkt(const KArgs<T> a, const SArgs<T> g) {
+template <typename T, int MPAD, int NT, int FK = 0>
+__global__ void __launch_bounds__(NT, (NT == 128 ? (FK == 1 ? 4 : 5) : 1)) k_fast_kkt(const KArgs<T> a, const SArgs<T> g) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int prob = blockIdx.x, tid = threadIdx.x;
   const int n = a.n, m = a.m, p = a.p;
   FS<T> S;
-  fast_carve(S, smem_raw, n, m, p, a.ldn, a.ldm, a.ldp, NT, MPAD);
+  fast_carve(S, smem_raw, n, m, p, a.ldn, a.ldm, a.ldp, NT, MPAD, FK);
   fast_stage(S, a, prob, tid, NT);
   for (int i = tid; i < m; i += NT) {
     S.d[i] = g.d[(size_t)prob * m + i];
+    S.scr[i] = T(1) / S.d[i];
     S.rsc[i] = g.rs[(size_t)prob * m + i];
     S.rz[i] = g.rz[(size_t)prob * m + i];
   }
   for (int c = tid; c < n; c += NT) S.rx[c] = g.rx[(size_t)prob * n + c];
   for (int j = tid; j < p; j += NT) S.ry[j] = g.ry[(size_t)prob * p + j];
   cta_sync<NT>();
-  fast_factor<T, MPAD, NT>(a.R + (size_t)prob * a.sR, S.d, S.Up, S.pinvT, S.colbuf, m, tid);
+  factor_any<T, MPAD, NT, FK>(a.R + (size_t)prob * a.sR, S, (const T*)nullptr, m, tid);
   cp_async_wait_all();
   cta_sync<NT>();
-  fast_kkt_solve<T, MPAD, NT>(S, a, prob, true, S.rx, S.rsc, S.rz, S.ry, false, g.dx + (size_t)prob * n,
+  fast_kkt_solve<T, MPAD, NT, FK>(S, a, prob, true, S.rx, S.rsc, S.rz, S.ry, false, g.dx + (size_t)prob * n,
                               g.ds + (size_t)prob * m, g.dz + (size_t)prob * m, p > 0 ? g.dy + (size_t)prob * p : (T*)nullptr, tid);
 }
 

@@ -22,6 +22,7 @@ constexpr size_t kSmemMax = 227 * 1024;
 struct Layout {
   int nb, n, m, p, ldn, ldm, ldp, nt, mpad;
   bool smem, fast;
+  int fk;  // 1: DMMA factorisation + fragment-order R (qp_dmma.cuh)
   size_t es, smem_bytes;
   long long sQi, sBQi, sR, sV, sUA, sF, sT;
   size_t oQi, oBQi, oR, oV, oUA, opinvA, oF, opinvF, oT, opinvT;
@@ -45,20 +46,25 @@ inline int make_layout(const b200qp_problem_t* pr, Layout& L) {
   L.smem_bytes = L.smem ? full : vecs;
   // fast path (qp_fast.cuh): nineq <= 64 with 128 threads, <= 128 with 256 threads
   L.mpad = L.m <= 32 ? 32 : (L.m <= 64 ? 64 : 128);
+  L.fk = 0;
   L.fast = L.m <= 128 && (L.m <= 64 || widest <= 256) && getenv("B200QP_FORCE_GENERIC") == nullptr;
   if (L.fast) {
     const int generic_nt = L.nt;
     const char* fnt = getenv("B200QP_FAST_NT");  // "32": one warp per QP up to nineq = 64
     L.nt = L.m <= 64 ? ((fnt && atoi(fnt) == 32) ? 32 : 128) : 256;
-    const size_t fb = fast_smem_elems(L.n, L.m, L.p, L.ldn, L.ldm, L.ldp, L.nt, L.mpad) * L.es;
-    if ((L.nt == 128 && widest > 128) || fb > kSmemResidentLimit) { L.fast = false; L.nt = generic_nt; }
+    // DMMA factorisation: fp64, 128-thread CTAs, one spare row for the bordered right-hand side
+    const char* fke = getenv("B200QP_FACTOR");
+    L.fk = (pr->dtype == B200QP_F64 && L.nt == 128 && L.m < 64 && !(fke && fke[0] == 't')) ? 1 : 0;
+    if (L.fk) L.mpad = L.m < 32 ? 32 : 64;
+    const size_t fb = fast_smem_elems(L.n, L.m, L.p, L.ldn, L.ldm, L.ldp, L.nt, L.mpad, L.fk) * L.es;
+    if ((L.nt == 128 && widest > 128) || fb > kSmemResidentLimit) { L.fast = false; L.fk = 0; L.nt = generic_nt; }
     else { L.smem = true; L.smem_bytes = fb; }
   }
   if (L.smem_bytes > kSmemMax) return B200QP_ETOOBIG;
   const int pp = L.p > 0 ? L.p : 1;
   L.sQi = round4(L.n * L.ldn);
   L.sBQi = round4((L.p + L.m) * L.ldn);
-  L.sR = L.fast ? round4(rtile_elems(L.mpad, L.nt)) : round4(L.m * L.ldm);
+  L.sR = L.fk ? frag_elems(L.mpad) : (L.fast ? round4(rtile_elems(L.mpad, L.nt)) : round4(L.m * L.ldm));
   L.sV = round4(pp * L.ldm);
   L.sUA = round4(pp * L.ldp);
   L.sF = round4(L.n * L.ldn);

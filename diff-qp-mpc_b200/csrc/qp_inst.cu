@@ -1,5 +1,6 @@
 // qp_inst.cu -- kernel instantiations for one (dtype, residency) pair; compiled four times:
 //   -DINST_T=double|float  -DINST_SMEM=true|false   (+ -DINST_PREFACTOR for the prefactor kernel)
+#include <type_traits>
 #include "qp_host.cuh"
 
 namespace b200qp {
@@ -27,7 +28,12 @@ static cudaError_t ensure_smem(K kernel, size_t bytes) {
   do { auto k = KEXPR; CK(ensure_smem(k, L.smem_bytes)); k<<<L.nb, NTV, L.smem_bytes, st>>>(__VA_ARGS__); } while (0)
 #define LAUNCH_FAST(KN, TAIL, ...)                                                                 \
   do {                                                                                             \
-    if (L.mpad == 128) LAUNCH_ONE((KN<T, 128, 256 TAIL>), 256, __VA_ARGS__);                       \
+    if (L.fk) {                                                                                    \
+      if constexpr (std::is_same<T, double>::value) {                                              \
+        if (L.mpad == 32) LAUNCH_ONE((KN<T, 32, 128 TAIL COMMA 1>), 128, __VA_ARGS__);             \
+        else LAUNCH_ONE((KN<T, 64, 128 TAIL COMMA 1>), 128, __VA_ARGS__);                          \
+      }                                                                                            \
+    } else if (L.mpad == 128) LAUNCH_ONE((KN<T, 128, 256 TAIL>), 256, __VA_ARGS__);                \
     else if (L.nt == 32) {                                                                         \
       if (L.mpad == 32) LAUNCH_ONE((KN<T, 32, 32 TAIL>), 32, __VA_ARGS__);                         \
       else LAUNCH_ONE((KN<T, 64, 32 TAIL>), 32, __VA_ARGS__);                                      \

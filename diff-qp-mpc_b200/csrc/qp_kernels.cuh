@@ -51,6 +51,10 @@ struct Control {                    // lives after the slots
 // over the (a,b) blocks that touch the lower triangle), thread t = (k%TC)*TR + i%TR, with a
 // TR x TC thread grid (TR = 8 for one-warp CTAs, 16 otherwise).
 __host__ __device__ inline int rtile_index(int i, int k, int mpad, int nt) {
+  if (nt < 0) {  // DMMA accumulator-fragment order (qp_dmma.cuh: frag_index)
+    const int I = i >> 3, K = k >> 3, r = i & 7, c = k & 7;
+    return (I * (I + 1) / 2 + K) * 64 + (r * 4 + (c >> 1)) * 2 + (c & 1);
+  }
   const int TR = nt == 32 ? 8 : 16, TC = nt / TR, NB = mpad / TC;
   const int a = i / TR, ti = i - a * TR, b = k / TC, tk = k - b * TC;
   int q = b;
@@ -94,7 +98,7 @@ struct KArgs {
   int iter, max_iter, lim;
   double eps;
   int launches;
-  int rtile_mpad, rtile_nt;  // != 0: R is stored in register-tile order (qp_fast.cuh)
+  int rtile_mpad, rtile_nt;  // != 0: R is stored in register-tile order (qp_fast.cuh); nt = -1: DMMA fragment order
 };
 
 // ------------------------------------------------------------------------------------------
