@@ -25,8 +25,8 @@ EXPORTS = (
     "b200dyn_step", "b200dyn_jac",
 )
 
-ENV_PENDULUM, ENV_INTEGRATOR, ENV_PENDULUM_DX, ENV_CARTPOLE_DX = 0, 1, 2, 3
-MPC_MAX_PARAMS = 16
+ENV_PENDULUM, ENV_INTEGRATOR, ENV_PENDULUM_DX, ENV_CARTPOLE_DX, ENV_REX_QUADROTOR = 0, 1, 2, 3, 4
+MPC_MAX_PARAMS = 64
 
 
 class MpcProblem(ctypes.Structure):

@@ -46,8 +46,17 @@ def dyn_spec(dx):
         polemass_length = masspole * length
         return (_lib.ENV_CARTPOLE_DX, [float(dx.dt), float(gravity), float(masscart), float(masspole), float(length),
                                        float(total_mass), float(polemass_length), float(dx.force_mag)], 5, 1)
+    if base == "RexQuadrotor_dynamics":
+        f32 = lambda t: [float(v) for v in torch.as_tensor(t).detach().to(dtype=torch.float32, device="cpu").reshape(-1)]
+        mg = torch.as_tensor(dx.g).detach().to(dtype=torch.float32, device="cpu") * float(dx.m)  # float32, as self.m * self.g
+        params = ([float(dx.dt), float(dx.m), float(dx.act_scale), 0.0244101, float(dx.kf), float(dx.km), float(dx.bf),
+                   float(dx.motor_dist)] + f32(mg) + f32(dx.Bf) + f32(dx.J) + f32(dx.Jinv) + f32(dx.ss) + f32(dx.cd)
+                  + f32(dx.cross_A))
+        assert len(params) == 50
+        return _lib.ENV_REX_QUADROTOR, params, 12, 4
     raise NotImplementedError(f"b200qp: no fused kernel for dynamics {name!r}; supported: PendulumDynamics, "
-                              "IntegratorDynamics, PendulumDx, CartpoleDx (and their *_jac variants)")
+                              "IntegratorDynamics, PendulumDx, CartpoleDx, RexQuadrotor_dynamics (and their *_jac "
+                              "variants)")
 
 
 def _run(spec, x, u, want_jac):
@@ -191,3 +200,40 @@ class CartpoleDx(_EnvDx):
 
 class CartpoleDx_jac(_DynamicsJac, CartpoleDx):
     """Jacobian companion (see PendulumDx_jac)."""
+
+
+class RexQuadrotor_dynamics(_Dynamics):
+    """deqmpc/rex_quadrotor.py:7-49: 12-state MRP rigid body, RK4, controls scaled by 100.  Model
+    constants live in float32 tensors exactly as in the reference (they enter the fp64 arithmetic
+    rounded through float32)."""
+
+    def __init__(self, bsz=1, mass=2.0,
+                 J=[[0.01566089, 0.00000318037, 0.0], [0.00000318037, 0.01562078, 0.0], [0.0, 0.0, 0.02226868]],
+                 gravity=[0, 0, -9.81], motor_dist=0.28, kf=0.0244101, bf=-30.48576, km=0.00029958, bm=-0.367697,
+                 quad_min_throttle=1148.0, quad_max_throttle=1832.0, ned=False, cross_A_x=0.25, cross_A_y=0.25,
+                 cross_A_z=0.5, cd=[0.0, 0.0, 0.0], max_steps=100, dt=0.05, device=torch.device('cpu'), jacobian=False):
+        super().__init__()
+        import numpy as np
+        self.m = mass
+        Jn = np.array(J)
+        self.J = (torch.diag(torch.FloatTensor(Jn)) if Jn.ndim == 1 else torch.FloatTensor(Jn)).unsqueeze(0)
+        self.Jinv = torch.linalg.inv(self.J)
+        self.g = torch.FloatTensor(gravity).unsqueeze(0)
+        self.motor_dist, self.kf, self.km, self.bf, self.bm, self.bsz = motor_dist, kf, km, bf, bm, bsz
+        self.Bf = torch.zeros((1, 3))
+        self.Bf[0, 2] = 4 * bf
+        self.quad_min_throttle, self.quad_max_throttle, self.ned = quad_min_throttle, quad_max_throttle, ned
+        self.cross_A = torch.FloatTensor(np.array([cross_A_x, cross_A_y, cross_A_y])).unsqueeze(0)
+        self.nx = self.state_dim = 12
+        self.nu = self.control_dim = 4
+        self._max_episode_steps = max_steps
+        self.dt = dt
+        self.act_scale = 100.0
+        self.cd = torch.tensor(cd).unsqueeze(0)
+        ss = torch.tensor([[1., 1, 0], [1., -1, 0], [-1., -1, 0], [-1., 1, 0]]).unsqueeze(0)
+        self.ss = ss / ss.norm(dim=-1).unsqueeze(-1)
+        self.device = device
+
+
+class RexQuadrotor_dynamics_jac(_DynamicsJac, RexQuadrotor_dynamics):
+    """deqmpc/rex_quadrotor.py:130-146"""

@@ -25,6 +25,7 @@ static bool env_dims(int env, int& nx, int& nu) {
     case ENV_INTEGRATOR: nx = Integrator::NX; nu = Integrator::NU; return true;
     case ENV_PENDULUM_DX: nx = PendulumDx::NX; nu = PendulumDx::NU; return true;
     case ENV_CARTPOLE_DX: nx = CartpoleDx::NX; nu = CartpoleDx::NU; return true;
+    case ENV_REX_QUADROTOR: nx = RexQuadrotor::NX; nu = RexQuadrotor::NU; return true;
   }
   return false;
 }
@@ -98,6 +99,7 @@ static int dyn_t(const double* params, const void* x, const void* u, void* xn, v
     case ENV_INTEGRATOR: EXPR_MACRO(Integrator);              \
     case ENV_PENDULUM_DX: EXPR_MACRO(PendulumDx);             \
     case ENV_CARTPOLE_DX: EXPR_MACRO(CartpoleDx);             \
+    case ENV_REX_QUADROTOR: EXPR_MACRO(RexQuadrotor);         \
   }                                                           \
   return B200QP_EINVAL
 

@@ -127,21 +127,28 @@ template <class Dyn, typename R>
 __device__ __forceinline__ void assemble(const ALScratch<R, Dyn::NX, Dyn::NU>& S, const DynParams& P, int T, R rho, int lane) {
   constexpr int NX = Dyn::NX, NU = Dyn::NU, NT = NX + NU;
   const int neq = T * NX;
-  typedef Dual<R, NT> DR;
+  // Jacobians by forward-mode duals, DW directions at a time (bounds the register footprint)
+  constexpr int DW = NT <= 4 ? NT : 4;
+  typedef Dual<R, DW> DR;
   for (int t = lane; t < T; t += 32) {
     if (t < T - 1) {
-      DR z[NT], f[NX];
+#pragma unroll 1
+      for (int c0 = 0; c0 < NT; c0 += DW) {
+        DR z[NT], f[NX];
 #pragma unroll
-      for (int j = 0; j < NT; j++) {
-        z[j] = DR(S.xu[t * NT + j]);
-        z[j].d[j] = R(1);
-      }
-      Dyn::template step<DR>(P, z, z + NX, f);
+        for (int j = 0; j < NT; j++) {
+          z[j] = DR(S.xu[t * NT + j]);
 #pragma unroll
-      for (int i = 0; i < NX; i++) {
+          for (int q = 0; q < DW; q++) z[j].d[q] = (j == c0 + q) ? R(1) : R(0);
+        }
+        Dyn::template step<DR>(P, z, z + NX, f);
 #pragma unroll
-        for (int j = 0; j < NT; j++) S.E[(t * NX + i) * NT + j] = f[i].d[j];
-        S.w[t * NX + i] = S.lam[t * NX + i] + rho * (S.xu[(t + 1) * NT + i] - f[i].v);
+        for (int i = 0; i < NX; i++) {
+#pragma unroll
+          for (int q = 0; q < DW; q++)
+            if (c0 + q < NT) S.E[(t * NX + i) * NT + c0 + q] = f[i].d[q];
+          if (c0 == 0) S.w[t * NX + i] = S.lam[t * NX + i] + rho * (S.xu[(t + 1) * NT + i] - f[i].v);
+        }
       }
     }
     if (t == 0) {
@@ -477,21 +484,28 @@ __global__ void k_dyn_step(DynParams P, const R* x, const R* u, R* xn, R* A, R* 
 #pragma unroll
     for (int j = 0; j < NX; j++) xn[i * NX + j] = f[j];
   } else {
-    typedef Dual<R, NT> DR;
-    DR z[NT], f[NX];
+    constexpr int DW = NT <= 4 ? NT : 4;
+    typedef Dual<R, DW> DR;
+#pragma unroll 1
+    for (int c0 = 0; c0 < NT; c0 += DW) {
+      DR z[NT], f[NX];
 #pragma unroll
-    for (int j = 0; j < NT; j++) {
-      z[j] = DR(j < NX ? x[i * NX + j] : u[i * NU + (j - NX)]);
-      z[j].d[j] = R(1);
-    }
-    Dyn::template step<DR>(P, z, z + NX, f);
+      for (int j = 0; j < NT; j++) {
+        z[j] = DR(j < NX ? x[i * NX + j] : u[i * NU + (j - NX)]);
 #pragma unroll
-    for (int r = 0; r < NX; r++) {
-      xn[i * NX + r] = f[r].v;
+        for (int q = 0; q < DW; q++) z[j].d[q] = (j == c0 + q) ? R(1) : R(0);
+      }
+      Dyn::template step<DR>(P, z, z + NX, f);
 #pragma unroll
-      for (int j = 0; j < NX; j++) A[(i * NX + r) * NX + j] = f[r].d[j];
+      for (int r = 0; r < NX; r++) {
+        if (c0 == 0) xn[i * NX + r] = f[r].v;
 #pragma unroll
-      for (int j = 0; j < NU; j++) Bm[(i * NX + r) * NU + j] = f[r].d[NX + j];
+        for (int q = 0; q < DW; q++) {
+          const int j = c0 + q;
+          if (j < NX) A[(i * NX + r) * NX + j] = f[r].d[q];
+          else if (j < NT) Bm[(i * NX + r) * NU + (j - NX)] = f[r].d[q];
+        }
+      }
     }
   }
 }

@@ -8,6 +8,7 @@
 //   Integrator  deqmpc/envs.py:182-214     double integrator, semi-implicit Euler
 //   PendulumDx  qpth/env_dx/pendulum.py:49-84   (cos, sin, thdot) state, clamped torque
 //   CartpoleDx  qpth/env_dx/cartpole.py:63-96   (x, dx, cos, sin, dth) state, clamped force
+//   RexQuadrotor deqmpc/rex_quadrotor.py:7-146  12-state MRP rigid body, RK4, act_scale = 100
 #pragma once
 #include <cuda_runtime.h>
 
@@ -102,12 +103,17 @@ template <typename R, int N> __device__ __forceinline__ Dual<R, N> m_clamp(const
   return a;
 }
 
+// sign with zero derivative (torch.sign)
+__device__ __forceinline__ double m_sign(double x) { return x > 0.0 ? 1.0 : (x < 0.0 ? -1.0 : 0.0); }
+__device__ __forceinline__ float m_sign(float x) { return x > 0.f ? 1.f : (x < 0.f ? -1.f : 0.f); }
+template <typename R, int N> __device__ __forceinline__ R m_sign(const Dual<R, N>& a) { return m_sign(a.v); }
+
 template <typename S> struct real_of { typedef S type; };
 template <typename R, int N> struct real_of<Dual<R, N>> { typedef R type; };
 
 // ---------------------------------------------------------------------------- environments
-constexpr int ENV_PENDULUM = 0, ENV_INTEGRATOR = 1, ENV_PENDULUM_DX = 2, ENV_CARTPOLE_DX = 3;
-constexpr int MAX_PARAMS = 16;
+constexpr int ENV_PENDULUM = 0, ENV_INTEGRATOR = 1, ENV_PENDULUM_DX = 2, ENV_CARTPOLE_DX = 3, ENV_REX_QUADROTOR = 4;
+constexpr int MAX_PARAMS = 64;
 
 struct DynParams { double v[MAX_PARAMS]; };
 
@@ -178,6 +184,126 @@ struct CartpoleDx {
     xn[2] = m_cos(nth);
     xn[3] = m_sin(nth);
     xn[4] = dth + dt * th_acc;
+  }
+};
+
+// params (deqmpc/rex_quadrotor.py:9-49; values the reference keeps in float32 tensors are passed
+// already rounded through float32 by the host):
+//   0 dt, 1 mass, 2 act_scale, 3 kf used by forces() (literal 0.0244101), 4 kf, 5 km, 6 bf,
+//   7 motor_dist, 8..10 mass*g, 11..13 Bf, 14..22 J, 23..31 J^-1, 32..43 ss (4 x 3), 44..46 cd,
+//   47..49 cross_A
+struct RexQuadrotor {
+  static constexpr int NX = 12, NU = 4;
+
+  template <typename S, typename R>
+  __device__ static __forceinline__ void quatrot(const S* q, const R* r, S* out) {  // rexquad_utils.py:211-220, constant r
+    const S qs = q[0];
+    const S dotqq = q[1] * q[1] + q[2] * q[2] + q[3] * q[3];
+    const S dotqr = q[1] * r[0] + q[2] * r[1] + q[3] * r[2];
+    const S c0 = q[2] * r[2] - q[3] * r[1], c1 = q[3] * r[0] - q[1] * r[2], c2 = q[1] * r[1] - q[2] * r[0];
+    const S a = qs * qs - dotqq;
+    out[0] = a * r[0] + R(2) * q[1] * dotqr + R(2) * qs * c0;
+    out[1] = a * r[1] + R(2) * q[2] * dotqr + R(2) * qs * c1;
+    out[2] = a * r[2] + R(2) * q[3] * dotqr + R(2) * qs * c2;
+  }
+  template <typename S, typename R>
+  __device__ static __forceinline__ void quatrot_v(const S* q, const S* r, S* out) {  // same, variable r
+    const S qs = q[0];
+    const S dotqq = q[1] * q[1] + q[2] * q[2] + q[3] * q[3];
+    const S dotqr = q[1] * r[0] + q[2] * r[1] + q[3] * r[2];
+    const S c0 = q[2] * r[2] - q[3] * r[1], c1 = q[3] * r[0] - q[1] * r[2], c2 = q[1] * r[1] - q[2] * r[0];
+    const S a = qs * qs - dotqq;
+    out[0] = a * r[0] + R(2) * q[1] * dotqr + R(2) * qs * c0;
+    out[1] = a * r[1] + R(2) * q[2] * dotqr + R(2) * qs * c1;
+    out[2] = a * r[2] + R(2) * q[3] * dotqr + R(2) * qs * c2;
+  }
+  template <typename S, typename R>
+  __device__ static __forceinline__ void mrp2quat(const S* m, R sgn, S* q) {  // rexquad_utils.py:297-300 on sgn * m
+    const S sq = m[0] * m[0] + m[1] * m[1] + m[2] * m[2];
+    const S inv = R(1) / (R(1) + sq);
+    q[0] = (R(1) - sq) * inv;
+    q[1] = (R(2) * sgn) * m[0] * inv;
+    q[2] = (R(2) * sgn) * m[1] * inv;
+    q[3] = (R(2) * sgn) * m[2] * inv;
+  }
+
+  // continuous dynamics (rex_quadrotor.py:113-128); us = act_scale * u
+  template <typename S>
+  __device__ static __forceinline__ void deriv(const DynParams& P, const S* x, const S* us, S* dxdt) {
+    typedef typename real_of<S>::type R;
+    const S* pm = x + 3; const S* v = x + 6; const S* w = x + 9;
+    S q[4], qn[4];
+    mrp2quat<S, R>(pm, R(1), q);
+    mrp2quat<S, R>(pm, R(-1), qn);
+    // forces (rex_quadrotor.py:51-68)
+    const R kff = (R)P.v[3];
+    const S Fz = kff * us[0] + kff * us[1] + kff * us[2] + kff * us[3];
+    R mg[3] = {(R)P.v[8], (R)P.v[9], (R)P.v[10]};
+    S grav[3];
+    quatrot<S, R>(qn, mg, grav);
+    S f[3];
+#pragma unroll
+    for (int i = 0; i < 3; i++) {
+      const S df = (-m_sign(pm[i]) * R(0.5) * R(1.27)) * (pm[i] * pm[i]) * ((R)P.v[44 + i] * (R)P.v[47 + i]);
+      f[i] = df + grav[i] + (R)P.v[11 + i];
+    }
+    f[2] = f[2] + Fz;
+    // moments (rex_quadrotor.py:70-86)
+    const R kf = (R)P.v[4], km = (R)P.v[5], bf = (R)P.v[6], L = (R)P.v[7];
+    S tau[3];
+    tau[0] = S(R(0)); tau[1] = S(R(0));
+    tau[2] = km * us[0] - km * us[1] + km * us[2] - km * us[3];
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+      const S bz = kf * us[i] + bf;
+      const R ax = L * (R)P.v[32 + 3 * i], ay = L * (R)P.v[32 + 3 * i + 1];
+      tau[0] = tau[0] + ay * bz;
+      tau[1] = tau[1] - ax * bz;
+    }
+    // kinematics (rexquad_utils.py:393-403)
+    const S p0 = pm[0], p1 = pm[1], p2 = pm[2];
+    const S a00 = R(1) + p0 * p0 - p1 * p1 - p2 * p2, a01 = R(2) * (p0 * p1 - p2), a02 = R(2) * (p0 * p2 + p1);
+    const S a10 = R(2) * (p1 * p0 + p2), a11 = R(1) - p0 * p0 + p1 * p1 - p2 * p2, a12 = R(2) * (p1 * p2 - p0);
+    const S a20 = R(2) * (p2 * p0 - p1), a21 = R(2) * (p2 * p1 + p0), a22 = R(1) - p0 * p0 - p1 * p1 + p2 * p2;
+    S pdot[3];
+    quatrot_v<S, R>(q, v, pdot);
+    dxdt[0] = pdot[0]; dxdt[1] = pdot[1]; dxdt[2] = pdot[2];
+    dxdt[3] = R(0.25) * (a00 * w[0] + a01 * w[1] + a02 * w[2]);
+    dxdt[4] = R(0.25) * (a10 * w[0] + a11 * w[1] + a12 * w[2]);
+    dxdt[5] = R(0.25) * (a20 * w[0] + a21 * w[1] + a22 * w[2]);
+    const R im = R(1) / (R)P.v[1];
+    dxdt[6] = f[0] * im - (w[1] * v[2] - w[2] * v[1]);
+    dxdt[7] = f[1] * im - (w[2] * v[0] - w[0] * v[2]);
+    dxdt[8] = f[2] * im - (w[0] * v[1] - w[1] * v[0]);
+    S Jw[3], tt[3];
+#pragma unroll
+    for (int i = 0; i < 3; i++) Jw[i] = (R)P.v[14 + 3 * i] * w[0] + (R)P.v[15 + 3 * i] * w[1] + (R)P.v[16 + 3 * i] * w[2];
+    tt[0] = tau[0] - (w[1] * Jw[2] - w[2] * Jw[1]);
+    tt[1] = tau[1] - (w[2] * Jw[0] - w[0] * Jw[2]);
+    tt[2] = tau[2] - (w[0] * Jw[1] - w[1] * Jw[0]);
+#pragma unroll
+    for (int i = 0; i < 3; i++) dxdt[9 + i] = (R)P.v[23 + 3 * i] * tt[0] + (R)P.v[24 + 3 * i] * tt[1] + (R)P.v[25 + 3 * i] * tt[2];
+  }
+
+  template <typename S>
+  __device__ static void step(const DynParams& P, const S* x, const S* u, S* xn) {  // RK4, rex_quadrotor.py:98-108
+    typedef typename real_of<S>::type R;
+    const R dt = (R)P.v[0], dt2 = dt / R(2), as = (R)P.v[2];
+    S us[NU], y[NX], k1[NX], k2[NX], k3[NX], k4[NX];
+#pragma unroll
+    for (int i = 0; i < NU; i++) us[i] = as * u[i];
+    deriv<S>(P, x, us, k1);
+#pragma unroll
+    for (int i = 0; i < NX; i++) y[i] = x[i] + dt2 * k1[i];
+    deriv<S>(P, y, us, k2);
+#pragma unroll
+    for (int i = 0; i < NX; i++) y[i] = x[i] + dt2 * k2[i];
+    deriv<S>(P, y, us, k3);
+#pragma unroll
+    for (int i = 0; i < NX; i++) y[i] = x[i] + dt * k3[i];
+    deriv<S>(P, y, us, k4);
+#pragma unroll
+    for (int i = 0; i < NX; i++) xn[i] = x[i] + (dt / R(6)) * (k1[i] + R(2) * k2[i] + R(2) * k3[i] + k4[i]);
   }
 };
 

@@ -34,7 +34,10 @@ extern "C" {
 #define B200MPC_ENV_PENDULUM_DX 2   /* qpth/env_dx/pendulum.py PendulumDx: params dt,g,m,l,max_torque  */
 #define B200MPC_ENV_CARTPOLE_DX 3   /* qpth/env_dx/cartpole.py CartpoleDx: params dt,gravity,masscart,
                                        masspole,length,total_mass,polemass_length,force_mag           */
-#define B200MPC_MAX_PARAMS 16
+#define B200MPC_ENV_REX_QUADROTOR 4 /* deqmpc/rex_quadrotor.py RexQuadrotor_dynamics (nx=12, nu=4, RK4): params dt,
+                                       mass,act_scale,kf(forces),kf,km,bf,motor_dist,mass*g[3],Bf[3],J[9],Jinv[9],
+                                       ss[12],cd[3],cross_A[3]  (float32-rounded where the reference is float32)  */
+#define B200MPC_MAX_PARAMS 64
 
 typedef struct {
   int32_t B, T;                  /* batch, horizon                                               */

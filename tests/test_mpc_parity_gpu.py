@@ -137,3 +137,51 @@ def test_al_mpc_vs_oracle_seeded_large_horizon(cuda_device):
     assert rel(ctrl.lamda_prev.cpu(), st.lam) < RTOL64
     assert rel(Cf.grad.diagonal(dim1=-2, dim2=-1).cpu(), dC) < RTOL64 and rel(cg.grad.cpu(), dc) < RTOL64
     assert torch.equal(ctrl.status.cpu(), ctx["status"])
+
+
+def _npz(name):
+    import os
+    import numpy as np
+    from tests.mpc_cases import GOLDEN_DIR
+    return {k: torch.as_tensor(v) for k, v in dict(np.load(os.path.join(GOLDEN_DIR, name))).items()}
+
+
+def test_rex_quadrotor_dynamics_golden(cuda_device):
+    """b200dyn_step / b200dyn_jac for the rex quadrotor (RK4, MRP attitude) against outputs of the
+    reference's RexQuadrotor_dynamics(_jac) (oracle/gen_golden_rex.py)."""
+    from b200qp import envs
+    g = _npz("dyn_rex.npz")
+    mod = envs.RexQuadrotor_dynamics_jac()
+    xn, (A, B) = mod(g["x"].to(cuda_device), g["u"].to(cuda_device))
+    assert rel(xn.cpu(), g["xn"]) < 1e-13
+    assert rel(A.cpu(), g["A"]) < 1e-12 and rel(B.cpu(), g["B"]) < 1e-12
+    y = envs.RexQuadrotor_dynamics()(g["x"].to(cuda_device), g["u"].to(cuda_device))
+    assert rel(y.cpu(), g["xn"]) < 1e-13
+
+
+def test_al_mpc_rex_quadrotor_golden(cuda_device):
+    """AL-MPC on the rex quadrotor (nx=12, nu=4, T=8, B=4) against the real reference run."""
+    from b200qp import envs
+    from b200qp.AL_mpc import MPC
+    from b200qp.al_utils import QuadCost
+    g = _npz("mpc_rex_B4_T8.npz")
+    dev = cuda_device
+    B, T, nu = g["u_init"].shape
+    nx = g["x0"].shape[1]
+    ul, uu = 11.5 * torch.ones(nu, dtype=torch.float64, device=dev), 18.3 * torch.ones(nu, dtype=torch.float64, device=dev)
+    ctrl = MPC(nx, nu, T, u_lower=ul, u_upper=uu, exit_unconverged=False, eps=1e-5, n_batch=B, backprop=False, verbose=0,
+               u_init=g["u_init"].to(dev), solver_type="dense", dtype=torch.float64)
+    x0 = g["x0"].to(dev)
+    ctrl.reinitialize(x0, None)
+    ctrl.u_init = g["u_init"].to(dev)
+    Cfull = torch.diag_embed(g["Cd"]).to(dev).requires_grad_(True)
+    c = (-(g["Cd"] * g["xref"])).to(dev).requires_grad_(True)
+    x, u = ctrl(x0, QuadCost(Cfull, c), envs.RexQuadrotor_dynamics(), envs.RexQuadrotor_dynamics_jac())
+    (x.sum() + u.sum()).backward()
+    errs = dict(x=rel(x.detach().cpu(), g["out_x"]), u=rel(u.detach().cpu(), g["out_u"]), lam=rel(ctrl.lamda_prev.cpu(), g["out_lam"]),
+                rho=rel(ctrl.rho_prev.cpu(), g["out_rho"]), dC=rel(Cfull.grad.diagonal(dim1=-2, dim2=-1).cpu(), g["out_dC"]),
+                dc=rel(c.grad.cpu(), g["out_dc"]))
+    print("rex", {a: f"{b:.1e}" for a, b in errs.items()})
+    assert errs["x"] <= RTOL32 and errs["u"] <= RTOL32, errs
+    for key in ("lam", "rho", "dC", "dc"):
+        assert errs[key] <= RTOL64, (key, errs)
