@@ -185,3 +185,40 @@ def test_al_mpc_rex_quadrotor_golden(cuda_device):
     assert errs["x"] <= RTOL32 and errs["u"] <= RTOL32, errs
     for key in ("lam", "rho", "dC", "dc"):
         assert errs[key] <= RTOL64, (key, errs)
+
+
+def test_al_mpc_float32_solver_precision(cuda_device):
+    """dtype=float32 (the reference's non-"double" Tracking_MPC setting): the fp32 kernels land
+    within fp32 conditioning of the fp64 solve; MPC state stays float32."""
+    from b200qp import envs
+    from b200qp.AL_mpc import MPC
+    from b200qp.al_utils import QuadCost
+    torch.manual_seed(3)
+    dev = cuda_device
+    B, T, nx, nu = 32, 6, 2, 1
+    x0 = torch.stack((torch.rand(B) * 2 - 1, torch.rand(B) - 0.5), 1).to(dev)
+    u0 = (0.1 * torch.randn(B, T, nu)).to(dev)
+    Cd = torch.tensor([10.0, 1.0, 0.01]).repeat(B, T, 1).to(dev)
+    outs = {}
+    for dt in (torch.float64, torch.float32):
+        ub = (3.0 * torch.ones(nu)).to(dev)
+        ctrl = MPC(nx, nu, T, u_lower=-ub, u_upper=ub, n_batch=B, u_init=u0, dtype=dt)
+        ctrl.reinitialize(x0, None)
+        ctrl.u_init = u0
+        x, u = ctrl(x0, QuadCost(torch.diag_embed(Cd), torch.zeros(B, T, nx + nu, device=dev)), envs.PendulumDynamics(),
+                    envs.PendulumDynamics_jac())
+        assert ctrl.lamda_prev.dtype == dt and x.dtype == torch.float32
+        outs[dt] = (x, u)
+    assert rel(outs[torch.float32][0].cpu(), outs[torch.float64][0].cpu()) < 5e-3
+    assert rel(outs[torch.float32][1].cpu(), outs[torch.float64][1].cpu()) < 5e-2
+
+
+def test_unknown_dynamics_is_rejected(cuda_device):
+    from b200qp.envs import dyn_spec
+
+    class Mystery(torch.nn.Module):
+        def forward(self, x, u):
+            return x
+
+    with pytest.raises(NotImplementedError, match="no fused kernel"):
+        dyn_spec(Mystery())
