@@ -327,6 +327,7 @@ def main():
     ms_buf = (ctypes.c_float * 256)()
     kind_buf = (ctypes.c_int * 256)()
     iter_ms, all_kernel_ms, n_iters = [], [], []
+    kind_ms = {0: [], 1: [], 2: [], 4: []}
     sampler = ClockSampler(local_rank)
     barrier()
     sampler.start()
@@ -340,6 +341,8 @@ def main():
         k2 = [ms_buf[i] for i in range(n) if kind_buf[i] == 2]
         iter_ms.extend(k2[:ni])
         all_kernel_ms.append(sum(ms_buf[i] for i in range(n) if kind_buf[i] != 3))
+        for kd in kind_ms:
+            kind_ms[kd].append(sum(ms_buf[i] for i in range(n) if kind_buf[i] == kd))
     e1.record()
     barrier()
     clocks = sampler.stop()
@@ -379,7 +382,9 @@ def main():
                 "bytes_per_launch": iter_kernel_bytes(NZ, NINEQ) * nb, "peak_source": hbm_src},
         "whole_solve": {"flops_per_solve": fl["total"], "bytes_per_solve": algorithmic_bytes_per_solve(NZ, NINEQ),
                         "tflops": fl["total"] * value / 1e12, "frac_of_fp64_peak": fl["total"] * value / 1e12 / (fp64_peak * world),
-                        "kernel_share_of_step": sum(iter_ms) / max(sum(all_kernel_ms), 1e-9)},
+                        "kernel_share_of_step": sum(iter_ms) / max(sum(all_kernel_ms), 1e-9),
+                        "ms_per_step_by_kernel": {name: statistics.mean(kind_ms[kd]) for name, kd in
+                                                  (("prefactor", 0), ("initial_point", 1), ("iterations", 2), ("backward", 4))}},
     }
 
     # ---- end to end through the C ABI with HOST buffers ------------------------------------

@@ -69,9 +69,13 @@ template int launch_backward<INST_T, INST_SMEM>(const KArgs<INST_T>&, const BArg
 template int launch_kkt_solve<INST_T, INST_SMEM>(const KArgs<INST_T>&, const SArgs<INST_T>&, const Layout&, cudaStream_t);
 
 #ifdef INST_PREFACTOR
-template <typename T> int launch_prefactor(const KArgs<T>& a, const Layout& L, cudaStream_t st) {
-  if (L.nt == 128) k_prefactor<T, 128><<<L.nb, 128, 0, st>>>(a);
-  else k_prefactor<T, 256><<<L.nb, 256, 0, st>>>(a);
+template <typename T> int launch_prefactor(const KArgs<T>& a_in, const Layout& L, cudaStream_t st) {
+  KArgs<T> a = a_in;
+  const size_t bytes = ((size_t)2 * round4(L.n * L.ldn) + round4(L.n)) * sizeof(T);
+  a.pre_smem = bytes <= kSmemResidentLimit ? 1 : 0;
+  const size_t dyn = a.pre_smem ? bytes : 0;
+  if (L.nt == 128) { auto k = k_prefactor<T, 128>; CK(ensure_smem(k, dyn)); k<<<L.nb, 128, dyn, st>>>(a); }
+  else { auto k = k_prefactor<T, 256>; CK(ensure_smem(k, dyn)); k<<<L.nb, 256, dyn, st>>>(a); }
   CK(cudaGetLastError());
   return B200QP_OK;
 }

@@ -98,6 +98,7 @@ struct KArgs {
   int iter, max_iter, lim;
   double eps;
   int launches;
+  int pre_smem;              // prefactor: F / Qi working copies live in dynamic shared memory
   int rtile_mpad, rtile_nt;  // != 0: R is stored in register-tile order (qp_fast.cuh); nt = -1: DMMA fragment order
 };
 
@@ -564,26 +565,49 @@ __global__ void __launch_bounds__(NT) k_prefactor(const KArgs<T> a) {
   T* UA = a.UA + (size_t)prob * a.sUA;
   T* pinvA = a.pinvA + (size_t)prob * round4(p > 0 ? p : 1);
 
-  // F = Q ; LDL^T
-  for (int i = tid; i < n * n; i += NT) { const int r = i / n, c = i - r * n; F[(size_t)r * ldn + c] = Qg[i]; }
-  __syncthreads();
-  const bool okQ = ldlt_factor(F, ldn, n, pinvF, tid, NT);
-  if (!okQ && tid == 0) atomicAdd(&a.ctl->q_fail, 1u);
-  // Qi column c by thread c:  L y = e_c ; y *= pinv ; L^T x = y   (columns are independent)
-  for (int c = tid; c < n; c += NT) {
-    for (int k = 0; k < n; k++) Qi[(size_t)k * ldn + c] = (k == c) ? T(1) : T(0);
-    for (int j = c; j < n; j++) {
-      const T yj = Qi[(size_t)j * ldn + c];
-      const T* row = F + (size_t)j * ldn;
-      for (int i = j + 1; i < n; i++) Qi[(size_t)i * ldn + c] -= row[i] * yj;
-    }
-    for (int k = c; k < n; k++) Qi[(size_t)k * ldn + c] *= pinvF[k];
-    for (int j = n - 1; j > 0; j--) {
-      const T xj = Qi[(size_t)j * ldn + c];
-      for (int i = 0; i < j; i++) Qi[(size_t)i * ldn + c] -= F[(size_t)i * ldn + j] * xj;
-    }
+  // F = Q ; LDL^T ; Qi = Q^-1.  F and the working copy of Qi sit in shared memory when they fit
+  // (a.pre_smem), else in the global workspace; the inversion is two CTA-parallel triangular
+  // sweeps over the whole n x n identity (one barrier per column) instead of one thread per column.
+  extern __shared__ __align__(16) unsigned char pre_smem_raw[];
+  T* Fs = a.pre_smem ? reinterpret_cast<T*>(pre_smem_raw) : F;
+  T* Qs = a.pre_smem ? Fs + round4(n * ldn) : Qi;
+  T* pinvFs = a.pre_smem ? Qs + round4(n * ldn) : pinvF;
+  for (int i = tid; i < n * n; i += NT) {
+    const int r = i / n, c = i - r * n;
+    Fs[(size_t)r * ldn + c] = Qg[i];
+    Qs[(size_t)r * ldn + c] = (r == c) ? T(1) : T(0);
   }
   __syncthreads();
+  const bool okQ = ldlt_factor(Fs, ldn, n, pinvFs, tid, NT);
+  if (!okQ && tid == 0) atomicAdd(&a.ctl->q_fail, 1u);
+  // L^-1: column j of L eliminates below row j; only columns c <= j of the identity are non-zero
+  for (int j = 0; j + 1 < n; j++) {
+    const int rows = n - 1 - j, cols = j + 1;
+    for (int e = tid; e < rows * cols; e += NT) {
+      const int i = j + 1 + e / cols, c = e % cols;
+      Qs[(size_t)i * ldn + c] -= Fs[(size_t)j * ldn + i] * Qs[(size_t)j * ldn + c];
+    }
+    __syncthreads();
+  }
+  for (int e = tid; e < n * n; e += NT) {
+    const int k = e / n, c = e - k * n;
+    if (c <= k) Qs[(size_t)k * ldn + c] *= pinvFs[k];
+  }
+  __syncthreads();
+  // L^-T: row j eliminates above
+  for (int j = n - 1; j > 0; j--) {
+    for (int e = tid; e < j * n; e += NT) {
+      const int i = e / n, c = e - i * n;
+      Qs[(size_t)i * ldn + c] -= Fs[(size_t)i * ldn + j] * Qs[(size_t)j * ldn + c];
+    }
+    __syncthreads();
+  }
+  if (a.pre_smem) {
+    for (int e = tid; e < n * n; e += NT) {
+      const int r = e / n, c = e - r * n;
+      Qi[(size_t)r * ldn + c] = Qs[(size_t)r * ldn + c];
+    }
+  }
   // BQi = [A;G] Qi
   const int pm = p + m;
   for (int e = tid; e < pm * n; e += NT) {
@@ -591,8 +615,8 @@ __global__ void __launch_bounds__(NT) k_prefactor(const KArgs<T> a) {
     const T* brow = r < p ? Ag + (size_t)r * n : Gg + (size_t)(r - p) * n;
     T a0 = 0, a1 = 0;
     int k = 0;
-    for (; k + 1 < n; k += 2) { a0 += brow[k] * Qi[(size_t)k * ldn + c]; a1 += brow[k + 1] * Qi[(size_t)(k + 1) * ldn + c]; }
-    if (k < n) a0 += brow[k] * Qi[(size_t)k * ldn + c];
+    for (; k + 1 < n; k += 2) { a0 += brow[k] * Qs[(size_t)k * ldn + c]; a1 += brow[k + 1] * Qs[(size_t)(k + 1) * ldn + c]; }
+    if (k < n) a0 += brow[k] * Qs[(size_t)k * ldn + c];
     BQi[(size_t)r * ldn + c] = a0 + a1;
   }
   __syncthreads();
