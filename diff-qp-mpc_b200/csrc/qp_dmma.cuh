@@ -42,18 +42,18 @@ __device__ __forceinline__ void dmma_m8n8k4(double& c0, double& c1, double a, do
 
 // Issue the global loads of this thread's accumulator tiles early (whole 16-byte fragments, the
 // buffer is fully allocated) so that their latency hides behind the residual computation.
-template <int MPAD>
+template <int MPAD, int NW = 4>
 struct DmmaTiles {
-  static constexpr int SLOTS = (MPAD / 8 * (MPAD / 8 + 1) / 2 + 3) / 4;
+  static constexpr int SLOTS = (MPAD / 8 * (MPAD / 8 + 1) / 2 + NW - 1) / NW;
   double2 raw[SLOTS];
 };
-template <int MPAD>
-__device__ __forceinline__ void dmma_prefetch(const double* __restrict__ Rf, int tid, DmmaTiles<MPAD>& tl) {
+template <int MPAD, int NW = 4>
+__device__ __forceinline__ void dmma_prefetch(const double* __restrict__ Rf, int tid, DmmaTiles<MPAD, NW>& tl) {
   constexpr int NTILES = MPAD / 8 * (MPAD / 8 + 1) / 2;
   const int lane = tid & 31, warp = tid >> 5;
 #pragma unroll
-  for (int s = 0; s < DmmaTiles<MPAD>::SLOTS; s++) {
-    const int t = 4 * s + warp;
+  for (int s = 0; s < DmmaTiles<MPAD, NW>::SLOTS; s++) {
+    const int t = NW * s + warp;
     tl.raw[s] = make_double2(0.0, 0.0);
     if (t < NTILES) tl.raw[s] = *reinterpret_cast<const double2*>(Rf + (size_t)t * 64 + lane * 2);
   }
@@ -66,11 +66,11 @@ __device__ __forceinline__ void dmma_prefetch(const double* __restrict__ Rf, int
 //   Pb    shared panel buffer, MPAD * kPanelStride doubles (+8 for the panel's pivots)
 // Returns false (uniformly) when a pivot of a real column is <= 0 or NaN; Up/pinv are then NaN.
 // Must be called by all 128 threads; begins and ends with a CTA barrier.
-template <int MPAD>
+template <int MPAD, int NW = 4>
 __device__ __forceinline__ bool dmma_factor(const double* __restrict__ Rf, const double* dinv, const double* hz, double* Up,
                                             double* pinv, double* Pb, int m, int tid,
-                                            const DmmaTiles<MPAD>* pre = nullptr) {
-  constexpr int NTI = MPAD / 8, NTILES = NTI * (NTI + 1) / 2, SLOTS = (NTILES + 3) / 4, PS = kPanelStride;
+                                            const DmmaTiles<MPAD, NW>* pre = nullptr) {
+  constexpr int NTI = MPAD / 8, NTILES = NTI * (NTI + 1) / 2, SLOTS = (NTILES + NW - 1) / NW, PS = kPanelStride, NTH = 32 * NW;
   const int lane = tid & 31, warp = tid >> 5;
   const int fr = lane >> 2, fc = (lane & 3) * 2;  // accumulator fragment: row fr, columns fc, fc+1
   const int mm = m + 1;
@@ -78,7 +78,7 @@ __device__ __forceinline__ bool dmma_factor(const double* __restrict__ Rf, const
   int tI[SLOTS], tK[SLOTS];
 #pragma unroll
   for (int s = 0; s < SLOTS; s++) {
-    const int t = 4 * s + warp;
+    const int t = NW * s + warp;
     int I = (int)((sqrtf(8.0f * (float)t + 1.0f) - 1.0f) * 0.5f);  // exact for the <= 136 tiles used
     if ((I + 1) * (I + 2) / 2 <= t) I++;
     const int K = t - I * (I + 1) / 2;
@@ -116,7 +116,7 @@ __device__ __forceinline__ bool dmma_factor(const double* __restrict__ Rf, const
     // (a) owners publish the panel's tiles
 #pragma unroll
     for (int s = 0; s < SLOTS; s++) {
-      if (4 * s + warp < NTILES && tK[s] == J) {
+      if (NW * s + warp < NTILES && tK[s] == J) {
         *reinterpret_cast<double2*>(Pb + (8 * tI[s] + fr) * PS + fc) = make_double2(C[s][0], C[s][1]);
       }
     }
@@ -193,7 +193,7 @@ __device__ __forceinline__ bool dmma_factor(const double* __restrict__ Rf, const
       if (is_nan(ppan[0] + ppan[1] + ppan[2] + ppan[3] + ppan[4] + ppan[5] + ppan[6] + ppan[7])) ok = false;  // uniform
 #pragma unroll
       for (int s = 0; s < SLOTS; s++) {
-        if (4 * s + warp < NTILES && tK[s] > J) {
+        if (NW * s + warp < NTILES && tK[s] > J) {
           const double* ra = Pb + (8 * tI[s] + fr) * PS + kc;
           const double* rb = Pb + (8 * tK[s] + fr) * PS + kc;
           dmma_m8n8k4(C[s][0], C[s][1], ra[0] * s0, rb[0]);
@@ -204,8 +204,8 @@ __device__ __forceinline__ bool dmma_factor(const double* __restrict__ Rf, const
     __syncthreads();  // the next panel's tiles overwrite the buffer these fragments were read from
   }
   if (!ok) {
-    for (int i = tid; i < m; i += 128) pinv[i] = t_nan<double>();
-    for (int i = tid; i < mm * (mm - 1) / 2; i += 128) Up[i] = t_nan<double>();
+    for (int i = tid; i < m; i += NTH) pinv[i] = t_nan<double>();
+    for (int i = tid; i < mm * (mm - 1) / 2; i += NTH) Up[i] = t_nan<double>();
     __syncthreads();
   }
   return ok;

@@ -348,10 +348,9 @@ __device__ __forceinline__ void fast_kkt_post(const FS<T>& S, const KArgs<T>& a,
 // bordered row, see dmma_factor.
 template <typename T, int MPAD, int NT, int FK>
 __device__ __forceinline__ bool factor_any(const T* __restrict__ Rt, const FS<T>& S, const T* hz, int m, int tid,
-                                           const DmmaTiles<MPAD>* pre = nullptr) {
+                                           const DmmaTiles<MPAD, NT / 32>* pre = nullptr) {
   if constexpr (FK == 1) {
-    static_assert(NT == 128, "the DMMA factorisation is written for 4 warps");
-    return dmma_factor<MPAD>(Rt, S.scr, hz, S.Up, S.pinvT, S.colbuf, m, tid, pre);  // S.scr = 1/d, filled by the caller
+    return dmma_factor<MPAD, NT / 32>(Rt, S.scr, hz, S.Up, S.pinvT, S.colbuf, m, tid, pre);  // S.scr = 1/d, filled by the caller
   } else {
     return fast_factor<T, MPAD, NT>(Rt, S.d, S.Up, S.pinvT, S.colbuf, m, tid);
   }
@@ -409,7 +408,7 @@ __device__ __forceinline__ T warp_sum(T v) {
 // ------------------------------------------------------------------------------------------
 // INIT=true: initial point (batch.py:60-86).  INIT=false: PDIPM iteration a.iter (batch.py:91-204).
 template <typename T, int MPAD, int NT, bool INIT, int FK = 0>
-__global__ void __launch_bounds__(NT, (NT == 128 ? (FK == 1 ? 4 : 5) : 1)) k_fast_iter(const KArgs<T> a) {
+__global__ void __launch_bounds__(NT, (NT == 128 ? (FK == 1 ? 4 : 5) : (NT == 64 && FK == 1 ? 5 : 1))) k_fast_iter(const KArgs<T> a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int prob = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int n = a.n, m = a.m, p = a.p, it = a.iter;
@@ -497,8 +496,8 @@ __global__ void __launch_bounds__(NT, (NT == 128 ? (FK == 1 ? 4 : 5) : 1)) k_fas
     const T* Qg = a.Q + (size_t)prob * a.sQ;
     const T* Gg = a.G + (size_t)prob * a.sG;
     const T* Ag = a.A + (size_t)prob * a.sA;
-    DmmaTiles<MPAD> tiles;
-    if constexpr (FK == 1) dmma_prefetch<MPAD>(Rt, tid, tiles);
+    DmmaTiles<MPAD, NT / 32> tiles;
+    if constexpr (FK == 1) dmma_prefetch<MPAD, NT / 32>(Rt, tid, tiles);
     // ---- iterate + previous step
     {
       T alpha = T(0);
@@ -628,7 +627,7 @@ __global__ void __launch_bounds__(NT, (NT == 128 ? (FK == 1 ? 4 : 5) : 1)) k_fas
 
 // ------------------------------------------------------------------------------------------
 template <typename T, int MPAD, int NT, int FK = 0>
-__global__ void __launch_bounds__(NT, (NT == 128 ? (FK == 1 ? 4 : 5) : 1)) k_fast_backward(const KArgs<T> a, const BArgs<T> g) {
+__global__ void __launch_bounds__(NT, (NT == 128 ? (FK == 1 ? 4 : 5) : (NT == 64 && FK == 1 ? 5 : 1))) k_fast_backward(const KArgs<T> a, const BArgs<T> g) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int prob = blockIdx.x, tid = threadIdx.x;
   const int n = a.n, m = a.m, p = a.p;
@@ -682,7 +681,7 @@ __global__ void __launch_bounds__(NT, (NT == 128 ? (FK == 1 ? 4 : 5) : 1)) k_fas
 }
 
 template <typename T, int MPAD, int NT, int FK = 0>
-__global__ void __launch_bounds__(NT, (NT == 128 ? (FK == 1 ? 4 : 5) : 1)) k_fast_kkt(const KArgs<T> a, const SArgs<T> g) {
+__global__ void __launch_bounds__(NT, (NT == 128 ? (FK == 1 ? 4 : 5) : (NT == 64 && FK == 1 ? 5 : 1))) k_fast_kkt(const KArgs<T> a, const SArgs<T> g) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int prob = blockIdx.x, tid = threadIdx.x;
   const int n = a.n, m = a.m, p = a.p;

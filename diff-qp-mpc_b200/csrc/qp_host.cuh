@@ -55,6 +55,7 @@ inline int make_layout(const b200qp_problem_t* pr, Layout& L) {
     // DMMA factorisation: fp64, 128-thread CTAs, one spare row for the bordered right-hand side
     const char* fke = getenv("B200QP_FACTOR");
     L.fk = (pr->dtype == B200QP_F64 && L.nt == 128 && L.m < 64 && !(fke && fke[0] == 't')) ? 1 : 0;
+    if (L.fk && fnt && atoi(fnt) == 64 && L.m >= 32) L.nt = 64;  // experimental: 2-warp CTAs (MPAD = 64 only)
     if (L.fk) L.mpad = L.m < 32 ? 32 : 64;
     const size_t fb = fast_smem_elems(L.n, L.m, L.p, L.ldn, L.ldm, L.ldp, L.nt, L.mpad, L.fk) * L.es;
     if ((L.nt == 128 && widest > 128) || fb > kSmemResidentLimit) { L.fast = false; L.fk = 0; L.nt = generic_nt; }

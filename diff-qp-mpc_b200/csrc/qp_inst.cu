@@ -30,7 +30,8 @@ static cudaError_t ensure_smem(K kernel, size_t bytes) {
   do {                                                                                             \
     if (L.fk) {                                                                                    \
       if constexpr (std::is_same<T, double>::value) {                                              \
-        if (L.mpad == 32) LAUNCH_ONE((KN<T, 32, 128 TAIL COMMA 1>), 128, __VA_ARGS__);             \
+        if (L.nt == 64) LAUNCH_ONE((KN<T, 64, 64 TAIL COMMA 1>), 64, __VA_ARGS__);                 \
+        else if (L.mpad == 32) LAUNCH_ONE((KN<T, 32, 128 TAIL COMMA 1>), 128, __VA_ARGS__);        \
         else LAUNCH_ONE((KN<T, 64, 128 TAIL COMMA 1>), 128, __VA_ARGS__);                          \
       }                                                                                            \
     } else if (L.mpad == 128) LAUNCH_ONE((KN<T, 128, 256 TAIL>), 256, __VA_ARGS__);                \
