@@ -22,7 +22,7 @@ from torch.nn import Module
 
 from . import al_utils
 from .al_utils import ALSolve, ALState, QuadCost, LinDx  # noqa: F401
-from .envs import dyn_spec, _run
+from .envs import dyn_spec, rollout as _rollout
 
 
 class GradMethods(Enum):
@@ -82,8 +82,8 @@ class MPC(Module):
         self.lamda_prev = torch.zeros(self.n_batch, self.neq + self.nineq).to(self.u_upper) if n_batch else None
         self.dyn_res_prev = 1000000
         self.just_initialized = True
-        self.cost_lam_hist = None
         self._hist = None
+        self._bound_cache = None
         self.status = None
 
     # ------------------------------------------------------------------------------------
@@ -139,24 +139,32 @@ class MPC(Module):
         state.hist = None if self.just_initialized else self._hist
         C = cost.C.to(self.dtype)
         c = cost.c.to(self.dtype)
-        shape = (B, self.T, self.n_ctrl)
-        ul = self.u_lower.to(dev).expand(shape) if self.u_lower.dim() > 0 else self.u_lower.to(dev).reshape(1, 1, 1).expand(shape)
-        uu = self.u_upper.to(dev).expand(shape) if self.u_upper.dim() > 0 else self.u_upper.to(dev).reshape(1, 1, 1).expand(shape)
+        ul, uu = self._bounds(B, dev)
         xs, us, status = ALSolve.apply(C, c, x.to(self.dtype), u.to(self.dtype), x0.to(self.dtype), ul, uu, state, spec,
                                        self.al_iter)
         self._hist = state.hist
-        self.cost_lam_hist = [list(state.hist[0]), list(state.hist[1]), [r.unsqueeze(-1) for r in state.hist[2]]]
         self.lamda_prev, self.rho_prev, self.status = state.lam, state.rho, status
         self.just_initialized = False
         return xs, us
 
+    @property
+    def cost_lam_hist(self):
+        """[[cost_0..], [lam_0..], [rho_0..]] of the last call (qpth/AL_mpc.py:314), built on demand."""
+        if self._hist is None:
+            return None
+        return [list(self._hist[0]), list(self._hist[1]), [r.unsqueeze(-1) for r in self._hist[2]]]
+
+    def _bounds(self, B, dev):
+        key = (B, str(dev))
+        if self._bound_cache is None or self._bound_cache[0] != key:
+            shape = (B, self.T, self.n_ctrl)
+            f = lambda t: (t.to(dev).expand(shape) if t.dim() > 0 else t.to(dev).reshape(1, 1, 1).expand(shape)).contiguous()
+            self._bound_cache = (key, f(self.u_lower), f(self.u_upper))
+        return self._bound_cache[1], self._bound_cache[2]
+
     def rollout(self, x, actions, dynamics):
         """qpth/AL_mpc.py:398-411"""
-        spec = dyn_spec(dynamics)
-        xs = [x]
-        for t in range(self.T - 1):
-            xs.append(_run(spec, xs[t], actions[:, t], False)[0])
-        return torch.stack(xs, 1)
+        return _rollout(dyn_spec(dynamics), x, actions[:, :self.T])
 
     def reinitialize(self, x, mask):
         """qpth/AL_mpc.py:432-439"""

@@ -22,7 +22,7 @@ EXPORTS = (
     "b200qp_solve_host", "b200qp_last_cuda_error", "b200qp_version", "b200qp_profile_enable",
     "b200qp_profile_read",
     "b200mpc_env_dims", "b200mpc_factor_elems", "b200mpc_scratch_bytes", "b200mpc_al_solve", "b200mpc_al_backward",
-    "b200dyn_step", "b200dyn_jac",
+    "b200dyn_step", "b200dyn_jac", "b200dyn_rollout",
 )
 
 ENV_PENDULUM, ENV_INTEGRATOR, ENV_PENDULUM_DX, ENV_CARTPOLE_DX, ENV_REX_QUADROTOR = 0, 1, 2, 3, 4
@@ -105,6 +105,8 @@ def lib():
     L.b200dyn_step.argtypes = [ctypes.c_int, ctypes.c_int, dparr, vp, vp, vp, ctypes.c_int64, vp]
     L.b200dyn_jac.restype = ctypes.c_int
     L.b200dyn_jac.argtypes = [ctypes.c_int, ctypes.c_int, dparr, vp, vp, vp, vp, vp, ctypes.c_int64, vp]
+    L.b200dyn_rollout.restype = ctypes.c_int
+    L.b200dyn_rollout.argtypes = [ctypes.c_int, ctypes.c_int, dparr, vp, vp, vp, ctypes.c_int64, ctypes.c_int32, vp]
     L.b200qp_last_cuda_error.restype = ctypes.c_char_p
     L.b200qp_version.restype = ctypes.c_char_p
     _lib = L

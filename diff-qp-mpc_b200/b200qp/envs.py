@@ -84,6 +84,23 @@ def _run(spec, x, u, want_jac):
     return xn.reshape(*lead, nx), A, Bm
 
 
+def rollout(spec, x0, u):
+    """xs (B,T,nx) with xs[:,0] = x0 and xs[:,t+1] = f(xs[:,t], u[:,t]) in ONE launch."""
+    env, params, nx, nu = spec
+    if not x0.is_cuda:
+        raise RuntimeError("b200qp dynamics run on CUDA tensors only (no CPU fallback)")
+    B, T = u.shape[0], u.shape[1]
+    x0c = x0.detach().contiguous()
+    uc = u.detach().to(x0.dtype).contiguous()
+    xs = torch.empty(B, T, nx, device=x0.device, dtype=x0.dtype)
+    code = _lib.F64 if x0.dtype == torch.float64 else _lib.F32
+    st = ctypes.c_void_p(torch.cuda.current_stream(x0.device).cuda_stream)
+    with torch.cuda.device(x0.device):
+        rc = _lib.lib().b200dyn_rollout(env, code, _params_array(params), _p(x0c), _p(uc), _p(xs), B, T, st)
+    _lib.check(rc, "b200dyn_rollout")
+    return xs
+
+
 class _Step(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, u, spec):

@@ -93,6 +93,16 @@ static int dyn_t(const double* params, const void* x, const void* u, void* xn, v
   return B200QP_OK;
 }
 
+template <class Dyn, typename R>
+static int rollout_t(const double* params, const void* x0, const void* u, void* xs, long long B, int T, cudaStream_t st) {
+  DynParams P;
+  for (int i = 0; i < MAX_PARAMS; i++) P.v[i] = params[i];
+  const int nt = 128;
+  k_dyn_rollout<Dyn, R><<<(unsigned)((B + nt - 1) / nt), nt, 0, st>>>(P, (const R*)x0, (const R*)u, (R*)xs, B, T);
+  CKM(cudaGetLastError());
+  return B200QP_OK;
+}
+
 #define ENV_DISPATCH(ENV, EXPR_MACRO)                         \
   switch (ENV) {                                              \
     case ENV_PENDULUM: EXPR_MACRO(Pendulum);                  \
@@ -167,6 +177,17 @@ int b200dyn_jac(int env, int dtype, const double* params, const void* x, const v
 #define DYN_CASE(DYN) \
   return dtype == B200QP_F64 ? dyn_t<DYN, double>(params, x, u, xn, A, Bm, N, st) : dyn_t<DYN, float>(params, x, u, xn, A, Bm, N, st)
   ENV_DISPATCH(env, DYN_CASE);
+}
+
+int b200dyn_rollout(int env, int dtype, const double* params, const void* x0, const void* u, void* xs, int64_t B,
+                    int32_t T, b200qp_stream_t stream) {
+  if (!params || !x0 || !u || !xs || B < 0 || T < 1) return B200QP_EINVAL;
+  if (dtype != B200QP_F64 && dtype != B200QP_F32) return B200QP_EINVAL;
+  if (B == 0) return B200QP_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+#define ROLL_CASE(DYN) \
+  return dtype == B200QP_F64 ? rollout_t<DYN, double>(params, x0, u, xs, B, T, st) : rollout_t<DYN, float>(params, x0, u, xs, B, T, st)
+  ENV_DISPATCH(env, ROLL_CASE);
 }
 
 int b200dyn_step(int env, int dtype, const double* params, const void* x, const void* u, void* xn, int64_t N,

@@ -510,4 +510,22 @@ __global__ void k_dyn_step(DynParams P, const R* x, const R* u, R* xn, R* A, R* 
   }
 }
 
+// Open-loop rollout x_{t+1} = f(x_t, u_t), t < T-1 (AL_mpc.py:398-411), one thread per trajectory.
+template <class Dyn, typename R>
+__global__ void k_dyn_rollout(DynParams P, const R* x0, const R* u, R* xs, long long B, int T) {
+  constexpr int NX = Dyn::NX, NU = Dyn::NU;
+  const long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  R x[NX], uu[NU], xn[NX];
+#pragma unroll
+  for (int j = 0; j < NX; j++) { x[j] = x0[b * NX + j]; xs[(b * T) * NX + j] = x[j]; }
+  for (int t = 0; t + 1 < T; t++) {
+#pragma unroll
+    for (int j = 0; j < NU; j++) uu[j] = u[(b * T + t) * NU + j];
+    Dyn::template step<R>(P, x, uu, xn);
+#pragma unroll
+    for (int j = 0; j < NX; j++) { x[j] = xn[j]; xs[(b * T + t + 1) * NX + j] = xn[j]; }
+  }
+}
+
 }  // namespace b200mpc

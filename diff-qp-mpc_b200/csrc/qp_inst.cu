@@ -73,8 +73,9 @@ template int launch_kkt_solve<INST_T, INST_SMEM>(const KArgs<INST_T>&, const SAr
 template <typename T> int launch_prefactor(const KArgs<T>& a_in, const Layout& L, cudaStream_t st) {
   KArgs<T> a = a_in;
   const size_t bytes = ((size_t)2 * round4(L.n * L.ldn) + round4(L.n)) * sizeof(T);
-  a.pre_smem = bytes <= kSmemResidentLimit ? 1 : 0;
-  const size_t dyn = a.pre_smem ? bytes : 0;
+  const size_t bytes2 = bytes + (size_t)2 * round4((L.p + L.m) * L.ldn) * sizeof(T);
+  a.pre_smem = bytes2 <= 100 * 1024 ? 2 : (bytes <= kSmemResidentLimit ? 1 : 0);
+  const size_t dyn = a.pre_smem == 2 ? bytes2 : (a.pre_smem ? bytes : 0);
   if (L.nt == 128) { auto k = k_prefactor<T, 128>; CK(ensure_smem(k, dyn)); k<<<L.nb, 128, dyn, st>>>(a); }
   else { auto k = k_prefactor<T, 256>; CK(ensure_smem(k, dyn)); k<<<L.nb, 256, dyn, st>>>(a); }
   CK(cudaGetLastError());

@@ -608,16 +608,31 @@ __global__ void __launch_bounds__(NT) k_prefactor(const KArgs<T> a) {
       Qi[(size_t)r * ldn + c] = Qs[(size_t)r * ldn + c];
     }
   }
-  // BQi = [A;G] Qi
+  // BQi = [A;G] Qi  and  M = BQi [A;G]^T.  With a.pre_smem == 2 the stacked constraint matrix
+  // B = [A;G] and BQi are staged in shared memory ((p+m) x ldn each, odd leading dimension =>
+  // conflict-free row and column walks); otherwise operands come from global memory.
   const int pm = p + m;
+  T* Bs = nullptr;
+  T* BQs = BQi;
+  if (a.pre_smem == 2) {
+    Bs = pinvFs + round4(n);
+    BQs = Bs + round4(pm * ldn);
+    for (int e = tid; e < pm * n; e += NT) {
+      const int r = e / n, c = e - r * n;
+      Bs[(size_t)r * ldn + c] = r < p ? Ag[(size_t)r * n + c] : Gg[(size_t)(r - p) * n + c];
+    }
+    __syncthreads();
+  }
   for (int e = tid; e < pm * n; e += NT) {
     const int r = e / n, c = e - r * n;
-    const T* brow = r < p ? Ag + (size_t)r * n : Gg + (size_t)(r - p) * n;
+    const T* brow = Bs ? Bs + (size_t)r * ldn : (r < p ? Ag + (size_t)r * n : Gg + (size_t)(r - p) * n);
     T a0 = 0, a1 = 0;
     int k = 0;
     for (; k + 1 < n; k += 2) { a0 += brow[k] * Qs[(size_t)k * ldn + c]; a1 += brow[k + 1] * Qs[(size_t)(k + 1) * ldn + c]; }
     if (k < n) a0 += brow[k] * Qs[(size_t)k * ldn + c];
-    BQi[(size_t)r * ldn + c] = a0 + a1;
+    const T v = a0 + a1;
+    BQi[(size_t)r * ldn + c] = v;
+    if (Bs) BQs[(size_t)r * ldn + c] = v;
   }
   __syncthreads();
   // M = BQi [A;G]^T  ->  Saa (UA, lower), Sag (V), Sgg (R, lower incl. diagonal)
@@ -625,8 +640,8 @@ __global__ void __launch_bounds__(NT) k_prefactor(const KArgs<T> a) {
     const int r = e / pm, q = e - r * pm;
     const bool need = (r < p && q < p && q <= r) || (r < p && q >= p) || (r >= p && q >= p && q <= r);
     if (!need) continue;
-    const T* brow = q < p ? Ag + (size_t)q * n : Gg + (size_t)(q - p) * n;
-    const T* qrow = BQi + (size_t)r * ldn;
+    const T* brow = Bs ? Bs + (size_t)q * ldn : (q < p ? Ag + (size_t)q * n : Gg + (size_t)(q - p) * n);
+    const T* qrow = BQs + (size_t)r * ldn;
     T a0 = 0, a1 = 0;
     int k = 0;
     for (; k + 1 < n; k += 2) { a0 += qrow[k] * brow[k]; a1 += qrow[k + 1] * brow[k + 1]; }

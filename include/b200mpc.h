@@ -90,6 +90,10 @@ int b200dyn_step(int env, int dtype, const double* params, const void* x, const 
 int b200dyn_jac(int env, int dtype, const double* params, const void* x, const void* u, void* xn, void* A, void* Bm,
                 int64_t N, b200qp_stream_t stream);
 
+/* open-loop rollout xs (B,T,nx): xs[:,0] = x0, xs[:,t+1] = f(xs[:,t], u[:,t])  (qpth/AL_mpc.py:398-411) */
+int b200dyn_rollout(int env, int dtype, const double* params, const void* x0, const void* u, void* xs, int64_t B,
+                    int32_t T, b200qp_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif
