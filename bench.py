@@ -370,14 +370,21 @@ def main():
     except Exception:
         hbm_peak, hbm_src = 6650.0, "fallback"
     fp64_peak = peaks_fp64.get("dfma_tflops_sustained", 34.0)
+    traffic = None
+    try:  # DRAM bytes of one launch, from the committed `ncu --set full` capture, scaled to this batch
+        tj = json.load(open(os.path.join(ROOT, "profiles", "r01", "ncu_traffic.json")))
+        traffic = tj["dram_bytes_per_problem_per_launch"] * nb
+    except Exception:
+        pass
     ach_tf = fl["iter"] * nb / (avg_iter_ms * 1e-3) / 1e12
     ach_gbs = iter_kernel_bytes(NZ, NINEQ) * nb / (avg_iter_ms * 1e-3) / 1e9
     roofline = {
-        "kernel": "k_pdipm_iter<double,smem,128>", "bound": "fp64",
+        "kernel": "k_fast_iter<double,MPAD=64,NT=128,DMMA factor> (one PDIPM iteration, one CTA per QP)", "bound": "fp64",
         "achieved": ach_tf, "peak": fp64_peak, "unit": "TFLOP/s", "frac": ach_tf / fp64_peak,
         "peak_source": "profiles/fp64_peaks_r01.json (DFMA microbenchmark on this pool's B200; MEASURED_PEAKS.json has no FP64 figure)",
         "flops_per_launch": fl["iter"] * nb, "avg_launch_ms": avg_iter_ms, "launches_timed": len(iter_ms),
-        "traffic": None,
+        "traffic": traffic,
+        "traffic_source": "profiles/r01/ncu_traffic.json: dram__bytes_read+write of one launch at nb=4096, per problem, x this batch",
         "hbm": {"achieved": ach_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": ach_gbs / hbm_peak,
                 "bytes_per_launch": iter_kernel_bytes(NZ, NINEQ) * nb, "peak_source": hbm_src},
         "whole_solve": {"flops_per_solve": fl["total"], "bytes_per_solve": algorithmic_bytes_per_solve(NZ, NINEQ),
