@@ -85,27 +85,31 @@ __device__ __forceinline__ bool dmma_factor(const double* __restrict__ Rf, const
     tI[s] = I; tK[s] = K;
     C[s][0] = 0.0; C[s][1] = 0.0;
     if (t < NTILES) {
-      const int i = 8 * I + fr, k = 8 * K + fc;
-      double v0 = 0.0, v1 = 0.0;
-      if (i < m && k < m) {  // k even, m may be odd: guard the second element separately
-        const double2 rr = pre ? pre->raw[s] : *reinterpret_cast<const double2*>(Rf + (size_t)t * 64 + lane * 2);
-        v0 = (k <= i) ? rr.x : 0.0;  // the strict upper part of a diagonal tile is never used
-        v1 = (k + 1 <= i) ? rr.y : 0.0;
-        if (I == K) {  // uniform per slot
-          if (i == k) v0 += dinv[i];
-          if (i == k + 1) v1 += dinv[i];
+      const double2 rr = pre ? pre->raw[s] : *reinterpret_cast<const double2*>(Rf + (size_t)t * 64 + lane * 2);
+      if (I != K && 8 * I + 8 <= m) {  // uniform: interior tile, every entry is a real strictly-lower one
+        C[s][0] = rr.x; C[s][1] = rr.y;
+      } else {
+        const int i = 8 * I + fr, k = 8 * K + fc;
+        double v0 = 0.0, v1 = 0.0;
+        if (i < m && k < m) {  // k even, m may be odd: guard the second element separately
+          v0 = (k <= i) ? rr.x : 0.0;  // the strict upper part of a diagonal tile is never used
+          v1 = (k + 1 <= i) ? rr.y : 0.0;
+          if (I == K) {
+            if (i == k) v0 += dinv[i];
+            if (i == k + 1) v1 += dinv[i];
+          }
+        } else if (i == m) {
+          if (hz != nullptr) {
+            if (k < m) v0 = hz[k];
+            if (k + 1 < m) v1 = hz[k + 1];
+          }
         }
-      } else if (i == m) {
-        if (hz != nullptr) {
-          if (k < m) v0 = hz[k];
-          if (k + 1 < m) v1 = hz[k + 1];
+        if (i >= m) {  // bordered row / padding: unit diagonal
+          if (i == k) v0 = 1.0;
+          if (i == k + 1) v1 = 1.0;
         }
+        C[s][0] = v0; C[s][1] = v1;
       }
-      if (i >= m) {  // bordered row / padding: unit diagonal
-        if (i == k) v0 = 1.0;
-        if (i == k + 1) v1 = 1.0;
-      }
-      C[s][0] = v0; C[s][1] = v1;
     }
   }
   double* ppan = Pb + MPAD * PS;  // the current panel's 8 reciprocal pivots (1 for bordered/padding columns)

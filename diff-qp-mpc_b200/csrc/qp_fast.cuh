@@ -70,25 +70,41 @@ __host__ __device__ inline size_t fast_smem_elems(int n, int m, int p, int ldn, 
   return e;
 }
 
-template <typename T>
-__device__ __forceinline__ void fast_carve(FS<T>& S, unsigned char* raw, int n, int m, int p, int ldn, int ldm,
-                                           int ldp, int nt, int mpad, int fk = 0) {
-  T* q = reinterpret_cast<T*>(raw);
-  auto take = [&](int cnt) { T* r = q; q += round4(cnt); return r; };
+// Element offsets of the carve-up, computed ONCE on the host (KArgs::fso) so that the kernels form
+// each shared-memory pointer with one constant-bank load instead of re-deriving the whole chain
+// of rounded sizes (ncu: ~1.9 k instructions per problem-iteration went into that).
+constexpr int kFsoCount = 28;
+__host__ __device__ inline void fast_offsets(int n, int m, int p, int ldn, int ldm, int ldp, int nt, int mpad, int fk,
+                                             int* o) {
+  int q = 0, i = 0;
+  auto take = [&](int cnt) { o[i++] = q; q += round4(cnt); };
   const int pp = p > 0 ? p : 1;
-  S.Up = take(fast_up_elems(m, fk));
-  S.pinvT = take(m);
-  S.BQi = take((p + m) * ldn);
-  if (p > 0) { S.V = take(p * ldm); S.UA = take(p * ldp); S.pinvA = take(p); }
+  take(fast_up_elems(m, fk));           // 0 Up
+  take(m);                              // 1 pinvT
+  take((p + m) * ldn);                  // 2 BQi
+  if (p > 0) { take(p * ldm); take(p * ldp); take(p); } else { o[i++] = 0; o[i++] = 0; o[i++] = 0; }  // 3 V 4 UA 5 pinvA
+  take(n); take(n); take(n); take(n); take(n);                                   // 6 x 7 rx 8 t 9 dx 10 scrn
+  take(m); take(m); take(m); take(m); take(m); take(m); take(m); take(m);        // 11 s 12 z 13 d 14 rz 15 ds 16 dz 17 rsc 18 scr
+  take(pp); take(pp); take(pp); take(pp);                                        // 19 y 20 ry 21 u 22 dy
+  take(p + m);                          // 23 hv
+  take(nt);                             // 24 part
+  take(4 * 32);                         // 25 red
+  take(fast_colbuf_elems(mpad, fk));    // 26 colbuf
+  take(16);                             // 27 small
+}
+
+template <typename T>
+__device__ __forceinline__ void fast_carve(FS<T>& S, unsigned char* raw, const KArgs<T>& a) {
+  T* q = reinterpret_cast<T*>(raw);
+  const int* o = a.fso;
+  S.Up = q + o[0]; S.pinvT = q + o[1]; S.BQi = q + o[2];
+  if (a.p > 0) { S.V = q + o[3]; S.UA = q + o[4]; S.pinvA = q + o[5]; }
   else { S.V = S.UA = S.pinvA = nullptr; }
-  S.x = take(n); S.rx = take(n); S.t = take(n); S.dx = take(n); S.scrn = take(n);
-  S.s = take(m); S.z = take(m); S.d = take(m); S.rz = take(m); S.ds = take(m); S.dz = take(m); S.rsc = take(m); S.scr = take(m);
-  S.y = take(pp); S.ry = take(pp); S.u = take(pp); S.dy = take(pp);
-  S.hv = take(p + m);
-  S.part = take(nt);
-  S.red = take(4 * 32);
-  S.colbuf = take(fast_colbuf_elems(mpad, fk));
-  S.small = take(16);
+  S.x = q + o[6]; S.rx = q + o[7]; S.t = q + o[8]; S.dx = q + o[9]; S.scrn = q + o[10];
+  S.s = q + o[11]; S.z = q + o[12]; S.d = q + o[13]; S.rz = q + o[14]; S.ds = q + o[15]; S.dz = q + o[16];
+  S.rsc = q + o[17]; S.scr = q + o[18];
+  S.y = q + o[19]; S.ry = q + o[20]; S.u = q + o[21]; S.dy = q + o[22];
+  S.hv = q + o[23]; S.part = q + o[24]; S.red = q + o[25]; S.colbuf = q + o[26]; S.small = q + o[27];
 }
 
 template <typename T>
@@ -413,7 +429,7 @@ __global__ void __launch_bounds__(NT, (NT == 128 ? (FK == 1 ? 4 : 5) : (NT == 64
   const int prob = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int n = a.n, m = a.m, p = a.p, it = a.iter;
   FS<T> S;
-  fast_carve(S, smem_raw, n, m, p, a.ldn, a.ldm, a.ldp, NT, MPAD, FK);
+  fast_carve(S, smem_raw, a);
   int* ictl = reinterpret_cast<int*>(S.small);
 
   T fill_z = T(1), fill_s = T(1);
@@ -632,7 +648,7 @@ __global__ void __launch_bounds__(NT, (NT == 128 ? (FK == 1 ? 4 : 5) : (NT == 64
   const int prob = blockIdx.x, tid = threadIdx.x;
   const int n = a.n, m = a.m, p = a.p;
   FS<T> S;
-  fast_carve(S, smem_raw, n, m, p, a.ldn, a.ldm, a.ldp, NT, MPAD, FK);
+  fast_carve(S, smem_raw, a);
   fast_stage(S, a, prob, tid, NT);
   const T* zh = g.zhat + (size_t)prob * n;
   const T* lam = g.lams + (size_t)prob * m;
@@ -686,7 +702,7 @@ __global__ void __launch_bounds__(NT, (NT == 128 ? (FK == 1 ? 4 : 5) : (NT == 64
   const int prob = blockIdx.x, tid = threadIdx.x;
   const int n = a.n, m = a.m, p = a.p;
   FS<T> S;
-  fast_carve(S, smem_raw, n, m, p, a.ldn, a.ldm, a.ldp, NT, MPAD, FK);
+  fast_carve(S, smem_raw, a);
   fast_stage(S, a, prob, tid, NT);
   for (int i = tid; i < m; i += NT) {
     S.d[i] = g.d[(size_t)prob * m + i];

@@ -98,6 +98,7 @@ struct KArgs {
   int iter, max_iter, lim;
   double eps;
   int launches;
+  int fso[28];               // fast path: shared-memory carve-up offsets in elements (qp_fast.cuh:fast_offsets)
   int pre_smem;              // prefactor: F / Qi working copies live in dynamic shared memory
   int rtile_mpad, rtile_nt;  // != 0: R is stored in register-tile order (qp_fast.cuh); nt = -1: DMMA fragment order
 };
