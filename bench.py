@@ -212,6 +212,56 @@ def bench_mpc(dev, B=1024, T=5, reps=20):
             "launches_per_call": 1 + (T - 1) * 2 + 1}
 
 
+def bench_mpc_shapes(dev):
+    """Fused AL-MPC solve + backward at the other BASELINE config shapes (device-resident, fp64):
+    configs[2] shape with the env_dx cartpole, configs[3] shape with the rex quadrotor."""
+    from b200qp import envs
+    from b200qp.AL_mpc import MPC
+    from b200qp.al_utils import QuadCost
+    out = {}
+    one = lambda v, n: v * torch.ones(n, dtype=torch.float64, device=dev)
+    g = torch.Generator(device="cpu").manual_seed(0)
+    r = lambda *sh: torch.rand(*sh, generator=g, dtype=torch.float64)
+
+    def run(name, dx, dxj, nx, nu, T, B, x0, u0, qd, lo, hi, reps):
+        Cd = torch.tensor(qd, dtype=torch.float64, device=dev).repeat(B, T, 1)
+        ctrl = MPC(nx, nu, T, u_lower=lo, u_upper=hi, n_batch=B, u_init=u0, eps=1e-5, dtype=torch.float64)
+        Cfull = torch.diag_embed(Cd).requires_grad_(True)
+        c = torch.zeros(B, T, nx + nu, dtype=torch.float64, device=dev, requires_grad=True)
+
+        def step():
+            ctrl.reinitialize(x0, None)
+            ctrl.u_init = u0
+            Cfull.grad = None
+            c.grad = None
+            x, u = ctrl(x0, QuadCost(Cfull, c), dx, dxj)
+            (x.sum() + u.sum()).backward()
+
+        step()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            step()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / reps
+        out[name] = {"B": B, "T": T, "nx": nx, "nu": nu, "ms_per_call": ms, "rollouts_per_s": B / (ms * 1e-3)}
+
+    B, T = 4096, 20
+    th = r(B) * 0.6 - 0.3
+    x0 = torch.stack((r(B) - 0.5, torch.zeros(B, dtype=torch.float64), torch.cos(th), torch.sin(th),
+                      torch.zeros(B, dtype=torch.float64)), 1).to(dev)
+    run("cartpole_env_dx_T20_B4096", envs.CartpoleDx(), envs.CartpoleDx_jac(), 5, 1, T, B, x0,
+        (0.1 * (r(B, T, 1) - 0.5)).to(dev), [0.1, 0.1, 1., 1., 0.1, 0.001], one(-100., 1), one(100., 1), 5)
+    B, T = 1024, 40
+    x0 = torch.cat((r(B, 3) * 2 - 1, r(B, 3) * 0.2 - 0.1, r(B, 6) * 0.2 - 0.1), 1).to(dev)
+    run("rex_quadrotor_T40_B1024", envs.RexQuadrotor_dynamics(), envs.RexQuadrotor_dynamics_jac(), 12, 4, T, B, x0,
+        (14.9 + 0.1 * (r(B, T, 4) - 0.5)).to(dev), [10.] * 3 + [0.01] * 3 + [1.] * 3 + [0.01] * 3 + [1e-4] * 4,
+        one(11.5, 4), one(18.3, 4), 2)
+    return out
+
+
 def cpu_mpc_rate(B=256, T=5, threads=1):
     """The reference's AL-MPC algorithm (oracle port) on the host cores, bounded sample."""
     from oracle import mpc_oracle as MO
@@ -472,6 +522,7 @@ def main():
     if rank == 0:
         try:
             mpc = bench_mpc(dev)
+            mpc["other_shapes"] = bench_mpc_shapes(dev)
             if world == 1 and not args.no_cpu:
                 threads = os.cpu_count() or 1
                 rate, sec = cpu_mpc_rate(256, 5, threads)

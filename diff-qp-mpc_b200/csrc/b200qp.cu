@@ -99,18 +99,20 @@ static int run_prefactor(KArgs<T>& a, const Layout& L, cudaStream_t st) { return
 template <typename T>
 static int forward_t(const b200qp_problem_t* pr, const Layout& L, const void* Q, const void* p, const void* G,
                      const void* h, const void* A, const void* b, void* zhat, void* lams, void* nus, void* slacks,
-                     void* ws, double* status, cudaStream_t st) {
+                     void* ws, double* status, cudaStream_t st, bool prefactored = false) {
   KArgs<T> a;
   fill_args(a, pr, L, ws);
   a.Q = (const T*)Q; a.pv = (const T*)p; a.G = (const T*)G; a.h = (const T*)h;
   a.A = (const T*)(A ? A : G); a.b = (const T*)(b ? b : h);
   a.bx = (T*)zhat; a.bz = (T*)lams; a.bs = (T*)slacks; a.by = (T*)nus;
   a.status = status;
-  CK(cudaMemsetAsync(a.slots, 0, sizeof(Slot) * B200QP_MAX_ITER_CAP + sizeof(Control), st));
   int launches = 0;
   prof_begin(st);
-  int rc = run_prefactor(a, L, st);
-  if (rc) return rc;
+  if (!prefactored) {  // the host-buffer path pre-factors chunk by chunk while the inputs arrive
+    CK(cudaMemsetAsync(a.slots, 0, sizeof(Slot) * B200QP_MAX_ITER_CAP + sizeof(Control), st));
+    int rc = run_prefactor(a, L, st);
+    if (rc) return rc;
+  }
   prof_mark(0, st);
   launches++;
   a.iter = -1;
@@ -133,9 +135,10 @@ static int forward_t(const b200qp_problem_t* pr, const Layout& L, const void* Q,
 template <typename T>
 static int backward_t(const b200qp_problem_t* pr, const Layout& L, const void* zhat, const void* lams, const void* nus,
                       const void* slacks, const void* gz, void* dQ, void* dp, void* dG, void* dh, void* dA, void* db,
-                      void* ws, cudaStream_t st) {
+                      void* ws, cudaStream_t st, int lo = 0, int cnt = -1) {
   KArgs<T> a;
   fill_args(a, pr, L, ws);
+  if (cnt >= 0) { a.prob0 = lo; a.nb = cnt; }  // a chunk of the batch (host-buffer path)
   BArgs<T> g;
   g.zhat = (const T*)zhat; g.lams = (const T*)lams; g.nus = (const T*)(nus ? nus : zhat); g.slacks = (const T*)slacks;
   g.gz = (const T*)gz;
@@ -192,17 +195,41 @@ static int prefactor_t(const b200qp_problem_t* pr, const Layout& L, const void* 
   return B200QP_OK;
 }
 
+// Pre-factorisation of problems [lo, lo + cnt) only (host-buffer path: overlaps the H2D copies).
+template <typename T>
+static int prefactor_range_t(const b200qp_problem_t* pr, const Layout& L, const void* Q, const void* G, const void* A,
+                             void* ws, int lo, int cnt, cudaStream_t st) {
+  KArgs<T> a;
+  fill_args(a, pr, L, ws);
+  a.Q = (const T*)Q; a.G = (const T*)G; a.A = (const T*)(A ? A : G);
+  a.prob0 = lo; a.nb = cnt;
+  return run_prefactor(a, L, st);
+}
+
 // ---------------------------------------------------------------------------- host-buffer path
 struct Arena {
   char* base = nullptr;
   size_t cap = 0;
-  cudaStream_t stream = nullptr;
+  cudaStream_t stream = nullptr;   // compute
+  cudaStream_t copy = nullptr;     // H2D / D2H
+  static constexpr int kMaxChunks = 8;
+  cudaEvent_t ev_in[kMaxChunks], ev_out[kMaxChunks], ev_misc[2];
+  bool events = false;
   std::mutex mu;
 };
 static Arena g_arena;
 
 static int arena_reserve(size_t bytes) {
   if (!g_arena.stream) CK(cudaStreamCreateWithFlags(&g_arena.stream, cudaStreamNonBlocking));
+  if (!g_arena.copy) CK(cudaStreamCreateWithFlags(&g_arena.copy, cudaStreamNonBlocking));
+  if (!g_arena.events) {
+    for (int i = 0; i < Arena::kMaxChunks; i++) {
+      CK(cudaEventCreateWithFlags(&g_arena.ev_in[i], cudaEventDisableTiming));
+      CK(cudaEventCreateWithFlags(&g_arena.ev_out[i], cudaEventDisableTiming));
+    }
+    for (int i = 0; i < 2; i++) CK(cudaEventCreateWithFlags(&g_arena.ev_misc[i], cudaEventDisableTiming));
+    g_arena.events = true;
+  }
   if (bytes <= g_arena.cap) return B200QP_OK;
   if (g_arena.base) CK(cudaFree(g_arena.base));
   g_arena.base = nullptr;
@@ -305,39 +332,88 @@ int b200qp_solve_host(const b200qp_problem_t* prob, const void* Q, const void* p
   rc = arena_reserve(off);
   if (rc) return rc;
   char* d = g_arena.base;
-  cudaStream_t st = g_arena.stream;
-  CK(cudaMemcpyAsync(d + oQ, Q, bQ, cudaMemcpyHostToDevice, st));
-  CK(cudaMemcpyAsync(d + op, p, bp, cudaMemcpyHostToDevice, st));
-  CK(cudaMemcpyAsync(d + oG, G, bG, cudaMemcpyHostToDevice, st));
-  CK(cudaMemcpyAsync(d + oh, h, bh, cudaMemcpyHostToDevice, st));
-  if (pe > 0) {
-    CK(cudaMemcpyAsync(d + oA, A, bA, cudaMemcpyHostToDevice, st));
-    CK(cudaMemcpyAsync(d + ob, b, bb, cudaMemcpyHostToDevice, st));
+  cudaStream_t st = g_arena.stream, cs = g_arena.copy;
+  // Pipeline: the batch is cut into chunks; the pre-factorisation of chunk c runs while chunk
+  // c+1 is still on the PCIe bus, and the gradients of chunk c go back to the host while the
+  // backward kernel works on chunk c+1.  The PDIPM loop itself needs the whole batch (its
+  // termination and step fill are batch-global), so it sits between the two pipelines.
+  const int nch = (int)nb >= 4096 ? Arena::kMaxChunks : 1;
+  auto lo_of = [&](int c) { return (int)((size_t)c * nb / nch); };
+  auto slice_h2d = [&](size_t off, const void* src, int64_t stride, size_t per, int lo, int cnt) -> cudaError_t {
+    if (stride == 0 || per == 0) return cudaSuccess;  // shared parameters are copied once, below
+    return cudaMemcpyAsync(d + off + (size_t)lo * per * es, (const char*)src + (size_t)lo * per * es, (size_t)cnt * per * es,
+                           cudaMemcpyHostToDevice, cs);
+  };
+  auto shared_h2d = [&](size_t off, const void* src, int64_t stride, size_t bytes) -> cudaError_t {
+    if (stride != 0 || bytes == 0) return cudaSuccess;
+    return cudaMemcpyAsync(d + off, src, bytes, cudaMemcpyHostToDevice, cs);
+  };
+  CK(shared_h2d(oQ, Q, prob->sQ, bQ)); CK(shared_h2d(op, p, prob->sp, bp)); CK(shared_h2d(oG, G, prob->sG, bG));
+  CK(shared_h2d(oh, h, prob->sh, bh));
+  if (pe > 0) { CK(shared_h2d(oA, A, prob->sA, bA)); CK(shared_h2d(ob, b, prob->sb, bb)); }
+  {
+    KArgs<double> a0;  // only for the slot / control block address (same for both dtypes)
+    fill_args(a0, prob, L, d + ows);
+    CK(cudaMemsetAsync(a0.slots, 0, sizeof(Slot) * B200QP_MAX_ITER_CAP + sizeof(Control), st));
   }
-  if (bwd) CK(cudaMemcpyAsync(d + ogz, dl_dzhat, bz, cudaMemcpyHostToDevice, st));
-  rc = b200qp_forward(prob, d + oQ, d + op, d + oG, d + oh, pe ? d + oA : nullptr, pe ? d + ob : nullptr, d + oz,
-                      d + ol, d + on, d + os, d + ows, (double*)(d + ost), st);
-  if (rc) return rc;
-  if (bwd) {
-    rc = b200qp_backward(prob, d + oz, d + ol, d + on, d + os, d + ogz, d + odQ, d + odp, d + odG, d + odh,
-                         d + odA, d + odb, d + ows, st);
+  for (int c = 0; c < nch; c++) {
+    const int lo = lo_of(c), cnt = lo_of(c + 1) - lo;
+    CK(slice_h2d(oQ, Q, prob->sQ, n * n, lo, cnt));
+    CK(slice_h2d(oG, G, prob->sG, m * n, lo, cnt));
+    if (pe > 0) CK(slice_h2d(oA, A, prob->sA, pe * n, lo, cnt));
+    CK(cudaEventRecord(g_arena.ev_in[c], cs));
+    CK(cudaStreamWaitEvent(st, g_arena.ev_in[c], 0));
+    rc = prob->dtype == B200QP_F64
+             ? prefactor_range_t<double>(prob, L, d + oQ, d + oG, pe ? d + oA : nullptr, d + ows, lo, cnt, st)
+             : prefactor_range_t<float>(prob, L, d + oQ, d + oG, pe ? d + oA : nullptr, d + ows, lo, cnt, st);
     if (rc) return rc;
   }
-  CK(cudaMemcpyAsync(zhat, d + oz, bz, cudaMemcpyDeviceToHost, st));
-  CK(cudaMemcpyAsync(lams, d + ol, bl, cudaMemcpyDeviceToHost, st));
-  CK(cudaMemcpyAsync(slacks, d + os, bl, cudaMemcpyDeviceToHost, st));
-  if (pe > 0) CK(cudaMemcpyAsync(nus, d + on, bn, cudaMemcpyDeviceToHost, st));
-  CK(cudaMemcpyAsync(status, d + ost, 8 * sizeof(double), cudaMemcpyDeviceToHost, st));
+  // the vectors are not needed by the pre-factorisation: they travel behind the matrices
+  CK(slice_h2d(op, p, prob->sp, n, 0, (int)nb));
+  CK(slice_h2d(oh, h, prob->sh, m, 0, (int)nb));
+  if (pe > 0) CK(slice_h2d(ob, b, prob->sb, pe, 0, (int)nb));
+  if (bwd) CK(cudaMemcpyAsync(d + ogz, dl_dzhat, bz, cudaMemcpyHostToDevice, cs));
+  CK(cudaEventRecord(g_arena.ev_misc[0], cs));
+  CK(cudaStreamWaitEvent(st, g_arena.ev_misc[0], 0));
+  void* dA_ = pe ? (void*)(d + oA) : nullptr;
+  void* db_ = pe ? (void*)(d + ob) : nullptr;
+  rc = prob->dtype == B200QP_F64
+           ? forward_t<double>(prob, L, d + oQ, d + op, d + oG, d + oh, dA_, db_, d + oz, d + ol, d + on, d + os, d + ows,
+                               (double*)(d + ost), st, true)
+           : forward_t<float>(prob, L, d + oQ, d + op, d + oG, d + oh, dA_, db_, d + oz, d + ol, d + on, d + os, d + ows,
+                              (double*)(d + ost), st, true);
+  if (rc) return rc;
+  CK(cudaEventRecord(g_arena.ev_misc[1], st));
+  CK(cudaStreamWaitEvent(cs, g_arena.ev_misc[1], 0));
+  CK(cudaMemcpyAsync(zhat, d + oz, bz, cudaMemcpyDeviceToHost, cs));
+  CK(cudaMemcpyAsync(lams, d + ol, bl, cudaMemcpyDeviceToHost, cs));
+  CK(cudaMemcpyAsync(slacks, d + os, bl, cudaMemcpyDeviceToHost, cs));
+  if (pe > 0) CK(cudaMemcpyAsync(nus, d + on, bn, cudaMemcpyDeviceToHost, cs));
+  CK(cudaMemcpyAsync(status, d + ost, 8 * sizeof(double), cudaMemcpyDeviceToHost, cs));
   if (bwd) {
-    CK(cudaMemcpyAsync(dQ, d + odQ, nb * n * n * es, cudaMemcpyDeviceToHost, st));
-    CK(cudaMemcpyAsync(dp, d + odp, bz, cudaMemcpyDeviceToHost, st));
-    CK(cudaMemcpyAsync(dG, d + odG, nb * m * n * es, cudaMemcpyDeviceToHost, st));
-    CK(cudaMemcpyAsync(dh, d + odh, bl, cudaMemcpyDeviceToHost, st));
-    if (pe > 0) {
-      CK(cudaMemcpyAsync(dA, d + odA, nb * pe * n * es, cudaMemcpyDeviceToHost, st));
-      CK(cudaMemcpyAsync(db, d + odb, bn, cudaMemcpyDeviceToHost, st));
+    auto slice_d2h = [&](void* dst, size_t off, size_t per, int lo, int cnt) -> cudaError_t {
+      if (per == 0) return cudaSuccess;
+      return cudaMemcpyAsync((char*)dst + (size_t)lo * per * es, d + off + (size_t)lo * per * es, (size_t)cnt * per * es,
+                             cudaMemcpyDeviceToHost, cs);
+    };
+    for (int c = 0; c < nch; c++) {
+      const int lo = lo_of(c), cnt = lo_of(c + 1) - lo;
+      rc = prob->dtype == B200QP_F64
+               ? backward_t<double>(prob, L, d + oz, d + ol, d + on, d + os, d + ogz, d + odQ, d + odp, d + odG, d + odh,
+                                    d + odA, d + odb, d + ows, st, lo, cnt)
+               : backward_t<float>(prob, L, d + oz, d + ol, d + on, d + os, d + ogz, d + odQ, d + odp, d + odG, d + odh,
+                                   d + odA, d + odb, d + ows, st, lo, cnt);
+      if (rc) return rc;
+      CK(cudaEventRecord(g_arena.ev_out[c], st));
+      CK(cudaStreamWaitEvent(cs, g_arena.ev_out[c], 0));
+      CK(slice_d2h(dQ, odQ, n * n, lo, cnt));
+      CK(slice_d2h(dp, odp, n, lo, cnt));
+      CK(slice_d2h(dG, odG, m * n, lo, cnt));
+      CK(slice_d2h(dh, odh, m, lo, cnt));
+      if (pe > 0) { CK(slice_d2h(dA, odA, pe * n, lo, cnt)); CK(slice_d2h(db, odb, pe, lo, cnt)); }
     }
   }
+  CK(cudaStreamSynchronize(cs));
   CK(cudaStreamSynchronize(st));
   return B200QP_OK;
 }

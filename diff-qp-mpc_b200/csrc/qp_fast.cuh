@@ -645,7 +645,7 @@ __global__ void __launch_bounds__(NT, (NT == 128 ? (FK == 1 ? 4 : 5) : (NT == 64
 template <typename T, int MPAD, int NT, int FK = 0>
 __global__ void __launch_bounds__(NT, (NT == 128 ? (FK == 1 ? 4 : 5) : (NT == 64 && FK == 1 ? 5 : 1))) k_fast_backward(const KArgs<T> a, const BArgs<T> g) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  const int prob = blockIdx.x, tid = threadIdx.x;
+  const int prob = blockIdx.x + a.prob0, tid = threadIdx.x;
   const int n = a.n, m = a.m, p = a.p;
   FS<T> S;
   fast_carve(S, smem_raw, a);

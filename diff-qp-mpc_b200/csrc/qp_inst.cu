@@ -15,8 +15,8 @@ static cudaError_t ensure_smem(K kernel, size_t bytes) {
 
 #define LAUNCH_NT(KNAME, ...)                                                                  \
   do {                                                                                         \
-    if (L.nt == 128) { auto k = KNAME<T, SMEM, 128>; CK(ensure_smem(k, L.smem_bytes)); k<<<L.nb, 128, L.smem_bytes, st>>>(__VA_ARGS__); } \
-    else { auto k = KNAME<T, SMEM, 256>; CK(ensure_smem(k, L.smem_bytes)); k<<<L.nb, 256, L.smem_bytes, st>>>(__VA_ARGS__); } \
+    if (L.nt == 128) { auto k = KNAME<T, SMEM, 128>; CK(ensure_smem(k, L.smem_bytes)); k<<<(unsigned)a.nb, 128, L.smem_bytes, st>>>(__VA_ARGS__); } \
+    else { auto k = KNAME<T, SMEM, 256>; CK(ensure_smem(k, L.smem_bytes)); k<<<(unsigned)a.nb, 256, L.smem_bytes, st>>>(__VA_ARGS__); } \
     CK(cudaGetLastError());                                                                    \
     return B200QP_OK;                                                                          \
   } while (0)
@@ -25,7 +25,7 @@ static cudaError_t ensure_smem(K kernel, size_t bytes) {
 // fast path: (MPAD, NT) in {(32,128), (64,128), (32,32), (64,32), (128,256)}; NT = 32 is the
 // one-warp-per-QP variant (B200QP_FAST_NT=32).
 #define LAUNCH_ONE(KEXPR, NTV, ...)                                                                \
-  do { auto k = KEXPR; CK(ensure_smem(k, L.smem_bytes)); k<<<L.nb, NTV, L.smem_bytes, st>>>(__VA_ARGS__); } while (0)
+  do { auto k = KEXPR; CK(ensure_smem(k, L.smem_bytes)); k<<<(unsigned)a.nb, NTV, L.smem_bytes, st>>>(__VA_ARGS__); } while (0)
 #define LAUNCH_FAST(KN, TAIL, ...)                                                                 \
   do {                                                                                             \
     if (L.fk) {                                                                                    \
@@ -76,8 +76,8 @@ template <typename T> int launch_prefactor(const KArgs<T>& a_in, const Layout& L
   const size_t bytes2 = bytes + (size_t)2 * round4((L.p + L.m) * L.ldn) * sizeof(T);
   a.pre_smem = bytes2 <= 100 * 1024 ? 2 : (bytes <= kSmemResidentLimit ? 1 : 0);
   const size_t dyn = a.pre_smem == 2 ? bytes2 : (a.pre_smem ? bytes : 0);
-  if (L.nt == 128) { auto k = k_prefactor<T, 128>; CK(ensure_smem(k, dyn)); k<<<L.nb, 128, dyn, st>>>(a); }
-  else { auto k = k_prefactor<T, 256>; CK(ensure_smem(k, dyn)); k<<<L.nb, 256, dyn, st>>>(a); }
+  if (L.nt == 128) { auto k = k_prefactor<T, 128>; CK(ensure_smem(k, dyn)); k<<<(unsigned)a.nb, 128, dyn, st>>>(a); }
+  else { auto k = k_prefactor<T, 256>; CK(ensure_smem(k, dyn)); k<<<(unsigned)a.nb, 256, dyn, st>>>(a); }
   CK(cudaGetLastError());
   return B200QP_OK;
 }

@@ -98,6 +98,7 @@ struct KArgs {
   int iter, max_iter, lim;
   double eps;
   int launches;
+  int prob0;                 // first problem of this launch (chunked pre-factorisation / backward)
   int fso[28];               // fast path: shared-memory carve-up offsets in elements (qp_fast.cuh:fast_offsets)
   int pre_smem;              // prefactor: F / Qi working copies live in dynamic shared memory
   int rtile_mpad, rtile_nt;  // != 0: R is stored in register-tile order (qp_fast.cuh); nt = -1: DMMA fragment order
@@ -552,7 +553,7 @@ __global__ void __launch_bounds__(NT) k_pdipm_iter(const KArgs<T> a) {
 // Pre-factorisation (d-independent part).  Works in global memory (L1/L2 resident: one-off).
 template <typename T, int NT>
 __global__ void __launch_bounds__(NT) k_prefactor(const KArgs<T> a) {
-  const int prob = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int prob = blockIdx.x + a.prob0, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int n = a.n, m = a.m, p = a.p, ldn = a.ldn, ldm = a.ldm, ldp = a.ldp;
   const T* Qg = a.Q + (size_t)prob * a.sQ;
   const T* Gg = a.G + (size_t)prob * a.sG;
@@ -689,7 +690,7 @@ struct BArgs {
 template <typename T, bool SMEM, int NT>
 __global__ void __launch_bounds__(NT) k_backward(const KArgs<T> a, const BArgs<T> g) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  const int prob = blockIdx.x, tid = threadIdx.x;
+  const int prob = blockIdx.x + a.prob0, tid = threadIdx.x;
   const int n = a.n, m = a.m, p = a.p;
   Smem<T> S;
   carve<T, SMEM>(S, smem_raw, a, prob, NT);

@@ -141,3 +141,30 @@ def test_kkt_solver_backends_agree(cuda_device):
     gate(z.cpu(), fwd["lams"], 1e-6, "z")
     gate(s.cpu(), fwd["slacks"], 1e-6, "s")
     gate(y.cpu(), fwd["nus"], 1e-6, "y")
+
+
+@pytest.mark.parametrize("nb", [37, 4099])
+def test_host_buffer_entry_point_matches_device_path(nb, cuda_device):
+    """b200qp_solve_host (chunked H2D -> pre-factorisation and backward -> D2H pipelines around the
+    whole-batch PDIPM loop) returns bit-identical results to the device-resident QPFunction path;
+    nb = 4099 exercises the 8-chunk pipeline with ragged chunks."""
+    import ctypes
+    from b200qp import _lib
+    from oracle import qp_oracle as O
+    nz, m = 12, 18
+    Q, p, G, h, A, b = O.random_qp(nb, nz, m, 0, seed=77)
+    out, info = run_ours(dict(Q=Q, p=p, G=G, h=h, A=A, b=b), cuda_device)
+    L = _lib.lib()
+    prob = _lib.Problem(nb, nz, m, 0, _lib.F64, 20, 3, 0, 1e-12, nz * nz, nz, m * nz, m, 0, 0)
+    host = {k: torch.empty(s, dtype=torch.float64) for k, s in dict(
+        zhat=(nb, nz), lams=(nb, m), slacks=(nb, m), dQ=(nb, nz, nz), dp=(nb, nz), dG=(nb, m, nz), dh=(nb, m)).items()}
+    st = torch.zeros(8, dtype=torch.float64)
+    gz = torch.ones(nb, nz, dtype=torch.float64)
+    P = lambda t: ctypes.c_void_p(t.data_ptr())
+    N0 = ctypes.c_void_p(0)
+    rc = L.b200qp_solve_host(ctypes.byref(prob), P(Q), P(p), P(G), P(h), N0, N0, P(gz), P(host["zhat"]), P(host["lams"]), N0,
+                             P(host["slacks"]), P(host["dQ"]), P(host["dp"]), P(host["dG"]), P(host["dh"]), N0, N0, P(st))
+    assert rc == 0
+    assert int(st[0]) == info["n_iter"]
+    for k in ("zhat", "lams", "slacks", "dQ", "dp", "dG", "dh"):
+        assert torch.equal(host[k], out[k]), k
