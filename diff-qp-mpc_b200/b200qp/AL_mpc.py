@@ -140,8 +140,9 @@ class MPC(Module):
         C = cost.C.to(self.dtype)
         c = cost.c.to(self.dtype)
         ul, uu = self._bounds(B, dev)
-        xs, us, status = ALSolve.apply(C, c, x.to(self.dtype), u.to(self.dtype), x0.to(self.dtype), ul, uu, state, spec,
-                                       self.al_iter)
+        # the reference detaches the initial trajectory (AL_mpc.py:284) and never differentiates x0
+        xs, us, status = ALSolve.apply(C, c, x.detach().to(self.dtype), u.detach().to(self.dtype), x0.detach().to(self.dtype),
+                                       ul, uu, state, spec, self.al_iter)
         self._hist = state.hist
         self.lamda_prev, self.rho_prev, self.status = state.lam, state.rho, status
         self.just_initialized = False

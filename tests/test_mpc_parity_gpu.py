@@ -222,3 +222,36 @@ def test_unknown_dynamics_is_rejected(cuda_device):
 
     with pytest.raises(NotImplementedError, match="no fused kernel"):
         dyn_spec(Mystery())
+
+
+def test_tracking_mpc_matches_reference_golden(cuda_device):
+    """The production caller (deqmpc/policies.py Tracking_MPC, solver_type='al'): three consecutive
+    calls with warm start hand-off and gradients w.r.t. the tracked references, against the real
+    reference run on its jit-scripted PendulumEnv (oracle/gen_golden_tracking.py)."""
+    import types
+    import numpy as np
+    from b200qp import envs
+    from b200qp.policies import Tracking_MPC
+    g = _npz("tracking_pend_B8_T5.npz")
+    dev = cuda_device
+    B, T = g["x_ref0"].shape[:2]
+    space = types.SimpleNamespace(high=np.array([3.0]), low=np.array([-3.0]))
+    env = types.SimpleNamespace(nx=2, nu=1, nq=1, dt=0.05, dynamics=envs.PendulumDynamics(),
+                                dynamics_derivatives=envs.PendulumDynamics_jac(), action_space=space)
+    # PendulumEnv keeps Qlqr / Rlqr in float32 (deqmpc/envs.py:100-101): 0.01 enters rounded through float32
+    args = types.SimpleNamespace(T=T, bsz=B, Q=torch.Tensor([10.0, 1.0]).double(),
+                                 R=torch.Tensor([0.01]).double(), dtype="double", solver_type="al", qp_iter=2,
+                                 eps=1e-2, warm_start=True, device=dev)
+    mpc = Tracking_MPC(args, env)
+    x0 = g["x0"].to(dev)
+    mpc.reinitialize(x0, None)
+    for k in range(3):
+        x_ref = g[f"x_ref{k}"].to(dev).requires_grad_(True)
+        u_ref = g[f"u_ref{k}"].to(dev).requires_grad_(True)
+        xs, us = mpc(x0, None, x_ref, u_ref)
+        (xs.sum() + 2 * us.sum()).backward()
+        errs = dict(x=rel(xs.detach().cpu(), g[f"out_x{k}"]), u=rel(us.detach().cpu(), g[f"out_u{k}"]),
+                    gx=rel(x_ref.grad.cpu(), g[f"g_xref{k}"]), gu=rel(u_ref.grad.cpu(), g[f"g_uref{k}"]))
+        print("tracking call", k, {a: f"{b:.1e}" for a, b in errs.items()})
+        assert errs["x"] <= RTOL32 and errs["u"] <= RTOL32, errs
+        assert errs["gx"] <= RTOL64 and errs["gu"] <= RTOL64, errs
