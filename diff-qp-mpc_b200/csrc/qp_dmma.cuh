@@ -139,7 +139,6 @@ __device__ __forceinline__ bool dmma_factor(const double* __restrict__ Rf, const
         a1[2 * q] = w.x; a1[2 * q + 1] = w.y;
       }
       __syncwarp();
-      double pk[8];
 #pragma unroll
       for (int k = 0; k < 8; k++) {
         const double dk = shfl_d(a0[k], k);
@@ -152,9 +151,10 @@ __device__ __forceinline__ bool dmma_factor(const double* __restrict__ Rf, const
         e = fma(-dk, r, 1.0);
         r = fma(r, e, r);
         if (!(dk > 1e-290 && dk < 1e290)) r = (dk > 0.0) ? 1.0 / dk : t_nan<double>();  // rare
-        pk[k] = (rbase + k < m) ? r : 1.0;
+        const double pkk = (rbase + k < m) ? r : 1.0;
+        if (lane == 0) ppan[k] = pkk;  // re-read below: keeping eight pivots live costs 16 registers
         const double w0 = a0[k], w1 = a1[k];
-        const double l0 = w0 * pk[k], l1 = w1 * pk[k];
+        const double l0 = w0 * pkk, l1 = w1 * pkk;
 #pragma unroll
         for (int c = k + 1; c < 8; c++) {
           const double wck = shfl_d(w0, c);
@@ -163,21 +163,17 @@ __device__ __forceinline__ bool dmma_factor(const double* __restrict__ Rf, const
         }
       }
       // off the critical path: reciprocal pivots, packed unit-lower columns for the sweeps
-      if (lane < 8) {
-        double pv = pk[0];
-#pragma unroll
-        for (int k = 1; k < 8; k++) pv = (lane == k) ? pk[k] : pv;
-        ppan[lane] = pv;
-        if (rbase + lane < m) pinv[rbase + lane] = pv;
-      }
+      __syncwarp();
+      if (lane < 8 && rbase + lane < m) pinv[rbase + lane] = ppan[lane];
       {
         int ub = urow(rbase, mm);
 #pragma unroll
         for (int k = 0; k < 8; k++) {
           const int j = rbase + k;
           if (j < m) {
-            if (i0 > j && i0 < mm) Up[ub + i0] = a0[k] * pk[k];
-            if (i1 < mm) Up[ub + i1] = a1[k] * pk[k];
+            const double pkk = ppan[k];
+            if (i0 > j && i0 < mm) Up[ub + i0] = a0[k] * pkk;
+            if (i1 < mm) Up[ub + i1] = a1[k] * pkk;
           }
           ub += mm - j - 2;  // urow(j + 1) - urow(j)
         }

@@ -16,6 +16,10 @@
 #pragma once
 #include "qp_kernels.cuh"
 
+#ifndef FAST_DMMA_MIN_CTAS
+#define FAST_DMMA_MIN_CTAS 4
+#endif
+
 namespace b200qp {
 
 template <int MPAD, int NT>
@@ -424,7 +428,7 @@ __device__ __forceinline__ T warp_sum(T v) {
 // ------------------------------------------------------------------------------------------
 // INIT=true: initial point (batch.py:60-86).  INIT=false: PDIPM iteration a.iter (batch.py:91-204).
 template <typename T, int MPAD, int NT, bool INIT, int FK = 0>
-__global__ void __launch_bounds__(NT, (NT == 128 ? (FK == 1 ? 4 : 5) : (NT == 64 && FK == 1 ? 5 : 1))) k_fast_iter(const KArgs<T> a) {
+__global__ void __launch_bounds__(NT, (NT == 128 ? (FK == 1 ? FAST_DMMA_MIN_CTAS : 5) : (NT == 64 && FK == 1 ? 5 : 1))) k_fast_iter(const KArgs<T> a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int prob = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int n = a.n, m = a.m, p = a.p, it = a.iter;
@@ -643,7 +647,7 @@ __global__ void __launch_bounds__(NT, (NT == 128 ? (FK == 1 ? 4 : 5) : (NT == 64
 
 // ------------------------------------------------------------------------------------------
 template <typename T, int MPAD, int NT, int FK = 0>
-__global__ void __launch_bounds__(NT, (NT == 128 ? (FK == 1 ? 4 : 5) : (NT == 64 && FK == 1 ? 5 : 1))) k_fast_backward(const KArgs<T> a, const BArgs<T> g) {
+__global__ void __launch_bounds__(NT, (NT == 128 ? (FK == 1 ? FAST_DMMA_MIN_CTAS : 5) : (NT == 64 && FK == 1 ? 5 : 1))) k_fast_backward(const KArgs<T> a, const BArgs<T> g) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int prob = blockIdx.x + a.prob0, tid = threadIdx.x;
   const int n = a.n, m = a.m, p = a.p;
@@ -697,7 +701,7 @@ __global__ void __launch_bounds__(NT, (NT == 128 ? (FK == 1 ? 4 : 5) : (NT == 64
 }
 
 template <typename T, int MPAD, int NT, int FK = 0>
-__global__ void __launch_bounds__(NT, (NT == 128 ? (FK == 1 ? 4 : 5) : (NT == 64 && FK == 1 ? 5 : 1))) k_fast_kkt(const KArgs<T> a, const SArgs<T> g) {
+__global__ void __launch_bounds__(NT, (NT == 128 ? (FK == 1 ? FAST_DMMA_MIN_CTAS : 5) : (NT == 64 && FK == 1 ? 5 : 1))) k_fast_kkt(const KArgs<T> a, const SArgs<T> g) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int prob = blockIdx.x, tid = threadIdx.x;
   const int n = a.n, m = a.m, p = a.p;
