@@ -173,6 +173,84 @@ __device__ __forceinline__ void gemv_cols_nt(const T* __restrict__ M, int ld, in
   cta_sync<NT>();
 }
 
+// ----------------------------------------------------------------------------- register-resident GEMV
+// Reduce K (8 or 16) per-lane values across the warp with a halving butterfly (K + log2(32/K) - 1
+// shuffles instead of 5 K).  On return v[0] of lane l is the warp-wide sum of value index
+// (l >> 1) & 15 for K = 16, (l >> 2) & 7 for K = 8.
+template <int K, typename T>
+__device__ __forceinline__ void warp_reduce_multi(T (&v)[K], int lane) {
+  static_assert(K == 8 || K == 16, "K must be 8 or 16");
+  if (K == 16) {
+    const bool up = (lane & 16) != 0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) { const T snd = up ? v[i] : v[i + 8], kp = up ? v[i + 8] : v[i]; v[i] = kp + shfl_x(snd, 16); }
+  }
+  {
+    const int off = K == 16 ? 8 : 16;
+    const bool up = (lane & off) != 0;
+#pragma unroll
+    for (int i = 0; i < 4; i++) { const T snd = up ? v[i] : v[i + 4], kp = up ? v[i + 4] : v[i]; v[i] = kp + shfl_x(snd, off); }
+  }
+  {
+    const int off = K == 16 ? 4 : 8;
+    const bool up = (lane & off) != 0;
+#pragma unroll
+    for (int i = 0; i < 2; i++) { const T snd = up ? v[i] : v[i + 2], kp = up ? v[i + 2] : v[i]; v[i] = kp + shfl_x(snd, off); }
+  }
+  {
+    const int off = K == 16 ? 2 : 4;
+    const bool up = (lane & off) != 0;
+    const T snd = up ? v[0] : v[1], kp = up ? v[1] : v[0];
+    v[0] = kp + shfl_x(snd, off);
+  }
+  if (K == 8) v[0] += shfl_x(v[0], 2);
+  v[0] += shfl_x(v[0], 1);
+}
+
+// A (rows x cols <= 4*RPW x 32) matrix held in the registers of a 4-warp CTA: lane = column,
+// warp w owns rows w, w+4, ...  Loaded ONCE with coalesced loads (issue it early: the latency
+// hides behind whatever follows) and then used for M v (regmat_rows) and M^T u (regmat_cols).
+template <int RPW, typename T>
+struct RegMat { T e[RPW]; };
+
+template <int RPW, typename T>
+__device__ __forceinline__ void regmat_load(RegMat<RPW, T>& M, const T* __restrict__ g, int ld, int rows, int cols, int lane,
+                                            int warp) {
+#pragma unroll
+  for (int k = 0; k < RPW; k++) {
+    const int r = warp + 4 * k;
+    M.e[k] = (r < rows && lane < cols) ? g[(size_t)r * ld + lane] : T(0);
+  }
+}
+// out[r] = sum_c M[r][c] v[c];  v, out in shared memory.  No barrier.
+template <int RPW, typename T>
+__device__ __forceinline__ void regmat_rows(const RegMat<RPW, T>& M, const T* v, T* out, int rows, int cols, int lane, int warp) {
+  const T vc = lane < cols ? v[lane] : T(0);
+  T pr[RPW];
+#pragma unroll
+  for (int k = 0; k < RPW; k++) pr[k] = M.e[k] * vc;
+  warp_reduce_multi<RPW>(pr, lane);
+  const int k = RPW == 16 ? (lane >> 1) & 15 : (lane >> 2) & 7;
+  const bool writer = RPW == 16 ? (lane & 1) == 0 : (lane & 3) == 0;
+  const int r = warp + 4 * k;
+  if (writer && r < rows) out[r] = pr[0];
+}
+// part[warp*32 + c] = sum over this warp's rows of M[r][c] u[r];  the caller adds the four
+// partials after a barrier (regmat_colsum).  u in shared memory.
+template <int RPW, typename T>
+__device__ __forceinline__ void regmat_cols(const RegMat<RPW, T>& M, const T* u, T* part, int rows, int lane, int warp) {
+  T a0 = T(0), a1 = T(0);
+#pragma unroll
+  for (int k = 0; k < RPW; k += 2) {
+    const int r0 = warp + 4 * k, r1 = r0 + 4;
+    a0 += M.e[k] * (r0 < rows ? u[r0] : T(0));
+    a1 += M.e[k + 1] * (r1 < rows ? u[r1] : T(0));
+  }
+  part[warp * 32 + lane] = a0 + a1;
+}
+template <typename T>
+__device__ __forceinline__ T regmat_colsum(const T* part, int c) { return (part[c] + part[32 + c]) + (part[64 + c] + part[96 + c]); }
+
 // out[r] = sum_c M[r*ld + c] * v[c]  (r < rows), one thread per row: conflict free in shared
 // memory when ld is odd.  No trailing barrier.
 template <typename T>

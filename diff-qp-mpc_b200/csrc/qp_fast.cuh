@@ -295,12 +295,20 @@ __device__ __forceinline__ void fast_ldlt_solve(const T* Up, int m, const T* pin
 // dx/ds/dz/dy to global memory.  Each stage ends with a barrier.
 template <typename T, int NT>
 __device__ __forceinline__ void fast_kkt_pre(const FS<T>& S, const KArgs<T>& a, int prob, bool has_rx, const T* rx,
-                                             const T* rs, const T* rz, const T* ry, int tid) {
+                                             const T* rs, const T* rz, const T* ry, int tid,
+                                             const RegMat<8, T>* qi_regs = nullptr) {
   const int n = a.n, m = a.m, p = a.p, ldn = a.ldn, ldm = a.ldm, ldp = a.ldp;
   const int lane = tid & 31, warp = tid >> 5;
   if (has_rx) {
     gemv_rows_thread(S.BQi, ldn, p + m, n, rx, S.hv, tid, NT);
-    gemv_cols_nt<T, NT>(a.Qi + (size_t)prob * a.sQi, ldn, n, n, rx, S.t, S.part, tid);  // t = Qi rx
+    if (qi_regs != nullptr) {  // t = Qi^T rx from the register-resident copy (NT = 128, n <= 32)
+      regmat_cols<8, T>(*qi_regs, rx, S.part, n, lane, warp);
+      cta_sync<NT>();
+      if (tid < n) S.t[tid] = regmat_colsum(S.part, tid);
+      cta_sync<NT>();
+    } else {
+      gemv_cols_nt<T, NT>(a.Qi + (size_t)prob * a.sQi, ldn, n, n, rx, S.t, S.part, tid);  // t = Qi rx
+    }
   }
   for (int i = tid; i < m; i += NT) {
     T v = rs[i] / S.d[i];
@@ -518,6 +526,15 @@ __global__ void __launch_bounds__(NT, (NT == 128 ? (FK == 1 ? FAST_DMMA_MIN_CTAS
     const T* Ag = a.A + (size_t)prob * a.sA;
     DmmaTiles<MPAD, NT / 32> tiles;
     if constexpr (FK == 1) dmma_prefetch<MPAD, NT / 32>(Rt, tid, tiles);
+    // register-resident Q and G for the residual mat-vecs (loads in flight while the iterate arrives)
+    constexpr bool REGMV = NT == 128 && MPAD <= 64;
+    const bool regmv = REGMV && n <= 32;
+    RegMat<16, T> Gm;
+    RegMat<8, T> Qm;
+    if (regmv) {
+      regmat_load<16, T>(Gm, Gg, n, m, n, lane, warp);
+      regmat_load<8, T>(Qm, Qg, n, n, n, lane, warp);
+    }
     // ---- iterate + previous step
     {
       T alpha = T(0);
@@ -537,10 +554,22 @@ __global__ void __launch_bounds__(NT, (NT == 128 ? (FK == 1 ? FAST_DMMA_MIN_CTAS
     }
     cta_sync<NT>();
     // ---- residuals
-    gemv_rows_warp(Qg, n, n, n, S.x, S.rx, tid, NT);
-    gemv_rows_warp(Gg, n, m, n, S.x, S.rz, tid, NT);
-    if (p > 0) gemv_rows_warp(Ag, n, p, n, S.x, S.ry, tid, NT);
-    gemv_cols_nt<T, NT>(Gg, n, m, n, S.z, S.t, S.part, tid);  // G^T z
+    RegMat<8, T> Qim;
+    if (regmv) {
+      regmat_rows<8, T>(Qm, S.x, S.rx, n, n, lane, warp);
+      regmat_rows<16, T>(Gm, S.x, S.rz, m, n, lane, warp);
+      regmat_cols<16, T>(Gm, S.z, S.part, m, lane, warp);  // G^T z, four partials per column
+      if constexpr (FK == 1) regmat_load<8, T>(Qim, a.Qi + (size_t)prob * a.sQi, a.ldn, n, n, lane, warp);
+      if (p > 0) gemv_rows_warp(Ag, n, p, n, S.x, S.ry, tid, NT);
+      cta_sync<NT>();
+      if (tid < n) S.t[tid] = regmat_colsum(S.part, tid);
+      cta_sync<NT>();
+    } else {
+      gemv_rows_warp(Qg, n, n, n, S.x, S.rx, tid, NT);
+      gemv_rows_warp(Gg, n, m, n, S.x, S.rz, tid, NT);
+      if (p > 0) gemv_rows_warp(Ag, n, p, n, S.x, S.ry, tid, NT);
+      gemv_cols_nt<T, NT>(Gg, n, m, n, S.z, S.t, S.part, tid);  // G^T z
+    }
     if (p > 0) gemv_cols_nt<T, NT>(Ag, n, p, n, S.y, S.scrn, S.part, tid);  // A^T y
     T acc[4] = {T(0), T(0), T(0), T(0)};
     for (int c = tid; c < n; c += NT) {
@@ -576,7 +605,7 @@ __global__ void __launch_bounds__(NT, (NT == 128 ? (FK == 1 ? FAST_DMMA_MIN_CTAS
       // forward substitution is free (qp_dmma.cuh)
       cp_async_wait_all();
       cta_sync<NT>();
-      fast_kkt_pre<T, NT>(S, a, prob, true, S.rx, S.z, S.rz, S.ry, tid);
+      fast_kkt_pre<T, NT>(S, a, prob, true, S.rx, S.z, S.rz, S.ry, tid, regmv ? &Qim : nullptr);
       ok = factor_any<T, MPAD, NT, FK>(Rt, S, S.hv + p, m, tid, &tiles);
     } else {
       ok = factor_any<T, MPAD, NT, FK>(Rt, S, (const T*)nullptr, m, tid);
