@@ -139,16 +139,9 @@ __device__ __forceinline__ bool dmma_factor(const double* __restrict__ Rf, const
         a1[2 * q] = w.x; a1[2 * q + 1] = w.y;
       }
       __syncwarp();
-      // Pivot chain with one-step lookahead: the two entries of row k+1 that decide pivot k+1
-      // (its diagonal and its column-k entry, both final before step k) are broadcast ahead of
-      // the reciprocal of pivot k, and every lane then forms pivot k+1 itself -- the chain per
-      // column is rcp -> mul -> fma without a shuffle.  Same operands as the owner lane's own
-      // update, so the value is bit-identical.
-      double dk = shfl_d(a0[0], 0);
 #pragma unroll
       for (int k = 0; k < 8; k++) {
-        double dn = 0.0, wn = 0.0;
-        if (k < 7) { dn = shfl_d(a0[k + 1 < 8 ? k + 1 : 7], k + 1); wn = shfl_d(a0[k], k + 1); }
+        const double dk = shfl_d(a0[k], k);
         // 1/dk: MUFU seed + two Newton steps, no branches on the critical path; a non-positive or
         // NaN pivot of a real column poisons the factor, bordered/padding columns use 1
         double r;
@@ -162,7 +155,6 @@ __device__ __forceinline__ bool dmma_factor(const double* __restrict__ Rf, const
         if (lane == 0) ppan[k] = pkk;  // re-read below: keeping eight pivots live costs 16 registers
         const double w0 = a0[k], w1 = a1[k];
         const double l0 = w0 * pkk, l1 = w1 * pkk;
-        dk = dn - (wn * pkk) * wn;  // pivot k+1, formed by every lane
 #pragma unroll
         for (int c = k + 1; c < 8; c++) {
           const double wck = shfl_d(w0, c);
@@ -234,29 +226,20 @@ __device__ __forceinline__ void dmma_ldlt_solve(const double* Up, int m, int mm,
     if (from_border) r[s] = i < m ? Up[rb[s] + m] : 0.0;
     else r[s] = i < m ? v[i] : 0.0;
   }
-  // One-step lookahead: the entry that becomes the next pivot value is broadcast BEFORE the
-  // current update (it does not depend on it), and every lane then applies the current update to
-  // that copy itself, so the chain per column is one FMA (+ an off-chain shuffle) instead of
-  // shuffle -> FMA.  The redundant FMA has the operands of the owner lane's: identical bits.
   if (!from_border) {
-    double xj = shfl_d(r[0], 0);
 #pragma unroll
     for (int s = 0; s < RPL; s++) {
       const int jend = min(32, m - s * 32);
 #pragma unroll 4
       for (int jj = 0; jj < jend; jj++) {
         const int j = s * 32 + jj;
-        double rn = 0.0;
-        if (jj + 1 < 32) rn = shfl_d(r[s], jj + 1);
-        else if (s + 1 < RPL) rn = shfl_d(r[s + 1 < RPL ? s + 1 : s], 0);
+        const double yj = shfl_d(r[s], jj);
         const double* row = Up + urow(j, mm);
-        const double un = (j + 1 < m) ? row[j + 1] : 0.0;
 #pragma unroll
         for (int s2 = s; s2 < RPL; s2++) {
           const int i = s2 * 32 + lane;
-          if (i > j && i < m) r[s2] -= row[i] * xj;
+          if (i > j && i < m) r[s2] -= row[i] * yj;
         }
-        xj = rn - un * xj;
       }
     }
 #pragma unroll
@@ -265,28 +248,17 @@ __device__ __forceinline__ void dmma_ldlt_solve(const double* Up, int m, int mm,
       if (i < m) r[s] *= pinv[i];
     }
   }
-  {
-    const int jl = m - 1;
-    double xj = 0.0;
 #pragma unroll
-    for (int s = 0; s < RPL; s++)
-      if ((jl >> 5) == s) xj = shfl_d(r[s], jl & 31);
-#pragma unroll
-    for (int s = RPL - 1; s >= 0; s--) {
-      const int jend = min(32, m - s * 32);
+  for (int s = RPL - 1; s >= 0; s--) {
+    const int jend = min(32, m - s * 32);
 #pragma unroll 4
-      for (int jj = jend - 1; jj >= 0; jj--) {
-        const int j = s * 32 + jj;
-        double rn = 0.0;
-        if (jj > 0) rn = shfl_d(r[s], jj - 1);
-        else if (s > 0) rn = shfl_d(r[s > 0 ? s - 1 : 0], 31);
-        const double up = (j > 0) ? Up[urow(j - 1, mm) + j] : 0.0;  // U[j-1][j]
+    for (int jj = jend - 1; jj >= 0; jj--) {
+      const int j = s * 32 + jj;
+      const double xj = shfl_d(r[s], jj);
 #pragma unroll
-        for (int s2 = 0; s2 <= s; s2++) {
-          const int i = s2 * 32 + lane;
-          if (i < j) r[s2] -= Up[rb[s2] + j] * xj;
-        }
-        xj = rn - up * xj;
+      for (int s2 = 0; s2 <= s; s2++) {
+        const int i = s2 * 32 + lane;
+        if (i < j) r[s2] -= Up[rb[s2] + j] * xj;
       }
     }
   }

@@ -50,7 +50,7 @@ inline int make_layout(const b200qp_problem_t* pr, Layout& L) {
   L.fast = L.m <= 128 && (L.m <= 64 || widest <= 256) && getenv("B200QP_FORCE_GENERIC") == nullptr;
   if (L.fast) {
     const int generic_nt = L.nt;
-    const char* fnt = getenv("B200QP_FAST_NT");  // "32": one warp per QP up to nineq = 64
+    const char* fnt = nullptr;  // 32/64-thread CTA variants were measured slower and are not instantiated
     L.nt = L.m <= 64 ? ((fnt && atoi(fnt) == 32) ? 32 : 128) : 256;
     // DMMA factorisation: fp64, 128-thread CTAs, one spare row for the bordered right-hand side
     const char* fke = getenv("B200QP_FACTOR");
@@ -106,5 +106,9 @@ template <typename T, bool SMEM> int launch_iter(const KArgs<T>& a, const Layout
 template <typename T, bool SMEM> int launch_backward(const KArgs<T>& a, const BArgs<T>& g, const Layout& L, cudaStream_t st);
 template <typename T, bool SMEM> int launch_kkt_solve(const KArgs<T>& a, const SArgs<T>& g, const Layout& L, cudaStream_t st);
 template <typename T> int launch_prefactor(const KArgs<T>& a, const Layout& L, cudaStream_t st);
+// fast-path launchers, explicitly instantiated in qp_inst.cu -DINST_FAST=1 for T in {double,float}
+template <typename T> int fast_iter(const KArgs<T>& a, const Layout& L, cudaStream_t st);
+template <typename T> int fast_backward(const KArgs<T>& a, const BArgs<T>& g, const Layout& L, cudaStream_t st);
+template <typename T> int fast_kkt(const KArgs<T>& a, const SArgs<T>& g, const Layout& L, cudaStream_t st);
 
 }  // namespace b200qp

@@ -1,5 +1,6 @@
-// qp_inst.cu -- kernel instantiations for one (dtype, residency) pair; compiled four times:
-//   -DINST_T=double|float  -DINST_SMEM=true|false   (+ -DINST_PREFACTOR for the prefactor kernel)
+// qp_inst.cu -- kernel instantiations, compiled six times (parallel build):
+//   -DINST_T=double|float -DINST_FAST=1                      the fast-path kernels (qp_fast.cuh, qp_dmma.cuh)
+//   -DINST_T=double|float -DINST_FAST=0 -DINST_SMEM=1|0      the generic kernels (+ -DINST_PREFACTOR once per dtype)
 #include <type_traits>
 #include "qp_host.cuh"
 
@@ -21,24 +22,21 @@ static cudaError_t ensure_smem(K kernel, size_t bytes) {
     return B200QP_OK;                                                                          \
   } while (0)
 
-#if INST_SMEM
-// fast path: (MPAD, NT) in {(32,128), (64,128), (32,32), (64,32), (128,256)}; NT = 32 is the
-// one-warp-per-QP variant (B200QP_FAST_NT=32).
+#if INST_FAST
+// fast path: (MPAD, NT) in {(32,128), (64,128), (128,256)}; FK = 1 (DMMA) for fp64 with nineq < 64
 #define LAUNCH_ONE(KEXPR, NTV, ...)                                                                \
   do { auto k = KEXPR; CK(ensure_smem(k, L.smem_bytes)); k<<<(unsigned)a.nb, NTV, L.smem_bytes, st>>>(__VA_ARGS__); } while (0)
+// (One-warp and two-warp CTA variants of these kernels were measured slower -- profiles/r01/ -- and
+// are not instantiated; the kernel templates stay generic in NT.)
 #define LAUNCH_FAST(KN, TAIL, ...)                                                                 \
   do {                                                                                             \
     if (L.fk) {                                                                                    \
       if constexpr (std::is_same<T, double>::value) {                                              \
-        if (L.nt == 64) LAUNCH_ONE((KN<T, 64, 64 TAIL COMMA 1>), 64, __VA_ARGS__);                 \
-        else if (L.mpad == 32) LAUNCH_ONE((KN<T, 32, 128 TAIL COMMA 1>), 128, __VA_ARGS__);        \
+        if (L.mpad == 32) LAUNCH_ONE((KN<T, 32, 128 TAIL COMMA 1>), 128, __VA_ARGS__);        \
         else LAUNCH_ONE((KN<T, 64, 128 TAIL COMMA 1>), 128, __VA_ARGS__);                          \
       }                                                                                            \
     } else if (L.mpad == 128) LAUNCH_ONE((KN<T, 128, 256 TAIL>), 256, __VA_ARGS__);                \
-    else if (L.nt == 32) {                                                                         \
-      if (L.mpad == 32) LAUNCH_ONE((KN<T, 32, 32 TAIL>), 32, __VA_ARGS__);                         \
-      else LAUNCH_ONE((KN<T, 64, 32 TAIL>), 32, __VA_ARGS__);                                      \
-    } else {                                                                                       \
+    else {                                                                                       \
       if (L.mpad == 32) LAUNCH_ONE((KN<T, 32, 128 TAIL>), 128, __VA_ARGS__);                       \
       else LAUNCH_ONE((KN<T, 64, 128 TAIL>), 128, __VA_ARGS__);                                    \
     }                                                                                              \
@@ -46,16 +44,21 @@ static cudaError_t ensure_smem(K kernel, size_t bytes) {
     return B200QP_OK;                                                                              \
   } while (0)
 #define COMMA ,
-template <typename T> static int fast_iter(const KArgs<T>& a, const Layout& L, cudaStream_t st) {
+template <typename T> int fast_iter(const KArgs<T>& a, const Layout& L, cudaStream_t st) {
   if (a.iter < 0) LAUNCH_FAST(k_fast_iter, COMMA true, a);
   LAUNCH_FAST(k_fast_iter, COMMA false, a);
 }
-template <typename T> static int fast_backward(const KArgs<T>& a, const BArgs<T>& g, const Layout& L, cudaStream_t st) {
+template <typename T> int fast_backward(const KArgs<T>& a, const BArgs<T>& g, const Layout& L, cudaStream_t st) {
   LAUNCH_FAST(k_fast_backward, , a, g);
 }
-template <typename T> static int fast_kkt(const KArgs<T>& a, const SArgs<T>& g, const Layout& L, cudaStream_t st) {
+template <typename T> int fast_kkt(const KArgs<T>& a, const SArgs<T>& g, const Layout& L, cudaStream_t st) {
   LAUNCH_FAST(k_fast_kkt, , a, g);
 }
+template int fast_iter<INST_T>(const KArgs<INST_T>&, const Layout&, cudaStream_t);
+template int fast_backward<INST_T>(const KArgs<INST_T>&, const BArgs<INST_T>&, const Layout&, cudaStream_t);
+template int fast_kkt<INST_T>(const KArgs<INST_T>&, const SArgs<INST_T>&, const Layout&, cudaStream_t);
+#else  // generic kernels (+ dispatch to the fast launchers, which live in their own translation unit)
+#if INST_SMEM
 #define FAST_OR(FN, ...) if (L.fast) return FN(__VA_ARGS__, L, st)
 #else
 #define FAST_OR(FN, ...)
@@ -83,5 +86,6 @@ template <typename T> int launch_prefactor(const KArgs<T>& a_in, const Layout& L
 }
 template int launch_prefactor<INST_T>(const KArgs<INST_T>&, const Layout&, cudaStream_t);
 #endif
+#endif  // INST_FAST
 
 }  // namespace b200qp
