@@ -19,7 +19,7 @@ MAX_ITER_CAP = 64
 
 EXPORTS = (
     "b200qp_workspace_bytes", "b200qp_prefactor", "b200qp_forward", "b200qp_backward", "b200qp_kkt_solve",
-    "b200qp_solve_host", "b200qp_last_cuda_error", "b200qp_version", "b200qp_profile_enable",
+    "b200qp_solve_host", "b200qp_solve_host_submit", "b200qp_solve_host_wait", "b200qp_last_cuda_error", "b200qp_version", "b200qp_profile_enable",
     "b200qp_profile_read",
     "b200mpc_env_dims", "b200mpc_factor_elems", "b200mpc_scratch_bytes", "b200mpc_al_solve", "b200mpc_al_backward",
     "b200dyn_step", "b200dyn_jac", "b200dyn_rollout",
@@ -84,6 +84,10 @@ def lib():
     L.b200qp_kkt_solve.argtypes = [pp, ctypes.c_int] + [vp] * 14
     L.b200qp_solve_host.restype = ctypes.c_int
     L.b200qp_solve_host.argtypes = [pp] + [vp] * 18
+    L.b200qp_solve_host_submit.restype = ctypes.c_int
+    L.b200qp_solve_host_submit.argtypes = [ctypes.c_int, pp] + [vp] * 18
+    L.b200qp_solve_host_wait.restype = ctypes.c_int
+    L.b200qp_solve_host_wait.argtypes = [ctypes.c_int]
     L.b200qp_profile_enable.restype = None
     L.b200qp_profile_enable.argtypes = [ctypes.c_int]
     L.b200qp_profile_read.restype = ctypes.c_int

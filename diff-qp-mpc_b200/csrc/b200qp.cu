@@ -207,35 +207,43 @@ static int prefactor_range_t(const b200qp_problem_t* pr, const Layout& L, const 
 }
 
 // ---------------------------------------------------------------------------- host-buffer path
+// Two device arenas so that consecutive host-buffer solves overlap: the inputs of solve k+1 cross
+// the PCIe bus (stream g_cin) and the gradients of solve k go back (stream g_cout) while the kernels
+// of either run (stream g_st).  b200qp_solve_host uses slot 0 synchronously.
 struct Arena {
   char* base = nullptr;
   size_t cap = 0;
-  cudaStream_t stream = nullptr;   // compute
-  cudaStream_t copy = nullptr;     // H2D / D2H
   static constexpr int kMaxChunks = 8;
-  cudaEvent_t ev_in[kMaxChunks], ev_out[kMaxChunks], ev_misc[2];
+  cudaEvent_t ev_in[kMaxChunks], ev_out[kMaxChunks], ev_misc[2], ev_done;
   bool events = false;
-  std::mutex mu;
+  bool busy = false;
 };
-static Arena g_arena;
+static Arena g_arenas[2];
+static cudaStream_t g_st = nullptr, g_cin = nullptr, g_cout = nullptr;
+static std::mutex g_host_mu;
 
-static int arena_reserve(size_t bytes) {
-  if (!g_arena.stream) CK(cudaStreamCreateWithFlags(&g_arena.stream, cudaStreamNonBlocking));
-  if (!g_arena.copy) CK(cudaStreamCreateWithFlags(&g_arena.copy, cudaStreamNonBlocking));
-  if (!g_arena.events) {
+static int arena_reserve(Arena& A, size_t bytes) {
+  if (!g_st) CK(cudaStreamCreateWithFlags(&g_st, cudaStreamNonBlocking));
+  if (!g_cin) CK(cudaStreamCreateWithFlags(&g_cin, cudaStreamNonBlocking));
+  if (!g_cout) CK(cudaStreamCreateWithFlags(&g_cout, cudaStreamNonBlocking));
+  if (!A.events) {
     for (int i = 0; i < Arena::kMaxChunks; i++) {
-      CK(cudaEventCreateWithFlags(&g_arena.ev_in[i], cudaEventDisableTiming));
-      CK(cudaEventCreateWithFlags(&g_arena.ev_out[i], cudaEventDisableTiming));
+      CK(cudaEventCreateWithFlags(&A.ev_in[i], cudaEventDisableTiming));
+      CK(cudaEventCreateWithFlags(&A.ev_out[i], cudaEventDisableTiming));
     }
-    for (int i = 0; i < 2; i++) CK(cudaEventCreateWithFlags(&g_arena.ev_misc[i], cudaEventDisableTiming));
-    g_arena.events = true;
+    for (int i = 0; i < 2; i++) CK(cudaEventCreateWithFlags(&A.ev_misc[i], cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&A.ev_done, cudaEventDisableTiming));
+    A.events = true;
   }
-  if (bytes <= g_arena.cap) return B200QP_OK;
-  if (g_arena.base) CK(cudaFree(g_arena.base));
-  g_arena.base = nullptr;
-  g_arena.cap = 0;
-  CK(cudaMalloc(&g_arena.base, bytes));
-  g_arena.cap = bytes;
+  if (bytes <= A.cap) return B200QP_OK;
+  if (A.base) {
+    CK(cudaDeviceSynchronize());  // the other slot may still be running: keep it simple and safe
+    CK(cudaFree(A.base));
+  }
+  A.base = nullptr;
+  A.cap = 0;
+  CK(cudaMalloc(&A.base, bytes));
+  A.cap = bytes;
   return B200QP_OK;
 }
 
@@ -305,9 +313,20 @@ int b200qp_kkt_solve(const b200qp_problem_t* prob, int prefactor, const void* Q,
   return kkt_solve_t<float>(prob, L, prefactor, Q, G, A, d, rx, rs, rz, ry, dx, ds, dz, dy, workspace, st);
 }
 
-int b200qp_solve_host(const b200qp_problem_t* prob, const void* Q, const void* p, const void* G, const void* h,
-                      const void* A, const void* b, const void* dl_dzhat, void* zhat, void* lams, void* nus,
-                      void* slacks, void* dQ, void* dp, void* dG, void* dh, void* dA, void* db, double* status) {
+int b200qp_solve_host_wait(int slot) {
+  if (slot < 0 || slot > 1) return B200QP_EINVAL;
+  Arena& AR = g_arenas[slot];
+  if (!AR.busy) return B200QP_OK;
+  CK(cudaEventSynchronize(AR.ev_done));
+  AR.busy = false;
+  return B200QP_OK;
+}
+
+int b200qp_solve_host_submit(int slot, const b200qp_problem_t* prob, const void* Q, const void* p, const void* G,
+                             const void* h, const void* A, const void* b, const void* dl_dzhat, void* zhat, void* lams,
+                             void* nus, void* slacks, void* dQ, void* dp, void* dG, void* dh, void* dA, void* db,
+                             double* status) {
+  if (slot < 0 || slot > 1) return B200QP_EINVAL;
   Layout L;
   int rc = make_layout(prob, L);
   if (rc) return rc;
@@ -316,7 +335,12 @@ int b200qp_solve_host(const b200qp_problem_t* prob, const void* Q, const void* p
   if (pe > 0 && (!A || !b || !nus)) return B200QP_EINVAL;
   const bool bwd = dl_dzhat != nullptr;
   if (bwd && (!dQ || !dp || !dG || !dh || (pe > 0 && (!dA || !db)))) return B200QP_EINVAL;
-  std::lock_guard<std::mutex> lock(g_arena.mu);
+  std::lock_guard<std::mutex> lock(g_host_mu);
+  Arena& AR = g_arenas[slot];
+  if (AR.busy) {  // the previous job of this slot still owns the arena (and the caller's output buffers)
+    int rcw = b200qp_solve_host_wait(slot);
+    if (rcw) return rcw;
+  }
   auto cnt = [&](int64_t stride, size_t per) { return (stride == 0 ? 1 : nb) * per; };
   const size_t bQ = cnt(prob->sQ, n * n) * es, bp = cnt(prob->sp, n) * es, bG = cnt(prob->sG, m * n) * es,
                bh = cnt(prob->sh, m) * es, bA = cnt(prob->sA, pe * n) * es, bb = cnt(prob->sb, pe) * es;
@@ -329,10 +353,10 @@ int b200qp_solve_host(const b200qp_problem_t* prob, const void* Q, const void* p
                odG = put(bwd ? nb * m * n * es : 0), odh = put(bwd ? bl : 0), odA = put(bwd ? nb * pe * n * es : 0),
                odb = put(bwd ? bn : 0);
   const size_t ows = put(L.total);
-  rc = arena_reserve(off);
+  rc = arena_reserve(AR, off);
   if (rc) return rc;
-  char* d = g_arena.base;
-  cudaStream_t st = g_arena.stream, cs = g_arena.copy;
+  char* d = AR.base;
+  cudaStream_t st = g_st, cs = g_cin, co = g_cout;
   // Pipeline: the batch is cut into chunks; the pre-factorisation of chunk c runs while chunk
   // c+1 is still on the PCIe bus, and the gradients of chunk c go back to the host while the
   // backward kernel works on chunk c+1.  The PDIPM loop itself needs the whole batch (its
@@ -361,8 +385,8 @@ int b200qp_solve_host(const b200qp_problem_t* prob, const void* Q, const void* p
     CK(slice_h2d(oQ, Q, prob->sQ, n * n, lo, cnt));
     CK(slice_h2d(oG, G, prob->sG, m * n, lo, cnt));
     if (pe > 0) CK(slice_h2d(oA, A, prob->sA, pe * n, lo, cnt));
-    CK(cudaEventRecord(g_arena.ev_in[c], cs));
-    CK(cudaStreamWaitEvent(st, g_arena.ev_in[c], 0));
+    CK(cudaEventRecord(AR.ev_in[c], cs));
+    CK(cudaStreamWaitEvent(st, AR.ev_in[c], 0));
     rc = prob->dtype == B200QP_F64
              ? prefactor_range_t<double>(prob, L, d + oQ, d + oG, pe ? d + oA : nullptr, d + ows, lo, cnt, st)
              : prefactor_range_t<float>(prob, L, d + oQ, d + oG, pe ? d + oA : nullptr, d + ows, lo, cnt, st);
@@ -373,8 +397,8 @@ int b200qp_solve_host(const b200qp_problem_t* prob, const void* Q, const void* p
   CK(slice_h2d(oh, h, prob->sh, m, 0, (int)nb));
   if (pe > 0) CK(slice_h2d(ob, b, prob->sb, pe, 0, (int)nb));
   if (bwd) CK(cudaMemcpyAsync(d + ogz, dl_dzhat, bz, cudaMemcpyHostToDevice, cs));
-  CK(cudaEventRecord(g_arena.ev_misc[0], cs));
-  CK(cudaStreamWaitEvent(st, g_arena.ev_misc[0], 0));
+  CK(cudaEventRecord(AR.ev_misc[0], cs));
+  CK(cudaStreamWaitEvent(st, AR.ev_misc[0], 0));
   void* dA_ = pe ? (void*)(d + oA) : nullptr;
   void* db_ = pe ? (void*)(d + ob) : nullptr;
   rc = prob->dtype == B200QP_F64
@@ -383,18 +407,18 @@ int b200qp_solve_host(const b200qp_problem_t* prob, const void* Q, const void* p
            : forward_t<float>(prob, L, d + oQ, d + op, d + oG, d + oh, dA_, db_, d + oz, d + ol, d + on, d + os, d + ows,
                               (double*)(d + ost), st, true);
   if (rc) return rc;
-  CK(cudaEventRecord(g_arena.ev_misc[1], st));
-  CK(cudaStreamWaitEvent(cs, g_arena.ev_misc[1], 0));
-  CK(cudaMemcpyAsync(zhat, d + oz, bz, cudaMemcpyDeviceToHost, cs));
-  CK(cudaMemcpyAsync(lams, d + ol, bl, cudaMemcpyDeviceToHost, cs));
-  CK(cudaMemcpyAsync(slacks, d + os, bl, cudaMemcpyDeviceToHost, cs));
-  if (pe > 0) CK(cudaMemcpyAsync(nus, d + on, bn, cudaMemcpyDeviceToHost, cs));
-  CK(cudaMemcpyAsync(status, d + ost, 8 * sizeof(double), cudaMemcpyDeviceToHost, cs));
+  CK(cudaEventRecord(AR.ev_misc[1], st));
+  CK(cudaStreamWaitEvent(co, AR.ev_misc[1], 0));
+  CK(cudaMemcpyAsync(zhat, d + oz, bz, cudaMemcpyDeviceToHost, co));
+  CK(cudaMemcpyAsync(lams, d + ol, bl, cudaMemcpyDeviceToHost, co));
+  CK(cudaMemcpyAsync(slacks, d + os, bl, cudaMemcpyDeviceToHost, co));
+  if (pe > 0) CK(cudaMemcpyAsync(nus, d + on, bn, cudaMemcpyDeviceToHost, co));
+  CK(cudaMemcpyAsync(status, d + ost, 8 * sizeof(double), cudaMemcpyDeviceToHost, co));
   if (bwd) {
     auto slice_d2h = [&](void* dst, size_t off, size_t per, int lo, int cnt) -> cudaError_t {
       if (per == 0) return cudaSuccess;
       return cudaMemcpyAsync((char*)dst + (size_t)lo * per * es, d + off + (size_t)lo * per * es, (size_t)cnt * per * es,
-                             cudaMemcpyDeviceToHost, cs);
+                             cudaMemcpyDeviceToHost, co);
     };
     for (int c = 0; c < nch; c++) {
       const int lo = lo_of(c), cnt = lo_of(c + 1) - lo;
@@ -404,8 +428,8 @@ int b200qp_solve_host(const b200qp_problem_t* prob, const void* Q, const void* p
                : backward_t<float>(prob, L, d + oz, d + ol, d + on, d + os, d + ogz, d + odQ, d + odp, d + odG, d + odh,
                                    d + odA, d + odb, d + ows, st, lo, cnt);
       if (rc) return rc;
-      CK(cudaEventRecord(g_arena.ev_out[c], st));
-      CK(cudaStreamWaitEvent(cs, g_arena.ev_out[c], 0));
+      CK(cudaEventRecord(AR.ev_out[c], st));
+      CK(cudaStreamWaitEvent(co, AR.ev_out[c], 0));
       CK(slice_d2h(dQ, odQ, n * n, lo, cnt));
       CK(slice_d2h(dp, odp, n, lo, cnt));
       CK(slice_d2h(dG, odG, m * n, lo, cnt));
@@ -413,9 +437,18 @@ int b200qp_solve_host(const b200qp_problem_t* prob, const void* Q, const void* p
       if (pe > 0) { CK(slice_d2h(dA, odA, pe * n, lo, cnt)); CK(slice_d2h(db, odb, pe, lo, cnt)); }
     }
   }
-  CK(cudaStreamSynchronize(cs));
-  CK(cudaStreamSynchronize(st));
+  CK(cudaEventRecord(AR.ev_done, co));
+  AR.busy = true;
   return B200QP_OK;
+}
+
+int b200qp_solve_host(const b200qp_problem_t* prob, const void* Q, const void* p, const void* G, const void* h,
+                      const void* A, const void* b, const void* dl_dzhat, void* zhat, void* lams, void* nus,
+                      void* slacks, void* dQ, void* dp, void* dG, void* dh, void* dA, void* db, double* status) {
+  int rc = b200qp_solve_host_submit(0, prob, Q, p, G, h, A, b, dl_dzhat, zhat, lams, nus, slacks, dQ, dp, dG, dh, dA, db,
+                                    status);
+  if (rc) return rc;
+  return b200qp_solve_host_wait(0);
 }
 
 void b200qp_profile_enable(int on) { g_prof.on = on != 0; g_prof.n = 0; }

@@ -108,6 +108,21 @@ int b200qp_solve_host(const b200qp_problem_t* prob,
                       void* dQ, void* dp, void* dG, void* dh, void* dA, void* db,
                       double* status);
 
+/* Pipelined form of b200qp_solve_host for back-to-back batches (serving): two slots, each with its
+ * own device arena.  submit(slot, ...) enqueues H2D copies, the solve and the D2H copies and
+ * returns; wait(slot) blocks until that job's results are in the caller's host buffers.  Inputs
+ * of job k+1 travel while job k computes and job k's gradients travel back while job k+1
+ * computes (three streams, PCIe full duplex).  A slot's host buffers must stay untouched between
+ * submit and wait; submitting to a busy slot waits for it first.  Host buffers should be pinned
+ * (pageable memory makes the copies synchronous). */
+int b200qp_solve_host_submit(int slot, const b200qp_problem_t* prob,
+                             const void* Q, const void* p, const void* G, const void* h,
+                             const void* A, const void* b, const void* dl_dzhat,
+                             void* zhat, void* lams, void* nus, void* slacks,
+                             void* dQ, void* dp, void* dG, void* dh, void* dA, void* db,
+                             double* status);
+int b200qp_solve_host_wait(int slot);
+
 /* Launch profiling for bench.py's roofline leg (no reference counterpart): when enabled, every
  * kernel launch of forward/backward is bracketed by CUDA events on the caller's stream.
  * b200qp_profile_read synchronises on the last event and returns the number of launches n,

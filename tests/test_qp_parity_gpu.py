@@ -168,3 +168,43 @@ def test_host_buffer_entry_point_matches_device_path(nb, cuda_device):
     assert int(st[0]) == info["n_iter"]
     for k in ("zhat", "lams", "slacks", "dQ", "dp", "dG", "dh"):
         assert torch.equal(host[k], out[k]), k
+
+
+def test_pipelined_host_entry_points(cuda_device):
+    """b200qp_solve_host_submit / _wait: two jobs in flight in the two slots return what the
+    synchronous call returns (different inputs per slot, pinned buffers)."""
+    import ctypes
+    from b200qp import _lib
+    from oracle import qp_oracle as O
+    nb, nz, m = 4100, 10, 14
+    L = _lib.lib()
+    prob = _lib.Problem(nb, nz, m, 0, _lib.F64, 20, 3, 0, 1e-12, nz * nz, nz, m * nz, m, 0, 0)
+    P = lambda t: ctypes.c_void_p(t.data_ptr())
+    N0 = ctypes.c_void_p(0)
+    jobs = []
+    for seed in (5, 6):
+        Q, p, G, h, A, b = O.random_qp(nb, nz, m, 0, seed=seed)
+        inp = {k: v.pin_memory() for k, v in dict(Q=Q, p=p, G=G, h=h).items()}
+        out = {k: torch.empty(s, dtype=torch.float64).pin_memory() for k, s in dict(
+            zhat=(nb, nz), lams=(nb, m), slacks=(nb, m), dQ=(nb, nz, nz), dp=(nb, nz), dG=(nb, m, nz), dh=(nb, m)).items()}
+        jobs.append((inp, out, torch.zeros(8, dtype=torch.float64).pin_memory()))
+    gz = torch.ones(nb, nz, dtype=torch.float64).pin_memory()
+
+    def call(fn, *pre):
+        def run(inp, out, st):
+            return fn(*pre, ctypes.byref(prob), P(inp["Q"]), P(inp["p"]), P(inp["G"]), P(inp["h"]), N0, N0, P(gz), P(out["zhat"]),
+                      P(out["lams"]), N0, P(out["slacks"]), P(out["dQ"]), P(out["dp"]), P(out["dG"]), P(out["dh"]), N0, N0, P(st))
+        return run
+
+    for slot, job in enumerate(jobs):
+        assert call(L.b200qp_solve_host_submit, slot)(*job) == 0
+    assert L.b200qp_solve_host_wait(0) == 0 and L.b200qp_solve_host_wait(1) == 0
+    got = [{k: v.clone() for k, v in job[1].items()} for job in jobs]
+    iters = [int(job[2][0]) for job in jobs]
+    for i, job in enumerate(jobs):
+        for v in job[1].values():
+            v.zero_()
+        assert call(L.b200qp_solve_host)(*job) == 0
+        assert int(job[2][0]) == iters[i]
+        for k in got[i]:
+            assert torch.equal(got[i][k], job[1][k]), (i, k)
