@@ -625,33 +625,85 @@ __global__ void __launch_bounds__(NT) k_prefactor(const KArgs<T> a) {
     }
     __syncthreads();
   }
-  for (int e = tid; e < pm * n; e += NT) {
-    const int r = e / n, c = e - r * n;
-    const T* brow = Bs ? Bs + (size_t)r * ldn : (r < p ? Ag + (size_t)r * n : Gg + (size_t)(r - p) * n);
-    T a0 = 0, a1 = 0;
-    int k = 0;
-    for (; k + 1 < n; k += 2) { a0 += brow[k] * Qs[(size_t)k * ldn + c]; a1 += brow[k + 1] * Qs[(size_t)(k + 1) * ldn + c]; }
-    if (k < n) a0 += brow[k] * Qs[(size_t)k * ldn + c];
-    const T v = a0 + a1;
-    BQi[(size_t)r * ldn + c] = v;
-    if (Bs) BQs[(size_t)r * ldn + c] = v;
+  bool done = false;
+  if constexpr (sizeof(T) == 8) {
+    // fp64, no equalities, fragment-order R: both products on the FP64 tensor cores (m8n8k4), the
+    // Schur block leaves the accumulators straight into R's fragment order (one 16-byte store per
+    // lane per tile instead of an index computation per element).
+    if (Bs != nullptr && p == 0 && a.rtile_nt < 0) {
+      const int fr = lane >> 2, kc = lane & 3, fc = kc * 2, nw = NT >> 5;
+      const int MT = (m + 7) >> 3, NTn = (n + 7) >> 3;
+      const double* Bd = reinterpret_cast<const double*>(Bs);
+      const double* Qd = reinterpret_cast<const double*>(Qs);
+      double* BQd = reinterpret_cast<double*>(BQs);
+      double* BQg = reinterpret_cast<double*>(BQi);
+      double* Rd = reinterpret_cast<double*>(R);
+      for (int t = warp; t < MT * NTn; t += nw) {
+        const int I = t / NTn, J = t - I * NTn;
+        const int row = 8 * I + fr, colb = 8 * J + fr;
+        double c0 = 0.0, c1 = 0.0;
+        for (int k0 = 0; k0 < n; k0 += 4) {
+          const int k = k0 + kc;
+          const double av = (row < m && k < n) ? Bd[(size_t)row * ldn + k] : 0.0;
+          const double bv = (k < n && colb < n) ? Qd[(size_t)k * ldn + colb] : 0.0;
+          asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+                       : "+d"(c0), "+d"(c1) : "d"(av), "d"(bv));
+        }
+        const int col = 8 * J + fc;
+        if (row < m) {
+          if (col < n) { BQd[(size_t)row * ldn + col] = c0; BQg[(size_t)row * ldn + col] = c0; }
+          if (col + 1 < n) { BQd[(size_t)row * ldn + col + 1] = c1; BQg[(size_t)row * ldn + col + 1] = c1; }
+        }
+      }
+      __syncthreads();
+      const int ntl = MT * (MT + 1) / 2;
+      for (int t = warp; t < ntl; t += nw) {
+        int I = (int)((sqrtf(8.0f * (float)t + 1.0f) - 1.0f) * 0.5f);
+        if ((I + 1) * (I + 2) / 2 <= t) I++;
+        const int K = t - I * (I + 1) / 2;
+        const int row = 8 * I + fr, rowk = 8 * K + fr;
+        double c0 = 0.0, c1 = 0.0;
+        for (int k0 = 0; k0 < n; k0 += 4) {
+          const int k = k0 + kc;
+          const double av = (row < m && k < n) ? BQd[(size_t)row * ldn + k] : 0.0;
+          const double bv = (rowk < m && k < n) ? Bd[(size_t)rowk * ldn + k] : 0.0;
+          asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+                       : "+d"(c0), "+d"(c1) : "d"(av), "d"(bv));
+        }
+        *reinterpret_cast<double2*>(Rd + (size_t)t * 64 + lane * 2) = make_double2(c0, c1);
+      }
+      done = true;
+    }
   }
-  __syncthreads();
-  // M = BQi [A;G]^T  ->  Saa (UA, lower), Sag (V), Sgg (R, lower incl. diagonal)
-  for (int e = tid; e < pm * pm; e += NT) {
-    const int r = e / pm, q = e - r * pm;
-    const bool need = (r < p && q < p && q <= r) || (r < p && q >= p) || (r >= p && q >= p && q <= r);
-    if (!need) continue;
-    const T* brow = Bs ? Bs + (size_t)q * ldn : (q < p ? Ag + (size_t)q * n : Gg + (size_t)(q - p) * n);
-    const T* qrow = BQs + (size_t)r * ldn;
-    T a0 = 0, a1 = 0;
-    int k = 0;
-    for (; k + 1 < n; k += 2) { a0 += qrow[k] * brow[k]; a1 += qrow[k + 1] * brow[k + 1]; }
-    if (k < n) a0 += qrow[k] * brow[k];
-    const T v = a0 + a1;
-    if (r < p && q < p) UA[(size_t)r * ldp + q] = v;
-    else if (r < p) V[(size_t)r * ldm + (q - p)] = v;
-    else R[a.rtile_mpad ? (size_t)rtile_index(r - p, q - p, a.rtile_mpad, a.rtile_nt) : (size_t)(r - p) * ldm + (q - p)] = v;
+  if (!done) {
+    for (int e = tid; e < pm * n; e += NT) {
+      const int r = e / n, c = e - r * n;
+      const T* brow = Bs ? Bs + (size_t)r * ldn : (r < p ? Ag + (size_t)r * n : Gg + (size_t)(r - p) * n);
+      T a0 = 0, a1 = 0;
+      int k = 0;
+      for (; k + 1 < n; k += 2) { a0 += brow[k] * Qs[(size_t)k * ldn + c]; a1 += brow[k + 1] * Qs[(size_t)(k + 1) * ldn + c]; }
+      if (k < n) a0 += brow[k] * Qs[(size_t)k * ldn + c];
+      const T v = a0 + a1;
+      BQi[(size_t)r * ldn + c] = v;
+      if (Bs) BQs[(size_t)r * ldn + c] = v;
+    }
+    __syncthreads();
+    // M = BQi [A;G]^T  ->  Saa (UA, lower), Sag (V), Sgg (R, lower incl. diagonal)
+    for (int e = tid; e < pm * pm; e += NT) {
+      const int r = e / pm, q = e - r * pm;
+      const bool need = (r < p && q < p && q <= r) || (r < p && q >= p) || (r >= p && q >= p && q <= r);
+      if (!need) continue;
+      const T* brow = Bs ? Bs + (size_t)q * ldn : (q < p ? Ag + (size_t)q * n : Gg + (size_t)(q - p) * n);
+      const T* qrow = BQs + (size_t)r * ldn;
+      T a0 = 0, a1 = 0;
+      int k = 0;
+      for (; k + 1 < n; k += 2) { a0 += qrow[k] * brow[k]; a1 += qrow[k + 1] * brow[k + 1]; }
+      if (k < n) a0 += qrow[k] * brow[k];
+      const T v = a0 + a1;
+      if (r < p && q < p) UA[(size_t)r * ldp + q] = v;
+      else if (r < p) V[(size_t)r * ldm + (q - p)] = v;
+      else R[a.rtile_mpad ? (size_t)rtile_index(r - p, q - p, a.rtile_mpad, a.rtile_nt) : (size_t)(r - p) * ldm + (q - p)] = v;
+    }
   }
   __syncthreads();
   if (p > 0) {
