@@ -582,27 +582,30 @@ __global__ void __launch_bounds__(NT) k_prefactor(const KArgs<T> a) {
   __syncthreads();
   const bool okQ = ldlt_factor(Fs, ldn, n, pinvFs, tid, NT);
   if (!okQ && tid == 0) atomicAdd(&a.ctl->q_fail, 1u);
-  // L^-1: column j of L eliminates below row j; only columns c <= j of the identity are non-zero
-  for (int j = 0; j + 1 < n; j++) {
-    const int rows = n - 1 - j, cols = j + 1;
-    for (int e = tid; e < rows * cols; e += NT) {
-      const int i = j + 1 + e / cols, c = e % cols;
-      Qs[(size_t)i * ldn + c] -= Fs[(size_t)j * ldn + i] * Qs[(size_t)j * ldn + c];
+  // L^-1: column j of L eliminates below row j; only columns c <= j of the identity are non-zero.
+  // Lane = column, warp w takes rows j+1+w, j+1+w+nw, ...: no index divisions, conflict-free.
+  {
+    const int nw = NT >> 5;
+    for (int j = 0; j + 1 < n; j++) {
+      for (int c = lane; c <= j; c += 32) {
+        const T qjc = Qs[(size_t)j * ldn + c];
+        for (int i = j + 1 + warp; i < n; i += nw) Qs[(size_t)i * ldn + c] -= Fs[(size_t)j * ldn + i] * qjc;
+      }
+      __syncthreads();
+    }
+    for (int k = warp; k < n; k += nw) {
+      const T pk = pinvFs[k];
+      for (int c = lane; c <= k; c += 32) Qs[(size_t)k * ldn + c] *= pk;
     }
     __syncthreads();
-  }
-  for (int e = tid; e < n * n; e += NT) {
-    const int k = e / n, c = e - k * n;
-    if (c <= k) Qs[(size_t)k * ldn + c] *= pinvFs[k];
-  }
-  __syncthreads();
-  // L^-T: row j eliminates above
-  for (int j = n - 1; j > 0; j--) {
-    for (int e = tid; e < j * n; e += NT) {
-      const int i = e / n, c = e - i * n;
-      Qs[(size_t)i * ldn + c] -= Fs[(size_t)i * ldn + j] * Qs[(size_t)j * ldn + c];
+    // L^-T: row j eliminates above
+    for (int j = n - 1; j > 0; j--) {
+      for (int c = lane; c < n; c += 32) {
+        const T qjc = Qs[(size_t)j * ldn + c];
+        for (int i = warp; i < j; i += nw) Qs[(size_t)i * ldn + c] -= Fs[(size_t)i * ldn + j] * qjc;
+      }
+      __syncthreads();
     }
-    __syncthreads();
   }
   if (a.pre_smem) {
     for (int e = tid; e < n * n; e += NT) {
