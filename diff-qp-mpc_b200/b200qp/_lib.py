@@ -16,6 +16,7 @@ F64, F32 = 0, 1
 STATUS_DOUBLES = 8
 ST_NITER, ST_BEST_MAX, ST_Q_FAIL, ST_AQA_FAIL, ST_LAUNCHES = 0, 1, 2, 3, 4
 MAX_ITER_CAP = 64
+FLAG_DENSE = 1
 
 EXPORTS = (
     "b200qp_workspace_bytes", "b200qp_prefactor", "b200qp_forward", "b200qp_backward", "b200qp_kkt_solve",
@@ -52,9 +53,9 @@ class Problem(ctypes.Structure):
     _fields_ = [
         ("nb", ctypes.c_int32), ("nz", ctypes.c_int32), ("nineq", ctypes.c_int32), ("neq", ctypes.c_int32),
         ("dtype", ctypes.c_int32), ("max_iter", ctypes.c_int32), ("not_improved_lim", ctypes.c_int32),
-        ("reserved", ctypes.c_int32), ("eps", ctypes.c_double),
+        ("flags", ctypes.c_int32), ("eps", ctypes.c_double),
         ("sQ", ctypes.c_int64), ("sp", ctypes.c_int64), ("sG", ctypes.c_int64), ("sh", ctypes.c_int64),
-        ("sA", ctypes.c_int64), ("sb", ctypes.c_int64),
+        ("sA", ctypes.c_int64), ("sb", ctypes.c_int64), ("kkt_reg", ctypes.c_double),
     ]
 
 

@@ -77,7 +77,7 @@ def _prep(X, nBatch, nDim, ref):
 class _Plan:
     """Sizes + the C problem descriptor + workspace for one call."""
 
-    def __init__(self, Q_, p_, G_, h_, A_, b_, eps, notImprovedLim, maxIter):
+    def __init__(self, Q_, p_, G_, h_, A_, b_, eps, notImprovedLim, maxIter, flags=0, kkt_reg=0.0):
         if not Q_.is_cuda:
             raise RuntimeError("b200qp.QPFunction runs on CUDA tensors only (no CPU fallback); got " + str(Q_.device))
         nBatch = extract_nBatch(Q_, p_, G_, h_, A_, b_)
@@ -102,8 +102,8 @@ class _Plan:
             self.A, sA, self.A_e, self.b, sb, self.b_e = None, 0, False, None, 0, False
         if maxIter > _lib.MAX_ITER_CAP:
             raise RuntimeError(f"b200qp: maxIter > {_lib.MAX_ITER_CAP} is not supported")
-        self.prob = _lib.Problem(nBatch, nz, nineq, neq, _dtype_code(Q_), int(maxIter), int(notImprovedLim), 0,
-                                 float(eps), sQ, sp, sG, sh, sA, sb)
+        self.prob = _lib.Problem(nBatch, nz, nineq, neq, _dtype_code(Q_), int(maxIter), int(notImprovedLim), int(flags),
+                                 float(eps), sQ, sp, sG, sh, sA, sb, float(kkt_reg))
         L = _lib.lib()
         nbytes = L.b200qp_workspace_bytes(ctypes.byref(self.prob))
         if nbytes == 0:
@@ -197,6 +197,88 @@ def QPFunction(eps=1e-12, verbose=0, notImprovedLim=3,
 
     apply.info = info
     apply.Function = QPFunctionFn
+    return apply
+
+
+DENSE_KKT_EPS = 1e-7  # qpth/solvers/pdipm/batch_LU.py:40
+
+
+def DenseQPFunction(bsz=1, eps=1e-12, verbose=0, notImprovedLim=3, maxIter=20):
+    """Drop-in for the reference's full-KKT variant (qpth/qp.py:187-271 + qpth/solvers/pdipm/batch_LU.py):
+
+        DenseQPFunction(...)(Q, p, G, h, A, b, dyn_res[, cost_grad]) -> zhat
+
+    Same iteration as the reference -- every KKT solve is a solve with K + 1e-7 diag(+I,+I,-I,-I)
+    followed by one refinement step against K, unscaled complementarity residual, the dv == 0 rule
+    of its get_step, backward with the best iterate's K without clamping -- but the 2 x LU of the
+    (nz + 2 nineq + neq)^2 matrix per solve is replaced by the same Schur-complement kernels as
+    QPFunction (b200qp_forward with B200QP_FLAG_DENSE), which solve the identical regularised system.
+    All six parameters are batched (as in the reference).  `dyn_res` / `cost_grad` must be the
+    canonical Ax - b / Qx + p (checked on a probe point)."""
+    info = {}
+
+    class Solver(Function):
+        @staticmethod
+        def forward(ctx, Q, p, G, h, A, b, dyn_res=None, cost_grad=None):
+            if Q.dim() != 3 or G.dim() != 3 or A.dim() != 3:
+                raise RuntimeError("b200qp.DenseQPFunction: batched (3-D) Q, G, A are required, as in the reference")
+            plan = _Plan(Q, p, G, h, A, b, eps, notImprovedLim, maxIter, flags=_lib.FLAG_DENSE, kkt_reg=DENSE_KKT_EPS)
+            _check_callbacks(plan, dyn_res, cost_grad)
+            L = _lib.lib()
+            nb, nz, nineq, neq = plan.nBatch, plan.nz, plan.nineq, plan.neq
+            opt = dict(dtype=Q.dtype, device=Q.device)
+            zhats, lams, slacks = torch.empty(nb, nz, **opt), torch.empty(nb, nineq, **opt), torch.empty(nb, nineq, **opt)
+            nus = torch.empty(nb, neq, **opt)
+            status = torch.empty(_lib.STATUS_DOUBLES, dtype=torch.float64, device=Q.device)
+            with torch.cuda.device(Q.device):
+                rc = L.b200qp_forward(ctypes.byref(plan.prob), _ptr(plan.Q), _ptr(plan.p), _ptr(plan.G), _ptr(plan.h),
+                                      _ptr(plan.A), _ptr(plan.b), _ptr(zhats), _ptr(lams), _ptr(nus), _ptr(slacks),
+                                      _ptr(plan.workspace), _ptr(status), _stream(Q.device))
+            if rc == -3:
+                raise NotImplementedError("b200qp.DenseQPFunction: this problem size is outside the fused kernels "
+                                          "(nineq <= 128 and nz, neq + nineq <= 128)")
+            _lib.check(rc, "b200qp_forward (dense)")
+            st = status.tolist()
+            info.update(n_iter=int(st[_lib.ST_NITER]), best_resid_max=st[_lib.ST_BEST_MAX])
+            if st[_lib.ST_Q_FAIL] > 0 or st[_lib.ST_AQA_FAIL] > 0:
+                raise RuntimeError("b200qp.DenseQPFunction: the regularised KKT matrix is singular (Q must be PSD "
+                                   "and A full rank)")
+            ctx.plan = plan
+            ctx.nus, ctx.lams, ctx.slacks = nus, lams, slacks
+            ctx.save_for_backward(zhats)
+            return zhats
+
+        @staticmethod
+        def backward(ctx, dl_dzhat):
+            zhats, = ctx.saved_tensors
+            plan = ctx.plan
+            L = _lib.lib()
+            nb, nz, nineq, neq = plan.nBatch, plan.nz, plan.nineq, plan.neq
+            opt = dict(dtype=zhats.dtype, device=zhats.device)
+            gz = dl_dzhat.contiguous()
+            dQ, dp = torch.empty(nb, nz, nz, **opt), torch.empty(nb, nz, **opt)
+            dG, dh = torch.empty(nb, nineq, nz, **opt), torch.empty(nb, nineq, **opt)
+            dA = torch.empty(nb, neq, nz, **opt) if neq > 0 else None
+            db = torch.empty(nb, neq, **opt) if neq > 0 else None
+            # the adjoint system uses the UNregularised K of the best iterate (qp.py:248-252): redo
+            # the d-independent pre-factorisation without the regularisation, then solve
+            pr0 = _lib.Problem.from_buffer_copy(plan.prob)
+            pr0.flags, pr0.kkt_reg = 0, 0.0
+            with torch.cuda.device(zhats.device):
+                rc = L.b200qp_prefactor(ctypes.byref(pr0), _ptr(plan.Q), _ptr(plan.G), _ptr(plan.A), _ptr(plan.workspace),
+                                        ctypes.c_void_p(0), _stream(zhats.device))
+                _lib.check(rc, "b200qp_prefactor (dense backward)")
+                rc = L.b200qp_backward(ctypes.byref(plan.prob), _ptr(zhats), _ptr(ctx.lams), _ptr(ctx.nus), _ptr(ctx.slacks),
+                                       _ptr(gz), _ptr(dQ), _ptr(dp), _ptr(dG), _ptr(dh), _ptr(dA), _ptr(db),
+                                       _ptr(plan.workspace), _stream(zhats.device))
+            _lib.check(rc, "b200qp_backward (dense)")
+            return (dQ, dp, dG, dh, dA, db, None, None)
+
+    def apply(Q, p, G, h, A, b, dyn_res=None, cost_grad=None):
+        return Solver.apply(Q, p, G, h, A, b, dyn_res, cost_grad)
+
+    apply.info = info
+    apply.Function = Solver
     return apply
 
 

@@ -54,6 +54,7 @@ static void fill_args(KArgs<T>& a, const b200qp_problem_t* pr, const Layout& L, 
   a.slots = (Slot*)(w + L.oslots);
   a.ctl = (Control*)(w + L.octl);
   a.max_iter = pr->max_iter; a.lim = pr->not_improved_lim; a.eps = pr->eps;
+  a.dense = (pr->flags & B200QP_FLAG_DENSE) ? 1 : 0; a.reg = a.dense ? pr->kkt_reg : 0.0;
   if (L.fast) fast_offsets(L.n, L.m, L.p, L.ldn, L.ldm, L.ldp, L.nt, L.mpad, L.fk, a.fso);
   a.rtile_mpad = L.fast ? L.mpad : 0; a.rtile_nt = L.fk ? -1 : (L.fast ? L.nt : 0);
 }

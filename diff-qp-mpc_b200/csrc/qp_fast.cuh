@@ -59,6 +59,7 @@ template <typename T>
 struct FS {  // shared-memory carve-up of the fast path
   T *Up, *pinvT, *BQi, *V, *UA, *pinvA;
   T *x, *s, *z, *y, *d, *rx, *rz, *ry, *t, *hv, *u, *dx, *ds, *dz, *dy, *rsc, *scr, *scrn, *part, *red, *colbuf, *small;
+  T *ax, *as, *az, *ay, *r2x, *r2s, *r2z, *r2y;  // dense mode: saved predictor solution, refinement right-hand side
 };
 
 // fk = 1: DMMA factorisation (qp_dmma.cuh): the packed factor carries one bordered column and the
@@ -71,13 +72,15 @@ __host__ __device__ inline size_t fast_smem_elems(int n, int m, int p, int ldn, 
   if (p > 0) e += round4(p * ldm) + round4(p * ldp) + round4(p);
   e += (size_t)5 * round4(n) + (size_t)8 * round4(m) + (size_t)4 * round4(pp) + round4(p + m);
   e += round4(nt) + 4 * 32 + round4(fast_colbuf_elems(mpad, fk)) + 16;
+  e += (size_t)2 * round4(n) + (size_t)4 * round4(m) + (size_t)2 * round4(pp);  // dense-mode vectors
   return e;
 }
 
 // Element offsets of the carve-up, computed ONCE on the host (KArgs::fso) so that the kernels form
 // each shared-memory pointer with one constant-bank load instead of re-deriving the whole chain
 // of rounded sizes (ncu: ~1.9 k instructions per problem-iteration went into that).
-constexpr int kFsoCount = 28;
+constexpr int kFsoCount = 36;
+static_assert(sizeof(((KArgs<double>*)nullptr)->fso) / sizeof(int) >= kFsoCount, "KArgs::fso is too small for the carve-up");
 __host__ __device__ inline void fast_offsets(int n, int m, int p, int ldn, int ldm, int ldp, int nt, int mpad, int fk,
                                              int* o) {
   int q = 0, i = 0;
@@ -95,6 +98,8 @@ __host__ __device__ inline void fast_offsets(int n, int m, int p, int ldn, int l
   take(4 * 32);                         // 25 red
   take(fast_colbuf_elems(mpad, fk));    // 26 colbuf
   take(16);                             // 27 small
+  take(n); take(m); take(m); take(pp);  // 28 ax 29 as 30 az 31 ay
+  take(n); take(m); take(m); take(pp);  // 32 r2x 33 r2s 34 r2z 35 r2y
 }
 
 template <typename T>
@@ -109,6 +114,8 @@ __device__ __forceinline__ void fast_carve(FS<T>& S, unsigned char* raw, const K
   S.rsc = q + o[17]; S.scr = q + o[18];
   S.y = q + o[19]; S.ry = q + o[20]; S.u = q + o[21]; S.dy = q + o[22];
   S.hv = q + o[23]; S.part = q + o[24]; S.red = q + o[25]; S.colbuf = q + o[26]; S.small = q + o[27];
+  S.ax = q + o[28]; S.as = q + o[29]; S.az = q + o[30]; S.ay = q + o[31];
+  S.r2x = q + o[32]; S.r2s = q + o[33]; S.r2z = q + o[34]; S.r2y = q + o[35];
 }
 
 template <typename T>
@@ -400,16 +407,61 @@ __device__ __forceinline__ void fast_kkt_solve(const FS<T>& S, const KArgs<T>& a
   fast_kkt_post<T, NT>(S, a, prob, has_rx, rs, accumulate, gdx, gds, gdz, gdy, tid);
 }
 
+// DenseQPFunction's iterative refinement (batch_LU.py:228-236): given the solution l0 =
+// (S.dx, S.ds, S.dz, S.dy) of the REGULARISED system for the right-hand side (rx, rs, rz, ry)
+// [rs in the kernels' scaled form rs_ref / s], form r2 = K l0 + (rx, rs, rz, ry) with the
+// UNREGULARISED K (s-row z ds + s dz), solve the regularised system for it and add: l = l0 + d.
+// has_rx=false: rx = rz = ry = 0.  Entry: l0 visible.  Exit: refined solution visible (barrier).
+template <typename T, int MPAD, int NT, int FK>
+__device__ __forceinline__ void dense_refine(const FS<T>& S, const KArgs<T>& a, int prob, bool has_rx, const T* rx,
+                                             const T* rs, const T* rz, const T* ry, const T* zv, const T* sv, int tid) {
+  const int n = a.n, m = a.m, p = a.p;
+  const T* Qg = a.Q + (size_t)prob * a.sQ;
+  const T* Gg = a.G + (size_t)prob * a.sG;
+  const T* Ag = a.A + (size_t)prob * a.sA;
+  gemv_rows_warp(Qg, n, n, n, S.dx, S.r2x, tid, NT);            // Q dx
+  gemv_rows_warp(Gg, n, m, n, S.dx, S.r2z, tid, NT);            // G dx
+  if (p > 0) gemv_rows_warp(Ag, n, p, n, S.dx, S.r2y, tid, NT);  // A dx
+  gemv_cols_nt<T, NT>(Gg, n, m, n, S.dz, S.t, S.part, tid);     // G^T dz  (barrier inside)
+  if (p > 0) gemv_cols_nt<T, NT>(Ag, n, p, n, S.dy, S.scrn, S.part, tid);
+  for (int c = tid; c < n; c += NT) {
+    T v = S.r2x[c] + S.t[c];
+    if (p > 0) v += S.scrn[c];
+    if (has_rx) v += rx[c];
+    S.r2x[c] = v;
+  }
+  for (int i = tid; i < m; i += NT) {
+    S.r2s[i] = rs[i] + (zv[i] / sv[i]) * S.ds[i] + S.dz[i];
+    T v = S.r2z[i] + S.ds[i];
+    if (has_rx) v += rz[i];
+    S.r2z[i] = v;
+  }
+  for (int j = tid; j < p; j += NT) {
+    T v = S.r2y[j];
+    if (has_rx) v += ry[j];
+    S.r2y[j] = v;
+  }
+  cta_sync<NT>();
+  fast_kkt_pre<T, NT>(S, a, prob, true, S.r2x, S.r2s, S.r2z, S.r2y, tid);
+  if ((tid >> 5) == 0) tri_solve_any<T, MPAD, FK>(S, m, S.hv + p, false, tid & 31);
+  cta_sync<NT>();
+  fast_kkt_post<T, NT>(S, a, prob, true, S.r2s, true, (T*)nullptr, (T*)nullptr, (T*)nullptr, (T*)nullptr, tid);
+}
+
 // get_step pieces for (z,dz) and (s,ds) at once, by ONE warp: out = {rmu_z, rmu_s, amax_z, amax_s},
 // has = bit0 (some dz > 0) | bit1 (some ds > 0).  Every lane returns the same values.
 template <typename T>
 __device__ __forceinline__ void warp_step_pieces(const T* z, const T* dz, const T* s, const T* ds, int m, int lane,
-                                                 T (&out)[4], int& has) {
+                                                 T (&out)[4], int& has, bool zero_is_one = false) {
   T rz = t_inf<T>(), rs = t_inf<T>(), az = -t_inf<T>(), as = -t_inf<T>();
   bool hz = false, hs = false;
   for (int i = lane; i < m; i += 32) {
     const T dzi = dz[i], dsi = ds[i];
-    const T a1 = -z[i] / dzi, a2 = -s[i] / dsi;
+    T a1 = -z[i] / dzi, a2 = -s[i] / dsi;
+    if (zero_is_one) {  // batch_LU.py:208: a[dv == 0] = 1.0
+      if (dzi == T(0)) a1 = T(1);
+      if (dsi == T(0)) a2 = T(1);
+    }
     if (dzi > T(0)) hz = true; else rz = nanmin(rz, a1);
     if (dsi > T(0)) hs = true; else rs = nanmin(rs, a2);
     az = nanmax(az, a1);
@@ -479,7 +531,11 @@ __global__ void __launch_bounds__(NT, (NT == 128 ? (FK == 1 ? FAST_DMMA_MIN_CTAS
   const T* bg = a.b + (size_t)prob * a.sb;
 
   if (INIT) {
-    for (int i = tid; i < m; i += NT) { S.d[i] = T(1); S.scr[i] = T(1); S.rsc[i] = T(0); S.rz[i] = -hg[i]; }
+    const T d_init = T(1) + (T)a.reg;  // (z + reg) / s at z = s = 1
+    for (int i = tid; i < m; i += NT) {
+      S.d[i] = d_init; S.scr[i] = T(1) / d_init + (T)a.reg; S.rsc[i] = T(0); S.rz[i] = -hg[i];
+      S.z[i] = T(1); S.s[i] = T(1);
+    }
     for (int c = tid; c < n; c += NT) S.rx[c] = pg[c];
     for (int j = tid; j < p; j += NT) S.ry[j] = -bg[j];
     cta_sync<NT>();
@@ -492,6 +548,7 @@ __global__ void __launch_bounds__(NT, (NT == 128 ? (FK == 1 ? FAST_DMMA_MIN_CTAS
     }
     fast_kkt_solve<T, MPAD, NT, FK>(S, a, prob, true, S.rx, S.rsc, S.rz, S.ry, false, (T*)nullptr, (T*)nullptr,
                                 (T*)nullptr, (T*)nullptr, tid);
+    if (a.dense) dense_refine<T, MPAD, NT, FK>(S, a, prob, true, S.rx, S.rsc, S.rz, S.ry, S.z, S.s, tid);
     T mn[2] = {t_inf<T>(), t_inf<T>()};
     for (int i = tid; i < m; i += NT) { mn[0] = nanmin(mn[0], S.ds[i]); mn[1] = nanmin(mn[1], S.dz[i]); }
     block_reduce<2>(mn, OpNanMin(), S.red, tid, NT);
@@ -584,9 +641,9 @@ __global__ void __launch_bounds__(NT, (NT == 128 ? (FK == 1 ? FAST_DMMA_MIN_CTAS
       S.rz[i] = v;
       acc[1] += v * v;
       acc[3] += sv * zv;
-      const T dv = zv / sv;
+      const T dv = (zv + (T)a.reg) / sv;  // reg = 0 unless DenseQPFunction
       S.d[i] = dv;
-      S.scr[i] = T(1) / dv;
+      S.scr[i] = T(1) / dv + (T)a.reg;
     }
     for (int j = tid; j < p; j += NT) {
       const T v = S.ry[j] - bg[j];
@@ -644,11 +701,30 @@ __global__ void __launch_bounds__(NT, (NT == 128 ? (FK == 1 ? FAST_DMMA_MIN_CTAS
       if (!(FK == 1 && aff)) fast_kkt_pre<T, NT>(S, a, prob, aff, S.rx, rs_, S.rz, S.ry, tid);
       if (warp == 0) tri_solve_any<T, MPAD, FK>(S, m, S.hv + p, FK == 1 && aff, lane);
       cta_sync<NT>();
-      fast_kkt_post<T, NT>(S, a, prob, aff, rs_, !aff, aff ? (T*)nullptr : gdx, aff ? (T*)nullptr : gds,
-                           aff ? (T*)nullptr : gdz, aff ? (T*)nullptr : gdy, tid);
+      if (!a.dense) {
+        fast_kkt_post<T, NT>(S, a, prob, aff, rs_, !aff, aff ? (T*)nullptr : gdx, aff ? (T*)nullptr : gds,
+                             aff ? (T*)nullptr : gdz, aff ? (T*)nullptr : gdy, tid);
+      } else {
+        // DenseQPFunction: regularised solve + one refinement step per KKT solve (batch_LU.py:212-244)
+        fast_kkt_post<T, NT>(S, a, prob, aff, rs_, false, (T*)nullptr, (T*)nullptr, (T*)nullptr, (T*)nullptr, tid);
+        dense_refine<T, MPAD, NT, FK>(S, a, prob, aff, S.rx, rs_, S.rz, S.ry, S.z, S.s, tid);
+        if (aff) {
+          for (int c = tid; c < n; c += NT) S.ax[c] = S.dx[c];
+          for (int i = tid; i < m; i += NT) { S.as[i] = S.ds[i]; S.az[i] = S.dz[i]; }
+          for (int j = tid; j < p; j += NT) S.ay[j] = S.dy[j];
+        } else {
+          for (int c = tid; c < n; c += NT) { const T v = S.dx[c] + S.ax[c]; S.dx[c] = v; gdx[c] = v; }
+          for (int i = tid; i < m; i += NT) {
+            const T vs = S.ds[i] + S.as[i], vz = S.dz[i] + S.az[i];
+            S.ds[i] = vs; S.dz[i] = vz; gds[i] = vs; gdz[i] = vz;
+          }
+          for (int j = tid; j < p; j += NT) { const T v = S.dy[j] + S.ay[j]; S.dy[j] = v; gdy[j] = v; }
+        }
+        cta_sync<NT>();
+      }
       if (warp == 0) {
         T pc[4]; int has;
-        warp_step_pieces(S.z, S.dz, S.s, S.ds, m, lane, pc, has);
+        warp_step_pieces(S.z, S.dz, S.s, S.ds, m, lane, pc, has, a.dense != 0);
         if (aff) {
           // the clamp at 1 makes alpha_aff independent of the batch-global fill
           const T stz = (has & 1) ? nanmin(pc[0], T(1)) : pc[0];
@@ -691,7 +767,8 @@ __global__ void __launch_bounds__(NT, (NT == 128 ? (FK == 1 ? FAST_DMMA_MIN_CTAS
   for (int i = tid; i < m; i += NT) {
     const T lv = lam[i], sv = sl[i];
     S.z[i] = lv;
-    const T lc = (lv < T(1e-8)) ? T(1e-8) : lv, sc = (sv < T(1e-8)) ? T(1e-8) : sv;
+    // QPFunction clamps (qp.py:146-149); DenseQPFunction solves with the best iterate's K as is
+    const T lc = (!a.dense && lv < T(1e-8)) ? T(1e-8) : lv, sc = (!a.dense && sv < T(1e-8)) ? T(1e-8) : sv;
     S.d[i] = lc / sc;
     S.scr[i] = T(1) / (lc / sc);
     S.rsc[i] = T(0);

@@ -62,6 +62,7 @@ inline int make_layout(const b200qp_problem_t* pr, Layout& L) {
     else { L.smem = true; L.smem_bytes = fb; }
   }
   if (L.smem_bytes > kSmemMax) return B200QP_ETOOBIG;
+  if ((pr->flags & B200QP_FLAG_DENSE) && !L.fast) return B200QP_ETOOBIG;  // dense mode lives in the fast kernels
   const int pp = L.p > 0 ? L.p : 1;
   L.sQi = round4(L.n * L.ldn);
   L.sBQi = round4((L.p + L.m) * L.ldn);

@@ -98,8 +98,10 @@ struct KArgs {
   int iter, max_iter, lim;
   double eps;
   int launches;
+  int dense;                 // DenseQPFunction semantics (B200QP_FLAG_DENSE)
+  double reg;                // KKT regularisation of the dense mode, else 0
   int prob0;                 // first problem of this launch (chunked pre-factorisation / backward)
-  int fso[28];               // fast path: shared-memory carve-up offsets in elements (qp_fast.cuh:fast_offsets)
+  int fso[36];               // fast path: shared-memory carve-up offsets in elements (qp_fast.cuh:fast_offsets)
   int pre_smem;              // prefactor: F / Qi working copies live in dynamic shared memory
   int rtile_mpad, rtile_nt;  // != 0: R is stored in register-tile order (qp_fast.cuh); nt = -1: DMMA fragment order
 };
@@ -576,7 +578,7 @@ __global__ void __launch_bounds__(NT) k_prefactor(const KArgs<T> a) {
   T* pinvFs = a.pre_smem ? Qs + round4(n * ldn) : pinvF;
   for (int i = tid; i < n * n; i += NT) {
     const int r = i / n, c = i - r * n;
-    Fs[(size_t)r * ldn + c] = Qg[i];
+    Fs[(size_t)r * ldn + c] = Qg[i] + ((r == c) ? (T)a.reg : T(0));
     Qs[(size_t)r * ldn + c] = (r == c) ? T(1) : T(0);
   }
   __syncthreads();
@@ -703,7 +705,7 @@ __global__ void __launch_bounds__(NT) k_prefactor(const KArgs<T> a) {
       for (; k + 1 < n; k += 2) { a0 += qrow[k] * brow[k]; a1 += qrow[k + 1] * brow[k + 1]; }
       if (k < n) a0 += qrow[k] * brow[k];
       const T v = a0 + a1;
-      if (r < p && q < p) UA[(size_t)r * ldp + q] = v;
+      if (r < p && q < p) UA[(size_t)r * ldp + q] = v + ((r == q) ? (T)a.reg : T(0));
       else if (r < p) V[(size_t)r * ldm + (q - p)] = v;
       else R[a.rtile_mpad ? (size_t)rtile_index(r - p, q - p, a.rtile_mpad, a.rtile_nt) : (size_t)(r - p) * ldm + (q - p)] = v;
     }

@@ -39,6 +39,12 @@ extern "C" {
 #define B200QP_ECUDA (-2)    /* a CUDA runtime call failed (see b200qp_last_cuda_error)   */
 #define B200QP_ETOOBIG (-3)  /* problem does not fit the kernels' shared/global workspace */
 
+/* DenseQPFunction semantics (qpth/qp.py:187-271, qpth/solvers/pdipm/batch_LU.py): every KKT solve is
+ * a solve with the matrix regularised by kkt_reg * diag(+I_x, +I_s, -I_z, -I_y) followed by one step
+ * of iterative refinement against the unregularised matrix; get_step maps dv == 0 to 1; backward uses
+ * d = lams / slacks without the 1e-8 clamp. */
+#define B200QP_FLAG_DENSE 1
+
 #define B200QP_MAX_ITER_CAP 64
 #define B200QP_STATUS_DOUBLES 8
 
@@ -56,9 +62,10 @@ typedef struct {
   int32_t dtype;                 /* B200QP_F64 | B200QP_F32                                   */
   int32_t max_iter;              /* maxIter        (qpth/qp.py:19-21 default 20)              */
   int32_t not_improved_lim;      /* notImprovedLim (default 3)                                */
-  int32_t reserved;
+  int32_t flags;                 /* B200QP_FLAG_* (0 for QPFunction)                           */
   double eps;                    /* eps            (default 1e-12)                            */
   int64_t sQ, sp, sG, sh, sA, sb; /* batch strides in elements, 0 = shared                    */
+  double kkt_reg;                /* DenseQPFunction's KKT regularisation (1e-7), else 0       */
 } b200qp_problem_t;
 
 /* Bytes of device workspace forward needs; the same buffer must be handed to backward. */

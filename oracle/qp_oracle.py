@@ -347,3 +347,134 @@ def random_qp(nb, nz, nineq, neq=0, seed=0, dtype=torch.float64, well_conditione
     A = rs.randn(nb, neq, nz)
     b = np.matmul(A, z0[:, :, None])[:, :, 0]
     return tuple(torch.tensor(a, dtype=dtype) for a in (Q, p, G, h, A, b))
+
+
+# ------------------------------------------------------------------------------------------------
+# DenseQPFunction: full-KKT LU variant (qpth/qp.py:187-271, qpth/solvers/pdipm/batch_LU.py)
+# ------------------------------------------------------------------------------------------------
+DENSE_KKT_EPS = 1e-7  # batch_LU.py:40
+
+
+def dense_kkt_matrix(Q, G, A):
+    """K of qp.py:195-215: unknowns [x (n), s (m), z (m), y (p)], the s-row is [0, diag(z), diag(s), 0]
+    (its diagonals are rewritten every iteration)."""
+    nb, m, n = G.shape
+    p = A.shape[1]
+    Z = lambda r, c: torch.zeros(nb, r, c, dtype=Q.dtype)
+    I = torch.eye(m, dtype=Q.dtype)[None].repeat(nb, 1, 1)
+    GT, AT = G.transpose(1, 2), A.transpose(1, 2)
+    K1 = torch.cat([Q, GT * 0, GT, AT], dim=-1)
+    K2 = torch.cat([G * 0, I, I, Z(m, p)], dim=-1)
+    K3 = torch.cat([G, I, Z(m, m), Z(m, p)], dim=-1)
+    K4 = torch.cat([A, Z(p, m), Z(p, m), Z(p, p)], dim=-1)
+    return torch.cat([K1, K2, K3, K4], dim=-2)
+
+
+def dense_solve_kkt(K, Ktilde, rx, rs, rz, ry, niter=1):
+    """batch_LU.py:212-244: LU of the regularised matrix + one step of iterative refinement."""
+    n, m, p = rx.size(1), rz.size(1), ry.size(1)
+    r = -torch.cat((rx, rs, rz, ry), 1)
+    K_LU = torch.linalg.lu_factor(Ktilde)
+    l = torch.linalg.lu_solve(*K_LU, r.clone().unsqueeze(-1)).squeeze(-1)
+    res = r - K.bmm(l.unsqueeze(-1)).squeeze(-1)
+    for _ in range(niter):
+        d = torch.linalg.lu_solve(*K_LU, res.clone().unsqueeze(-1)).squeeze(-1)
+        l = l + d
+        res = r - K.bmm(l.unsqueeze(-1)).squeeze(-1)
+    return l[:, :n], l[:, n:n + m], l[:, n + m:n + 2 * m], l[:, n + 2 * m:n + 2 * m + p]
+
+
+def _dense_step(v, dv):
+    """batch_LU.py:204-210 (get_step with the dv == 0 -> 1 rule)."""
+    a = -v / dv
+    a[dv == 0] = 1.0
+    a[dv > 0] = max(1.0, a.max())
+    return a.min(1)[0].squeeze()
+
+
+def dense_forward(Q, p, G, h, A, b, eps=1e-12, notImprovedLim=3, maxIter=20):
+    """DenseQPFunction forward with the canonical residual callbacks (dyn_res = Ax - b,
+    cost_grad = None): batch_LU.forward (batch_LU.py:29-201).  Returns best iterates and the best K."""
+    nb, m, n = G.shape
+    neq = A.shape[1]
+    K = dense_kkt_matrix(Q, G, A)
+    zi = torch.arange(n, n + m)
+    si_r, si_c = torch.arange(n, n + m), torch.arange(n + m, n + 2 * m)
+    K[:, si_r, si_c] = torch.ones(nb, m, dtype=Q.dtype)
+    K[:, zi, zi] = torch.ones(nb, m, dtype=Q.dtype)
+    I = torch.ones(nb, K.shape[1], dtype=Q.dtype)
+    I[:, n + m:] *= -1
+    Ktilde = K + DENSE_KKT_EPS * torch.diag_embed(I)
+    x, s, z, y = dense_solve_kkt(K, Ktilde, p, torch.zeros(nb, m, dtype=Q.dtype), -h, -b)
+    x, s, z, y = x.clone(), s.clone(), z.clone(), y.clone()
+    M = torch.min(s, 1)[0][:, None].repeat(1, m)
+    sel = M < 0
+    s[sel] -= M[sel] - 1
+    M = torch.min(z, 1)[0][:, None].repeat(1, m)
+    sel = M < 0
+    z[sel] -= M[sel] - 1
+    best = None
+    stall = 0
+    n_iter = 0
+    GT, AT = G.transpose(1, 2), A.transpose(1, 2)
+    for i in range(maxIter):
+        n_iter = i + 1
+        rx = ((AT.bmm(y.unsqueeze(-1)).squeeze(-1) if neq > 0 else 0.) + GT.bmm(z.unsqueeze(-1)).squeeze(-1)
+              + Q.bmm(x.unsqueeze(-1)).squeeze(-1) + p)
+        rs = s * z
+        rz = G.bmm(x.unsqueeze(-1)).squeeze(-1) + s - h
+        ry = A.bmm(x.unsqueeze(-1)).squeeze(-1) - b
+        mu = torch.abs((s * z).sum(1).squeeze() / m)
+        z_resid = torch.norm(rz, 2, 1).squeeze()
+        y_resid = torch.norm(ry, 2, 1).squeeze() if neq > 0 else 0
+        resids = y_resid + z_resid + torch.norm(rx, 2, 1).squeeze() + m * mu
+        K[:, zi, zi] = z
+        K[:, si_r, si_c] = s
+        Ktilde[:, zi, zi] = z + DENSE_KKT_EPS
+        Ktilde[:, si_r, si_c] = s
+        if best is None:
+            best = dict(resids=resids, x=x.clone(), z=z.clone(), s=s.clone(), y=y.clone(), K=K.clone())
+            stall = 0
+        else:
+            sel = resids < best["resids"]
+            stall = 0 if sel.sum() > 0 else stall + 1
+            best["resids"][sel] = resids[sel]
+            best["x"][sel] = x[sel]
+            best["z"][sel] = z[sel]
+            best["s"][sel] = s[sel]
+            best["K"][sel] = K[sel]
+            if neq > 0:
+                best["y"][sel] = y[sel]
+        if stall == notImprovedLim or best["resids"].max() < eps or mu.min() > 1e32:
+            break
+        dx_a, ds_a, dz_a, dy_a = dense_solve_kkt(K, Ktilde, rx, rs, rz, ry)
+        alpha = torch.min(torch.min(_dense_step(z, dz_a), _dense_step(s, ds_a)), torch.ones(nb, dtype=Q.dtype))
+        an = alpha.repeat(m, 1).t()
+        t3 = torch.sum((s + an * ds_a) * (z + an * dz_a), 1).squeeze()
+        t4 = torch.sum(s * z, 1).squeeze()
+        sig = (t3 / t4) ** 3
+        rs_c = (-mu * sig).repeat(m, 1).t() + ds_a * dz_a
+        dx_c, ds_c, dz_c, dy_c = dense_solve_kkt(K, Ktilde, torch.zeros(nb, n, dtype=Q.dtype), rs_c,
+                                                 torch.zeros(nb, m, dtype=Q.dtype), torch.zeros(nb, neq, dtype=Q.dtype))
+        dx, ds, dz = dx_a + dx_c, ds_a + ds_c, dz_a + dz_c
+        dy = dy_a + dy_c if neq > 0 else None
+        alpha = torch.min(0.999 * torch.min(_dense_step(z, dz), _dense_step(s, ds)), torch.ones(nb, dtype=Q.dtype))
+        x = x + alpha.repeat(n, 1).t() * dx
+        s = s + alpha.repeat(m, 1).t() * ds
+        z = z + alpha.repeat(m, 1).t() * dz
+        if neq > 0:
+            y = y + alpha.repeat(neq, 1).t() * dy
+    return dict(zhat=best["x"], nus=best["y"], lams=best["z"], slacks=best["s"], K=best["K"], n_iter=n_iter)
+
+
+def dense_backward(fwd, dl_dzhat):
+    """qp.py:235-268: adjoint solve with the (unregularised) best K, outer-product gradients."""
+    K = fwd["K"]
+    nb = K.shape[0]
+    zhat, lams, nus = fwd["zhat"], fwd["lams"], fwd["nus"]
+    m, neq = lams.shape[1], nus.shape[1]
+    zm = torch.zeros(nb, m, dtype=K.dtype)
+    dx, _, dlam, dnu = dense_solve_kkt(K, K, dl_dzhat, zm, zm, torch.zeros(nb, neq, dtype=K.dtype))
+    outer = lambda u, v: u.unsqueeze(2) * v.unsqueeze(1)
+    return dict(dQ=0.5 * (outer(dx, zhat) + outer(zhat, dx)), dp=dx, dG=outer(dlam, zhat) + outer(lams, dx), dh=-dlam,
+                dA=outer(dnu, zhat) + outer(nus, dx), db=-dnu)

@@ -208,3 +208,30 @@ def test_pipelined_host_entry_points(cuda_device):
         assert int(job[2][0]) == iters[i]
         for k in got[i]:
             assert torch.equal(got[i][k], job[1][k]), (i, k)
+
+
+@pytest.mark.parametrize("case", ["dense_nb16_nz10_m12_p4", "dense_nb32_nz30_m60_p0", "dense_nb8_nz15_m10_p10"])
+def test_dense_qp_function_golden(case, cuda_device):
+    """DenseQPFunction (full-KKT variant: regularised solve + refinement, qp.py:187-271) against the
+    real reference's outputs and gradients (oracle/gen_golden_dense.py)."""
+    import os
+    from b200qp.qp import DenseQPFunction
+    from oracle.gen_golden_dense import make_inputs as dense_inputs
+    from tests.qp_cases import GOLDEN_DIR
+    g = dict(np.load(os.path.join(GOLDEN_DIR, f"{case}.npz")))
+    inp = dense_inputs(case)
+    t = {k: v.to(cuda_device).requires_grad_(True) for k, v in inp.items()}
+    neq = inp["A"].shape[1]
+    dyn_res = lambda x: torch.bmm(t["A"], x.unsqueeze(-1)).squeeze(-1) - t["b"]
+    fn = DenseQPFunction(verbose=-1)
+    z = fn(t["Q"], t["p"], t["G"], t["h"], t["A"], t["b"], dyn_res)
+    z.backward(torch.ones_like(z))
+    ctx = z.grad_fn
+    assert fn.info["n_iter"] == int(g["n_iter"]), (fn.info["n_iter"], int(g["n_iter"]))
+    gate(z.detach().cpu(), g["zhat"], 1e-6, "zhat")
+    gate(ctx.lams.cpu(), g["lams"], 1e-6, "lams")
+    gate(ctx.slacks.cpu(), g["slacks"], 1e-6, "slacks")
+    for k in ("dQ", "dp", "dG", "dh") + (("dA", "db") if neq > 0 else ()):
+        gate(t[k[1:]].grad.cpu(), g[k], 1e-6, k)
+    if neq > 0:
+        gate(ctx.nus.cpu(), g["nus"], 1e-6, "nus")
