@@ -66,3 +66,21 @@ def test_block_kkt_equals_full_kkt():
     fx, fs, fz, fy = O.full_kkt_solve(Q, torch.diag_embed(d), G, A, rx, rs, rz, ry)
     for a_, b_ in ((dx, fx), (ds, fs), (dz, fz), (dy, fy)):
         assert torch.allclose(a_, b_, rtol=1e-8, atol=1e-10)
+
+
+@pytest.mark.parametrize("case", ["dense_nb16_nz10_m12_p4", "dense_nb8_nz15_m10_p10"])
+def test_dense_oracle_matches_reference_golden(case):
+    """qp_oracle.dense_forward/backward (DenseQPFunction restatement) against the reference's outputs."""
+    import os
+    import numpy as np
+    from oracle import qp_oracle as O
+    from oracle.gen_golden_dense import make_inputs as dense_inputs
+    from tests.qp_cases import GOLDEN_DIR, gate
+    g = dict(np.load(os.path.join(GOLDEN_DIR, f"{case}.npz")))
+    inp = dense_inputs(case)
+    fwd = O.dense_forward(*(inp[k].clone() for k in "QpGhAb"))
+    gr = O.dense_backward(fwd, torch.ones_like(fwd["zhat"]))
+    assert fwd["n_iter"] == int(g["n_iter"])
+    gate(fwd["zhat"], g["zhat"], 1e-9, "zhat")
+    for k in ("dQ", "dp", "dG", "dh", "dA", "db"):
+        gate(gr[k], g[k], 1e-9, k)
