@@ -17,9 +17,10 @@ STATUS_DOUBLES = 8
 ST_NITER, ST_BEST_MAX, ST_Q_FAIL, ST_AQA_FAIL, ST_LAUNCHES = 0, 1, 2, 3, 4
 MAX_ITER_CAP = 64
 FLAG_DENSE = 1
+PHASE_ALL, PHASE_BEGIN, PHASE_END = -1000, -1001, -1002
 
 EXPORTS = (
-    "b200qp_workspace_bytes", "b200qp_prefactor", "b200qp_forward", "b200qp_backward", "b200qp_kkt_solve",
+    "b200qp_workspace_bytes", "b200qp_prefactor", "b200qp_forward", "b200qp_forward_phase", "b200qp_slot_offset", "b200qp_backward", "b200qp_kkt_solve",
     "b200qp_solve_host", "b200qp_solve_host_submit", "b200qp_solve_host_wait", "b200qp_last_cuda_error", "b200qp_version", "b200qp_profile_enable",
     "b200qp_profile_read",
     "b200mpc_env_dims", "b200mpc_factor_elems", "b200mpc_scratch_bytes", "b200mpc_al_solve", "b200mpc_al_backward",
@@ -77,6 +78,10 @@ def lib():
     L.b200qp_workspace_bytes.argtypes = [pp]
     L.b200qp_forward.restype = ctypes.c_int
     L.b200qp_forward.argtypes = [pp] + [vp] * 13
+    L.b200qp_forward_phase.restype = ctypes.c_int
+    L.b200qp_forward_phase.argtypes = [pp, ctypes.c_int] + [vp] * 13
+    L.b200qp_slot_offset.restype = ctypes.c_size_t
+    L.b200qp_slot_offset.argtypes = [pp]
     L.b200qp_backward.restype = ctypes.c_int
     L.b200qp_backward.argtypes = [pp] + [vp] * 13
     L.b200qp_prefactor.restype = ctypes.c_int

@@ -111,11 +111,53 @@ class _Plan:
         self.workspace = torch.empty(nbytes, dtype=torch.uint8, device=Q_.device)
 
 
+_I64_MIN = -(1 << 63)
+
+
+def _forward_exact_sharded(L, plan, bufs, status, device, group):
+    """The forward with the batch sharded over the ranks of `group`, bit-for-bit what the reference
+    does on the UNSHARDED batch: its termination test and get_step fill are whole-batch reductions
+    (qpth/solvers/pdipm/batch.py:127-131,141,213), here one 64-byte slot per iteration whose fields
+    are unsigned MAX reductions -- all-reduced across the ranks between iteration launches."""
+    import torch.distributed as dist
+    args = [_ptr(plan.Q), _ptr(plan.p), _ptr(plan.G), _ptr(plan.h), _ptr(plan.A), _ptr(plan.b)] + [_ptr(t) for t in bufs] + \
+           [_ptr(plan.workspace), _ptr(status), _stream(device)]
+    pr = ctypes.byref(plan.prob)
+    _lib.check(L.b200qp_forward_phase(pr, _lib.PHASE_BEGIN, *args), "b200qp_forward_phase(begin)")
+    off = L.b200qp_slot_offset(pr)
+    max_iter = plan.prob.max_iter
+    slots = plan.workspace[off: off + 64 * max_iter].view(max_iter, 64)
+    for it in range(max_iter):
+        _lib.check(L.b200qp_forward_phase(pr, it, *args), "b200qp_forward_phase(iter)")
+        keys = slots[it, :32].view(torch.int64)      # best_max, ~mu_min, amax_z, amax_s: unsigned order
+        flags = slots[it, 32:].view(torch.int32)     # improved + NaN flags (0/1)
+        red = torch.cat((keys ^ _I64_MIN, flags.to(torch.int64)))  # signed order == unsigned order after the flip
+        dist.all_reduce(red, op=dist.ReduceOp.MAX, group=group)
+        keys.copy_(red[:4] ^ _I64_MIN)
+        flags.copy_(red[4:].to(torch.int32))
+    _lib.check(L.b200qp_forward_phase(pr, _lib.PHASE_END, *args), "b200qp_forward_phase(end)")
+
+
+def _global_mean(local_mean, local_nb, group):
+    """Mean over the GLOBAL batch from per-rank means (shared parameters, qpth/qp.py:160-178)."""
+    import torch.distributed as dist
+    buf = torch.cat([(local_mean * float(local_nb)).reshape(-1),
+                     torch.tensor([float(local_nb)], dtype=local_mean.dtype, device=local_mean.device)])
+    dist.all_reduce(buf, op=dist.ReduceOp.SUM, group=group)
+    return (buf[:-1] / buf[-1]).reshape(local_mean.shape)
+
+
 def QPFunction(eps=1e-12, verbose=0, notImprovedLim=3,
                maxIter=20, solver=QPSolvers.PDIPM_BATCHED,
-               check_Q_spd=True):
-    """Factory with the reference's signature (qpth/qp.py:19-21)."""
+               check_Q_spd=True, process_group=None):
+    """Factory with the reference's signature (qpth/qp.py:19-21).
+
+    `process_group` (extension): when given, the batch handed to each rank is treated as a shard of
+    ONE global batch and the solve reproduces the reference on that global batch exactly (the
+    batch-global termination test and step fill are all-reduced once per iteration, 96 bytes);
+    without it every rank solves its shard like an independent reference call."""
     info = {}
+    exact_group = process_group
 
     class QPFunctionFn(Function):
         @staticmethod
@@ -134,9 +176,13 @@ def QPFunction(eps=1e-12, verbose=0, notImprovedLim=3,
             nus = torch.empty(nb, neq, **opt)
             status = torch.empty(_lib.STATUS_DOUBLES, dtype=torch.float64, device=Q_.device)
             with torch.cuda.device(Q_.device):
-                rc = L.b200qp_forward(ctypes.byref(plan.prob), _ptr(plan.Q), _ptr(plan.p), _ptr(plan.G), _ptr(plan.h),
-                                      _ptr(plan.A), _ptr(plan.b), _ptr(zhats), _ptr(lams), _ptr(nus), _ptr(slacks),
-                                      _ptr(plan.workspace), _ptr(status), _stream(Q_.device))
+                if exact_group is not None:
+                    _forward_exact_sharded(L, plan, (zhats, lams, nus, slacks), status, Q_.device, exact_group)
+                    rc = 0
+                else:
+                    rc = L.b200qp_forward(ctypes.byref(plan.prob), _ptr(plan.Q), _ptr(plan.p), _ptr(plan.G), _ptr(plan.h),
+                                          _ptr(plan.A), _ptr(plan.b), _ptr(zhats), _ptr(lams), _ptr(nus), _ptr(slacks),
+                                          _ptr(plan.workspace), _ptr(status), _stream(Q_.device))
             _lib.check(rc, "b200qp_forward")
             st = status.tolist()  # one small D2H read; also surfaces asynchronous kernel faults
             info.update(n_iter=int(st[_lib.ST_NITER]), best_resid_max=st[_lib.ST_BEST_MAX],
@@ -176,20 +222,22 @@ def QPFunction(eps=1e-12, verbose=0, notImprovedLim=3,
                                        _ptr(ctx.slacks), _ptr(gz), _ptr(dQ), _ptr(dp), _ptr(dG), _ptr(dh), _ptr(dA),
                                        _ptr(db), _ptr(plan.workspace), _stream(zhats.device))
             _lib.check(rc, "b200qp_backward")
-            # parameters shared across the batch get the MEAN over it (qpth/qp.py:160-178)
+            # parameters shared across the batch get the MEAN over it (qpth/qp.py:160-178); over the
+            # GLOBAL batch when the call is a shard of one (process_group)
+            mean0 = (lambda t: t.mean(0)) if exact_group is None else (lambda t: _global_mean(t.mean(0), nb, exact_group))
             if plan.Q_e:
-                dQ = dQ.mean(0)
+                dQ = mean0(dQ)
             if plan.p_e:
-                dp = dp.mean(0)
+                dp = mean0(dp)
             if plan.G_e:
-                dG = dG.mean(0)
+                dG = mean0(dG)
             if plan.h_e:
-                dh = dh.mean(0)
+                dh = mean0(dh)
             if neq > 0:
                 if plan.A_e:
-                    dA = dA.mean(0)
+                    dA = mean0(dA)
                 if plan.b_e:
-                    db = db.mean(0)
+                    db = mean0(db)
             return (dQ, dp, dG, dh, dA, db, None, None)
 
     def apply(Q, p, G, h, A, b, dyn_res=None, cost_grad=None):

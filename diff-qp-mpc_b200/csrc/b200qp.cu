@@ -100,7 +100,8 @@ static int run_prefactor(KArgs<T>& a, const Layout& L, cudaStream_t st) { return
 template <typename T>
 static int forward_t(const b200qp_problem_t* pr, const Layout& L, const void* Q, const void* p, const void* G,
                      const void* h, const void* A, const void* b, void* zhat, void* lams, void* nus, void* slacks,
-                     void* ws, double* status, cudaStream_t st, bool prefactored = false) {
+                     void* ws, double* status, cudaStream_t st, bool prefactored = false,
+                     int phase = B200QP_PHASE_ALL) {
   KArgs<T> a;
   fill_args(a, pr, L, ws);
   a.Q = (const T*)Q; a.pv = (const T*)p; a.G = (const T*)G; a.h = (const T*)h;
@@ -108,28 +109,34 @@ static int forward_t(const b200qp_problem_t* pr, const Layout& L, const void* Q,
   a.bx = (T*)zhat; a.bz = (T*)lams; a.bs = (T*)slacks; a.by = (T*)nus;
   a.status = status;
   int launches = 0;
-  prof_begin(st);
-  if (!prefactored) {  // the host-buffer path pre-factors chunk by chunk while the inputs arrive
-    CK(cudaMemsetAsync(a.slots, 0, sizeof(Slot) * B200QP_MAX_ITER_CAP + sizeof(Control), st));
-    int rc = run_prefactor(a, L, st);
-    if (rc) return rc;
+  const bool all = phase == B200QP_PHASE_ALL;
+  if (all || phase == B200QP_PHASE_BEGIN) {
+    prof_begin(st);
+    if (!prefactored) {  // the host-buffer path pre-factors chunk by chunk while the inputs arrive
+      CK(cudaMemsetAsync(a.slots, 0, sizeof(Slot) * B200QP_MAX_ITER_CAP + sizeof(Control), st));
+      int rc = run_prefactor(a, L, st);
+      if (rc) return rc;
+    }
+    prof_mark(0, st);
+    launches++;
+    a.iter = -1;
+    DISPATCH_KERNEL(launch_iter, T, L, a);
+    prof_mark(1, st);
+    launches++;
   }
-  prof_mark(0, st);
-  launches++;
-  a.iter = -1;
-  DISPATCH_KERNEL(launch_iter, T, L, a);
-  prof_mark(1, st);
-  launches++;
   for (int it = 0; it < pr->max_iter; it++) {
+    if (!all && phase != it) continue;
     a.iter = it;
     DISPATCH_KERNEL(launch_iter, T, L, a);
     prof_mark(2, st);
     launches++;
   }
-  launches++;
-  k_finalize<<<1, 32, 0, st>>>(a.slots, a.ctl, status, pr->max_iter, pr->not_improved_lim, pr->eps, launches);
-  CK(cudaGetLastError());
-  prof_mark(3, st);
+  if (all || phase == B200QP_PHASE_END) {
+    launches = pr->max_iter + 3;
+    k_finalize<<<1, 32, 0, st>>>(a.slots, a.ctl, status, pr->max_iter, pr->not_improved_lim, pr->eps, launches);
+    CK(cudaGetLastError());
+    prof_mark(3, st);
+  }
   return B200QP_OK;
 }
 
@@ -258,6 +265,29 @@ size_t b200qp_workspace_bytes(const b200qp_problem_t* prob) {
   Layout L;
   if (make_layout(prob, L) != B200QP_OK) return 0;
   return L.total;
+}
+
+size_t b200qp_slot_offset(const b200qp_problem_t* prob) {
+  Layout L;
+  if (make_layout(prob, L) != B200QP_OK) return 0;
+  return L.oslots;
+}
+
+int b200qp_forward_phase(const b200qp_problem_t* prob, int phase, const void* Q, const void* p, const void* G,
+                         const void* h, const void* A, const void* b, void* zhat, void* lams, void* nus, void* slacks,
+                         void* workspace, double* status, b200qp_stream_t stream) {
+  Layout L;
+  int rc = make_layout(prob, L);
+  if (rc) return rc;
+  if (!Q || !p || !G || !h || !zhat || !lams || !slacks || !workspace || !status) return B200QP_EINVAL;
+  if (prob->neq > 0 && (!A || !b || !nus)) return B200QP_EINVAL;
+  if (phase != B200QP_PHASE_ALL && phase != B200QP_PHASE_BEGIN && phase != B200QP_PHASE_END &&
+      (phase < 0 || phase >= prob->max_iter))
+    return B200QP_EINVAL;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (prob->dtype == B200QP_F64)
+    return forward_t<double>(prob, L, Q, p, G, h, A, b, zhat, lams, nus, slacks, workspace, status, st, false, phase);
+  return forward_t<float>(prob, L, Q, p, G, h, A, b, zhat, lams, nus, slacks, workspace, status, st, false, phase);
 }
 
 int b200qp_forward(const b200qp_problem_t* prob, const void* Q, const void* p, const void* G, const void* h,

@@ -79,6 +79,24 @@ int b200qp_forward(const b200qp_problem_t* prob,
                    void* zhat, void* lams, void* nus, void* slacks,
                    void* workspace, double* status, b200qp_stream_t stream);
 
+/* The forward in phases, for callers that must couple several devices: the reference's termination
+ * test and its get_step fill are reductions over the WHOLE batch (qpth/solvers/pdipm/batch.py:127-131,
+ * 141,213); inside one call they live in one 64-byte slot per iteration at
+ * workspace + b200qp_slot_offset(prob) + 64 * it, every field of which is an unsigned 64/32-bit MAX
+ * reduction.  A batch sharded over R ranks is solved EXACTLY like the unsharded batch by running
+ *   phase BEGIN; for it in 0..max_iter-1 { phase it; element-wise unsigned MAX of slot `it` across ranks }
+ *   phase END
+ * (b200qp/qp.py does this with torch.distributed when `process_group` is given). */
+#define B200QP_PHASE_ALL (-1000)   /* what b200qp_forward does                                  */
+#define B200QP_PHASE_BEGIN (-1001) /* zero the slots, pre-factorise, initial point              */
+#define B200QP_PHASE_END (-1002)   /* iteration count / worst residual -> status                */
+size_t b200qp_slot_offset(const b200qp_problem_t* prob);
+int b200qp_forward_phase(const b200qp_problem_t* prob, int phase,
+                         const void* Q, const void* p, const void* G, const void* h,
+                         const void* A, const void* b,
+                         void* zhat, void* lams, void* nus, void* slacks,
+                         void* workspace, double* status, b200qp_stream_t stream);
+
 /* Adjoint solve.  Needs the forward's workspace (pre-factorisation) and outputs.
  * Writes PER-PROBLEM gradients: dQ (nb,nz,nz) dp (nb,nz) dG (nb,nineq,nz) dh (nb,nineq)
  * dA (nb,neq,nz) db (nb,neq); the caller averages them for shared parameters

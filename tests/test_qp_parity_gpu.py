@@ -235,3 +235,65 @@ def test_dense_qp_function_golden(case, cuda_device):
         gate(t[k[1:]].grad.cpu(), g[k], 1e-6, k)
     if neq > 0:
         gate(ctx.nus.cpu(), g["nus"], 1e-6, "nus")
+
+
+def _exact_worker(rank, world, port, nb, q):
+    import os
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    for p_ in (root, os.path.join(root, "diff-qp-mpc_b200")):
+        if p_ not in sys.path:
+            sys.path.insert(0, p_)
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    ndev = torch.cuda.device_count()
+    dev = torch.device("cuda", rank % ndev)
+    torch.cuda.set_device(dev)
+    # NCCL needs one device per rank; on a single-GPU box the two ranks share cuda:0 over gloo
+    dist.init_process_group("nccl" if ndev >= world else "gloo", rank=rank, world_size=world)
+    try:
+        from b200qp.dist import shard_slice
+        from b200qp.qp import QPFunction
+        from oracle import qp_oracle as O
+        Q, p, G, h, A, b = O.random_qp(nb, 30, 60, 0, seed=0)
+        sl = shard_slice(nb, rank, world)
+        t = [x[sl].to(dev).requires_grad_(True) for x in (Q, p, G, h)] + [A[sl].to(dev), b[sl].to(dev)]
+        fn = QPFunction(verbose=-1, check_Q_spd=False, process_group=dist.group.WORLD)
+        z = fn(*t)
+        z.backward(torch.ones_like(z))
+        # numpy, not tensors: torch shares CPU tensors through the sender's fd server, which dies with the worker
+        q.put((rank, fn.info["n_iter"], z.detach().cpu().numpy(), t[2].grad.cpu().numpy()))
+    except Exception as ex:  # pragma: no cover
+        q.put((rank, -1, repr(ex), None))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_exact_global_batch_mode_two_ranks(cuda_device):
+    """QPFunction(process_group=...): a batch sharded over two ranks is solved bit-for-bit like the
+    unsharded batch on one device (the batch-global termination and step fill are all-reduced per
+    iteration), whereas independent per-shard solves stop at different iterations."""
+    import socket
+    import torch.multiprocessing as mp
+    from b200qp.qp import QPFunction
+    from oracle import qp_oracle as O
+    nb, world = 256, 2
+    Q, p, G, h, A, b = O.random_qp(nb, 30, 60, 0, seed=0)
+    t = [x.to(cuda_device).requires_grad_(True) for x in (Q, p, G, h)] + [A.to(cuda_device), b.to(cuda_device)]
+    fn = QPFunction(verbose=-1, check_Q_spd=False)
+    z = fn(*t)
+    z.backward(torch.ones_like(z))
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_exact_worker, args=(r, world, port, nb, q)) for r in range(world)]
+    for pr in procs:
+        pr.start()
+    res = sorted([q.get(timeout=240) for _ in range(world)], key=lambda r: r[0])
+    for pr in procs:
+        pr.join(timeout=60)
+    assert all(r[1] >= 0 for r in res), res
+    assert all(r[1] == fn.info["n_iter"] for r in res), ([r[1] for r in res], fn.info["n_iter"])
+    assert np.array_equal(np.concatenate([r[2] for r in res]), z.detach().cpu().numpy())
+    assert np.array_equal(np.concatenate([r[3] for r in res]), t[2].grad.cpu().numpy())
