@@ -10,4 +10,5 @@ from . import al_utils  # noqa: F401
 from . import AL_mpc  # noqa: F401
 from . import AL_mpc as al_mpc  # noqa: F401
 from . import envs  # noqa: F401
+from . import my_envs  # noqa: F401
 from .qp import QPFunction, DenseQPFunction, QPSolvers  # noqa: F401

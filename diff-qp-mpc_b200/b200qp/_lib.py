@@ -28,6 +28,7 @@ EXPORTS = (
 )
 
 ENV_PENDULUM, ENV_INTEGRATOR, ENV_PENDULUM_DX, ENV_CARTPOLE_DX, ENV_REX_QUADROTOR = 0, 1, 2, 3, 4
+ENV_PENDULUM1L, ENV_CARTPOLE1L, ENV_CARTPOLE2L = 5, 6, 7
 MPC_MAX_PARAMS = 64
 
 

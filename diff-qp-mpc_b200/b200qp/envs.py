@@ -26,8 +26,13 @@ def _params_array(params):
 
 def dyn_spec(dx):
     """-> (env id, params, nx, nu)"""
+    if hasattr(dx, "__self__") and hasattr(dx, "__func__"):
+        dx = dx.__self__          # bound method, e.g. env.dynamics_derivatives (deqmpc/policies.py:577)
     name = getattr(dx, "original_name", type(dx).__name__)
     base = name[:-4] if name.endswith("_jac") else name
+    if hasattr(dx, "package"):    # deqmpc/my_envs: CartpoleDynamics / PendulumDynamics around a generated package
+        from .my_envs import package_spec
+        return package_spec(dx.package, dx.dt)
     if base == "PendulumDynamics":
         return _lib.ENV_PENDULUM, [float(dx.dt), float(dx.g), float(dx.m), float(dx.l)], 2, 1
     if base == "IntegratorDynamics":
@@ -56,7 +61,7 @@ def dyn_spec(dx):
         return _lib.ENV_REX_QUADROTOR, params, 12, 4
     raise NotImplementedError(f"b200qp: no fused kernel for dynamics {name!r}; supported: PendulumDynamics, "
                               "IntegratorDynamics, PendulumDx, CartpoleDx, RexQuadrotor_dynamics (and their *_jac "
-                              "variants)")
+                              "variants), and the deqmpc/my_envs CartpoleDynamics / PendulumDynamics")
 
 
 def _run(spec, x, u, want_jac):

@@ -26,6 +26,9 @@ static bool env_dims(int env, int& nx, int& nu) {
     case ENV_PENDULUM_DX: nx = PendulumDx::NX; nu = PendulumDx::NU; return true;
     case ENV_CARTPOLE_DX: nx = CartpoleDx::NX; nu = CartpoleDx::NU; return true;
     case ENV_REX_QUADROTOR: nx = RexQuadrotor::NX; nu = RexQuadrotor::NU; return true;
+    case ENV_PENDULUM1L: nx = Pendulum1L::NX; nu = Pendulum1L::NU; return true;
+    case ENV_CARTPOLE1L: nx = Cartpole1L::NX; nu = Cartpole1L::NU; return true;
+    case ENV_CARTPOLE2L: nx = Cartpole2L::NX; nu = Cartpole2L::NU; return true;
   }
   return false;
 }
@@ -110,6 +113,9 @@ static int rollout_t(const double* params, const void* x0, const void* u, void* 
     case ENV_PENDULUM_DX: EXPR_MACRO(PendulumDx);             \
     case ENV_CARTPOLE_DX: EXPR_MACRO(CartpoleDx);             \
     case ENV_REX_QUADROTOR: EXPR_MACRO(RexQuadrotor);         \
+    case ENV_PENDULUM1L: EXPR_MACRO(Pendulum1L);              \
+    case ENV_CARTPOLE1L: EXPR_MACRO(Cartpole1L);              \
+    case ENV_CARTPOLE2L: EXPR_MACRO(Cartpole2L);              \
   }                                                           \
   return B200QP_EINVAL
 

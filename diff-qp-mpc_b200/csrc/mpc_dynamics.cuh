@@ -9,6 +9,12 @@
 //   PendulumDx  qpth/env_dx/pendulum.py:49-84   (cos, sin, thdot) state, clamped torque
 //   CartpoleDx  qpth/env_dx/cartpole.py:63-96   (x, dx, cos, sin, dth) state, clamped force
 //   RexQuadrotor deqmpc/rex_quadrotor.py:7-146  12-state MRP rigid body, RK4, act_scale = 100
+//   Pendulum1L / Cartpole1L / Cartpole2L   deqmpc/my_envs/{pendulum1l,cartpole1l,cartpole1l_v2,cartpole2l}:
+//       the reference ships these as CasADi-GENERATED straight-line code (src/generated_dynamics.c,
+//       generated_derivatives.c, 300-10500 lines, one thread per batch row in dynamics_gpu.cu); here
+//       the rigid-body model behind that code is written out (M(q) qdd = tau - bias) and integrated
+//       by the same classical RK4, state (q, qd), control = force/torque on the first joint only
+//       (deqmpc/my_envs/dynamics.py:27-108)
 #pragma once
 #include <cuda_runtime.h>
 
@@ -113,6 +119,7 @@ template <typename R, int N> struct real_of<Dual<R, N>> { typedef R type; };
 
 // ---------------------------------------------------------------------------- environments
 constexpr int ENV_PENDULUM = 0, ENV_INTEGRATOR = 1, ENV_PENDULUM_DX = 2, ENV_CARTPOLE_DX = 3, ENV_REX_QUADROTOR = 4;
+constexpr int ENV_PENDULUM1L = 5, ENV_CARTPOLE1L = 6, ENV_CARTPOLE2L = 7;
 constexpr int MAX_PARAMS = 64;
 
 struct DynParams { double v[MAX_PARAMS]; };
@@ -306,5 +313,94 @@ struct RexQuadrotor {
     for (int i = 0; i < NX; i++) xn[i] = x[i] + (dt / R(6)) * (k1[i] + R(2) * k2[i] + R(2) * k3[i] + k4[i]);
   }
 };
+
+// ---- deqmpc/my_envs: second-order systems x = (q, qd), classical RK4 of qdd = Model::accel(q, qd, u)
+template <class Model>
+struct SecondOrderRK4 {
+  static constexpr int NQ = Model::NQ, NX = 2 * Model::NQ, NU = 1;
+  template <typename S>
+  __device__ static __forceinline__ void step(const DynParams& P, const S* x, const S* u, S* xn) {
+    typedef typename real_of<S>::type R;
+    const R h = (R)P.v[0], h2 = h / R(2);
+    S y[NX], a1[NQ], a2[NQ], a3[NQ], a4[NQ], v2[NQ], v3[NQ], v4[NQ];
+    Model::template accel<S>(P, x, x + NQ, u[0], a1);
+#pragma unroll
+    for (int i = 0; i < NQ; i++) { y[i] = x[i] + h2 * x[NQ + i]; v2[i] = x[NQ + i] + h2 * a1[i]; y[NQ + i] = v2[i]; }
+    Model::template accel<S>(P, y, y + NQ, u[0], a2);
+#pragma unroll
+    for (int i = 0; i < NQ; i++) { y[i] = x[i] + h2 * v2[i]; v3[i] = x[NQ + i] + h2 * a2[i]; y[NQ + i] = v3[i]; }
+    Model::template accel<S>(P, y, y + NQ, u[0], a3);
+#pragma unroll
+    for (int i = 0; i < NQ; i++) { y[i] = x[i] + h * v3[i]; v4[i] = x[NQ + i] + h * a3[i]; y[NQ + i] = v4[i]; }
+    Model::template accel<S>(P, y, y + NQ, u[0], a4);
+#pragma unroll
+    for (int i = 0; i < NQ; i++) {
+      xn[i] = x[i] + (h / R(6)) * (x[NQ + i] + R(2) * v2[i] + R(2) * v3[i] + v4[i]);
+      xn[NQ + i] = x[NQ + i] + (h / R(6)) * (a1[i] + R(2) * a2[i] + R(2) * a3[i] + a4[i]);
+    }
+  }
+};
+
+// params: dt, 1/I, m g l / I     (pendulum1l: thdd = 4 u - 2 g sin th, angle from the downward rest position)
+struct Pendulum1LModel {
+  static constexpr int NQ = 1;
+  template <typename S>
+  __device__ static __forceinline__ void accel(const DynParams& P, const S* q, const S* qd, const S& u, S* a) {
+    typedef typename real_of<S>::type R;
+    a[0] = (R)P.v[1] * u - (R)P.v[2] * m_sin(q[0]);
+  }
+};
+
+// params: dt, total mass mt, pole first moment ml, pole inertia about the joint I, g
+//   [mt  -ml c] [xdd ]   [u - ml s thd^2]
+//   [-ml c   I] [thdd] = [    ml g s    ]        (theta = 0 upright, counter-clockwise positive)
+// cartpole1l: (11, 1, 2, 9.81); cartpole1l_v2: (0.7, 0.1, 0.05, 9.81)
+struct Cartpole1LModel {
+  static constexpr int NQ = 2;
+  template <typename S>
+  __device__ static __forceinline__ void accel(const DynParams& P, const S* q, const S* qd, const S& u, S* a) {
+    typedef typename real_of<S>::type R;
+    const R mt = (R)P.v[1], ml = (R)P.v[2], I = (R)P.v[3], g = (R)P.v[4];
+    const S s = m_sin(q[1]), c = m_cos(q[1]);
+    const S mc = ml * c;
+    const S r0 = u - ml * s * (qd[1] * qd[1]);
+    const S r1 = (ml * g) * s;
+    const S f = mc / mt;                 // eliminate the cart row
+    a[1] = (r1 + f * r0) / (I - f * mc);
+    a[0] = (r0 + mc * a[1]) / mt;
+  }
+};
+
+// params: dt, mt, h1, h2, J1, J2, k, g  (cart + two links; Lagrange's equations in absolute link angles
+// phi1 = th1, phi2 = th1 + th2, joint torques on the relative angles; cartpole2l: 12, 2, 1, 3, 2, 1, 9.81)
+struct Cartpole2LModel {
+  static constexpr int NQ = 3;
+  template <typename S>
+  __device__ static __forceinline__ void accel(const DynParams& P, const S* q, const S* qd, const S& u, S* a) {
+    typedef typename real_of<S>::type R;
+    const R mt = (R)P.v[1], h1 = (R)P.v[2], h2 = (R)P.v[3], J1 = (R)P.v[4], J2 = (R)P.v[5], k = (R)P.v[6], g = (R)P.v[7];
+    const S p2 = q[1] + q[2], w1 = qd[1], w2 = qd[1] + qd[2];
+    const S s1 = m_sin(q[1]), c1 = m_cos(q[1]), s2 = m_sin(p2), c2 = m_cos(p2);
+    const S s12 = s1 * c2 - c1 * s2, c12 = c1 * c2 + s1 * s2;
+    const S m01 = -h1 * c1, m02 = -h2 * c2, m12 = k * c12;
+    const S r0 = u - h1 * s1 * (w1 * w1) - h2 * s2 * (w2 * w2);
+    const S r1 = (h1 * g) * s1 - k * s12 * (w2 * w2);
+    const S r2 = (h2 * g) * s2 + k * s12 * (w1 * w1);
+    // symmetric elimination, no pivoting (the mass matrix is SPD)
+    const S f1 = m01 / mt, f2 = m02 / mt;
+    const S b11 = J1 - f1 * m01, b12 = m12 - f1 * m02, b22 = J2 - f2 * m02;
+    const S t1 = r1 - f1 * r0, t2 = r2 - f2 * r0;
+    const S f3 = b12 / b11;
+    const S ph2 = (t2 - f3 * t1) / (b22 - f3 * b12);
+    const S ph1 = (t1 - b12 * ph2) / b11;
+    a[0] = (r0 - m01 * ph1 - m02 * ph2) / mt;
+    a[1] = ph1;
+    a[2] = ph2 - ph1;
+  }
+};
+
+typedef SecondOrderRK4<Pendulum1LModel> Pendulum1L;
+typedef SecondOrderRK4<Cartpole1LModel> Cartpole1L;
+typedef SecondOrderRK4<Cartpole2LModel> Cartpole2L;
 
 }  // namespace b200mpc

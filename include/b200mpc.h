@@ -37,6 +37,12 @@ extern "C" {
 #define B200MPC_ENV_REX_QUADROTOR 4 /* deqmpc/rex_quadrotor.py RexQuadrotor_dynamics (nx=12, nu=4, RK4): params dt,
                                        mass,act_scale,kf(forces),kf,km,bf,motor_dist,mass*g[3],Bf[3],J[9],Jinv[9],
                                        ss[12],cd[3],cross_A[3]  (float32-rounded where the reference is float32)  */
+/* deqmpc/my_envs (CasADi-generated in the reference: <env>/src/generated_dynamics.c, generated_derivatives.c,
+ * dynamics_gpu.cu; Python side deqmpc/my_envs/dynamics.py:27-108): state (q, qd), one control on the first joint,
+ * classical RK4 with step dt */
+#define B200MPC_ENV_PENDULUM1L 5    /* pendulum1l (nx=2): params dt, 1/I, mgl/I                          */
+#define B200MPC_ENV_CARTPOLE1L 6    /* cartpole1l, cartpole1l_v2 (nx=4): params dt, mt, ml, I, g         */
+#define B200MPC_ENV_CARTPOLE2L 7    /* cartpole2l (nx=6): params dt, mt, h1, h2, J1, J2, k, g            */
 #define B200MPC_MAX_PARAMS 64
 
 typedef struct {

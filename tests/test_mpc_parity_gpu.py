@@ -255,3 +255,75 @@ def test_tracking_mpc_matches_reference_golden(cuda_device):
         print("tracking call", k, {a: f"{b:.1e}" for a, b in errs.items()})
         assert errs["x"] <= RTOL32 and errs["u"] <= RTOL32, errs
         assert errs["gx"] <= RTOL64 and errs["gu"] <= RTOL64, errs
+
+
+MYENVS = ("pendulum1l", "cartpole1l", "cartpole1l_v2", "cartpole2l")
+
+
+def _my_dynamics(name, dt, dev):
+    from b200qp import my_envs
+    kw = dict(dtype=torch.float64, device=dev)
+    if name == "pendulum1l":
+        return my_envs.PendulumDynamics(nx=2, dt=dt, kwargs=kw)
+    return my_envs.CartpoleDynamics(nx=6 if name == "cartpole2l" else 4, dt=dt, kwargs=kw, version=2 if name.endswith("v2") else 1)
+
+
+@pytest.mark.parametrize("name", MYENVS)
+def test_myenvs_dynamics_golden(name, cuda_device):
+    """deqmpc/my_envs Dynamics.forward / derivatives / dynamics_derivatives (CasADi-generated code in the
+    reference) against outputs of that generated code driven through the reference's own dynamics.py
+    (oracle/gen_golden_myenvs.py), and against the oracle port on a larger seeded sample."""
+    import numpy as np
+    from oracle import myenvs_oracle as MO
+    g = _npz(f"dyn_myenvs_{name}.npz")
+    d = _my_dynamics(name, float(g["dt"]), cuda_device)
+    x, u = g["x"].to(cuda_device), g["u"].to(cuda_device)
+    xn, (A, B) = d.dynamics_derivatives(x, u)
+    assert rel(xn.cpu(), g["xn"]) < 1e-13 and rel(A.cpu(), g["A"]) < 1e-12 and rel(B.cpu(), g["B"]) < 1e-12
+    assert rel(d(x, u).cpu(), g["xn"]) < 1e-13
+    A2, B2 = d.derivatives(x, u)
+    assert torch.equal(A2, A) and torch.equal(B2, B)
+    # autograd through the step uses the same Jacobians
+    xr, ur = x.clone().requires_grad_(True), u.clone().requires_grad_(True)
+    d(xr, ur).sum().backward()
+    assert rel(xr.grad.cpu(), g["A"].sum(1)) < 1e-12 and rel(ur.grad.cpu(), g["B"].sum(1)) < 1e-12
+    # larger sample against the port
+    rs = np.random.RandomState(11)
+    nq, N = MO.NQ[name], 4096
+    xs = np.concatenate([rs.uniform(-7, 7, (N, nq)), rs.uniform(-6, 6, (N, nq))], 1)
+    us = rs.uniform(-50, 50, (N, 1))
+    pxn, (pA, pB) = MO.Dynamics(MO.PortPackage(name), 2 * nq, float(g["dt"])).dynamics_derivatives(xs, us)
+    xn, (A, B) = d.dynamics_derivatives(torch.tensor(xs, device=cuda_device), torch.tensor(us, device=cuda_device))
+    assert rel(xn.cpu(), pxn) < 1e-13 and rel(A.cpu(), pA) < 1e-12 and rel(B.cpu(), pB) < 1e-12
+
+
+@pytest.mark.parametrize("case", ("cartpole1l_B8_T10", "cartpole2l_B4_T8", "pendulum1l_B8_T6"))
+def test_al_mpc_myenvs_golden(case, cuda_device):
+    """AL-MPC on the my_envs dynamics (the production configuration: CartpoleEnv + Tracking_MPC's al_mpc.MPC)
+    against the real reference run on its generated code: cold call, warm-started call, state and backward."""
+    from b200qp.AL_mpc import MPC
+    from b200qp.al_utils import QuadCost
+    g = _npz(f"mpc_{case}.npz")
+    name = case.split("_B")[0]
+    dev = cuda_device
+    d = _my_dynamics(name, float(g["dt"]), dev)
+    B, T, nu = g["u_init"].shape
+    nx = g["x0"].shape[1]
+    ub = float(g["umax"]) * torch.ones(nu, dtype=torch.float64, device=dev)
+    ctrl = MPC(nx, nu, T, u_lower=-ub, u_upper=ub, exit_unconverged=False, eps=1e-5, n_batch=B, backprop=False, verbose=0,
+               u_init=g["u_init"].to(dev), solver_type="dense", dtype=torch.float64)
+    x0 = g["x0"].to(dev)
+    ctrl.reinitialize(x0, None)
+    ctrl.u_init = g["u_init"].to(dev)
+    for k in range(2):
+        Cfull = torch.diag_embed(g["Cd"]).to(dev).requires_grad_(True)
+        c = (-(g["Cd"] * g["xref"])).to(dev).requires_grad_(True)
+        x, u = ctrl(x0, QuadCost(Cfull, c), d, d.dynamics_derivatives)
+        (x.sum() + u.sum()).backward()
+        errs = dict(x=rel(x.detach().cpu(), g[f"out_x{k}"]), u=rel(u.detach().cpu(), g[f"out_u{k}"]),
+                    lam=rel(ctrl.lamda_prev.cpu(), g[f"out_lam{k}"]), rho=rel(ctrl.rho_prev.cpu(), g[f"out_rho{k}"]),
+                    dC=rel(Cfull.grad.diagonal(dim1=-2, dim2=-1).cpu(), g[f"out_dC{k}"]), dc=rel(c.grad.cpu(), g[f"out_dc{k}"]))
+        print(case, k, {a: f"{b:.1e}" for a, b in errs.items()})
+        assert errs["x"] <= RTOL32 and errs["u"] <= RTOL32, errs
+        for key in ("lam", "rho", "dC", "dc"):
+            assert errs[key] <= RTOL64, (key, errs)
