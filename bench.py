@@ -254,6 +254,15 @@ def bench_mpc_shapes(dev):
                       torch.zeros(B, dtype=torch.float64)), 1).to(dev)
     run("cartpole_env_dx_T20_B4096", envs.CartpoleDx(), envs.CartpoleDx_jac(), 5, 1, T, B, x0,
         (0.1 * (r(B, T, 1) - 0.5)).to(dev), [0.1, 0.1, 1., 1., 0.1, 0.001], one(-100., 1), one(100., 1), 5)
+    # configs[2] with the dynamics deqmpc actually trains on: my_envs CartpoleEnv(nx=4, dt=0.05), u in +-100,
+    # Qlqr = 1, Rlqr = 1e-8 (deqmpc/my_envs/cartpole.py:43-84, train.py:102); and the two-link variant (train.py:105)
+    from b200qp import my_envs
+    kw = dict(dtype=torch.float64, device=dev)
+    for nm, nx, dt_, um in (("cartpole1l_myenvs_T20_B4096", 4, 0.05, 100.), ("cartpole2l_myenvs_T20_B4096", 6, 0.03, 250.)):
+        d = my_envs.CartpoleDynamics(nx=nx, dt=dt_, kwargs=kw)
+        x0 = torch.cat((r(B, nx // 2) * 0.6 - 0.3, r(B, nx // 2) * 0.2 - 0.1), 1).to(dev)
+        run(nm, d, d.dynamics_derivatives, nx, 1, T, B, x0, (0.1 * (r(B, T, 1) - 0.5)).to(dev), [1.] * nx + [1e-8],
+            one(-um, 1), one(um, 1), 5)
     B, T = 1024, 40
     x0 = torch.cat((r(B, 3) * 2 - 1, r(B, 3) * 0.2 - 0.1, r(B, 6) * 0.2 - 0.1), 1).to(dev)
     run("rex_quadrotor_T40_B1024", envs.RexQuadrotor_dynamics(), envs.RexQuadrotor_dynamics_jac(), 12, 4, T, B, x0,

