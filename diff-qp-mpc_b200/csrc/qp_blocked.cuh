@@ -206,4 +206,98 @@ __device__ __forceinline__ void ldlt_solve_blocked(const double* __restrict__ U,
   }
 }
 
+// X = (L D L^T)^-1 from the factor above, ONE THREAD PER COLUMN, no barriers inside: thread c solves
+// L y = e_c, scales by D^-1 and solves L^T x = y, eight rows at a time in registers; its column of X is
+// its only working storage (coalesced across threads), the factor is read through warp-uniform
+// (broadcast) loads.  Loop bounds are warp-uniform (rows start at the warp's first column) so that the
+// broadcasts stay broadcasts.  X may be global or shared; call with all threads, barrier before/after.
+__device__ __forceinline__ void ldlt_inverse_cols(const double* __restrict__ U, int ld, int n, const double* pinv,
+                                                  double* X, int tid, int nt) {
+  constexpr int RB = 8;
+  const int lane = tid & 31;
+  for (int c = tid; c < n; c += nt) {
+    const int cw = c - lane;               // first column of this warp (warp-uniform)
+    const int ib = (cw / RB) * RB;
+    for (int i = 0; i < ib; i++) X[(size_t)i * ld + c] = 0.0;
+#pragma unroll 1
+    for (int i0 = ib; i0 < n; i0 += RB) {
+      double y[RB];
+#pragma unroll
+      for (int r = 0; r < RB; r++) y[r] = (i0 + r == c) ? 1.0 : 0.0;
+      for (int j = cw; j < i0; j++) {
+        const double yj = X[(size_t)j * ld + c];
+        const double* urow = U + (size_t)j * ld + i0;
+#pragma unroll
+        for (int r = 0; r < RB; r++) if (i0 + r < n) y[r] -= urow[r] * yj;
+      }
+#pragma unroll
+      for (int r = 1; r < RB; r++) {
+#pragma unroll
+        for (int r2 = 0; r2 < r; r2++) if (i0 + r < n) y[r] -= U[(size_t)(i0 + r2) * ld + i0 + r] * y[r2];
+      }
+#pragma unroll
+      for (int r = 0; r < RB; r++) if (i0 + r < n) X[(size_t)(i0 + r) * ld + c] = y[r];
+    }
+#pragma unroll 1
+    for (int i0 = ((n - 1) / RB) * RB; i0 >= 0; i0 -= RB) {
+      double x[RB];
+#pragma unroll
+      for (int r = 0; r < RB; r++) x[r] = (i0 + r < n) ? X[(size_t)(i0 + r) * ld + c] * pinv[i0 + r] : 0.0;
+      for (int j = i0 + RB; j < n; j++) {
+        const double xj = X[(size_t)j * ld + c];
+#pragma unroll
+        for (int r = 0; r < RB; r++) if (i0 + r < n) x[r] -= U[(size_t)(i0 + r) * ld + j] * xj;
+      }
+#pragma unroll
+      for (int r = RB - 2; r >= 0; r--) {
+#pragma unroll
+        for (int r2 = r + 1; r2 < RB; r2++) if (i0 + r2 < n) x[r] -= U[(size_t)(i0 + r) * ld + i0 + r2] * x[r2];
+      }
+#pragma unroll
+      for (int r = 0; r < RB; r++) if (i0 + r < n) X[(size_t)(i0 + r) * ld + c] = x[r];
+    }
+  }
+}
+
+// C = A B on the FP64 tensor cores, operands straight from global / shared memory, one 16 x 16 output
+// block (2 x 2 DMMA tiles) per warp and step.  arow(r) -> pointer to row r of A (K contiguous entries);
+// bval(k, c) -> B[k][c]; store(r, c, v) consumes the result; `lower` restricts to blocks J <= I.
+template <class ARow, class BVal, class Store>
+__device__ __forceinline__ void dmma_gemm(int rows, int cols, int K, bool lower, ARow arow, BVal bval, Store store,
+                                          int tid, int nt) {
+  const int lane = tid & 31, warp = tid >> 5, nw = nt >> 5;
+  const int fr = lane >> 2, kc = lane & 3, fc = kc * 2;
+  const int TR = (rows + 15) >> 4, TC = (cols + 15) >> 4;
+  for (int t = warp; t < TR * TC; t += nw) {
+    const int I = t / TC, J = t - I * TC;
+    if (lower && J > I) continue;
+    const int r0 = 16 * I + fr, r1 = r0 + 8, c0 = 16 * J + fr, c1 = c0 + 8;
+    const double* a0p = r0 < rows ? arow(r0) : nullptr;
+    const double* a1p = r1 < rows ? arow(r1) : nullptr;
+    double acc[2][2][2] = {{{0.0, 0.0}, {0.0, 0.0}}, {{0.0, 0.0}, {0.0, 0.0}}};
+#pragma unroll 2
+    for (int k0 = 0; k0 < K; k0 += 4) {
+      const int k = k0 + kc;
+      const bool kin = k < K;
+      const double a0 = (a0p && kin) ? a0p[k] : 0.0;
+      const double a1 = (a1p && kin) ? a1p[k] : 0.0;
+      const double b0 = (kin && c0 < cols) ? bval(k, c0) : 0.0;
+      const double b1 = (kin && c1 < cols) ? bval(k, c1) : 0.0;
+      dmma884(acc[0][0][0], acc[0][0][1], a0, b0);
+      dmma884(acc[0][1][0], acc[0][1][1], a0, b1);
+      dmma884(acc[1][0][0], acc[1][0][1], a1, b0);
+      dmma884(acc[1][1][0], acc[1][1][1], a1, b1);
+    }
+#pragma unroll
+    for (int ii = 0; ii < 2; ii++) {
+#pragma unroll
+      for (int jj = 0; jj < 2; jj++) {
+        const int r = 16 * I + 8 * ii + fr, c = 16 * J + 8 * jj + fc;
+        if (r < rows && c < cols) store(r, c, acc[ii][jj][0]);
+        if (r < rows && c + 1 < cols) store(r, c + 1, acc[ii][jj][1]);
+      }
+    }
+  }
+}
+
 }  // namespace b200qp

@@ -78,7 +78,12 @@ template <typename T> int launch_prefactor(const KArgs<T>& a_in, const Layout& L
   const size_t bytes = ((size_t)2 * round4(L.n * L.ldn) + round4(L.n)) * sizeof(T);
   const size_t bytes2 = bytes + (size_t)2 * round4((L.p + L.m) * L.ldn) * sizeof(T);
   a.pre_smem = bytes2 <= 100 * 1024 ? 2 : (bytes <= kSmemResidentLimit ? 1 : 0);
-  const size_t dyn = a.pre_smem == 2 ? bytes2 : (a.pre_smem ? bytes : 0);
+  size_t dyn = a.pre_smem == 2 ? bytes2 : (a.pre_smem ? bytes : 0);
+  a.pre_blocked = 0;
+  if (sizeof(T) == 8 && a.pre_smem != 2 && L.n >= 96) {  // blocked tensor-core route (qp_blocked.cuh)
+    a.pre_blocked = (int)dyn + 1;
+    dyn += (size_t)blk_panel_elems(L.n) * sizeof(double);
+  }
   if (L.nt == 128) { auto k = k_prefactor<T, 128>; CK(ensure_smem(k, dyn)); k<<<(unsigned)a.nb, 128, dyn, st>>>(a); }
   else { auto k = k_prefactor<T, 256>; CK(ensure_smem(k, dyn)); k<<<(unsigned)a.nb, 256, dyn, st>>>(a); }
   CK(cudaGetLastError());

@@ -105,6 +105,8 @@ struct KArgs {
   int prob0;                 // first problem of this launch (chunked pre-factorisation / backward)
   int fso[36];               // fast path: shared-memory carve-up offsets in elements (qp_fast.cuh:fast_offsets)
   int pre_smem;              // prefactor: F / Qi working copies live in dynamic shared memory
+  int pre_blocked;           // prefactor: byte offset (+1) of the panel buffer in dynamic shared memory when the
+                             // blocked tensor-core route is taken (fp64, large nz; qp_blocked.cuh), else 0
   int rtile_mpad, rtile_nt;  // != 0: R is stored in register-tile order (qp_fast.cuh); nt = -1: DMMA fragment order
 };
 
@@ -597,11 +599,26 @@ __global__ void __launch_bounds__(NT) k_prefactor(const KArgs<T> a) {
     Qs[(size_t)r * ldn + c] = (r == c) ? T(1) : T(0);
   }
   __syncthreads();
-  const bool okQ = ldlt_factor(Fs, ldn, n, pinvFs, tid, NT);
+  bool blocked = false;
+  if constexpr (sizeof(T) == 8) blocked = a.pre_blocked != 0;
+  bool okQ;
+  if constexpr (sizeof(T) == 8) {
+    if (blocked) {
+      double* panel = reinterpret_cast<double*>(pre_smem_raw + (a.pre_blocked - 1));
+      okQ = ldlt_factor_blocked(reinterpret_cast<double*>(Fs), ldn, n, reinterpret_cast<double*>(pinvFs), panel, tid, NT);
+      ldlt_inverse_cols(reinterpret_cast<const double*>(Fs), ldn, n, reinterpret_cast<const double*>(pinvFs),
+                        reinterpret_cast<double*>(Qs), tid, NT);
+      __syncthreads();
+    } else {
+      okQ = ldlt_factor(Fs, ldn, n, pinvFs, tid, NT);
+    }
+  } else {
+    okQ = ldlt_factor(Fs, ldn, n, pinvFs, tid, NT);
+  }
   if (!okQ && tid == 0) atomicAdd(&a.ctl->q_fail, 1u);
   // L^-1: column j of L eliminates below row j; only columns c <= j of the identity are non-zero.
   // Lane = column, warp w takes rows j+1+w, j+1+w+nw, ...: no index divisions, conflict-free.
-  {
+  if (!blocked) {
     const int nw = NT >> 5;
     for (int j = 0; j + 1 < n; j++) {
       for (int c = lane; c <= j; c += 32) {
@@ -692,6 +709,33 @@ __global__ void __launch_bounds__(NT) k_prefactor(const KArgs<T> a) {
         }
         *reinterpret_cast<double2*>(Rd + (size_t)t * 64 + lane * 2) = make_double2(c0, c1);
       }
+      done = true;
+    }
+    if (!done && blocked) {
+      // large nz: both products on the FP64 tensor cores with operands straight from global / shared
+      // memory (16 x 16 output blocks per warp); the full M when there are equalities (V needs the
+      // upper-right block), its lower triangle otherwise
+      const double* Qd = reinterpret_cast<const double*>(Qs);
+      double* BQg = reinterpret_cast<double*>(BQi);
+      auto brow = [&](int r) -> const double* {
+        return reinterpret_cast<const double*>(r < p ? Ag + (size_t)r * n : Gg + (size_t)(r - p) * n);
+      };
+      dmma_gemm(pm, n, n, false, brow, [&](int k, int c) { return Qd[(size_t)k * ldn + c]; },
+                [&](int r, int c, double v) { BQg[(size_t)r * ldn + c] = v; }, tid, NT);
+      __syncthreads();
+      double* UAd = reinterpret_cast<double*>(UA);
+      double* Vd = reinterpret_cast<double*>(V);
+      double* Rd = reinterpret_cast<double*>(R);
+      const double reg = a.reg;
+      const int rt_mpad = a.rtile_mpad, rt_nt = a.rtile_nt;
+      dmma_gemm(pm, pm, n, p == 0, [&](int r) -> const double* { return BQg + (size_t)r * ldn; },
+                [&](int k, int c) { return brow(c)[k]; },
+                [&](int r, int q, double v) {
+                  if (r < p && q < p) { if (q <= r) UAd[(size_t)r * ldp + q] = v + ((r == q) ? reg : 0.0); }
+                  else if (r < p) Vd[(size_t)r * ldm + (q - p)] = v;
+                  else if (q >= p && q <= r)
+                    Rd[rt_mpad ? (size_t)rtile_index(r - p, q - p, rt_mpad, rt_nt) : (size_t)(r - p) * ldm + (q - p)] = v;
+                }, tid, NT);
       done = true;
     }
   }
