@@ -32,8 +32,11 @@ __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double
 }
 
 // All threads of the CTA; begins and ends with a barrier.  Wp: blk_panel_elems(m) doubles of shared memory.
+// R0 != nullptr: the matrix to factor is R0 + diag(1 / dvec) (R0 read-only, same layout); it is read in place
+// by the first panel step, whose trailing update writes the first version of S -- no separate copy pass.
 __device__ __forceinline__ bool ldlt_factor_blocked(double* __restrict__ S, int ld, int m, double* pinv, double* Wp,
-                                                    int tid, int nt) {
+                                                    int tid, int nt, const double* __restrict__ R0 = nullptr,
+                                                    const double* dvec = nullptr) {
   constexpr int PW = kBlkPW, PS = kBlkPS;
   const int lane = tid & 31, warp = tid >> 5, nwarps = nt >> 5;
   const int fr = lane >> 2, fc = (lane & 3) * 2, kc = lane & 3;
@@ -49,8 +52,16 @@ __device__ __forceinline__ bool ldlt_factor_blocked(double* __restrict__ S, int 
     // (1) diagonal block, one warp: lane owns row c0 + lane
     if (warp == 0) {
       double a[PW];
+      {
+        const double* src = (c0 == 0 && R0) ? R0 : S;
 #pragma unroll
-      for (int c = 0; c < PW; c++) a[c] = (lane < pw && c <= lane) ? S[(size_t)(c0 + lane) * ld + c0 + c] : 0.0;
+        for (int c = 0; c < PW; c++) a[c] = (lane < pw && c <= lane) ? src[(size_t)(c0 + lane) * ld + c0 + c] : 0.0;
+        if (c0 == 0 && R0 && lane < pw) {
+          const double dl = 1.0 / dvec[lane];
+#pragma unroll
+          for (int c = 0; c < PW; c++) if (c == lane) a[c] += dl;
+        }
+      }
       bool bad = false;
 #pragma unroll
       for (int k = 0; k < PW; k++) {
@@ -80,7 +91,7 @@ __device__ __forceinline__ bool ldlt_factor_blocked(double* __restrict__ S, int 
     for (int i = c0 + pw + tid; i < m8; i += nt) {
       double a[PW];
       if (i < m) {
-        const double* row = S + (size_t)i * ld + c0;
+        const double* row = ((c0 == 0 && R0) ? R0 : S) + (size_t)i * ld + c0;
 #pragma unroll
         for (int c = 0; c < PW; c++) a[c] = c < pw ? row[c] : 0.0;
 #pragma unroll
@@ -115,8 +126,18 @@ __device__ __forceinline__ bool ldlt_factor_blocked(double* __restrict__ S, int 
         const bool v0 = gi < m && gk < m, v1 = gi < m && gk + 1 < m;
         double* cp = S + (size_t)gi * ld + gk;
         double x0 = 0.0, x1 = 0.0;
-        if (v0) x0 = cp[0];
-        if (v1) x1 = cp[1];
+        if (c0 == 0 && R0) {
+          const double* rp = R0 + (size_t)gi * ld + gk;
+          if (v0) x0 = rp[0];
+          if (v1) x1 = rp[1];
+          if (I == K && gi < m) {
+            if (gi == gk) x0 += 1.0 / dvec[gi];
+            if (gi == gk + 1) x1 += 1.0 / dvec[gi];
+          }
+        } else {
+          if (v0) x0 = cp[0];
+          if (v1) x1 = cp[1];
+        }
         const double* ra = Wp + (size_t)(pw + 8 * I + fr) * PS + kc;
         const double* rb = Wp + (size_t)(pw + 8 * K + fr) * PS + kc;
         dmma884(x0, x1, ra[0] * s0, rb[0]);

@@ -218,6 +218,10 @@ __device__ __forceinline__ void stage_mats(const Smem<T>& S, const KArgs<T>& a, 
 template <typename T, bool SMEM, int NT>
 __device__ __forceinline__ bool build_and_factor_T(const Smem<T>& S, const KArgs<T>& a, int prob, int tid, int nt) {
   const int m = a.m, ldm = a.ldm;
+  if constexpr (!SMEM && std::is_same<T, double>::value) {
+    // global-resident T: blocked tensor-core factorisation that reads R + diag(1/d) in place (qp_blocked.cuh)
+    return ldlt_factor_blocked(S.Tm, ldm, m, S.pinvT, S.panel, tid, nt, a.R + (size_t)prob * a.sR, S.d);
+  }
   if (SMEM) {
     cp_async_wait_all();
     __syncthreads();
@@ -228,7 +232,6 @@ __device__ __forceinline__ bool build_and_factor_T(const Smem<T>& S, const KArgs
   }
   for (int i = tid; i < m; i += nt) S.Tm[(size_t)i * ldm + i] += T(1) / S.d[i];
   __syncthreads();
-  if constexpr (!SMEM && std::is_same<T, double>::value) return ldlt_factor_blocked(S.Tm, ldm, m, S.pinvT, S.panel, tid, nt);
   if (SMEM) {
     if (NT == 128) {
       if (m <= 32) return ldlt_factor_reg<T, 32, 128>(S.Tm, ldm, m, S.pinvT, S.part, tid);
@@ -333,7 +336,7 @@ __device__ __forceinline__ void step_pieces(const T* v, const T* dv, int m, int 
 // ------------------------------------------------------------------------------------------
 // One PDIPM iteration (a.iter >= 0) or the initial point (a.iter == -1).
 template <typename T, bool SMEM, int NT>
-__global__ void __launch_bounds__(NT) k_pdipm_iter(const KArgs<T> a) {
+__global__ void __launch_bounds__(NT, (!SMEM && NT == 256 && sizeof(T) == 8) ? 3 : 1) k_pdipm_iter(const KArgs<T> a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int prob = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int n = a.n, m = a.m, p = a.p, it = a.iter;
