@@ -25,6 +25,20 @@ constexpr int kBlkPW = 16;  // panel width
 constexpr int kBlkPS = 20;  // doubles per row of the panel buffer
 __host__ __device__ inline int blk_panel_elems(int m) { return ((m + 7) & ~7) * kBlkPS + kBlkPW + 8; }
 
+__device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
+
+// 1/x for a positive pivot: MUFU seed + two Newton steps (full double accuracy away from the range ends)
+__device__ __forceinline__ double blk_rcp(double x) {
+  double r;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+  double e = fma(-x, r, 1.0);
+  r = fma(r, e, r);
+  e = fma(-x, r, 1.0);
+  r = fma(r, e, r);
+  if (!(x > 1e-290 && x < 1e290)) r = 1.0 / x;  // rare
+  return r;
+}
+
 __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
   asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
                : "+d"(c0), "+d"(c1)
@@ -68,7 +82,7 @@ __device__ __forceinline__ bool ldlt_factor_blocked(double* __restrict__ S, int 
         const double dk = shfl_d(a[k], k);
         double pkk = 0.0;
         if (k < pw) {
-          pkk = (dk > 0.0) ? 1.0 / dk : t_nan<double>();
+          pkk = (dk > 0.0) ? blk_rcp(dk) : t_nan<double>();
           if (!(dk > 0.0)) bad = true;
         }
         const double w = a[k];
@@ -117,35 +131,53 @@ __device__ __forceinline__ bool ldlt_factor_blocked(double* __restrict__ S, int 
     if (r0 < m) {
       const int nt8 = (m - r0 + 7) >> 3, ntiles = nt8 * (nt8 + 1) / 2;
       const double s0 = -ppan[kc], s1 = -ppan[4 + kc], s2 = -ppan[8 + kc], s3 = -ppan[12 + kc];
-      for (int t = warp; t < ntiles; t += nwarps) {
-        int I = (int)((sqrtf(8.0f * (float)t + 1.0f) - 1.0f) * 0.5f);
-        if ((I + 1) * (I + 2) / 2 <= t) I++;
-        if (I * (I + 1) / 2 > t) I--;
-        const int K = t - I * (I + 1) / 2;
-        const int gi = r0 + 8 * I + fr, gk = r0 + 8 * K + fc;
-        const bool v0 = gi < m && gk < m, v1 = gi < m && gk + 1 < m;
-        double* cp = S + (size_t)gi * ld + gk;
-        double x0 = 0.0, x1 = 0.0;
-        if (c0 == 0 && R0) {
-          const double* rp = R0 + (size_t)gi * ld + gk;
-          if (v0) x0 = rp[0];
-          if (v1) x1 = rp[1];
-          if (I == K && gi < m) {
-            if (gi == gk) x0 += 1.0 / dvec[gi];
-            if (gi == gk + 1) x1 += 1.0 / dvec[gi];
-          }
-        } else {
-          if (v0) x0 = cp[0];
-          if (v1) x1 = cp[1];
+      // (d) the next panel's diagonal block and first rows are touched next by ONE warp: pull them into L1 now
+      if (warp == nwarps - 1 && r0 + lane < m) {
+        const double* nx = S + (size_t)(r0 + lane) * ld + r0;
+        prefetch_l1(nx);
+        prefetch_l1(nx + 15);
+      }
+      // four tiles in flight per warp: their loads are issued together, then the DMMAs, then the stores
+      constexpr int TF = 4;
+      int I = 0, K = warp;  // tile t = warp, warp + nwarps, ... of the row-major lower-triangle enumeration
+      while (K > I) { K -= I + 1; I++; }
+      const bool first = (c0 == 0 && R0 != nullptr);
+      const double* src = first ? R0 : S;
+      for (int t = warp; t < ntiles; t += TF * nwarps) {
+        int tI[TF], tK[TF];
+        double x0[TF], x1[TF];
+        bool v0[TF], v1[TF];
+#pragma unroll
+        for (int f = 0; f < TF; f++) {
+          tI[f] = I; tK[f] = K;
+          const bool live = t + f * nwarps < ntiles;
+          const int gi = r0 + 8 * I + fr, gk = r0 + 8 * K + fc;
+          v0[f] = live && gi < m && gk < m;
+          v1[f] = live && gi < m && gk + 1 < m;
+          const double* rp = src + (size_t)gi * ld + gk;
+          x0[f] = v0[f] ? rp[0] : 0.0;
+          x1[f] = v1[f] ? rp[1] : 0.0;
+          K += nwarps;
+          while (K > I) { K -= I + 1; I++; }
         }
-        const double* ra = Wp + (size_t)(pw + 8 * I + fr) * PS + kc;
-        const double* rb = Wp + (size_t)(pw + 8 * K + fr) * PS + kc;
-        dmma884(x0, x1, ra[0] * s0, rb[0]);
-        dmma884(x0, x1, ra[4] * s1, rb[4]);
-        dmma884(x0, x1, ra[8] * s2, rb[8]);
-        dmma884(x0, x1, ra[12] * s3, rb[12]);
-        if (v0) cp[0] = x0;
-        if (v1) cp[1] = x1;
+#pragma unroll
+        for (int f = 0; f < TF; f++) {
+          if (t + f * nwarps >= ntiles) break;  // warp-uniform
+          const int gi = r0 + 8 * tI[f] + fr, gk = r0 + 8 * tK[f] + fc;
+          if (first && tI[f] == tK[f] && gi < m) {
+            if (gi == gk) x0[f] += 1.0 / dvec[gi];
+            if (gi == gk + 1) x1[f] += 1.0 / dvec[gi];
+          }
+          const double* ra = Wp + (size_t)(pw + 8 * tI[f] + fr) * PS + kc;
+          const double* rb = Wp + (size_t)(pw + 8 * tK[f] + fr) * PS + kc;
+          dmma884(x0[f], x1[f], ra[0] * s0, rb[0]);
+          dmma884(x0[f], x1[f], ra[4] * s1, rb[4]);
+          dmma884(x0[f], x1[f], ra[8] * s2, rb[8]);
+          dmma884(x0[f], x1[f], ra[12] * s3, rb[12]);
+          double* cp = S + (size_t)gi * ld + gk;
+          if (v0[f]) cp[0] = x0[f];
+          if (v1[f]) cp[1] = x1[f];
+        }
       }
     }
     __syncthreads();
@@ -179,15 +211,26 @@ __device__ __forceinline__ void ldlt_solve_blocked(const double* __restrict__ U,
       if (lane < bw) v[j0 + lane] = r;
     }
     __syncthreads();
+    if (warp == 1 && j0 + 32 + lane < m) {  // next diagonal block -> L1 while the update runs
+      const double* nx = U + (size_t)(j0 + 32 + lane) * ld + j0 + 32;
+      prefetch_l1(nx); prefetch_l1(nx + 16); prefetch_l1(nx + 31);
+    }
     for (int i = j0 + bw + tid; i < m; i += nt) {
       const double* col = U + (size_t)j0 * ld + i;
       double acc0 = v[i], acc1 = 0.0;
-      int jj = 0;
-      for (; jj + 1 < bw; jj += 2) {
-        acc0 -= col[(size_t)jj * ld] * v[j0 + jj];
-        acc1 -= col[(size_t)(jj + 1) * ld] * v[j0 + jj + 1];
+#pragma unroll
+      for (int j8 = 0; j8 < 32; j8 += 8) {
+        if (j8 < bw) {  // uniform
+          double u8[8];
+#pragma unroll
+          for (int q = 0; q < 8; q++) u8[q] = (j8 + q < bw) ? col[(size_t)(j8 + q) * ld] : 0.0;
+#pragma unroll
+          for (int q = 0; q < 8; q += 2) {
+            if (j8 + q < bw) acc0 -= u8[q] * v[j0 + j8 + q];
+            if (j8 + q + 1 < bw) acc1 -= u8[q + 1] * v[j0 + j8 + q + 1];
+          }
+        }
       }
-      if (jj < bw) acc0 -= col[(size_t)jj * ld] * v[j0 + jj];
       v[i] = acc0 + acc1;
     }
     __syncthreads();
@@ -212,15 +255,26 @@ __device__ __forceinline__ void ldlt_solve_blocked(const double* __restrict__ U,
       if (lane < bw) v[j0 + lane] = r;
     }
     __syncthreads();
+    if (warp == 1 && j0 >= 32) {  // previous diagonal block -> L1 while the update runs
+      const double* nx = U + (size_t)(j0 - 32 + lane) * ld + j0 - 32;
+      prefetch_l1(nx); prefetch_l1(nx + 16); prefetch_l1(nx + 31);
+    }
     for (int i = tid; i < j0; i += nt) {
       const double* row = U + (size_t)i * ld + j0;
       double acc0 = v[i], acc1 = 0.0;
-      int jj = 0;
-      for (; jj + 1 < bw; jj += 2) {
-        acc0 -= row[jj] * v[j0 + jj];
-        acc1 -= row[jj + 1] * v[j0 + jj + 1];
+#pragma unroll
+      for (int j8 = 0; j8 < 32; j8 += 8) {
+        if (j8 < bw) {  // uniform
+          double u8[8];
+#pragma unroll
+          for (int q = 0; q < 8; q++) u8[q] = (j8 + q < bw) ? row[j8 + q] : 0.0;
+#pragma unroll
+          for (int q = 0; q < 8; q += 2) {
+            if (j8 + q < bw) acc0 -= u8[q] * v[j0 + j8 + q];
+            if (j8 + q + 1 < bw) acc1 -= u8[q + 1] * v[j0 + j8 + q + 1];
+          }
+        }
       }
-      if (jj < bw) acc0 -= row[jj] * v[j0 + jj];
       v[i] = acc0 + acc1;
     }
     __syncthreads();
