@@ -72,6 +72,19 @@ def gen_batch(nb, device, seed, dtype=torch.float64):
     return Q, p, G, h, A, b
 
 
+def gen_batch_sized(nb, nz, m, device, seed):
+    """The same recipe at another size (BASELINE configs[4])."""
+    g = torch.Generator(device=device).manual_seed(seed)
+    L = torch.rand(nb, nz, nz, generator=g, device=device, dtype=torch.float64)
+    Q = torch.bmm(L, L.transpose(1, 2)) + 1e-3 * torch.eye(nz, device=device, dtype=torch.float64)
+    G = torch.randn(nb, m, nz, generator=g, device=device, dtype=torch.float64)
+    z0 = torch.randn(nb, nz, generator=g, device=device, dtype=torch.float64)
+    s0 = torch.rand(nb, m, generator=g, device=device, dtype=torch.float64)
+    p = torch.randn(nb, nz, generator=g, device=device, dtype=torch.float64)
+    h = torch.bmm(G, z0.unsqueeze(2)).squeeze(2) + s0
+    return Q, p, G, h
+
+
 class ClockSampler:
     """nvidia-smi clocks/throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
 
@@ -268,6 +281,45 @@ def bench_mpc_shapes(dev):
     run("rex_quadrotor_T40_B1024", envs.RexQuadrotor_dynamics(), envs.RexQuadrotor_dynamics_jac(), 12, 4, T, B, x0,
         (14.9 + 0.1 * (r(B, T, 4) - 0.5)).to(dev), [10.] * 3 + [0.01] * 3 + [1.] * 3 + [0.01] * 3 + [1e-4] * 4,
         one(11.5, 4), one(18.3, 4), 2)
+    return out
+
+
+def bench_qp_sizes(dev):
+    """BASELINE configs[4], the larger sizes of the sweep (device-resident, fp64, forward+backward): the
+    nineq x nineq system no longer fits in shared memory and the blocked tensor-core kernels of
+    csrc/qp_blocked.cuh take over."""
+    from b200qp.qp import QPFunction
+    out = {}
+    for nz, nbs in ((100, 1184), (200, 592)):
+        m = 2 * nz
+        Q, p, G, h = gen_batch_sized(nbs, nz, m, dev, 5)
+        A = torch.zeros(nbs, 0, nz, device=dev, dtype=torch.float64)
+        b = torch.zeros(nbs, 0, device=dev, dtype=torch.float64)
+        for t in (Q, p, G, h):
+            t.requires_grad_(True)
+        fn = QPFunction(verbose=-1, check_Q_spd=False)
+        ones = torch.ones(nbs, nz, device=dev, dtype=torch.float64)
+
+        def step():
+            for t in (Q, p, G, h):
+                t.grad = None
+            z = fn(Q, p, G, h, A, b)
+            z.backward(ones)
+            return z
+
+        step()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(2):
+            z = step()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / 2
+        n_it = fn.info["n_iter"]
+        fl = algorithmic_flops(nz, m, n_it)["total"]
+        out[f"nz{nz}_m{m}"] = {"nb": nbs, "ms_per_step": ms, "solves_per_s": nbs / (ms * 1e-3), "n_iter": n_it,
+                               "tflops_algorithmic": fl * nbs / (ms * 1e-3) / 1e12, "finite": bool(torch.isfinite(z).all())}
     return out
 
 
@@ -546,6 +598,13 @@ def main():
     except Exception as ex:  # pragma: no cover
         small = {"error": repr(ex)}
 
+    sizes = None
+    if rank == 0:
+        try:
+            sizes = bench_qp_sizes(dev)
+        except Exception as ex:  # pragma: no cover
+            sizes = {"error": repr(ex)}
+
     mpc = None
     if rank == 0:
         try:
@@ -578,7 +637,7 @@ def main():
                        "eps": 1e-12, "maxIter": 20, "parallelism": f"batch-sharded x{world}, no data-path collective",
                        "l2": "inputs+workspace per step exceed the 126 MB L2 (no flush needed)"},
             "clocks": clocks, "e2e": e2e, "gpu_launches": launches_per_step * args.steps,
-            "roofline": roofline, "cpu_baseline": cpu, "cfg1_nb128": small, "mpc": mpc,
+            "roofline": roofline, "cpu_baseline": cpu, "cfg1_nb128": small, "cfg4_sizes": sizes, "mpc": mpc,
         }
         print(json.dumps(line))
     if world > 1:

@@ -66,14 +66,19 @@ def main():
                     md.append(f"| {label} (`{key}`) | {r[i]} | {units[i]} |")
             md.append("")
             if "k_fast_iter" in name or "k_pdipm_iter" in name:
+                big = "k_pdipm_iter" in name
                 def to_bytes(k):
                     v, u = vals[k]
                     mult = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}[u]
                     return float(v) * mult
                 grid = float(vals["launch__grid_size"][0])
-                traffic = {"kernel": name, "problems_in_capture": grid,
+                rec = {"kernel": name, "problems_in_capture": grid,
                            "dram_bytes_per_problem_per_launch": (to_bytes("dram__bytes_read.sum") + to_bytes("dram__bytes_write.sum")) / grid,
                            "source": os.path.basename(path)}
+                if big:
+                    json.dump(rec, open(os.path.join(outdir, "ncu_traffic_large_qp.json"), "w"), indent=1)
+                else:
+                    traffic = rec
     open(os.path.join(outdir, f"ncu_summary_{rnd}.md"), "w").write("\n".join(md) + "\n")
     if traffic:
         json.dump(traffic, open(os.path.join(outdir, "ncu_traffic.json"), "w"), indent=1)
