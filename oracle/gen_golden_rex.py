@@ -56,6 +56,30 @@ def main():
                         out_dC=Cfull.grad.diagonal(dim1=-2, dim2=-1).numpy(), out_dc=c.grad.numpy())
     print("rex MPC: |x|", float(xs.norm()), "|u|", float(us.norm()), "|lam|", float(ctrl.lamda_prev.norm()))
 
+    # BASELINE configs[3] horizon (T = 40: the per-problem state no longer fits in shared memory, the kernel
+    # works out of its global scratch slab), bench-like inputs
+    torch.manual_seed(0)
+    Bsz, T = 4, 40
+    x0 = torch.cat((torch.rand(Bsz, 3, dtype=torch.float64) * 2 - 1, torch.rand(Bsz, 3, dtype=torch.float64) * 0.4 - 0.2,
+                    torch.rand(Bsz, 6, dtype=torch.float64) * 0.4 - 0.2), 1)
+    u_init = 14.9 + 0.1 * torch.randn(Bsz, T, 4, dtype=torch.float64)
+    Cd = torch.tensor([10.] * 3 + [0.01] * 3 + [1.] * 3 + [0.01] * 3 + [1e-4] * 4, dtype=torch.float64).repeat(Bsz, T, 1)
+    xref = torch.zeros(Bsz, T, nx + nu, dtype=torch.float64)
+    ctrl = al_mpc.MPC(nx, nu, T, u_lower=ul, u_upper=uu, exit_unconverged=False, eps=1e-5, n_batch=Bsz, backprop=False,
+                      verbose=0, u_init=u_init.clone(), solver_type="dense", dtype=torch.float64)
+    ctrl.reinitialize(x0, None)
+    ctrl.u_init = u_init.clone()
+    Cfull = torch.diag_embed(Cd).clone().requires_grad_(True)
+    c = (-(Cd * xref)).clone().requires_grad_(True)
+    xs, us = ctrl(x0, al_utils.QuadCost(Cfull, c), dyn, dynj)
+    (xs.sum() + us.sum()).backward()
+    assert torch.isfinite(xs).all() and torch.isfinite(us).all()
+    np.savez_compressed(os.path.join(ROOT, "tests", "golden", "mpc_rex_B4_T40.npz"), x0=x0.numpy(), u_init=u_init.numpy(),
+                        Cd=Cd.numpy(), xref=xref.numpy(), out_x=xs.detach().numpy(), out_u=us.detach().numpy(),
+                        out_lam=ctrl.lamda_prev.numpy(), out_rho=ctrl.rho_prev.numpy(),
+                        out_dC=Cfull.grad.diagonal(dim1=-2, dim2=-1).numpy(), out_dc=c.grad.numpy())
+    print("rex MPC T=40: |x|", float(xs.norm()), "|u|", float(us.norm()), "|lam|", float(ctrl.lamda_prev.norm()))
+
 
 if __name__ == "__main__":
     main()

@@ -47,7 +47,7 @@ x0 = torch.stack((torch.rand(B, dtype=torch.float64) - 0.5, torch.zeros(B, dtype
                   torch.zeros(B, dtype=torch.float64)), 1).to(dev)
 run("cartpole env_dx (cfg[2] shape)", envs.CartpoleDx(), envs.CartpoleDx_jac(), 5, 1, T, B, x0,
     0.1 * torch.randn(B, T, 1, dtype=torch.float64, device=dev), [0.1, 0.1, 1., 1., 0.1, 0.001], one(-100., 1), one(100., 1))
-for B in (256, 2048):
+for B in (1024, 4096, 8192):
     T = 40
     x0 = torch.cat((torch.rand(B, 3, dtype=torch.float64) * 2 - 1, torch.rand(B, 3, dtype=torch.float64) * 0.4 - 0.2,
                     torch.rand(B, 6, dtype=torch.float64) * 0.4 - 0.2), 1).to(dev)

@@ -159,12 +159,14 @@ def test_rex_quadrotor_dynamics_golden(cuda_device):
     assert rel(y.cpu(), g["xn"]) < 1e-13
 
 
-def test_al_mpc_rex_quadrotor_golden(cuda_device):
-    """AL-MPC on the rex quadrotor (nx=12, nu=4, T=8, B=4) against the real reference run."""
+@pytest.mark.parametrize("gold", ("mpc_rex_B4_T8.npz", "mpc_rex_B4_T40.npz"))
+def test_al_mpc_rex_quadrotor_golden(gold, cuda_device):
+    """AL-MPC on the rex quadrotor (nx=12, nu=4, B=4; T=8 and the configs[3] horizon T=40, where the kernel works
+    out of its global scratch slab) against the real reference run."""
     from b200qp import envs
     from b200qp.AL_mpc import MPC
     from b200qp.al_utils import QuadCost
-    g = _npz("mpc_rex_B4_T8.npz")
+    g = _npz(gold)
     dev = cuda_device
     B, T, nu = g["u_init"].shape
     nx = g["x0"].shape[1]
