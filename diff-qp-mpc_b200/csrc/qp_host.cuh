@@ -47,7 +47,12 @@ inline int make_layout(const b200qp_problem_t* pr, Layout& L) {
   // fast path (qp_fast.cuh): nineq <= 64 with 128 threads, <= 128 with 256 threads
   L.mpad = L.m <= 32 ? 32 : (L.m <= 64 ? 64 : 128);
   L.fk = 0;
-  L.fast = L.m <= 128 && (L.m <= 64 || widest <= 256) && getenv("B200QP_FORCE_GENERIC") == nullptr;
+  // fp64 problems with nineq > 64 take the global-resident blocked tensor-core route (qp_blocked.cuh): measured
+  // 2-3x faster than the register-tile fast path at 64 < nineq <= 128 (B200QP_MID=fast restores the old routing)
+  const char* mid = getenv("B200QP_MID");
+  const bool blocked_route = pr->dtype == B200QP_F64 && L.m > 64 && !(pr->flags & B200QP_FLAG_DENSE) && !(mid && mid[0] == 'f');
+  if (blocked_route) { L.smem = false; L.smem_bytes = vecs; }
+  L.fast = !blocked_route && L.m <= 128 && (L.m <= 64 || widest <= 256) && getenv("B200QP_FORCE_GENERIC") == nullptr;
   if (L.fast) {
     const int generic_nt = L.nt;
     const char* fnt = nullptr;  // 32/64-thread CTA variants were measured slower and are not instantiated

@@ -80,7 +80,7 @@ template <typename T> int launch_prefactor(const KArgs<T>& a_in, const Layout& L
   a.pre_smem = bytes2 <= 100 * 1024 ? 2 : (bytes <= kSmemResidentLimit ? 1 : 0);
   size_t dyn = a.pre_smem == 2 ? bytes2 : (a.pre_smem ? bytes : 0);
   a.pre_blocked = 0;
-  if (sizeof(T) == 8 && a.pre_smem != 2 && L.n >= 96) {  // blocked tensor-core route (qp_blocked.cuh)
+  if (sizeof(T) == 8 && a.pre_smem != 2 && L.n >= 48) {  // blocked tensor-core route (qp_blocked.cuh)
     a.pre_blocked = (int)dyn + 1;
     dyn += (size_t)blk_panel_elems(L.n) * sizeof(double);
   }

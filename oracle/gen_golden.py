@@ -36,6 +36,10 @@ CASES = {
     "big_nb8_nz100_m200": (8, 100, 200, 0, 7, "float64", False, ()),
     "mid_nb16_nz64_m64_p16": (16, 64, 64, 16, 8, "float64", False, ()),
     "fp32_nb32_nz30_m60": (32, 30, 60, 0, 9, "float32", False, ()),
+    # 64 < nineq <= 128 and equality-constrained large problems: the global-resident blocked kernels (qp_blocked.cuh)
+    "m96_nb8_nz40_m96": (8, 40, 96, 0, 10, "float64", False, ()),
+    "m80eq_nb8_nz48_m80_p8": (8, 48, 80, 8, 11, "float64", False, ()),
+    "bigeq_nb4_nz70_m150_p12": (4, 70, 150, 12, 12, "float64", False, ()),
 }
 FULL_GRAD_ROWS = 8  # dQ/dG/dA are stored in full for the first rows, as norms for the rest
 
@@ -120,7 +124,10 @@ def main():
     os.makedirs(outdir, exist_ok=True)
     import faulthandler
     faulthandler.dump_traceback_later(240, exit=True)
+    only = sys.argv[1:]   # optional: generate just these cases
     for case in CASES:
+        if only and case not in only:
+            continue
         inp = make_inputs(case)
         ref = run_reference(inp)
         ora = run_oracle(inp)
