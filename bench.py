@@ -202,6 +202,31 @@ def bench_mpc(dev, B=1024, T=5, reps=20):
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / reps
+    # the same step captured once in a CUDA graph and replayed (the launch-bound regime at this size: ~40 tiny
+    # launches of torch glue + autograd around one fused solve; everything is enqueued on the capturing stream)
+    graph_ms = None
+    try:
+        gs = torch.cuda.Stream()
+        gs.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(gs):
+            step()
+        torch.cuda.current_stream().wait_stream(gs)
+        torch.cuda.synchronize()
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph, stream=gs):
+            gx, gsim = step()
+        graph.replay()
+        torch.cuda.synchronize()
+        xe, sime = step()
+        assert torch.equal(gx, xe) and torch.equal(gsim, sime), "graph replay differs from the eager step"
+        e0.record()
+        for _ in range(reps):
+            graph.replay()
+        e1.record()
+        torch.cuda.synchronize()
+        graph_ms = e0.elapsed_time(e1) / reps
+    except Exception as ex:  # pragma: no cover
+        graph_ms = repr(ex)[:200]
     # kernel-only time of the fused AL solve (the rest of the step is torch glue + tiny kernels)
     c = -(Cd * xref).detach()
     Cdiag = Cd.clone()
@@ -222,6 +247,8 @@ def bench_mpc(dev, B=1024, T=5, reps=20):
     return {"workload": f"BASELINE configs[1] shape: pendulum AL-MPC (deqmpc/envs.py dynamics) T={T} batch={B} fp64, "
                         "forward + open-loop simulation + implicit backward",
             "rollouts_per_s": B / (ms * 1e-3), "ms_per_call": ms, "al_solve_call_ms": min(kms),
+            "cuda_graph_ms_per_call": graph_ms,
+            "cuda_graph_rollouts_per_s": (B / (graph_ms * 1e-3)) if isinstance(graph_ms, float) else None,
             "launches_per_call": 1 + (T - 1) * 2 + 1}
 
 
