@@ -206,6 +206,7 @@ def bench_mpc(dev, B=1024, T=5, reps=20):
     # launches of torch glue + autograd around one fused solve; everything is enqueued on the capturing stream)
     graph_ms = None
     try:
+        torch.autograd.graph.set_warn_on_accumulate_grad_stream_mismatch(False)
         gs = torch.cuda.Stream()
         gs.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(gs):
@@ -334,7 +335,8 @@ def bench_qp_sizes(dev):
             z.backward(ones)
             return z
 
-        step()
+        for _ in range(3):
+            step()
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
