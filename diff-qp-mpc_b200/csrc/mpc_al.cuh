@@ -302,7 +302,10 @@ __device__ __forceinline__ void block_solve(const R* D, const R* E, R* g, int T,
 }
 
 template <class Dyn, typename R>
-__global__ void __launch_bounds__(128) k_al_solve(const ALArgs<R> a) {
+#ifndef AL_MINB
+#define AL_MINB 1
+#endif
+__global__ void __launch_bounds__(128, (Dyn::NX <= 6 ? AL_MINB : 1)) k_al_solve(const ALArgs<R> a) {
   constexpr int NX = Dyn::NX, NU = Dyn::NU, NT = NX + NU;
   extern __shared__ __align__(16) unsigned char al_smem[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;

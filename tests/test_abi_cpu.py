@@ -83,3 +83,31 @@ def test_product_never_imports_oracle():
     for path in glob.glob(os.path.join(pkg, "**", "*.py"), recursive=True):
         src = open(path).read()
         assert not re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M), path
+
+
+def test_my_envs_host_mirror_selects_the_fused_models():
+    """deqmpc/my_envs call surface without a GPU: the env exposes what Tracking_MPC reads, and both
+    `env.dynamics` (module) and `env.dynamics_derivatives` (bound method, deqmpc/policies.py:576-577) map to the
+    same fused model + parameter vector; a reference-style module whose `.package` is an extension MODULE named
+    like the reference's packages is recognised by that name."""
+    import types
+    import torch
+    from b200qp import _lib, my_envs
+    from b200qp.envs import dyn_spec
+    kw = dict(dtype=torch.float64, device="cpu")
+    env = my_envs.CartpoleEnv(nx=4, dt=0.05, kwargs=kw)
+    assert (env.nx, env.nu, env.nq, env.T, env.u_bounds) == (4, 1, 2, 200, 100.0)
+    assert float(env.Rlqr[0]) == 1e-8 and env.action_space.high[0] == 100.0
+    s1, s2 = dyn_spec(env.dynamics), dyn_spec(env.dynamics_derivatives)
+    assert s1 == s2 and s1[0] == _lib.ENV_CARTPOLE1L and s1[1][:4] == [0.05, 11.0, 1.0, 2.0] and s1[2:] == (4, 1)
+    env2 = my_envs.CartpoleEnv(nx=6, dt=0.03, kwargs=kw)
+    assert dyn_spec(env2.dynamics)[0] == _lib.ENV_CARTPOLE2L and dyn_spec(env2.dynamics)[2:] == (6, 1)
+    pend = my_envs.PendulumEnv(nx=2, dt=0.05, kwargs=kw)
+    assert dyn_spec(pend.dynamics)[0] == _lib.ENV_PENDULUM1L
+    ref_like = types.SimpleNamespace(package=types.ModuleType("cartpole1l_v2"), dt=0.05)
+    assert dyn_spec(ref_like)[1][1:4] == [0.7, 0.1, 0.05]
+    import pytest
+    with pytest.raises(NotImplementedError):
+        my_envs.package_spec("cartpole3l", 0.05)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        env.dynamics(torch.zeros(2, 4, dtype=torch.float64), torch.zeros(2, 1, dtype=torch.float64))
