@@ -297,3 +297,19 @@ def test_exact_global_batch_mode_two_ranks(cuda_device):
     assert all(r[1] == fn.info["n_iter"] for r in res), ([r[1] for r in res], fn.info["n_iter"])
     assert np.array_equal(np.concatenate([r[2] for r in res]), z.detach().cpu().numpy())
     assert np.array_equal(np.concatenate([r[3] for r in res]), t[2].grad.cpu().numpy())
+
+
+@pytest.mark.parametrize("env,case", [("B200QP_FORCE_GENERIC", "cfg1_nb128_nz30_m60"), ("B200QP_FORCE_GENERIC", "eq_nb32_nz20_m16_p6"),
+                                      ("B200QP_FORCE_GENERIC", "mid_nb16_nz64_m64_p16"), ("B200QP_MID", "m96_nb8_nz40_m96"),
+                                      ("B200QP_MID", "m80eq_nb8_nz48_m80_p8")])
+def test_alternative_kernel_routes_golden(env, case, cuda_device, monkeypatch):
+    """The routes the default dispatch no longer takes stay parity-green: the generic shared-memory-resident
+    kernels (B200QP_FORCE_GENERIC: no fast path) and the register-tile fast path for 64 < nineq <= 128
+    (B200QP_MID=fast).  The library reads the variable at every call (csrc/qp_host.cuh:make_layout)."""
+    monkeypatch.setenv(env, "fast" if env == "B200QP_MID" else "1")
+    inp = make_inputs(case)
+    g = load_golden(case)
+    out, info = run_ours(inp, cuda_device)
+    worst = compare_with_golden(case, out, rtol=1e-6)
+    print(env, case, "n_iter", info["n_iter"], "ref", int(g["n_iter"]), {k: f"{v:.1e}" for k, v in worst.items()})
+    assert abs(info["n_iter"] - int(g["n_iter"])) <= 5
