@@ -128,7 +128,10 @@ __device__ __forceinline__ void assemble(const ALScratch<R, Dyn::NX, Dyn::NU>& S
   constexpr int NX = Dyn::NX, NU = Dyn::NU, NT = NX + NU;
   const int neq = T * NX;
   // Jacobians by forward-mode duals, DW directions at a time (bounds the register footprint)
-  constexpr int DW = NT <= 4 ? NT : 4;
+  // (two at a time for the my_envs cart-pole and the quadrotor: measured 5 % faster than four -- fewer live
+  // registers / less local memory outweigh the extra passes; four elsewhere)
+  constexpr int DWMAX = (NX == 4 || NX >= 12) ? 2 : 4;
+  constexpr int DW = NT <= DWMAX ? NT : DWMAX;
   typedef Dual<R, DW> DR;
   for (int t = lane; t < T; t += 32) {
     if (t < T - 1) {
@@ -305,7 +308,7 @@ template <class Dyn, typename R>
 // Occupancy: the cart-pole of deqmpc/my_envs (NX = 4, RK4 under 4-wide duals) compiles to 252 registers = 2 CTAs/SM;
 // capped at 128 (4 CTAs/SM, ~0.8 KB of spills) it runs 45 % faster (5.04 -> 3.48 ms at T=20, B=4096).  The two-link
 // model (NX = 6) loses 5-7 % under the same cap and the other environments already sit at <= 166 registers.
-__global__ void __launch_bounds__(128, (Dyn::NX == 4 ? 4 : 1)) k_al_solve(const ALArgs<R> a) {
+__global__ void __launch_bounds__(128, (Dyn::NX == 4 ? 4 : 0)) k_al_solve(const ALArgs<R> a) {
   constexpr int NX = Dyn::NX, NU = Dyn::NU, NT = NX + NU;
   extern __shared__ __align__(16) unsigned char al_smem[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
