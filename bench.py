@@ -339,12 +339,14 @@ def bench_qp_sizes(dev):
             step()
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for _ in range(2):
+        reps_ms = []
+        for _ in range(3):
+            e0.record()
             z = step()
-        e1.record()
-        torch.cuda.synchronize()
-        ms = e0.elapsed_time(e1) / 2
+            e1.record()
+            torch.cuda.synchronize()
+            reps_ms.append(e0.elapsed_time(e1))
+        ms = statistics.median(reps_ms)
         n_it = fn.info["n_iter"]
         fl = algorithmic_flops(nz, m, n_it)["total"]
         out[f"nz{nz}_m{m}"] = {"nb": nbs, "ms_per_step": ms, "solves_per_s": nbs / (ms * 1e-3), "n_iter": n_it,

@@ -105,6 +105,7 @@ __device__ __forceinline__ void gemv_cols(const T* __restrict__ M, int ld, int r
     if (g < groups) {
       T a0 = 0, a1 = 0;
       int r = g;
+#pragma unroll 4
       for (; r + groups < rows; r += 2 * groups) {
         a0 += M[(size_t)r * ld + c] * v[r];
         a1 += M[(size_t)(r + groups) * ld + c] * v[r + groups];
@@ -122,6 +123,7 @@ __device__ __forceinline__ void gemv_cols(const T* __restrict__ M, int ld, int r
     for (int c = tid; c < cols; c += nt) {
       T a0 = 0, a1 = 0;
       int r = 0;
+#pragma unroll 4
       for (; r + 1 < rows; r += 2) {
         a0 += M[(size_t)r * ld + c] * v[r];
         a1 += M[(size_t)(r + 1) * ld + c] * v[r + 1];
@@ -143,6 +145,7 @@ __device__ __forceinline__ void gemv_cols_nt(const T* __restrict__ M, int ld, in
     if (g < groups) {
       T a0 = 0, a1 = 0;
       int r = g;
+#pragma unroll 4
       for (; r + groups < rows; r += 2 * groups) {
         a0 += M[(size_t)r * ld + c] * v[r];
         a1 += M[(size_t)(r + groups) * ld + c] * v[r + groups];

@@ -252,7 +252,8 @@ __device__ __forceinline__ void kkt_solve(const Smem<T>& S, const KArgs<T>& a, i
   const int n = a.n, m = a.m, p = a.p, ldn = a.ldn, ldm = a.ldm, ldp = a.ldp;
   const int lane = tid & 31, warp = tid >> 5;
   if (rx) {
-    gemv_rows_thread(S.BQi, ldn, p + m, n, rx, S.hv, tid, nt);
+    if (S.panel != nullptr) gemv_rows_warp(S.BQi, ldn, p + m, n, rx, S.hv, tid, nt);  // BQi in global: coalesced rows
+    else gemv_rows_thread(S.BQi, ldn, p + m, n, rx, S.hv, tid, nt);
     gemv_cols(a.Qi + (size_t)prob * a.sQi, ldn, n, n, rx, S.t, S.part, tid, nt);  // ends with barrier
   }
   for (int i = tid; i < m; i += nt) {
