@@ -396,7 +396,7 @@ def run_reference(args, rank):
     dt = time.perf_counter() - t0
     value = nb * args.steps / dt
     sample = f"nb={nb} random QPs per step (same generator), {n_iter} PDIPM iterations, torch CPU fp64"
-    print(json.dumps({
+    emit({
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
@@ -405,10 +405,30 @@ def run_reference(args, rank):
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
-    }))
+    })
+
+
+_REAL_STDOUT = None
+
+
+def protect_stdout():
+    """The contract is ONE JSON line on stdout.  Libraries write there too (NCCL prints its version banner at
+    NCCL_DEBUG=VERSION/WARN): from here on file descriptor 1 is stderr, and only emit() writes to the real stdout."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+
+
+def emit(obj):
+    out = _REAL_STDOUT if _REAL_STDOUT is not None else sys.stdout
+    out.write(json.dumps(obj) + "\n")
+    out.flush()
 
 
 def main():
+    protect_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
@@ -670,7 +690,7 @@ def main():
             "clocks": clocks, "e2e": e2e, "gpu_launches": launches_per_step * args.steps,
             "roofline": roofline, "cpu_baseline": cpu, "cfg1_nb128": small, "cfg4_sizes": sizes, "mpc": mpc,
         }
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 
