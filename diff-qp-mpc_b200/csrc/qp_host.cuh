@@ -51,7 +51,18 @@ inline int make_layout(const b200qp_problem_t* pr, Layout& L) {
   // 2-3x faster than the register-tile fast path at 64 < nineq <= 128 (B200QP_MID=fast restores the old routing)
   const char* mid = getenv("B200QP_MID");
   const bool blocked_route = pr->dtype == B200QP_F64 && L.m > 64 && !(pr->flags & B200QP_FLAG_DENSE) && !(mid && mid[0] == 'f');
-  if (blocked_route) { L.smem = false; L.smem_bytes = vecs; }
+  if (blocked_route) {
+    L.smem = false;
+    L.smem_bytes = vecs;
+    // 128-thread CTAs (6 per SM instead of 3 x 256 threads) for the smaller blocked problems: the kernel is latency
+    // bound, more problems in flight win -- nineq = 80 / 100 / 128: 173 k -> 239 k, 133 k -> 193 k, 111 k -> 136 k
+    // solves/s (B200QP_BLK_NT=256 restores the wider CTAs)
+    const char* bnt = getenv("B200QP_BLK_NT");
+    if (!(bnt && atoi(bnt) == 256) && L.m <= 128 && widest <= 128) {
+      L.nt = 128;
+      L.smem_bytes = smem_elems(L.n, L.m, L.p, L.ldn, L.ldm, L.ldp, L.nt, false) * L.es;
+    }
+  }
   L.fast = !blocked_route && L.m <= 128 && (L.m <= 64 || widest <= 256) && getenv("B200QP_FORCE_GENERIC") == nullptr;
   if (L.fast) {
     const int generic_nt = L.nt;

@@ -84,7 +84,8 @@ template <typename T> int launch_prefactor(const KArgs<T>& a_in, const Layout& L
     a.pre_blocked = (int)dyn + 1;
     dyn += (size_t)blk_panel_elems(L.n) * sizeof(double);
   }
-  if (L.nt == 128) { auto k = k_prefactor<T, 128>; CK(ensure_smem(k, dyn)); k<<<(unsigned)a.nb, 128, dyn, st>>>(a); }
+  const bool narrow = L.nt == 128 && (L.fast || L.m <= 64);  // the blocked route's 128-thread choice is for the iteration
+  if (narrow) { auto k = k_prefactor<T, 128>; CK(ensure_smem(k, dyn)); k<<<(unsigned)a.nb, 128, dyn, st>>>(a); }
   else { auto k = k_prefactor<T, 256>; CK(ensure_smem(k, dyn)); k<<<(unsigned)a.nb, 256, dyn, st>>>(a); }
   CK(cudaGetLastError());
   return B200QP_OK;

@@ -337,7 +337,7 @@ __device__ __forceinline__ void step_pieces(const T* v, const T* dv, int m, int 
 // ------------------------------------------------------------------------------------------
 // One PDIPM iteration (a.iter >= 0) or the initial point (a.iter == -1).
 template <typename T, bool SMEM, int NT>
-__global__ void __launch_bounds__(NT, (!SMEM && NT == 256 && sizeof(T) == 8) ? 3 : 1) k_pdipm_iter(const KArgs<T> a) {
+__global__ void __launch_bounds__(NT, (!SMEM && sizeof(T) == 8) ? (NT == 256 ? 3 : 6) : 1) k_pdipm_iter(const KArgs<T> a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int prob = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int n = a.n, m = a.m, p = a.p, it = a.iter;
