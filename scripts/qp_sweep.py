@@ -30,7 +30,8 @@ quick = len(sys.argv) > 1 and sys.argv[1] == "quick"
 if len(sys.argv) > 2 and sys.argv[1] == "sizes":   # e.g. sizes 50:2000,64:2000
     cases = tuple(tuple(int(v) for v in c.split(":")) for c in sys.argv[2].split(","))
 else:
-    cases = ((100, 1000), (200, 500)) if quick else ((30, 1000), (30, 10000), (30, 100000), (100, 1000), (100, 10000), (200, 1000), (200, 4000))
+    cases = ((100, 1000), (200, 500)) if quick else ((30, 1000), (30, 10000), (30, 100000), (32, 10000), (40, 10000), (50, 10000), (64, 10000), (80, 4000),
+                                                    (100, 1000), (100, 10000), (200, 1000), (200, 4000))
 for nz, nb in cases:
     m = 2 * nz
     try:
