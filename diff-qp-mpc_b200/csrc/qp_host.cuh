@@ -58,9 +58,10 @@ inline int make_layout(const b200qp_problem_t* pr, Layout& L) {
     // bound, more problems in flight win -- nineq = 80 / 100 / 128: 173 k -> 239 k, 133 k -> 193 k, 111 k -> 136 k
     // solves/s (B200QP_BLK_NT=256 restores the wider CTAs)
     const char* bnt = getenv("B200QP_BLK_NT");
-    if (!(bnt && atoi(bnt) == 256) && L.m <= 128 && widest <= 128) {
+    const size_t s128 = smem_elems(L.n, L.m, L.p, L.ldn, L.ldm, L.ldp, 128, false) * L.es;
+    if (!(bnt && atoi(bnt) == 256) && kSmemMax / (s128 + 1024) >= 4) {  // at least four narrow CTAs fit on an SM
       L.nt = 128;
-      L.smem_bytes = smem_elems(L.n, L.m, L.p, L.ldn, L.ldm, L.ldp, L.nt, false) * L.es;
+      L.smem_bytes = s128;
     }
   }
   L.fast = !blocked_route && L.m <= 128 && (L.m <= 64 || widest <= 256) && getenv("B200QP_FORCE_GENERIC") == nullptr;
