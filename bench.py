@@ -439,6 +439,7 @@ def main():
     ap.add_argument("--cpu-nb", type=int, default=1024, help="bounded sample for cpu_baseline")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--quick", action="store_true", help="headline leg only (no size sweep, no MPC leg, no nb=128 leg)")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -489,7 +490,8 @@ def main():
     ms_buf = (ctypes.c_float * 256)()
     kind_buf = (ctypes.c_int * 256)()
     iter_ms, all_kernel_ms, n_iters = [], [], []
-    kind_ms = {0: [], 1: [], 2: [], 4: []}
+    kind_ms = {0: [], 1: [], 2: [], 4: [], 5: [], 6: []}
+    res_ms, res_launches = [], []  # resident route: the chunk launches of one step (kind 5)
     sampler = ClockSampler(local_rank)
     barrier()
     sampler.start()
@@ -502,6 +504,10 @@ def main():
         n_iters.append(ni)
         k2 = [ms_buf[i] for i in range(n) if kind_buf[i] == 2]
         iter_ms.extend(k2[:ni])
+        k5 = [ms_buf[i] for i in range(n) if kind_buf[i] == 5]
+        if k5:
+            res_ms.append(sum(k5))
+            res_launches.append(len(k5))
         all_kernel_ms.append(sum(ms_buf[i] for i in range(n) if kind_buf[i] != 3))
         for kd in kind_ms:
             kind_ms[kd].append(sum(ms_buf[i] for i in range(n) if kind_buf[i] == kd))
@@ -538,22 +544,50 @@ def main():
         traffic = tj["dram_bytes_per_problem_per_launch"] * nb
     except Exception:
         pass
-    ach_tf = fl["iter"] * nb / (avg_iter_ms * 1e-3) / 1e12
-    ach_gbs = iter_kernel_bytes(NZ, NINEQ) * nb / (avg_iter_ms * 1e-3) / 1e9
+    resident = len(res_ms) > 0
+    if resident:
+        # resident route: the iteration work of a step is spread over the k_res_chunk launches (several iterations of every
+        # problem per launch + one repair launch).  Algorithmic flops of those launches together: the initial point and
+        # n_iter iterations of EVERY problem, as the reference executes them; iterations the kernels skip for
+        # problems that are already NaN, and the repair launch, are not credited.
+        step_flops = (fl["init"] + n_iter * fl["iter"]) * nb
+        n_l = statistics.mean(res_launches)
+        avg_iter_ms = statistics.mean(res_ms) / n_l
+        flops_per_launch = step_flops / n_l
+        # bytes those launches must move in this design: Q, G, Q^-1 staged once per launch, R once per iteration (L2 hits
+        # after the first), the iterate history written once per iteration
+        ch_bytes = 8 * (n_l * (NZ * NZ + NINEQ * NZ + NZ * (NZ | 1)) + (n_iter + 1) * (36 * 64 + NZ + 2 * NINEQ + 2)) * nb
+        bytes_per_launch = ch_bytes / n_l
+        kname = "k_res_chunk<MPAD=64> (several PDIPM iterations of one QP per CTA and launch, matrices resident in shared memory)"
+        try:
+            tj = json.load(open(os.path.join(ROOT, "profiles", "r02", "ncu_traffic.json")))
+            traffic = tj["dram_bytes_per_problem_per_launch"] * nb
+            traffic_src = "profiles/r02/ncu_traffic.json: dram__bytes_read+write of one k_res_chunk launch, per problem, x this batch"
+        except Exception:
+            traffic, traffic_src = None, "no ncu capture of k_res_chunk committed yet"
+    else:
+        flops_per_launch = fl["iter"] * nb
+        bytes_per_launch = iter_kernel_bytes(NZ, NINEQ) * nb
+        kname = "k_fast_iter<double,MPAD=64,NT=128,DMMA factor> (one PDIPM iteration, one CTA per QP)"
+        traffic_src = "profiles/r01/ncu_traffic.json: dram__bytes_read+write of one launch at nb=4096, per problem, x this batch"
+    ach_tf = flops_per_launch / (avg_iter_ms * 1e-3) / 1e12
+    ach_gbs = bytes_per_launch / (avg_iter_ms * 1e-3) / 1e9
     roofline = {
-        "kernel": "k_fast_iter<double,MPAD=64,NT=128,DMMA factor> (one PDIPM iteration, one CTA per QP)", "bound": "fp64",
+        "kernel": kname, "bound": "fp64",
         "achieved": ach_tf, "peak": fp64_peak, "unit": "TFLOP/s", "frac": ach_tf / fp64_peak,
         "peak_source": "profiles/fp64_peaks_r01.json (DFMA microbenchmark on this pool's B200; MEASURED_PEAKS.json has no FP64 figure)",
-        "flops_per_launch": fl["iter"] * nb, "avg_launch_ms": avg_iter_ms, "launches_timed": len(iter_ms),
+        "flops_per_launch": flops_per_launch, "avg_launch_ms": avg_iter_ms,
+        "launches_timed": int(sum(res_launches)) if resident else len(iter_ms),
         "traffic": traffic,
-        "traffic_source": "profiles/r01/ncu_traffic.json: dram__bytes_read+write of one launch at nb=4096, per problem, x this batch",
+        "traffic_source": traffic_src,
         "hbm": {"achieved": ach_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": ach_gbs / hbm_peak,
-                "bytes_per_launch": iter_kernel_bytes(NZ, NINEQ) * nb, "peak_source": hbm_src},
+                "bytes_per_launch": bytes_per_launch, "peak_source": hbm_src},
         "whole_solve": {"flops_per_solve": fl["total"], "bytes_per_solve": algorithmic_bytes_per_solve(NZ, NINEQ),
                         "tflops": fl["total"] * value / 1e12, "frac_of_fp64_peak": fl["total"] * value / 1e12 / (fp64_peak * world),
-                        "kernel_share_of_step": sum(iter_ms) / max(sum(all_kernel_ms), 1e-9),
+                        "kernel_share_of_step": (sum(res_ms) if resident else sum(iter_ms)) / max(sum(all_kernel_ms), 1e-9),
                         "ms_per_step_by_kernel": {name: statistics.mean(kind_ms[kd]) for name, kd in
-                                                  (("prefactor", 0), ("initial_point", 1), ("iterations", 2), ("backward", 4))}},
+                                                  (("prefactor", 0), ("initial_point", 1), ("iterations", 2), ("backward", 4),
+                                                   ("resident_chunks", 5), ("reduce_select", 6))}},
     }
 
     # ---- end to end through the C ABI with HOST buffers ------------------------------------
@@ -623,6 +657,8 @@ def main():
     # ---- BASELINE configs[0] shape (nb=128) for reference: latency-bound -----------------------
     small = None
     try:
+        if args.quick:
+            raise RuntimeError("skipped (--quick)")
         Qs, ps, Gs, hs, As, bs = gen_batch(128, dev, seed=0)
         for t in (Qs, ps, Gs, hs):
             t.requires_grad_(True)
@@ -650,14 +686,14 @@ def main():
         small = {"error": repr(ex)}
 
     sizes = None
-    if rank == 0:
+    if rank == 0 and not args.quick:
         try:
             sizes = bench_qp_sizes(dev)
         except Exception as ex:  # pragma: no cover
             sizes = {"error": repr(ex)}
 
     mpc = None
-    if rank == 0:
+    if rank == 0 and not args.quick:
         try:
             mpc = bench_mpc(dev)
             mpc["other_shapes"] = bench_mpc_shapes(dev)
@@ -685,7 +721,8 @@ def main():
             "config": {"workload": f"random-QP batch (prof-linear.py:64-75 recipe, torch RNG) nz={NZ} nineq={NINEQ} neq=0 "
                                    f"fp64, QPFunction forward+backward; BASELINE configs[4] sweep point, {nb} QPs per GPU",
                        "batch_per_gpu": nb, "global_batch": nb * world, "pdipm_iterations": n_iter,
-                       "eps": 1e-12, "maxIter": 20, "parallelism": f"batch-sharded x{world}, no data-path collective",
+                       "eps": 1e-12, "maxIter": 20, "exact_rerun": bool(fn.info.get("exact_rerun", False)),
+                       "nan_onset_iteration": fn.info.get("nan_onset"), "parallelism": f"batch-sharded x{world}, no data-path collective",
                        "l2": "inputs+workspace per step exceed the 126 MB L2 (no flush needed)"},
             "clocks": clocks, "e2e": e2e, "gpu_launches": launches_per_step * args.steps,
             "roofline": roofline, "cpu_baseline": cpu, "cfg1_nb128": small, "cfg4_sizes": sizes, "mpc": mpc,

@@ -14,15 +14,16 @@ LIB_PATH = os.path.join(_HERE, "libb200qp.so")
 
 F64, F32 = 0, 1
 STATUS_DOUBLES = 8
-ST_NITER, ST_BEST_MAX, ST_Q_FAIL, ST_AQA_FAIL, ST_LAUNCHES = 0, 1, 2, 3, 4
+ST_NITER, ST_BEST_MAX, ST_Q_FAIL, ST_AQA_FAIL, ST_LAUNCHES, ST_SPEC_FAIL, ST_NAN_ONSET = 0, 1, 2, 3, 4, 5, 6
 MAX_ITER_CAP = 64
 FLAG_DENSE = 1
+FLAG_EXACT = 2
 PHASE_ALL, PHASE_BEGIN, PHASE_END = -1000, -1001, -1002
 
 EXPORTS = (
     "b200qp_workspace_bytes", "b200qp_prefactor", "b200qp_forward", "b200qp_forward_phase", "b200qp_slot_offset", "b200qp_backward", "b200qp_kkt_solve",
     "b200qp_solve_host", "b200qp_solve_host_submit", "b200qp_solve_host_wait", "b200qp_last_cuda_error", "b200qp_version", "b200qp_profile_enable",
-    "b200qp_profile_read",
+    "b200qp_profile_read", "b200qp_set_option",
     "b200mpc_env_dims", "b200mpc_factor_elems", "b200mpc_scratch_bytes", "b200mpc_al_solve", "b200mpc_al_backward",
     "b200dyn_step", "b200dyn_jac", "b200dyn_rollout",
 )
@@ -118,10 +119,19 @@ def lib():
     L.b200dyn_jac.argtypes = [ctypes.c_int, ctypes.c_int, dparr, vp, vp, vp, vp, vp, ctypes.c_int64, vp]
     L.b200dyn_rollout.restype = ctypes.c_int
     L.b200dyn_rollout.argtypes = [ctypes.c_int, ctypes.c_int, dparr, vp, vp, vp, ctypes.c_int64, ctypes.c_int32, vp]
+    L.b200qp_set_option.restype = ctypes.c_int
+    L.b200qp_set_option.argtypes = [ctypes.c_char_p, ctypes.c_int]
     L.b200qp_last_cuda_error.restype = ctypes.c_char_p
     L.b200qp_version.restype = ctypes.c_char_p
     _lib = L
     return L
+
+
+def set_option(name, value):
+    """Process-wide tuning knob of the library (include/b200qp.h: b200qp_set_option)."""
+    rc = lib().b200qp_set_option(name.encode(), int(value))
+    if rc:
+        raise ValueError(f"b200qp: unknown option {name!r}")
 
 
 def check(rc, what):

@@ -185,8 +185,20 @@ def QPFunction(eps=1e-12, verbose=0, notImprovedLim=3,
                                           _ptr(plan.workspace), _ptr(status), _stream(Q_.device))
             _lib.check(rc, "b200qp_forward")
             st = status.tolist()  # one small D2H read; also surfaces asynchronous kernel faults
+            info["exact_rerun"] = False
+            if st[_lib.ST_SPEC_FAIL] != 0 and exact_group is None:
+                # the resident route met a step-fill situation it never speculates (include/b200qp.h,
+                # B200QP_FLAG_EXACT): same problem, same workspace, one launch per iteration
+                plan.prob.flags |= _lib.FLAG_EXACT
+                with torch.cuda.device(Q_.device):
+                    rc = L.b200qp_forward(ctypes.byref(plan.prob), _ptr(plan.Q), _ptr(plan.p), _ptr(plan.G), _ptr(plan.h),
+                                          _ptr(plan.A), _ptr(plan.b), _ptr(zhats), _ptr(lams), _ptr(nus), _ptr(slacks),
+                                          _ptr(plan.workspace), _ptr(status), _stream(Q_.device))
+                _lib.check(rc, "b200qp_forward (exact route)")
+                st = status.tolist()
+                info["exact_rerun"] = True
             info.update(n_iter=int(st[_lib.ST_NITER]), best_resid_max=st[_lib.ST_BEST_MAX],
-                        launches=int(st[_lib.ST_LAUNCHES]))
+                        launches=int(st[_lib.ST_LAUNCHES]), nan_onset=int(st[_lib.ST_NAN_ONSET]))
             if st[_lib.ST_Q_FAIL] > 0:
                 if check_Q_spd:
                     raise RuntimeError('Q is not SPD.')
@@ -310,8 +322,10 @@ def DenseQPFunction(bsz=1, eps=1e-12, verbose=0, notImprovedLim=3, maxIter=20):
             db = torch.empty(nb, neq, **opt) if neq > 0 else None
             # the adjoint system uses the UNregularised K of the best iterate (qp.py:248-252): redo
             # the d-independent pre-factorisation without the regularisation, then solve
+            # (same flags => same workspace layout as the forward; only the regularisation is dropped)
             pr0 = _lib.Problem.from_buffer_copy(plan.prob)
-            pr0.flags, pr0.kkt_reg = 0, 0.0
+            pr0.kkt_reg = 0.0
+            assert L.b200qp_workspace_bytes(ctypes.byref(pr0)) == plan.workspace.numel()
             with torch.cuda.device(zhats.device):
                 rc = L.b200qp_prefactor(ctypes.byref(pr0), _ptr(plan.Q), _ptr(plan.G), _ptr(plan.A), _ptr(plan.workspace),
                                         ctypes.c_void_p(0), _stream(zhats.device))

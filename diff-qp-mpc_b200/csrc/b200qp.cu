@@ -5,6 +5,7 @@
 #include <string.h>
 
 #include <mutex>
+#include <type_traits>
 
 #include "../../include/b200qp.h"
 #include "qp_host.cuh"
@@ -12,6 +13,28 @@
 namespace b200qp {
 
 static thread_local char g_err[512] = "";
+
+static int env_int(const char* name, int dflt) {
+  const char* v = getenv(name);
+  return (v && v[0]) ? atoi(v) : dflt;
+}
+Options& options() {
+  static Options o = [] {
+    Options x;
+    x.res = env_int("B200QP_RES", x.res);
+    x.res_chunk = env_int("B200QP_RES_CH", x.res_chunk);
+    x.res_panel = env_int("B200QP_RES_PANEL", x.res_panel);
+    x.res_sweep = env_int("B200QP_RES_SWEEP", x.res_sweep);
+    const char* mid = getenv("B200QP_MID");
+    x.mid_fast = (mid && mid[0] == 'f') ? 1 : 0;
+    x.blk_nt = env_int("B200QP_BLK_NT", 0);
+    const char* fke = getenv("B200QP_FACTOR");
+    x.factor_tile = (fke && fke[0] == 't') ? 1 : 0;
+    x.force_generic = getenv("B200QP_FORCE_GENERIC") != nullptr;
+    return x;
+  }();
+  return o;
+}
 
 int cuda_fail(cudaError_t e, const char* what) {
   snprintf(g_err, sizeof(g_err), "%s: %s", what, cudaGetErrorString(e));
@@ -31,7 +54,7 @@ static __global__ void k_finalize(const Slot* slots, const Control* ctl, double*
     status[2] = (double)ctl->q_fail;
     status[3] = (double)ctl->aqa_fail;
     status[4] = (double)launches;
-    status[5] = status[6] = status[7] = 0.0;
+    status[5] = 0.0; status[6] = -1.0; status[7] = 0.0;
   }
 }
 
@@ -110,6 +133,42 @@ static int forward_t(const b200qp_problem_t* pr, const Layout& L, const void* Q,
   a.status = status;
   int launches = 0;
   const bool all = phase == B200QP_PHASE_ALL;
+  if constexpr (std::is_same<T, double>::value) {
+    if (L.res && all) {
+      // resident route (qp_resident.cuh): ceil(max_iter / chunk) launches + one repair launch + reduce/select
+      char* w = static_cast<char*>(ws);
+      RArgs ra;
+      ra.hist = (double*)(w + L.ohist); ra.rec = (double*)(w + L.orec); ra.pst = (int*)(w + L.opst);
+      ra.hs = res_hs(L.n, L.m);
+      prof_begin(st);
+      if (!prefactored) {
+        CK(cudaMemsetAsync(a.slots, 0, sizeof(Slot) * B200QP_MAX_ITER_CAP + sizeof(Control), st));
+        int rc = run_prefactor(a, L, st);
+        if (rc) return rc;
+      }
+      CK(cudaMemsetAsync(ra.pst, 0, sizeof(int) * kPst * (size_t)L.nb, st));
+      prof_mark(0, st);
+      launches = 2;
+      for (int e = L.res_chunk;; e += L.res_chunk) {
+        ra.it_end = e < pr->max_iter ? e : pr->max_iter;
+        int rc = res_chunk(a, ra, L, st);
+        if (rc) return rc;
+        prof_mark(5, st);
+        launches++;
+        if (ra.it_end == pr->max_iter) break;
+      }
+      {  // repair launch: problems whose last guesses were wrong redo their tail, everything else exits at once
+        int rc = res_chunk(a, ra, L, st);
+        if (rc) return rc;
+        prof_mark(5, st);
+        launches++;
+      }
+      int rc = res_finish(a, ra, status, launches + 2, st);
+      if (rc) return rc;
+      prof_mark(6, st);
+      return B200QP_OK;
+    }
+  }
   if (all || phase == B200QP_PHASE_BEGIN) {
     prof_begin(st);
     if (!prefactored) {  // the host-buffer path pre-factors chunk by chunk while the inputs arrive
@@ -225,6 +284,11 @@ struct Arena {
   cudaEvent_t ev_in[kMaxChunks], ev_out[kMaxChunks], ev_misc[2], ev_done;
   bool events = false;
   bool busy = false;
+  // the job in flight, kept so that b200qp_solve_host_wait can repeat it on the exact route (B200QP_ST_SPEC_FAIL)
+  b200qp_problem_t job_prob;
+  const void* job_in[7];
+  void* job_out[10];
+  double* job_status = nullptr;
 };
 static Arena g_arenas[2];
 static cudaStream_t g_st = nullptr, g_cin = nullptr, g_cout = nullptr;
@@ -284,6 +348,7 @@ int b200qp_forward_phase(const b200qp_problem_t* prob, int phase, const void* Q,
   if (phase != B200QP_PHASE_ALL && phase != B200QP_PHASE_BEGIN && phase != B200QP_PHASE_END &&
       (phase < 0 || phase >= prob->max_iter))
     return B200QP_EINVAL;
+  if (phase != B200QP_PHASE_ALL) L.res = false;  // the phased (exact-sharded) mode is one launch per iteration by definition
   cudaStream_t st = (cudaStream_t)stream;
   if (prob->dtype == B200QP_F64)
     return forward_t<double>(prob, L, Q, p, G, h, A, b, zhat, lams, nus, slacks, workspace, status, st, false, phase);
@@ -347,9 +412,27 @@ int b200qp_kkt_solve(const b200qp_problem_t* prob, int prefactor, const void* Q,
 int b200qp_solve_host_wait(int slot) {
   if (slot < 0 || slot > 1) return B200QP_EINVAL;
   Arena& AR = g_arenas[slot];
-  if (!AR.busy) return B200QP_OK;
+  {
+    std::lock_guard<std::mutex> lock(g_host_mu);
+    if (!AR.busy) return B200QP_OK;
+  }
   CK(cudaEventSynchronize(AR.ev_done));
-  AR.busy = false;
+  bool again = false;
+  {
+    std::lock_guard<std::mutex> lock(g_host_mu);
+    AR.busy = false;
+    again = AR.job_status && AR.job_status[B200QP_ST_SPEC_FAIL] != 0.0 && !(AR.job_prob.flags & B200QP_FLAG_EXACT);
+  }
+  if (again) {  // the resident route met something it never speculates: same job, one launch per iteration
+    b200qp_problem_t pr = AR.job_prob;
+    pr.flags |= B200QP_FLAG_EXACT;
+    int rc = b200qp_solve_host_submit(slot, &pr, AR.job_in[0], AR.job_in[1], AR.job_in[2], AR.job_in[3], AR.job_in[4],
+                                      AR.job_in[5], AR.job_in[6], AR.job_out[0], AR.job_out[1], AR.job_out[2], AR.job_out[3],
+                                      AR.job_out[4], AR.job_out[5], AR.job_out[6], AR.job_out[7], AR.job_out[8], AR.job_out[9],
+                                      AR.job_status);
+    if (rc) return rc;
+    return b200qp_solve_host_wait(slot);
+  }
   return B200QP_OK;
 }
 
@@ -366,11 +449,19 @@ int b200qp_solve_host_submit(int slot, const b200qp_problem_t* prob, const void*
   if (pe > 0 && (!A || !b || !nus)) return B200QP_EINVAL;
   const bool bwd = dl_dzhat != nullptr;
   if (bwd && (!dQ || !dp || !dG || !dh || (pe > 0 && (!dA || !db)))) return B200QP_EINVAL;
-  std::lock_guard<std::mutex> lock(g_host_mu);
   Arena& AR = g_arenas[slot];
-  if (AR.busy) {  // the previous job of this slot still owns the arena (and the caller's output buffers)
-    int rcw = b200qp_solve_host_wait(slot);
+  {
+    int rcw = b200qp_solve_host_wait(slot);  // the previous job of this slot still owns the arena (and its output buffers)
     if (rcw) return rcw;
+  }
+  std::lock_guard<std::mutex> lock(g_host_mu);
+  AR.job_prob = *prob;
+  {
+    const void* in_[7] = {Q, p, G, h, A, b, dl_dzhat};
+    void* out_[10] = {zhat, lams, nus, slacks, dQ, dp, dG, dh, dA, db};
+    for (int i = 0; i < 7; i++) AR.job_in[i] = in_[i];
+    for (int i = 0; i < 10; i++) AR.job_out[i] = out_[i];
+    AR.job_status = status;
   }
   auto cnt = [&](int64_t stride, size_t per) { return (stride == 0 ? 1 : nb) * per; };
   const size_t bQ = cnt(prob->sQ, n * n) * es, bp = cnt(prob->sp, n) * es, bG = cnt(prob->sG, m * n) * es,
@@ -497,8 +588,19 @@ int b200qp_profile_read(float* ms, int* kind, int cap) {
   return n;
 }
 
+int b200qp_set_option(const char* name, int value) {
+  if (!name) return B200QP_EINVAL;
+  Options& o = options();
+  if (!strcmp(name, "res")) o.res = value;
+  else if (!strcmp(name, "res_ch")) o.res_chunk = value;
+  else if (!strcmp(name, "res_panel")) o.res_panel = value;
+  else if (!strcmp(name, "res_sweep")) o.res_sweep = value;
+  else return B200QP_EINVAL;
+  return B200QP_OK;
+}
+
 const char* b200qp_last_cuda_error(void) { return g_err; }
 
-const char* b200qp_version(void) { return "b200qp 0.1 sm_100a"; }
+const char* b200qp_version(void) { return "b200qp 0.2 sm_100a"; }
 
 }  // extern "C"

@@ -6,6 +6,7 @@
 #include <stdlib.h>
 #include "qp_kernels.cuh"
 #include "qp_fast.cuh"
+#include "qp_resident.cuh"
 
 namespace b200qp {
 
@@ -27,7 +28,26 @@ struct Layout {
   long long sQi, sBQi, sR, sV, sUA, sF, sT;
   size_t oQi, oBQi, oR, oV, oUA, opinvA, oF, opinvF, oT, opinvT;
   size_t ox, os, oz, oy, odx, ods, odz, ody, ormu, oflags, obest, oslots, octl, total;
+  // resident route (qp_resident.cuh): several iterations per launch, history + records per problem
+  bool res;
+  int res_chunk, res_panel, res_sweep;
+  size_t res_smem, ohist, orec, opst;
 };
+
+// Process-wide tuning knobs.  Read from the environment ONCE (first use) and changeable through
+// b200qp_set_option; a layout never depends on anything else, so forward and backward of one problem
+// descriptor always agree on it.
+struct Options {
+  int res = 1;        // B200QP_RES       0: never take the resident route
+  int res_chunk = 4;  // B200QP_RES_CH    iterations per launch of the resident route
+  int res_panel = 1;  // B200QP_RES_PANEL 1: fraction-free panel factorisation, 0: reciprocal on the chain
+  int res_sweep = 1;  // B200QP_RES_SWEEP 1: eight columns per sweep step, 0: one
+  int mid_fast = 0;   // B200QP_MID=fast  64 < nineq <= 128 on the register-tile route
+  int blk_nt = 0;     // B200QP_BLK_NT    256 forces the wide CTAs of the blocked route
+  int factor_tile = 0;// B200QP_FACTOR=tile
+  int force_generic = 0;  // B200QP_FORCE_GENERIC
+};
+Options& options();
 
 inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
@@ -49,30 +69,26 @@ inline int make_layout(const b200qp_problem_t* pr, Layout& L) {
   L.fk = 0;
   // fp64 problems with nineq > 64 take the global-resident blocked tensor-core route (qp_blocked.cuh): measured
   // 2-3x faster than the register-tile fast path at 64 < nineq <= 128 (B200QP_MID=fast restores the old routing)
-  const char* mid = getenv("B200QP_MID");
-  const bool blocked_route = pr->dtype == B200QP_F64 && L.m > 64 && !(pr->flags & B200QP_FLAG_DENSE) && !(mid && mid[0] == 'f');
+  const Options& opt = options();
+  const bool blocked_route = pr->dtype == B200QP_F64 && L.m > 64 && !(pr->flags & B200QP_FLAG_DENSE) && !opt.mid_fast;
   if (blocked_route) {
     L.smem = false;
     L.smem_bytes = vecs;
     // 128-thread CTAs (6 per SM instead of 3 x 256 threads) for the smaller blocked problems: the kernel is latency
     // bound, more problems in flight win -- nineq = 80 / 100 / 128: 173 k -> 239 k, 133 k -> 193 k, 111 k -> 136 k
     // solves/s (B200QP_BLK_NT=256 restores the wider CTAs)
-    const char* bnt = getenv("B200QP_BLK_NT");
     const size_t s128 = smem_elems(L.n, L.m, L.p, L.ldn, L.ldm, L.ldp, 128, false) * L.es;
-    if (!(bnt && atoi(bnt) == 256) && kSmemMax / (s128 + 1024) >= 4) {  // at least four narrow CTAs fit on an SM
+    if (opt.blk_nt != 256 && kSmemMax / (s128 + 1024) >= 4) {  // at least four narrow CTAs fit on an SM
       L.nt = 128;
       L.smem_bytes = s128;
     }
   }
-  L.fast = !blocked_route && L.m <= 128 && (L.m <= 64 || widest <= 256) && getenv("B200QP_FORCE_GENERIC") == nullptr;
+  L.fast = !blocked_route && L.m <= 128 && (L.m <= 64 || widest <= 256) && !opt.force_generic;
   if (L.fast) {
     const int generic_nt = L.nt;
-    const char* fnt = nullptr;  // 32/64-thread CTA variants were measured slower and are not instantiated
-    L.nt = L.m <= 64 ? ((fnt && atoi(fnt) == 32) ? 32 : 128) : 256;
+    L.nt = L.m <= 64 ? 128 : 256;  // 32/64-thread CTA variants were measured slower and are not instantiated
     // DMMA factorisation: fp64, 128-thread CTAs, one spare row for the bordered right-hand side
-    const char* fke = getenv("B200QP_FACTOR");
-    L.fk = (pr->dtype == B200QP_F64 && L.nt == 128 && L.m < 64 && !(fke && fke[0] == 't')) ? 1 : 0;
-    if (L.fk && fnt && atoi(fnt) == 64 && L.m >= 32) L.nt = 64;  // experimental: 2-warp CTAs (MPAD = 64 only)
+    L.fk = (pr->dtype == B200QP_F64 && L.nt == 128 && L.m < 64 && !opt.factor_tile) ? 1 : 0;
     if (L.fk) L.mpad = L.m < 32 ? 32 : 64;
     const size_t fb = fast_smem_elems(L.n, L.m, L.p, L.ldn, L.ldm, L.ldp, L.nt, L.mpad, L.fk) * L.es;
     if ((L.nt == 128 && widest > 128) || fb > kSmemResidentLimit) { L.fast = false; L.fk = 0; L.nt = generic_nt; }
@@ -114,6 +130,19 @@ inline int make_layout(const b200qp_problem_t* pr, Layout& L) {
   L.obest = put(nb, sizeof(double));
   L.oslots = put(B200QP_MAX_ITER_CAP, sizeof(Slot));
   L.octl = put(1, sizeof(Control));
+  // resident route: fp64, no equalities, nineq < 64 (one spare row for the bordered right-hand side), nz <= 32
+  L.res = opt.res && L.fast && L.fk && L.p == 0 && L.n <= 32 && pr->max_iter <= kResMaxIter &&
+          !(pr->flags & (B200QP_FLAG_DENSE | B200QP_FLAG_EXACT));
+  L.res_chunk = opt.res_chunk < 1 ? 1 : opt.res_chunk;
+  L.res_panel = opt.res_panel ? 1 : 0;
+  L.res_sweep = opt.res_sweep ? 1 : 0;
+  L.res_smem = res_smem_elems(L.n, L.m, L.mpad) * sizeof(double);
+  L.ohist = L.orec = L.opst = 0;
+  if (L.res) {
+    L.ohist = put(nb * (size_t)(pr->max_iter + 1) * res_hs(L.n, L.m), sizeof(double));
+    L.orec = put(nb * (size_t)pr->max_iter * 2, sizeof(double));
+    L.opst = put(nb * kPst, sizeof(int));
+  }
   L.total = off;
   return B200QP_OK;
 }
@@ -128,5 +157,8 @@ template <typename T> int launch_prefactor(const KArgs<T>& a, const Layout& L, c
 template <typename T> int fast_iter(const KArgs<T>& a, const Layout& L, cudaStream_t st);
 template <typename T> int fast_backward(const KArgs<T>& a, const BArgs<T>& g, const Layout& L, cudaStream_t st);
 template <typename T> int fast_kkt(const KArgs<T>& a, const SArgs<T>& g, const Layout& L, cudaStream_t st);
+// resident route (qp_inst.cu -DINST_RES=1): one launch = the iterations [.., ra.it_end) of every problem
+int res_chunk(const KArgs<double>& a, const RArgs& ra, const Layout& L, cudaStream_t st);
+int res_finish(const KArgs<double>& a, const RArgs& ra, double* status, int launches, cudaStream_t st);
 
 }  // namespace b200qp

@@ -22,7 +22,32 @@ static cudaError_t ensure_smem(K kernel, size_t bytes) {
     return B200QP_OK;                                                                          \
   } while (0)
 
-#if INST_FAST
+#if INST_RES
+// resident route (qp_resident.cuh): MPAD in {32, 64} x PANEL in {0, 1} x SWEEP in {0, 1}
+template <int MPAD, int PANEL, int SWEEP>
+static int res_launch(const KArgs<double>& a, const RArgs& ra, const Layout& L, cudaStream_t st) {
+  auto k = k_res_chunk<MPAD, PANEL, SWEEP>;
+  CK(ensure_smem(k, L.res_smem));
+  k<<<(unsigned)a.nb, 128, L.res_smem, st>>>(a, ra);
+  CK(cudaGetLastError());
+  return B200QP_OK;
+}
+template <int MPAD>
+static int res_launch_m(const KArgs<double>& a, const RArgs& ra, const Layout& L, cudaStream_t st) {
+  if (L.res_panel) return L.res_sweep ? res_launch<MPAD, 1, 1>(a, ra, L, st) : res_launch<MPAD, 1, 0>(a, ra, L, st);
+  return L.res_sweep ? res_launch<MPAD, 0, 1>(a, ra, L, st) : res_launch<MPAD, 0, 0>(a, ra, L, st);
+}
+int res_chunk(const KArgs<double>& a, const RArgs& ra, const Layout& L, cudaStream_t st) {
+  return L.mpad == 32 ? res_launch_m<32>(a, ra, L, st) : res_launch_m<64>(a, ra, L, st);
+}
+int res_finish(const KArgs<double>& a, const RArgs& ra, double* status, int launches, cudaStream_t st) {
+  k_res_reduce<0><<<(unsigned)((a.nb + 127) / 128), 128, 0, st>>>(a, ra);
+  CK(cudaGetLastError());
+  k_res_select<0><<<(unsigned)((a.nb + 3) / 4), 128, 0, st>>>(a, ra, status, launches);
+  CK(cudaGetLastError());
+  return B200QP_OK;
+}
+#elif INST_FAST
 // fast path: (MPAD, NT) in {(32,128), (64,128), (128,256)}; FK = 1 (DMMA) for fp64 with nineq < 64
 #define LAUNCH_ONE(KEXPR, NTV, ...)                                                                \
   do { auto k = KEXPR; CK(ensure_smem(k, L.smem_bytes)); k<<<(unsigned)a.nb, NTV, L.smem_bytes, st>>>(__VA_ARGS__); } while (0)

@@ -45,7 +45,9 @@ static_assert(sizeof(Slot) == 64, "Slot must be 64 bytes");
 struct Control {                    // lives after the slots
   unsigned int q_fail;              // problems whose Q factorisation failed
   unsigned int aqa_fail;            // problems whose A Q^-1 A^T factorisation failed
-  unsigned int pad[14];
+  unsigned int kev_inv;             // resident route (qp_resident.cuh): kKevBase - first iteration with a NaN step ratio
+  unsigned int need_exact;          // resident route: something that is never speculated occurred -> rerun exactly
+  unsigned int pad[12];
 };
 
 

@@ -44,6 +44,13 @@ extern "C" {
  * of iterative refinement against the unregularised matrix; get_step maps dv == 0 to 1; backward uses
  * d = lams / slacks without the 1e-8 clamp. */
 #define B200QP_FLAG_DENSE 1
+/* Force the one-launch-per-iteration kernels.  Without it fp64 problems with neq == 0, nineq < 64, nz <= 32 take
+ * the RESIDENT route (csrc/qp_resident.cuh): several iterations per launch with the batch-global step fill of
+ * get_step (qpth/solvers/pdipm/batch.py:211-214) speculated and repaired, bit-identical results.  Two situations
+ * are never speculated (a ratio test that is fill-only while the fill is still unknown; z and s ratios that turn
+ * NaN at different iterations): forward then sets status[B200QP_ST_SPEC_FAIL] != 0, the outputs are NOT valid,
+ * and the caller repeats the call with this flag (b200qp_solve_host* and the Python layer do so themselves). */
+#define B200QP_FLAG_EXACT 2
 
 #define B200QP_MAX_ITER_CAP 64
 #define B200QP_STATUS_DOUBLES 8
@@ -54,6 +61,8 @@ extern "C" {
 #define B200QP_ST_Q_FAIL 2       /* number of problems whose Q factorisation failed           */
 #define B200QP_ST_AQA_FAIL 3     /* number of problems whose A Q^-1 A^T factorisation failed  */
 #define B200QP_ST_LAUNCHES 4     /* kernels launched by the call                              */
+#define B200QP_ST_SPEC_FAIL 5    /* resident route only: != 0 -> repeat with B200QP_FLAG_EXACT  */
+#define B200QP_ST_NAN_ONSET 6    /* resident route only: first iteration with a NaN step ratio (-1: none) */
 
 typedef void* b200qp_stream_t;   /* a cudaStream_t */
 
@@ -152,9 +161,16 @@ int b200qp_solve_host_wait(int slot);
  * kernel launch of forward/backward is bracketed by CUDA events on the caller's stream.
  * b200qp_profile_read synchronises on the last event and returns the number of launches n,
  * filling ms[i] (duration) and kind[i] (0 prefactor, 1 initial point, 2 PDIPM iteration,
- * 3 finalize, 4 backward) for i < min(n, cap). */
+ * 3 finalize, 4 backward, 5 one launch of the resident route = several iterations of every problem,
+ * 6 its history reduction + selection) for i < min(n, cap). */
 void b200qp_profile_enable(int on);
 int b200qp_profile_read(float* ms, int* kind, int cap);
+
+/* Process-wide tuning knobs (defaults come from the environment variables of the same upper-case name with the
+ * prefix B200QP_, read once): "res" (1) take the resident route when eligible, "res_ch" (4) its iterations per
+ * launch, "res_panel" (1) / "res_sweep" (1) its factorisation-panel / triangular-sweep variants.  Returns 0, or
+ * B200QP_EINVAL for an unknown name.  Not to be changed between the forward and the backward of one problem. */
+int b200qp_set_option(const char* name, int value);
 
 /* Text of the last CUDA error seen by this library on the calling thread ("" if none). */
 const char* b200qp_last_cuda_error(void);

@@ -1,0 +1,133 @@
+"""GPU tests of the RESIDENT route (csrc/qp_resident.cuh: several PDIPM iterations per launch, the batch-global
+get_step fill of qpth/solvers/pdipm/batch.py:211-214 speculated and repaired).  Through the C ABI, `-m gpu`.
+
+* chunk invariance: the same kernels with 1, 3, 4 or 20 iterations per launch return bit-identical results --
+  with one iteration per launch there is next to nothing to speculate wrongly, so this pins the repair logic;
+* the resident route against the one-launch-per-iteration route and against the oracle / reference goldens
+  (iteration count included);
+* the fallback (`B200QP_ST_SPEC_FAIL` -> exact route) on a problem family whose ratio tests are fill-only.
+"""
+import pytest
+import torch
+
+from tests.qp_cases import compare_with_golden, gate, make_inputs
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture()
+def opts():
+    from b200qp import _lib
+    yield _lib.set_option
+    for k, v in (("res", 1), ("res_ch", 4), ("res_panel", 1), ("res_sweep", 1)):
+        _lib.set_option(k, v)
+
+
+def solve(inp, device, backward=True):
+    from b200qp.qp import QPFunction
+    t = {k: v.to(device).requires_grad_(backward) for k, v in inp.items()}
+    fn = QPFunction(verbose=-1, check_Q_spd=False)
+    z = fn(t["Q"], t["p"], t["G"], t["h"], t["A"], t["b"])
+    out = dict(zhat=z.detach().cpu())
+    if backward:
+        z.backward(torch.ones_like(z))
+        ctx = z.grad_fn
+        out.update(lams=ctx.lams.cpu(), slacks=ctx.slacks.cpu(), nus=ctx.nus.cpu(), dQ=t["Q"].grad.cpu(), dp=t["p"].grad.cpu(),
+                   dG=t["G"].grad.cpu(), dh=t["h"].grad.cpu(), dA=None, db=None)
+    return out, dict(fn.info)
+
+
+def rand_inputs(nb, nz, m, seed, wc=False):
+    from oracle import qp_oracle as O
+    Q, p, G, h, A, b = O.random_qp(nb, nz, m, 0, seed=seed, well_conditioned=wc)
+    return dict(Q=Q, p=p, G=G, h=h, A=A, b=b)
+
+
+@pytest.mark.parametrize("shape", [(512, 30, 60, 0, False), (300, 30, 60, 3, True), (200, 12, 20, 7, False), (64, 32, 63, 9, False)])
+def test_chunk_invariance_bitwise(shape, cuda_device, opts):
+    nb, nz, m, seed, wc = shape
+    inp = rand_inputs(nb, nz, m, seed, wc)
+    for panel, sweep in ((1, 1), (0, 0), (1, 0), (0, 1)):
+        opts("res_panel", panel); opts("res_sweep", sweep)
+        ref = None
+        for ch in (1, 3, 4, 20):
+            opts("res_ch", ch)
+            out, info = solve(inp, cuda_device)
+            assert not info.get("exact_rerun"), "unexpected fallback"
+            if ref is None:
+                ref = (out, info)
+                continue
+            assert info["n_iter"] == ref[1]["n_iter"], (ch, info, ref[1])
+            for k in ("zhat", "lams", "slacks", "dp", "dG"):
+                a, b = out[k], ref[0][k]
+                same = (a == b) | (torch.isnan(a) & torch.isnan(b))
+                assert bool(same.all()), f"panel {panel} sweep {sweep} chunk {ch}: {k} differs from chunk 1 in {int((~same).sum())} entries"
+
+
+@pytest.mark.parametrize("shape", [(256, 30, 60, 11, False), (128, 30, 60, 0, False), (64, 30, 60, 3, True), (96, 10, 10, 5, False), (50, 20, 31, 6, False)])
+def test_resident_vs_per_iteration_route_and_oracle(shape, cuda_device, opts):
+    from oracle import qp_oracle as O
+    nb, nz, m, seed, wc = shape
+    inp = rand_inputs(nb, nz, m, seed, wc)
+    fwd = O.qp_forward(*(inp[k].clone() for k in "QpGhAb"))
+    gr = O.qp_backward(fwd, *(inp[k] for k in "QpGhAb"), torch.ones_like(fwd["zhat"]))
+    opts("res", 0)
+    ex, ex_info = solve(inp, cuda_device)
+    assert ex_info["n_iter"] == fwd["n_iter"]
+    opts("res", 1)
+    for panel, sweep in ((1, 1), (0, 0)):
+        opts("res_panel", panel); opts("res_sweep", sweep)
+        out, info = solve(inp, cuda_device)
+        assert info["n_iter"] == fwd["n_iter"], (panel, sweep, info["n_iter"], fwd["n_iter"])
+        for k in ("zhat", "lams", "slacks"):
+            gate(out[k], fwd[k], 1e-6, f"{k} vs oracle")
+            gate(out[k], ex[k], 1e-7, f"{k} vs per-iteration route")
+        for k in ("dp", "dG", "dQ", "dh"):
+            gate(out[k], gr[k], 1e-6, f"{k} vs oracle")
+
+
+@pytest.mark.parametrize("case", ["cfg1_nb128_nz30_m60", "wellcond_nb64_nz30_m60", "shared_ph_nb8_nz10_m10"])
+def test_resident_goldens_all_variants(case, cuda_device, opts):
+    from tests.qp_cases import load_golden
+    inp = make_inputs(case)
+    g = load_golden(case)
+    for panel, sweep, ch in ((1, 1, 4), (0, 0, 4), (1, 1, 7), (1, 0, 20), (0, 1, 1)):
+        opts("res_panel", panel); opts("res_sweep", sweep); opts("res_ch", ch)
+        from tests.test_qp_parity_gpu import run_ours
+        out, info = run_ours(inp, cuda_device)
+        compare_with_golden(case, out, rtol=1e-6)
+        assert info["n_iter"] == int(g["n_iter"]), (panel, sweep, ch, info["n_iter"], int(g["n_iter"]))
+
+
+def test_fill_only_problems_fall_back_to_exact_route(cuda_device, opts):
+    """nineq = 1: the single ratio of a problem is either unfilled or the whole test is fill-only, which the
+    resident route never speculates -> B200QP_ST_SPEC_FAIL -> the Python layer repeats the call on the exact route."""
+    from oracle import qp_oracle as O
+    inp = rand_inputs(24, 10, 1, 21)
+    fwd = O.qp_forward(*(inp[k].clone() for k in "QpGhAb"))
+    out, info = solve(inp, cuda_device)
+    gate(out["zhat"], fwd["zhat"], 1e-6, "zhat")
+    gate(out["lams"], fwd["lams"], 1e-6, "lams")
+    assert info["n_iter"] == fwd["n_iter"]
+    opts("res", 0)
+    ex, ex_info = solve(inp, cuda_device)
+    if info.get("exact_rerun"):
+        assert torch.equal(out["zhat"], ex["zhat"]), "the rerun must be the exact route"
+    print("fill-only family: exact_rerun =", info.get("exact_rerun", False))
+
+
+def test_bench_batch_against_oracle(cuda_device, opts):
+    """The bench configuration itself (BASELINE configs[1]: nb = 32768, nz = 30, nineq = 60, 20 iterations because of
+    the batch-global termination) against the oracle on the same inputs: iteration count, solution, duals, dp."""
+    from oracle import qp_oracle as O
+    torch.set_num_threads(max(1, torch.get_num_threads()))
+    inp = rand_inputs(32768, 30, 60, 0)
+    fwd = O.qp_forward(*(inp[k].clone() for k in "QpGhAb"))
+    gr = O.qp_backward(fwd, *(inp[k] for k in "QpGhAb"), torch.ones_like(fwd["zhat"]))
+    out, info = solve(inp, cuda_device)
+    print("bench batch: n_iter", info["n_iter"], "oracle", fwd["n_iter"], "exact_rerun", info.get("exact_rerun", False))
+    assert info["n_iter"] == fwd["n_iter"]
+    for k in ("zhat", "lams", "slacks"):
+        gate(out[k], fwd[k], 1e-6, k)
+    for k in ("dp", "dh", "dG", "dQ"):
+        gate(out[k], gr[k], 1e-6, k)
