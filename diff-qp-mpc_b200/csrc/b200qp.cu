@@ -210,7 +210,7 @@ static int backward_t(const b200qp_problem_t* pr, const Layout& L, const void* z
   g.zhat = (const T*)zhat; g.lams = (const T*)lams; g.nus = (const T*)(nus ? nus : zhat); g.slacks = (const T*)slacks;
   g.gz = (const T*)gz;
   g.dQ = (T*)dQ; g.dp = (T*)dp; g.dG = (T*)dG; g.dh = (T*)dh; g.dA = (T*)dA; g.db = (T*)db;
-  const bool chained = g_prof.on && g_prof.n > 0 && g_prof.kind[g_prof.n - 1] == 3;
+  const bool chained = g_prof.on && g_prof.n > 0 && (g_prof.kind[g_prof.n - 1] == 3 || g_prof.kind[g_prof.n - 1] == 6);
   if (g_prof.on && !chained) prof_begin(st);
   if (chained) cudaEventRecord(g_prof.ev[g_prof.n], st);  // restart the bracket after host-side gaps
   DISPATCH_KERNEL(launch_backward, T, L, a, g);
@@ -595,6 +595,10 @@ int b200qp_set_option(const char* name, int value) {
   else if (!strcmp(name, "res_ch")) o.res_chunk = value;
   else if (!strcmp(name, "res_panel")) o.res_panel = value;
   else if (!strcmp(name, "res_sweep")) o.res_sweep = value;
+  else if (!strcmp(name, "mid_fast")) o.mid_fast = value;
+  else if (!strcmp(name, "blk_nt")) o.blk_nt = value;
+  else if (!strcmp(name, "factor_tile")) o.factor_tile = value;
+  else if (!strcmp(name, "force_generic")) o.force_generic = value;
   else return B200QP_EINVAL;
   return B200QP_OK;
 }

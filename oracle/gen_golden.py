@@ -40,6 +40,14 @@ CASES = {
     "m96_nb8_nz40_m96": (8, 40, 96, 0, 10, "float64", False, ()),
     "m80eq_nb8_nz48_m80_p8": (8, 48, 80, 8, 11, "float64", False, ()),
     "bigeq_nb4_nz70_m150_p12": (4, 70, 150, 12, 12, "float64", False, ()),
+    # round 2: the largest size of BASELINE configs[4], fp32 above nineq = 128, the edges of the resident route
+    # (nineq = 63 / 31: the last size with a spare row for the bordered right-hand side) and a family whose ratio
+    # tests are fill-only (nineq = 1: the resident route must fall back to the exact one)
+    "huge_nb4_nz200_m400": (4, 200, 400, 0, 14, "float64", False, ()),
+    "fp32big_nb8_nz64_m160": (8, 64, 160, 0, 15, "float32", False, ()),
+    "m63_nb64_nz32_m63": (64, 32, 63, 0, 16, "float64", False, ()),
+    "m31_nb16_nz16_m31": (16, 16, 31, 0, 17, "float64", True, ()),
+    "fillonly_nb24_nz10_m1": (24, 10, 1, 0, 21, "float64", False, ()),
 }
 FULL_GRAD_ROWS = 8  # dQ/dG/dA are stored in full for the first rows, as norms for the rest
 

@@ -22,6 +22,9 @@ CASES = {
     "dense_nb16_nz10_m12_p4": (16, 10, 12, 4, 11),
     "dense_nb32_nz30_m60_p0": (32, 30, 60, 0, 12),
     "dense_nb8_nz15_m10_p10": (8, 15, 10, 10, 13),
+    # 64 < nineq <= 128: the size class where a second workspace layout used to be derived in backward
+    "dense_nb8_nz30_m96_p0": (8, 30, 96, 0, 14),
+    "dense_nb4_nz40_m100_p6": (4, 40, 100, 6, 15),
 }
 
 

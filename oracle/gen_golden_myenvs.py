@@ -69,7 +69,8 @@ def main():
 
     # AL-MPC on the generated dynamics (the production configuration: deqmpc/policies.py:560-661 with
     # my_envs/cartpole.py CartpoleEnv, Qlqr = 1, Rlqr = 1e-8): cold call, warm call, backward
-    for name, Bsz, T in (("cartpole1l", 8, 10), ("cartpole2l", 4, 8), ("pendulum1l", 8, 6)):
+    # (the T = 20 case is BASELINE configs[2]'s horizon; appended last so that the earlier cases keep their inputs)
+    for name, Bsz, T in (("cartpole1l", 8, 10), ("cartpole2l", 4, 8), ("pendulum1l", 8, 6), ("cartpole1l", 8, 20)):
         d = reference_dynamics(name)
         nx, nu = 2 * MO.NQ[name], 1
         x0 = torch.tensor(np.concatenate([rs.uniform(-1.0, 1.0, (Bsz, nx // 2)), rs.uniform(-0.5, 0.5, (Bsz, nx // 2))], 1))

@@ -1,9 +1,12 @@
 """GPU parity tests of the AL-MPC path: the fused kernels (through the C ABI, behind the MPC
 drop-in) against the golden vectors of the real reference and against the oracle."""
+import os
+
+import numpy as np
 import pytest
 import torch
 
-from tests.mpc_cases import CASES, load, oracle_dyn, rel
+from tests.mpc_cases import CASES, GOLDEN_DIR as GOLDEN, load, oracle_dyn, rel
 
 pytestmark = pytest.mark.gpu
 
@@ -52,6 +55,25 @@ def test_al_mpc_matches_reference_golden(case, cuda_device):
 
 
 @pytest.mark.parametrize("env", ["pendulum", "integrator", "pendulum_dx", "cartpole_dx"])
+@pytest.mark.parametrize("name", ["pendulum", "cartpole"])
+def test_envdx_against_reference_modules(name, cuda_device):
+    """PendulumDx / CartpoleDx kernels against goldens produced by the reference's OWN modules
+    (qpth/env_dx/pendulum.py:49-84, cartpole.py:63-96; oracle/gen_golden_envdx.py imports them from the reference
+    and differentiates their forward with autograd): next state and both Jacobians, controls on both sides of
+    the clamp."""
+    from b200qp import envs
+    g = dict(np.load(os.path.join(GOLDEN, f"dyn_envdx_{name}.npz")))
+    mod = envs.PendulumDx_jac() if name == "pendulum" else envs.CartpoleDx_jac()
+    x, u = torch.tensor(g["x"]).to(cuda_device), torch.tensor(g["u"]).to(cuda_device)
+    xn, (A, B) = mod(x, u)
+    assert rel(xn.cpu(), torch.tensor(g["xn"])) < 1e-12
+    assert rel(A.cpu(), torch.tensor(g["A"])) < 1e-12
+    assert rel(B.cpu(), torch.tensor(g["B"])) < 1e-12
+    clamped = torch.tensor(g["B"]).abs().sum((1, 2)) == 0
+    assert clamped.any() and not clamped.all(), "the golden must exercise both sides of the control clamp"
+    assert bool((B.cpu()[clamped] == 0).all())
+
+
 def test_dynamics_step_and_jacobian(env, cuda_device):
     """b200dyn_step / b200dyn_jac against a torch restatement + autograd Jacobians on the CPU."""
     from b200qp import envs

