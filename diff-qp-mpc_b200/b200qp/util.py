@@ -1,57 +1,69 @@
-"""Shape helpers that appear in the reference's signatures (qpth/util.py:22-101)."""
+"""Shape helpers that callers of the reference import from `qpth.util` (qpth/util.py:22-101): same names,
+argument meaning and error text, written against `_RANKS` -- the one table of what a batched parameter looks
+like -- instead of per-function copies.  Everything here is host-side shape logic on torch tensors; the
+batched products are one-line einsum forms (they are only used by callers around the solver, the solver
+itself never materialises them)."""
 import torch
+
+# name -> rank of the BATCHED form; one rank less means "shared across the batch"
+_RANKS = dict(Q=3, p=2, G=3, h=2, A=3, b=2)
+_ORDER = ("Q", "p", "G", "h", "A", "b")
 
 
 def get_sizes(G, A=None):
-    """qpth/util.py:22-33"""
-    if G.dim() == 2:
-        nineq, nz = G.size()
-        nBatch = 1
-    elif G.dim() == 3:
-        nBatch, nineq, nz = G.size()
-    if A is not None:
-        neq = A.size(1) if A.nelement() > 0 else 0
-    else:
-        neq = None
+    """(nineq, nz, neq, nBatch) of a QP given G (m, n) or (nb, m, n) and optionally A; neq is None when A is not
+    given and 0 for an empty A (qpth/util.py:22-33)."""
+    if G.dim() not in (2, 3):
+        raise RuntimeError("Unexpected number of dimensions.")
+    nineq, nz = G.shape[-2], G.shape[-1]
+    nBatch = G.shape[0] if G.dim() == 3 else 1
+    neq = None if A is None else (A.shape[1] if A.nelement() > 0 else 0)
     return nineq, nz, neq, nBatch
 
 
 def expandParam(X, nBatch, nDim):
-    """qpth/util.py:69-75 (the second, winning definition: no nelement()==0 escape)."""
-    if X.ndimension() in (0, nDim):
+    """Broadcast view of a parameter that is shared across the batch: returns (X', was_expanded).  The reference
+    defines this twice (qpth/util.py:36-42 and :69-75); the second definition -- no escape for empty tensors -- is
+    the one in effect, and the one mirrored here."""
+    rank = X.ndimension()
+    if rank == nDim or rank == 0:
         return X, False
-    elif X.ndimension() == nDim - 1:
-        return X.unsqueeze(0).expand(*([nBatch] + list(X.size()))), True
-    else:
-        raise RuntimeError("Unexpected number of dimensions.")
+    if rank + 1 == nDim:
+        return X.unsqueeze(0).expand(nBatch, *X.shape), True
+    raise RuntimeError("Unexpected number of dimensions.")
 
 
 def extract_nBatch(Q, p, G, h, A, b):
-    """qpth/util.py:45-51"""
-    dims = [3, 2, 3, 2, 3, 2]
-    params = [Q, p, G, h, A, b]
-    for param, dim in zip(params, dims):
-        if param.ndimension() == dim:
-            return param.size(0)
+    """Batch size = leading dimension of the first parameter (in the order Q, p, G, h, A, b) that comes in its
+    batched rank; 1 when every parameter is shared (qpth/util.py:45-51)."""
+    for name, X in zip(_ORDER, (Q, p, G, h, A, b)):
+        if X.ndimension() == _RANKS[name]:
+            return X.shape[0]
     return 1
 
 
 def bger(x, y):
-    return x.unsqueeze(2).bmm(y.unsqueeze(1))
+    """batched outer product (nb, r), (nb, c) -> (nb, r, c)"""
+    return torch.einsum("br,bc->brc", x, y)
 
 
 def bmv(X, y):
-    return X.bmm(y.unsqueeze(2)).squeeze(2)
+    """batched matrix-vector product (nb, r, c), (nb, c) -> (nb, r)"""
+    return torch.einsum("brc,bc->br", X, y)
 
 
 def bquad(x, Q):
-    return x.unsqueeze(1).bmm(Q).bmm(x.unsqueeze(2)).squeeze(1).squeeze(1)
+    """batched quadratic form x' Q x -> (nb,)"""
+    return torch.einsum("br,brc,bc->b", x, Q, x)
 
 
 def bdot(x, y):
-    return torch.bmm(x.unsqueeze(1), y.unsqueeze(2)).squeeze(1).squeeze(1)
+    """batched inner product -> (nb,)"""
+    return (x * y).sum(-1)
 
 
 def bdiag(d):
-    assert d.ndimension() == 2
+    """(nb, k) -> (nb, k, k) diagonal matrices"""
+    if d.ndimension() != 2:
+        raise AssertionError("bdiag expects a (nBatch, k) tensor")
     return torch.diag_embed(d)

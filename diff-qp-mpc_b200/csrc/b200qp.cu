@@ -23,8 +23,8 @@ Options& options() {
     Options x;
     x.res = env_int("B200QP_RES", x.res);
     x.res_chunk = env_int("B200QP_RES_CH", x.res_chunk);
-    x.res_panel = env_int("B200QP_RES_PANEL", x.res_panel);
-    x.res_sweep = env_int("B200QP_RES_SWEEP", x.res_sweep);
+    x.res_spec = env_int("B200QP_RES_SPEC", x.res_spec);
+    x.res_warp = env_int("B200QP_RES_WARP", x.res_warp);
     const char* mid = getenv("B200QP_MID");
     x.mid_fast = (mid && mid[0] == 'f') ? 1 : 0;
     x.blk_nt = env_int("B200QP_BLK_NT", 0);
@@ -140,6 +140,7 @@ static int forward_t(const b200qp_problem_t* pr, const Layout& L, const void* Q,
       RArgs ra;
       ra.hist = (double*)(w + L.ohist); ra.rec = (double*)(w + L.orec); ra.pst = (int*)(w + L.opst);
       ra.hs = res_hs(L.n, L.m);
+      ra.off = res_off(L.n, L.m, L.mpad);
       prof_begin(st);
       if (!prefactored) {
         CK(cudaMemsetAsync(a.slots, 0, sizeof(Slot) * B200QP_MAX_ITER_CAP + sizeof(Control), st));
@@ -593,8 +594,8 @@ int b200qp_set_option(const char* name, int value) {
   Options& o = options();
   if (!strcmp(name, "res")) o.res = value;
   else if (!strcmp(name, "res_ch")) o.res_chunk = value;
-  else if (!strcmp(name, "res_panel")) o.res_panel = value;
-  else if (!strcmp(name, "res_sweep")) o.res_sweep = value;
+  else if (!strcmp(name, "res_spec")) o.res_spec = value;
+  else if (!strcmp(name, "res_warp")) o.res_warp = value;
   else if (!strcmp(name, "mid_fast")) o.mid_fast = value;
   else if (!strcmp(name, "blk_nt")) o.blk_nt = value;
   else if (!strcmp(name, "factor_tile")) o.factor_tile = value;

@@ -7,6 +7,7 @@
 #include "qp_kernels.cuh"
 #include "qp_fast.cuh"
 #include "qp_resident.cuh"
+#include "qp_wres.cuh"
 
 namespace b200qp {
 
@@ -30,7 +31,7 @@ struct Layout {
   size_t ox, os, oz, oy, odx, ods, odz, ody, ormu, oflags, obest, oslots, octl, total;
   // resident route (qp_resident.cuh): several iterations per launch, history + records per problem
   bool res;
-  int res_chunk, res_panel, res_sweep;
+  int res_chunk, res_spec, res_warp;
   size_t res_smem, ohist, orec, opst;
 };
 
@@ -40,8 +41,8 @@ struct Layout {
 struct Options {
   int res = 1;        // B200QP_RES       0: never take the resident route
   int res_chunk = 4;  // B200QP_RES_CH    iterations per launch of the resident route
-  int res_panel = 1;  // B200QP_RES_PANEL 1: fraction-free panel factorisation, 0: reciprocal on the chain
-  int res_sweep = 1;  // B200QP_RES_SWEEP 1: eight columns per sweep step, 0: one
+  int res_spec = 1;   // B200QP_RES_SPEC  1: use the compile-time-size specialisation where one exists (nz=30, nineq=60)
+  int res_warp = 1;   // B200QP_RES_WARP  1: one warp per QP with the factor in registers (qp_wres.cuh), 0: 128-thread CTAs
   int mid_fast = 0;   // B200QP_MID=fast  64 < nineq <= 128 on the register-tile route
   int blk_nt = 0;     // B200QP_BLK_NT    256 forces the wide CTAs of the blocked route
   int factor_tile = 0;// B200QP_FACTOR=tile
@@ -134,9 +135,9 @@ inline int make_layout(const b200qp_problem_t* pr, Layout& L) {
   L.res = opt.res && L.fast && L.fk && L.p == 0 && L.n <= 32 && pr->max_iter <= kResMaxIter &&
           !(pr->flags & (B200QP_FLAG_DENSE | B200QP_FLAG_EXACT));
   L.res_chunk = opt.res_chunk < 1 ? 1 : opt.res_chunk;
-  L.res_panel = opt.res_panel ? 1 : 0;
-  L.res_sweep = opt.res_sweep ? 1 : 0;
-  L.res_smem = res_smem_elems(L.n, L.m, L.mpad) * sizeof(double);
+  L.res_spec = opt.res_spec ? 1 : 0;
+  L.res_warp = opt.res_warp ? 1 : 0;
+  L.res_smem = (size_t)res_off(L.n, L.m, L.mpad).total * sizeof(double);
   L.ohist = L.orec = L.opst = 0;
   if (L.res) {
     L.ohist = put(nb * (size_t)(pr->max_iter + 1) * res_hs(L.n, L.m), sizeof(double));

@@ -23,22 +23,37 @@ static cudaError_t ensure_smem(K kernel, size_t bytes) {
   } while (0)
 
 #if INST_RES
-// resident route (qp_resident.cuh): MPAD in {32, 64} x PANEL in {0, 1} x SWEEP in {0, 1}
-template <int MPAD, int PANEL, int SWEEP>
+// resident route (qp_resident.cuh): MPAD in {32, 64} with run-time sizes, plus the compile-time-size specialisation of the
+// headline shape of BASELINE.json (nz = 30, nineq = 60)
+template <int MPAD, int NC, int MC>
 static int res_launch(const KArgs<double>& a, const RArgs& ra, const Layout& L, cudaStream_t st) {
-  auto k = k_res_chunk<MPAD, PANEL, SWEEP>;
+  auto k = k_res_chunk<MPAD, NC, MC>;
   CK(ensure_smem(k, L.res_smem));
   k<<<(unsigned)a.nb, 128, L.res_smem, st>>>(a, ra);
   CK(cudaGetLastError());
   return B200QP_OK;
 }
-template <int MPAD>
-static int res_launch_m(const KArgs<double>& a, const RArgs& ra, const Layout& L, cudaStream_t st) {
-  if (L.res_panel) return L.res_sweep ? res_launch<MPAD, 1, 1>(a, ra, L, st) : res_launch<MPAD, 1, 0>(a, ra, L, st);
-  return L.res_sweep ? res_launch<MPAD, 0, 1>(a, ra, L, st) : res_launch<MPAD, 0, 0>(a, ra, L, st);
+template <int NTI, int NC, int MC>
+static int wres_launch(const KArgs<double>& a, const RArgs& ra, const Layout& L, cudaStream_t st) {
+  auto k = k_wres_chunk<NTI, NC, MC>;
+  const size_t smem = (size_t)wres_off(L.m).total * sizeof(double);
+  static bool once = false;  // per instantiation
+  if (!once) {
+    CK(cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    once = true;
+  }
+  CK(ensure_smem(k, smem));
+  k<<<(unsigned)a.nb, 32, smem, st>>>(a, ra);
+  CK(cudaGetLastError());
+  return B200QP_OK;
 }
 int res_chunk(const KArgs<double>& a, const RArgs& ra, const Layout& L, cudaStream_t st) {
-  return L.mpad == 32 ? res_launch_m<32>(a, ra, L, st) : res_launch_m<64>(a, ra, L, st);
+  if (L.res_warp) {  // one warp per QP (qp_wres.cuh)
+    if (L.res_spec && L.n == 30 && L.m == 60) return wres_launch<8, 30, 60>(a, ra, L, st);
+    return L.m < 32 ? wres_launch<4, 0, 0>(a, ra, L, st) : wres_launch<8, 0, 0>(a, ra, L, st);
+  }
+  if (L.res_spec && L.n == 30 && L.m == 60) return res_launch<64, 30, 60>(a, ra, L, st);
+  return L.mpad == 32 ? res_launch<32, 0, 0>(a, ra, L, st) : res_launch<64, 0, 0>(a, ra, L, st);
 }
 int res_finish(const KArgs<double>& a, const RArgs& ra, double* status, int launches, cudaStream_t st) {
   k_res_reduce<0><<<(unsigned)((a.nb + 127) / 128), 128, 0, st>>>(a, ra);

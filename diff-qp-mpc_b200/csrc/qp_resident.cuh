@@ -42,7 +42,12 @@ constexpr int kPst = 8;              // ints of per-problem state
 //  [3] sens  : bit it = the step length of iteration it differs between the two regimes
 //  [4] fo    : bit it = a ratio test of iteration it was fill-only while the fill was speculated
 //  [5] aznan / [6] asnan : bit it = this problem's z / s ratios of iteration it contain a NaN
+struct ResOff {  // shared-memory carve-up of k_res_chunk, offsets in doubles (res_off)
+  int G, Q, Qi, Up, pinv, Pb, x, rx, t, p, qx, s, z, d, di, rz, hz, dz, h, part, misc, total;
+};
+
 struct RArgs {
+  ResOff off;    // for run-time sizes (the compile-time specialisations ignore it)
   double* hist;  // [nb][max_iter + 1][hs]   x | s | z at the START of each iteration
   double* rec;   // [nb][max_iter][2]        residual, mu of each iteration
   int* pst;      // [nb][kPst]
@@ -52,13 +57,6 @@ struct RArgs {
 
 __host__ __device__ inline int res_hs(int n, int m) { return round4(n) + 2 * round4(m); }
 
-__host__ __device__ inline size_t res_smem_elems(int n, int m, int mpad) {
-  const int ldn = n | 1, n4 = round4(n), m4 = round4(m);
-  size_t e = round4(m * ldn) + 2 * (size_t)round4(n * ldn);      // G, Q, Qi
-  e += round4((m + 1) * m / 2 + 1) + m4 + round4(mpad * kPanelStride + 16);  // Up, pinv, panel buffer
-  e += (size_t)5 * n4 + (size_t)8 * m4 + 4 * 32 + 16;            // vectors, partials, scalars
-  return e;
-}
 
 __device__ __forceinline__ void cp_async8(double* dst_smem, const double* src) {
   const unsigned d = (unsigned)__cvta_generic_to_shared(dst_smem);
@@ -71,116 +69,150 @@ __device__ __forceinline__ double warp_sum_d(double v) {
   return v;
 }
 
-// exponent of a double (garbage in, garbage out: callers only use it to pick a power-of-two scale)
-__device__ __forceinline__ int dexp(double x) { return ((__double2hiint(x) >> 20) & 0x7ff) - 1023; }
-__device__ __forceinline__ double pow2i(int e) {
-  e = e < -1000 ? -1000 : (e > 1000 ? 1000 : e);
-  return __hiloint2double((1023 + e) << 20, 0);
+
+// ------------------------------------------------------------------------------------------------------------
+// Shared-memory carve-up (offsets in doubles).  With compile-time sizes (the <NC, MC> specialisations of the
+// kernel) every offset is an immediate; otherwise the host computes it once and it travels in the kernel
+// arguments (constant bank) -- ncu on the first version of this kernel showed 31 % of all executed instructions
+// re-deriving these sums of rounded sizes.
+__host__ __device__ constexpr int res_r4(int v) { return (v + 3) & ~3; }
+__host__ __device__ constexpr ResOff res_off(int n, int m, int mpad) {
+  ResOff o{};
+  const int ldn = n | 1;
+  int q = 0;
+  o.G = q; q += res_r4(m * ldn);
+  o.Q = q; q += res_r4(n * ldn);
+  o.Qi = q; q += res_r4(n * ldn);
+  o.Up = q; q += res_r4((m + 1) * m / 2 + 1);
+  o.pinv = q; q += res_r4(m);
+  o.Pb = q; q += res_r4(mpad * kPanelStride + 16);
+  o.x = q; q += res_r4(n); o.rx = q; q += res_r4(n); o.t = q; q += res_r4(n); o.p = q; q += res_r4(n); o.qx = q; q += res_r4(n);
+  o.s = q; q += res_r4(m); o.z = q; q += res_r4(m); o.d = q; q += res_r4(m); o.di = q; q += res_r4(m);
+  o.rz = q; q += res_r4(m); o.hz = q; q += res_r4(m); o.dz = q; q += res_r4(m); o.h = q; q += res_r4(m);
+  o.part = q; q += 128;
+  o.misc = q; q += 16;
+  o.total = q;
+  return o;
 }
 
 // ------------------------------------------------------------------------------------------------------------
-// Blocked right-looking LDL^T of T = R + diag(dinv), bordered by the row hz at index m, on the FP64 tensor cores.
-// Same data flow as dmma_factor (qp_dmma.cuh) with three changes: the tile map is computed once per launch, the
-// trailing update reads its operands as 16-byte fragments (the contraction index of the two DMMAs is permuted so
-// that a lane's two elements are adjacent columns), and (PANEL = 1) the one-warp panel uses a fraction-free
-// recurrence with power-of-two renormalisation so that no reciprocal sits on the pivot-to-pivot dependency chain:
-//     a'_ic = (b_k a_ic - a_ik a_kc) * 2^-e        a = mu_k * (Schur complement),  b_k = a_kk
-// (chain per pivot: one shuffle + one FMA instead of shuffle + reciprocal + multiply + FMA).  The unit-lower
-// columns, the reciprocal pivots and the scale of the trailing update are recovered off the chain.
+// Blocked right-looking LDL^T of T = R + diag(dinv), bordered by the row hz at index m, on the FP64 tensor cores
+// (same algorithm as dmma_factor, qp_dmma.cuh).  Differences that cut the executed instructions by ~3x:
+//   * tiles are owned by ROW: warp w holds tile rows w and NTI-1-w (9 tiles each at MPAD = 64), slot index = tile
+//     column, so every register-array index is static and a warp loads the scaled A fragment of a row once per
+//     panel and re-uses it (and the B fragment of a column) for all its tiles;
+//   * operands are 16-byte fragments: the contraction index of the two DMMAs of a tile is permuted so that a
+//     lane's two elements are adjacent columns;
+//   * with compile-time sizes the panel loop is unrolled, so offsets are immediates and predicates fold.
 template <int MPAD>
-struct ResTiles {
-  static constexpr int NTI = MPAD / 8, NTILES = NTI * (NTI + 1) / 2, SLOTS = (NTILES + 3) / 4;
-  unsigned long long ip, kp;  // 4 bits per slot: tile row / tile column of slot s of this warp
-  __device__ __forceinline__ void init(int warp) {
-    ip = 0; kp = 0;
-#pragma unroll
-    for (int s = 0; s < SLOTS; s++) {
-      const int t = 4 * s + warp;
-      int I = (int)((sqrtf(8.0f * (float)t + 1.0f) - 1.0f) * 0.5f);
-      if ((I + 1) * (I + 2) / 2 <= t) I++;
-      const int K = t - I * (I + 1) / 2;
-      ip |= (unsigned long long)(I & 15) << (4 * s);
-      kp |= (unsigned long long)(K & 15) << (4 * s);
-    }
-  }
-  __device__ __forceinline__ int I(int s) const { return (int)(ip >> (4 * s)) & 15; }
-  __device__ __forceinline__ int K(int s) const { return (int)(kp >> (4 * s)) & 15; }
+struct RowTiles {
+  static constexpr int NTI = MPAD / 8;
+  static constexpr int NA = NTI == 8 ? 4 : NTI;  // slots of row a = warp        (tile column K <= warp)
+  static constexpr int NB = NTI == 8 ? 8 : 1;    // slots of row b = NTI-1-warp  (MPAD = 64 only)
+  static constexpr bool HAS_B = NTI == 8;
 };
 
 template <int MPAD>
 __device__ __forceinline__ void res_prefetch(const double* __restrict__ Rf, int lane, int warp,
-                                             double (&C)[ResTiles<MPAD>::SLOTS][2]) {
-  using TT = ResTiles<MPAD>;
+                                             double (&Ca)[RowTiles<MPAD>::NA][2], double (&Cb)[RowTiles<MPAD>::NB][2]) {
+  using RT = RowTiles<MPAD>;
+  const int Ia = warp, Ib = RT::NTI - 1 - warp;
+  const double* ra = Rf + (size_t)(Ia * (Ia + 1) / 2) * 64 + lane * 2;
 #pragma unroll
-  for (int s = 0; s < TT::SLOTS; s++) {
-    const int t = 4 * s + warp;
+  for (int K = 0; K < RT::NA; K++) {
     double2 v = make_double2(0.0, 0.0);
-    if (t < TT::NTILES) v = *reinterpret_cast<const double2*>(Rf + (size_t)t * 64 + lane * 2);
-    C[s][0] = v.x; C[s][1] = v.y;
+    if (K <= Ia) v = *reinterpret_cast<const double2*>(ra + K * 64);
+    Ca[K][0] = v.x; Ca[K][1] = v.y;
+  }
+  if constexpr (RT::HAS_B) {
+    const double* rb = Rf + (size_t)(Ib * (Ib + 1) / 2) * 64 + lane * 2;
+#pragma unroll
+    for (int K = 0; K < RT::NB; K++) {
+      double2 v = make_double2(0.0, 0.0);
+      if (K <= Ib) v = *reinterpret_cast<const double2*>(rb + K * 64);
+      Cb[K][0] = v.x; Cb[K][1] = v.y;
+    }
   }
 }
 
-template <int MPAD, int PANEL, class Idle>
-__device__ __forceinline__ bool res_factor(double (&C)[ResTiles<MPAD>::SLOTS][2], const ResTiles<MPAD>& tm,
-                                           const double* dinv, const double* hz, double* Up, double* pinv, double* Pb,
-                                           int m, int tid, Idle&& idle) {
-  using TT = ResTiles<MPAD>;
-  constexpr int NTILES = TT::NTILES, SLOTS = TT::SLOTS, PS = kPanelStride;
-  const int lane = tid & 31, warp = tid >> 5;
-  const int fr = lane >> 2, fc = (lane & 3) * 2;
-  const int mm = m + 1;
-  // ---- diagonal, bordered row and padding of the tiles that are not interior
-#pragma unroll
-  for (int s = 0; s < SLOTS; s++) {
-    if (4 * s + warp < NTILES) {
-      const int I = tm.I(s), K = tm.K(s);
-      if (!(I != K && 8 * I + 8 <= m)) {
-        const int i = 8 * I + fr, k = 8 * K + fc;
-        double v0 = 0.0, v1 = 0.0;
-        if (i < m && k < m) {
-          v0 = (k <= i) ? C[s][0] : 0.0;
-          v1 = (k + 1 <= i) ? C[s][1] : 0.0;
-          if (I == K) {
-            if (i == k) v0 += dinv[i];
-            if (i == k + 1) v1 += dinv[i];
-          }
-        } else if (i == m) {
-          if (k < m) v0 = hz[k];
-          if (k + 1 < m) v1 = hz[k + 1];
-        }
-        if (i >= m) {
-          if (i == k) v0 = 1.0;
-          if (i == k + 1) v1 = 1.0;
-        }
-        C[s][0] = v0; C[s][1] = v1;
+// diagonal, bordered row and padding of one tile that is not interior
+__device__ __forceinline__ void res_fix_tile(double (&c)[2], int I, int K, int fr, int fc, int m, const double* dinv,
+                                             const double* hz) {
+  if (!(I != K && 8 * I + 8 <= m)) {
+    const int i = 8 * I + fr, k = 8 * K + fc;
+    double v0 = 0.0, v1 = 0.0;
+    if (i < m && k < m) {
+      v0 = (k <= i) ? c[0] : 0.0;
+      v1 = (k + 1 <= i) ? c[1] : 0.0;
+      if (I == K) {
+        if (i == k) v0 += dinv[i];
+        if (i == k + 1) v1 += dinv[i];
       }
+    } else if (i == m) {
+      if (k < m) v0 = hz[k];
+      if (k + 1 < m) v1 = hz[k + 1];
     }
+    if (i >= m) {
+      if (i == k) v0 = 1.0;
+      if (i == k + 1) v1 = 1.0;
+    }
+    c[0] = v0; c[1] = v1;
   }
-  double* ppan = Pb + MPAD * PS;  // [0..8): scale of the trailing update per panel column; [8..16): 1 / b_k (PANEL = 1)
+}
+
+template <int MPAD, int MC, class Idle>
+__device__ __forceinline__ bool res_factor(double (&Ca)[RowTiles<MPAD>::NA][2], double (&Cb)[RowTiles<MPAD>::NB][2],
+                                           const double* dinv, const double* hz, double* Up, double* pinv, double* Pb,
+                                           int m_rt, int tid, Idle&& idle) {
+  using RT = RowTiles<MPAD>;
+  constexpr int PS = kPanelStride;
+  const int m = MC > 0 ? MC : m_rt;
+  const int lane = tid & 31, warp = tid >> 5;
+  const int fr = lane >> 2, kc = lane & 3, fc = kc * 2;
+  const int mm = m + 1;
+  const int Ia = warp, Ib = RT::NTI - 1 - warp;
+#pragma unroll
+  for (int K = 0; K < RT::NA; K++)
+    if (K <= Ia) res_fix_tile(Ca[K], Ia, K, fr, fc, m, dinv, hz);
+  if constexpr (RT::HAS_B) {
+#pragma unroll
+    for (int K = 0; K < RT::NB; K++)
+      if (K <= Ib) res_fix_tile(Cb[K], Ib, K, fr, fc, m, dinv, hz);
+  }
+  double* ppan = Pb + MPAD * PS;  // [0..8): -1/D of the panel's columns (trailing-update scale); [8..16): 1/D
+  double* rowa = Pb + (8 * Ia + fr) * PS + fc;  // this lane's fragment of tile row a / b in the panel buffer
+  double* rowb = Pb + (8 * Ib + fr) * PS + fc;
+  const double* colk = Pb + fr * PS + fc;        // + 8 K PS: fragment of tile row K (the B operand)
   bool ok = true;
   const int npan = (mm + 7) >> 3;
-#pragma unroll 1
-  for (int J = 0; J < npan; J++) {
 #pragma unroll
-    for (int s = 0; s < SLOTS; s++) {
-      if (4 * s + warp < NTILES && tm.K(s) == J)
-        *reinterpret_cast<double2*>(Pb + (8 * tm.I(s) + fr) * PS + fc) = make_double2(C[s][0], C[s][1]);
-    }
-    __syncthreads();
-    if (warp == 0) {
-      const int rbase = 8 * J;
-      const int i0 = rbase + lane, i1 = rbase + 32 + lane;
-      const bool two = rbase + 32 < MPAD;  // uniform: the second row of a lane exists
-      double a0[8], a1[8];
+  for (int J = 0; J < (MC > 0 ? (MC + 8) / 8 : RT::NTI); J++) {
+    if (J < npan) {  // folds for compile-time sizes
+      // (a) owners publish the panel's tiles
 #pragma unroll
-      for (int q = 0; q < 4; q++) {
-        double2 v = make_double2(0.0, 0.0), w = make_double2(0.0, 0.0);
-        if (i0 < MPAD) v = *reinterpret_cast<const double2*>(Pb + i0 * PS + 2 * q);
-        if (two && i1 < MPAD) w = *reinterpret_cast<const double2*>(Pb + i1 * PS + 2 * q);
-        a0[2 * q] = v.x; a0[2 * q + 1] = v.y;
-        a1[2 * q] = w.x; a1[2 * q + 1] = w.y;
+      for (int K = 0; K < RT::NA; K++)
+        if (K == J && K <= Ia) *reinterpret_cast<double2*>(rowa) = make_double2(Ca[K][0], Ca[K][1]);
+      if constexpr (RT::HAS_B) {
+#pragma unroll
+        for (int K = 0; K < RT::NB; K++)
+          if (K == J && K <= Ib) *reinterpret_cast<double2*>(rowb) = make_double2(Cb[K][0], Cb[K][1]);
       }
-      if constexpr (PANEL == 0) {
+      __syncthreads();
+      // (b) one warp factors the panel: lane owns rows i0, i1
+      if (warp == 0) {
+        const int rbase = 8 * J;
+        const int i0 = rbase + lane, i1 = rbase + 32 + lane;
+        const bool two = rbase + 32 < MPAD;  // the second row of a lane exists
+        double a0[8], a1[8];
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+          double2 v = make_double2(0.0, 0.0), w = make_double2(0.0, 0.0);
+          if (i0 < MPAD) v = *reinterpret_cast<const double2*>(Pb + i0 * PS + 2 * q);
+          if (two && i1 < MPAD) w = *reinterpret_cast<const double2*>(Pb + i1 * PS + 2 * q);
+          a0[2 * q] = v.x; a0[2 * q + 1] = v.y;
+          a1[2 * q] = w.x; a1[2 * q + 1] = w.y;
+        }
+        double pk[8];
 #pragma unroll
         for (int k = 0; k < 8; k++) {
           const double dk = shfl_d(a0[k], k);
@@ -190,9 +222,9 @@ __device__ __forceinline__ bool res_factor(double (&C)[ResTiles<MPAD>::SLOTS][2]
           r = fma(r, e, r);
           e = fma(-dk, r, 1.0);
           r = fma(r, e, r);
-          if (!(dk > 1e-290 && dk < 1e290)) r = (dk > 0.0) ? 1.0 / dk : t_nan<double>();
-          const double pkk = (rbase + k < m) ? r : 1.0;
-          if (lane == 0) { ppan[k] = -pkk; ppan[8 + k] = pkk; }
+          if (!(dk > 1e-290 && dk < 1e290)) r = (dk > 0.0) ? 1.0 / dk : t_nan<double>();  // rare
+          const double pkk = (rbase + k < m) ? r : 1.0;  // bordered / padding columns: unit pivot
+          pk[k] = pkk;
           const double w0 = a0[k], w1 = a1[k];
           const double l0 = w0 * pkk, l1 = w1 * pkk;
 #pragma unroll
@@ -202,91 +234,83 @@ __device__ __forceinline__ bool res_factor(double (&C)[ResTiles<MPAD>::SLOTS][2]
             if (two) a1[c] -= l1 * wck;
           }
         }
-        __syncwarp();
-        if (lane < 8 && rbase + lane < m) pinv[rbase + lane] = ppan[8 + lane];
-      } else {
-        // fraction-free panel: a = mu_k * (Schur complement); mu renormalised by powers of two
-        const int kend = (m - rbase) < 8 ? (m - rbase) : 8;  // real columns of this panel (uniform)
-        double mu = 1.0;
+        // off the pivot chain: reciprocal pivots, packed unit-lower columns for the sweeps, W = L D for the update
+        if (lane < 8) {
+          double pl = pk[0];
 #pragma unroll
-        for (int k = 0; k < 8; k++) {
-          if (k < kend) {
-            const double bk = shfl_d(a0[k], k);                    // mu_k * d_k          [dependency chain]
-            const double est = Pb[(rbase + k) * PS + k];           // the panel's initial diagonal: >= d_k
-            const double rt = pow2i(-(2 * dexp(mu) + dexp(est)));  // 2^-e: mu_{k+1} ~ d_k / est_k
-            // off the chain: scale of the trailing update, reciprocal pivot, 1 / b_k
-            const double pm = mu * bk;
-            double g = -pivot_rcp(pm);                             // -1 / (mu_k b_k)
-            if (!(bk > 0.0) || !(pm < 1e300)) g = t_nan<double>();  // non-positive / NaN pivot poisons the factor
-            const double rb = -g * mu;                             // 1 / b_k
-            if (lane == 0) { ppan[k] = g; ppan[8 + k] = rb; pinv[rbase + k] = rb * mu; }
-            const double u0 = a0[k] * rt, u1 = a1[k] * rt;
+          for (int k = 1; k < 8; k++) pl = lane == k ? pk[k] : pl;
+          ppan[lane] = -pl; ppan[8 + lane] = pl;
+          if (rbase + lane < m) pinv[rbase + lane] = pl;
+        }
+        {
+          int ub = urow(rbase, mm);
 #pragma unroll
-            for (int c = k + 1; c < 8; c++) {
-              if (c < kend) {  // padding columns and the bordered row's own column are never used
-                const double wkc = shfl_d(a0[k], c);
-                a0[c] = fma(bk, a0[c] * rt, -(u0 * wkc));
-                if (two) a1[c] = fma(bk, a1[c] * rt, -(u1 * wkc));
-              }
+          for (int k = 0; k < 8; k++) {
+            const int j = rbase + k;
+            if (j < m) {
+              if (i0 > j && i0 < mm) Up[ub + i0] = a0[k] * pk[k];
+              if (two && i1 < mm) Up[ub + i1] = a1[k] * pk[k];
             }
-            mu = rt * pm;
-          } else if (lane == 0) {
-            ppan[k] = 0.0; ppan[8 + k] = 0.0;  // padding / border columns take no part in the trailing update
+            ub += mm - j - 2;
           }
         }
-        __syncwarp();
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+          if (i0 >= rbase + 8 && i0 < MPAD) *reinterpret_cast<double2*>(Pb + i0 * PS + 2 * q) = make_double2(a0[2 * q], a0[2 * q + 1]);
+          if (two && i1 < MPAD) *reinterpret_cast<double2*>(Pb + i1 * PS + 2 * q) = make_double2(a1[2 * q], a1[2 * q + 1]);
+        }
+      } else {
+        idle(J);
       }
-      // packed unit-lower columns for the sweeps (off the critical path)
+      __syncthreads();
+      // (c) trailing update  C_IK -= (W_I D^-1) W_K^T  of this warp's tiles right of the panel
       {
-        int ub = urow(rbase, mm);
+        const double2 sc = *reinterpret_cast<const double2*>(ppan + fc);
+        if (is_nan(ppan[0] + ppan[1] + ppan[2] + ppan[3] + ppan[4] + ppan[5] + ppan[6] + ppan[7])) ok = false;  // uniform
+        double2 aa = make_double2(0.0, 0.0), ab = make_double2(0.0, 0.0);
+        if (J < Ia) { aa = *reinterpret_cast<const double2*>(rowa); aa.x *= sc.x; aa.y *= sc.y; }
+        if (RT::HAS_B && J < Ib) { ab = *reinterpret_cast<const double2*>(rowb); ab.x *= sc.x; ab.y *= sc.y; }
 #pragma unroll
-        for (int k = 0; k < 8; k++) {
-          const int j = rbase + k;
-          if (j < m) {
-            const double pkk = ppan[8 + k];
-            if (i0 > j && i0 < mm) Up[ub + i0] = a0[k] * pkk;
-            if (two && i1 < mm) Up[ub + i1] = a1[k] * pkk;
+        for (int K = 1; K < RT::NTI; K++) {
+          if (K > J && (K <= Ia || (RT::HAS_B && K <= Ib))) {
+            const double2 bv = *reinterpret_cast<const double2*>(colk + 8 * K * PS);
+            if (K < RT::NA && K <= Ia) {
+              dmma_m8n8k4(Ca[K < RT::NA ? K : 0][0], Ca[K < RT::NA ? K : 0][1], aa.x, bv.x);
+              dmma_m8n8k4(Ca[K < RT::NA ? K : 0][0], Ca[K < RT::NA ? K : 0][1], aa.y, bv.y);
+            }
+            if (RT::HAS_B && K <= Ib) {
+              dmma_m8n8k4(Cb[K < RT::NB ? K : 0][0], Cb[K < RT::NB ? K : 0][1], ab.x, bv.x);
+              dmma_m8n8k4(Cb[K < RT::NB ? K : 0][0], Cb[K < RT::NB ? K : 0][1], ab.y, bv.y);
+            }
           }
-          ub += mm - j - 2;
         }
       }
-#pragma unroll
-      for (int q = 0; q < 4; q++) {
-        if (i0 >= rbase + 8 && i0 < MPAD) *reinterpret_cast<double2*>(Pb + i0 * PS + 2 * q) = make_double2(a0[2 * q], a0[2 * q + 1]);
-        if (two && i1 < MPAD) *reinterpret_cast<double2*>(Pb + i1 * PS + 2 * q) = make_double2(a1[2 * q], a1[2 * q + 1]);
-      }
-    } else {
-      idle(J);
+      __syncthreads();
     }
-    __syncthreads();
-    {
-      const int kc = lane & 3;
-      const double2 sc = *reinterpret_cast<const double2*>(ppan + 2 * kc);
-      if (is_nan(ppan[0] + ppan[1] + ppan[2] + ppan[3] + ppan[4] + ppan[5] + ppan[6] + ppan[7])) ok = false;  // uniform
-#pragma unroll
-      for (int s = 0; s < SLOTS; s++) {
-        if (4 * s + warp < NTILES && tm.K(s) > J) {
-          const double2 av = *reinterpret_cast<const double2*>(Pb + (8 * tm.I(s) + fr) * PS + 2 * kc);
-          const double2 bv = *reinterpret_cast<const double2*>(Pb + (8 * tm.K(s) + fr) * PS + 2 * kc);
-          dmma_m8n8k4(C[s][0], C[s][1], av.x * sc.x, bv.x);
-          dmma_m8n8k4(C[s][0], C[s][1], av.y * sc.y, bv.y);
-        }
-      }
-    }
-    __syncthreads();
   }
   return ok;
 }
 
 // ------------------------------------------------------------------------------------------------------------
-// Triangular sweeps of ONE warp with the working vector in registers (lane owns rows lane, lane + 32).
-//   SWEEP = 0: one column per step (the sweeps of dmma_ldlt_solve).
-//   SWEEP = 1: eight columns per step -- the eight right-hand-side entries of the diagonal block are broadcast at
-//              once, every lane runs the 8 x 8 substitution redundantly, then updates its rows with eight
-//              independent loads; the shuffle latency is paid once per block instead of once per column.
-template <int RPL, int SWEEP>
-__device__ __forceinline__ void res_fwd(const double* Up, int m, int mm, double (&r)[RPL], int lane) {
-  if constexpr (SWEEP == 0) {
+// Triangular sweeps of ONE warp with the working vector in registers (lane owns rows lane, lane + 32), packed
+// unit-lower factor `Up` (urow, qp_dmma.cuh).  With a compile-time size the column loop is unrolled: the row
+// offsets are immediates and most row predicates fold (6-7 instructions per column).
+template <int RPL, int MC>
+__device__ __forceinline__ void res_fwd(const double* Up, int m_rt, double (&r)[RPL], int lane) {
+  const int m = MC > 0 ? MC : m_rt, mm = m + 1;
+  if constexpr (MC > 0) {
+#pragma unroll
+    for (int j = 0; j < MC; j++) {
+      const int s = j >> 5;
+      const double yj = shfl_d(r[s], j & 31);
+      const double* row = Up + urow(j, MC + 1);
+#pragma unroll
+      for (int s2 = s; s2 < RPL; s2++) {
+        const int i = s2 * 32 + lane;
+        if (i > j && i < MC) r[s2] -= row[i] * yj;
+      }
+    }
+  } else {
 #pragma unroll
     for (int s = 0; s < RPL; s++) {
       const int jend = min(32, m - s * 32);
@@ -302,43 +326,30 @@ __device__ __forceinline__ void res_fwd(const double* Up, int m, int mm, double 
         }
       }
     }
-  } else {
-#pragma unroll
-    for (int J = 0; J < RPL * 4; J++) {
-      const int j0 = 8 * J;
-      if (j0 < m) {  // uniform
-        const int s = J >> 2, lb = j0 & 31;
-        const int kend = (m - j0) < 8 ? (m - j0) : 8;
-        double y[8];
-#pragma unroll
-        for (int c = 0; c < 8; c++) y[c] = shfl_d(r[s], lb + c);
-        int ub = urow(j0, mm);
-#pragma unroll
-        for (int k = 0; k < 8; k++) {
-          if (k < kend) {
-            const double* row = Up + ub;  // row[i] = L[i][j0 + k]
-#pragma unroll
-            for (int c = k + 1; c < 8; c++)
-              if (c < kend) y[c] -= row[j0 + c] * y[k];
-#pragma unroll
-            for (int s2 = s; s2 < RPL; s2++) {
-              const int i = s2 * 32 + lane;
-              if (i > j0 + k && i < m) r[s2] -= row[i] * y[k];
-            }
-          }
-          ub += mm - (j0 + k) - 2;
-        }
-      }
-    }
   }
 }
 
-template <int RPL, int SWEEP>
-__device__ __forceinline__ void res_bwd(const double* Up, int m, int mm, double (&r)[RPL], int lane) {
-  int rb[RPL];
+template <int RPL, int MC>
+__device__ __forceinline__ void res_bwd(const double* Up, int m_rt, double (&r)[RPL], int lane) {
+  const int m = MC > 0 ? MC : m_rt, mm = m + 1;
+  const double* rb[RPL];
 #pragma unroll
-  for (int s = 0; s < RPL; s++) rb[s] = urow(s * 32 + lane, mm);
-  if constexpr (SWEEP == 0) {
+  for (int s = 0; s < RPL; s++) {
+    const int i = s * 32 + lane;
+    rb[s] = Up + urow(i < m ? i : 0, mm);  // rb[s][j] = U[i][j]
+  }
+  if constexpr (MC > 0) {
+#pragma unroll
+    for (int j = MC - 1; j > 0; j--) {
+      const int s = j >> 5;
+      const double xj = shfl_d(r[s], j & 31);
+#pragma unroll
+      for (int s2 = 0; s2 <= s; s2++) {
+        const int i = s2 * 32 + lane;
+        if (i < j) r[s2] -= rb[s2][j] * xj;
+      }
+    }
+  } else {
 #pragma unroll
     for (int s = RPL - 1; s >= 0; s--) {
       const int jend = min(32, m - s * 32);
@@ -349,32 +360,7 @@ __device__ __forceinline__ void res_bwd(const double* Up, int m, int mm, double 
 #pragma unroll
         for (int s2 = 0; s2 <= s; s2++) {
           const int i = s2 * 32 + lane;
-          if (i < j) r[s2] -= Up[rb[s2] + j] * xj;
-        }
-      }
-    }
-  } else {
-#pragma unroll
-    for (int J = RPL * 4 - 1; J >= 0; J--) {
-      const int j0 = 8 * J;
-      if (j0 < m) {  // uniform
-        const int s = J >> 2, lb = j0 & 31;
-        const int kend = (m - j0) < 8 ? (m - j0) : 8;
-        double x[8];
-#pragma unroll
-        for (int c = 0; c < 8; c++) x[c] = shfl_d(r[s], lb + c);
-#pragma unroll
-        for (int k = 7; k >= 0; k--) {
-          if (k < kend) {
-            // x[k] is final; eliminate it from the rows above
-#pragma unroll
-            for (int c = 0; c < k; c++) x[c] -= Up[urow(j0 + c, mm) + j0 + k] * x[k];
-#pragma unroll
-            for (int s2 = 0; s2 <= s; s2++) {
-              const int i = s2 * 32 + lane;
-              if (i < j0 + k) r[s2] -= Up[rb[s2] + j0 + k] * x[k];
-            }
-          }
+          if (i < j) r[s2] -= rb[s2][j] * xj;
         }
       }
     }
@@ -382,9 +368,9 @@ __device__ __forceinline__ void res_bwd(const double* Up, int m, int mm, double 
 }
 
 // get_step pieces (batch.py:211-214) of (z, dz) and (s, ds) from registers: the NaN-propagating minimum over the
-// entries the fill does not overwrite (+inf if none), whether some entry is overwritten, and the NaN-propagating
-// maximum of a = -v / dv over all entries.  Every lane returns the same values.
-template <int RPL>
+// entries the fill does not overwrite (+inf if none), whether some entry is overwritten, and (AMAX) the
+// NaN-propagating maximum of a = -v / dv over all entries.  Every lane returns the same values.
+template <int RPL, bool AMAX>
 __device__ __forceinline__ void res_pieces(const double (&z)[RPL], const double (&dz)[RPL], const double (&s)[RPL],
                                            const double (&ds)[RPL], int m, int lane, double (&out)[4], int& has) {
   double rz = t_inf<double>(), rs = t_inf<double>(), az = -t_inf<double>(), as = -t_inf<double>();
@@ -395,16 +381,14 @@ __device__ __forceinline__ void res_pieces(const double (&z)[RPL], const double 
       const double a1 = -z[q] / dz[q], a2 = -s[q] / ds[q];
       if (dz[q] > 0.0) hz = true; else rz = nanmin(rz, a1);
       if (ds[q] > 0.0) hs = true; else rs = nanmin(rs, a2);
-      az = nanmax(az, a1);
-      as = nanmax(as, a2);
+      if (AMAX) { az = nanmax(az, a1); as = nanmax(as, a2); }
     }
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
     rz = nanmin(rz, shfl_x(rz, o));
     rs = nanmin(rs, shfl_x(rs, o));
-    az = nanmax(az, shfl_x(az, o));
-    as = nanmax(as, shfl_x(as, o));
+    if (AMAX) { az = nanmax(az, shfl_x(az, o)); as = nanmax(as, shfl_x(as, o)); }
   }
   has = (__any_sync(0xffffffffu, hz) ? 1 : 0) | (__any_sync(0xffffffffu, hs) ? 2 : 0);
   out[0] = rz; out[1] = rs; out[2] = az; out[3] = as;
@@ -451,28 +435,41 @@ __device__ __forceinline__ double res_mv4(const double* M, int ld, int rows, int
   return a;
 }
 // part[warp * 32 + c] = sum over the rows r = warp, warp + 4, ... of M[r * ld + c] u[r]   (c = lane < cols)
+template <int MC>
 __device__ __forceinline__ void res_mvt(const double* M, int ld, int rows, int cols, const double* u, double* part, int lane,
                                         int warp) {
   double a0 = 0.0, a1 = 0.0;
   if (lane < cols) {
-    int r = warp;
-    for (; r + 4 < rows; r += 8) {
-      a0 = fma(M[r * ld + lane], u[r], a0);
-      a1 = fma(M[(r + 4) * ld + lane], u[r + 4], a1);
+    if constexpr (MC > 0) {
+      const double* mp = M + warp * ld + lane;
+      const double* up = u + warp;
+#pragma unroll
+      for (int k = 0; k < (MC + 3) / 4; k += 2) {
+        if (4 * k + 3 < MC || warp + 4 * k < MC) a0 = fma(mp[4 * k * ld], up[4 * k], a0);
+        if (k + 1 < (MC + 3) / 4 && (4 * k + 7 < MC || warp + 4 * k + 4 < MC)) a1 = fma(mp[(4 * k + 4) * ld], up[4 * k + 4], a1);
+      }
+    } else {
+      int r = warp;
+      for (; r + 4 < rows; r += 8) {
+        a0 = fma(M[r * ld + lane], u[r], a0);
+        a1 = fma(M[(r + 4) * ld + lane], u[r + 4], a1);
+      }
+      if (r < rows) a0 = fma(M[r * ld + lane], u[r], a0);
     }
-    if (r < rows) a0 = fma(M[r * ld + lane], u[r], a0);
   }
   part[warp * 32 + lane] = a0 + a1;
 }
 
 // ------------------------------------------------------------------------------------------------------------
-template <int MPAD, int PANEL, int SWEEP>
+// One launch = the iterations [.., ra.it_end) of every problem.  <NC, MC> != 0: compile-time nz / nineq.
+template <int MPAD, int NC, int MC>
 __global__ void __launch_bounds__(128, 4) k_res_chunk(const KArgs<double> a, const RArgs ra) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  using TT = ResTiles<MPAD>;
+  using RT = RowTiles<MPAD>;
   constexpr int RPL = MPAD / 32;
   const int prob = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int n = a.n, m = a.m, mm = m + 1, ldn = a.ldn, n4 = round4(n), m4 = round4(m);
+  const int n = NC > 0 ? NC : a.n, m = MC > 0 ? MC : a.m, mm = m + 1, ldn = n | 1;
+  const int n4 = res_r4(n), m4 = res_r4(m), hs = n4 + 2 * m4;
 
   // ---- where does this problem (re)start?
   int* ps = ra.pst + (size_t)prob * kPst;
@@ -493,15 +490,15 @@ __global__ void __launch_bounds__(128, 4) k_res_chunk(const KArgs<double> a, con
   if (poison || it >= ra.it_end) return;  // uniform
 
   // ---- shared memory
-  double* q = reinterpret_cast<double*>(smem_raw);
-  auto take = [&](int cnt) { double* r = q; q += round4(cnt); return r; };
-  double* sG = take(m * ldn); double* sQ = take(n * ldn); double* sQi = take(n * ldn);
-  double* Up = take(mm * m / 2 + 1); double* pinv = take(m); double* Pb = take(MPAD * kPanelStride + 16);
-  double* vx = take(n); double* vrx = take(n); double* vt = take(n); double* vp = take(n); double* vqx = take(n);
-  double* vs = take(m); double* vz = take(m); double* vd = take(m); double* vdi = take(m); double* vrz = take(m);
-  double* vhz = take(m); double* vdz = take(m); double* vh = take(m);
-  double* part = take(128); double* misc = take(16);
-  (void)n4; (void)m4;
+  const ResOff o = (NC > 0 && MC > 0) ? res_off(NC > 0 ? NC : 1, MC > 0 ? MC : 1, MPAD) : ra.off;
+  double* sm = reinterpret_cast<double*>(smem_raw);
+  double* sG = sm + o.G; double* sQ = sm + o.Q; double* sQi = sm + o.Qi;
+  double* Up = sm + o.Up; double* pinv = sm + o.pinv; double* Pb = sm + o.Pb;
+  double* vx = sm + o.x; double* vrx = sm + o.rx; double* vt = sm + o.t; double* vp = sm + o.p; double* vqx = sm + o.qx;
+  double* vs = sm + o.s; double* vz = sm + o.z; double* vd = sm + o.d; double* vdi = sm + o.di; double* vrz = sm + o.rz;
+  double* vhz = sm + o.hz; double* vdz = sm + o.dz; double* vh = sm + o.h;
+  double* part = sm + o.part; double* misc = sm + o.misc;
+  double* hist = ra.hist + (size_t)prob * (a.max_iter + 1) * hs;
 
   // ---- stage Q, G (row stride n -> odd ldn), Q^-1, p, h and the iterate
   {
@@ -511,37 +508,35 @@ __global__ void __launch_bounds__(128, 4) k_res_chunk(const KArgs<double> a, con
       if (lane < n) cp_async8(sG + r * ldn + lane, Gg + r * n + lane);
     for (int r = warp; r < n; r += 4)
       if (lane < n) cp_async8(sQ + r * ldn + lane, Qg + r * n + lane);
-    cp_async_block(sQi, a.Qi + (size_t)prob * a.sQi, round4(n * ldn), tid, 128);
+    cp_async_block(sQi, a.Qi + (size_t)prob * a.sQi, res_r4(n * ldn), tid, 128);
     cp_async_commit();
     const double* pg = a.pv + (size_t)prob * a.sp;
     const double* hg = a.h + (size_t)prob * a.sh;
     if (tid < n) vp[tid] = pg[tid];
     if (tid < m) vh[tid] = hg[tid];
     if (it >= 0) {
-      const double* hh = ra.hist + ((size_t)prob * (a.max_iter + 1) + it) * ra.hs;
+      const double* hh = hist + (size_t)it * hs;
       if (tid < n) vx[tid] = hh[tid];
-      if (tid < m) { vs[tid] = hh[round4(n) + tid]; vz[tid] = hh[round4(n) + round4(m) + tid]; }
+      if (tid < m) { vs[tid] = hh[n4 + tid]; vz[tid] = hh[n4 + m4 + tid]; }
     }
   }
-  TT tm;
-  tm.init(warp);
   const double* Rf = a.R + (size_t)prob * a.sR;
-  double C[TT::SLOTS][2];
-  res_prefetch<MPAD>(Rf, lane, warp, C);
+  double Ca[RT::NA][2], Cb[RT::NB][2];
+  res_prefetch<MPAD>(Rf, lane, warp, Ca, Cb);
   cp_async_wait_all();
   __syncthreads();
 
   bool alive = true;
-  int restart_first = 1;  // the history entry of the first iteration of this launch already exists
+  bool have_hist = true;  // the history entry of the first iteration of this launch already exists
 #pragma unroll 1
-  for (; it < ra.it_end && alive; ++it) {
+  for (; it < ra.it_end; ++it) {
     const bool init = it < 0;
     // ---------------- residuals (batch.py:93-108)
     if (!init) {
-      if (!restart_first) {
-        double* hh = ra.hist + ((size_t)prob * (a.max_iter + 1) + it) * ra.hs;
+      if (!have_hist) {
+        double* hh = hist + (size_t)it * hs;
         if (tid < n) hh[tid] = vx[tid];
-        if (tid < m) { hh[round4(n) + tid] = vs[tid]; hh[round4(n) + round4(m) + tid] = vz[tid]; }
+        if (tid < m) { hh[n4 + tid] = vs[tid]; hh[n4 + m4 + tid] = vz[tid]; }
       }
       if (tid < m) {
         const double dv = vz[tid] / vs[tid];
@@ -558,7 +553,7 @@ __global__ void __launch_bounds__(128, 4) k_res_chunk(const KArgs<double> a, con
         const int row = warp * 8 + (lane & 7);
         if (lane < 8 && row < n) vqx[row] = qx;
       }
-      res_mvt(sG, ldn, m, n, vz, part, lane, warp);
+      res_mvt<MC>(sG, ldn, m, n, vz, part, lane, warp);
       __syncthreads();
       if (tid < n) vrx[tid] = ((part[tid] + part[32 + tid]) + (part[64 + tid] + part[96 + tid])) + (vqx[tid] + vp[tid]);
     } else {
@@ -566,7 +561,7 @@ __global__ void __launch_bounds__(128, 4) k_res_chunk(const KArgs<double> a, con
       if (tid < n) vrx[tid] = vp[tid];
       if (tid < m) { vd[tid] = 1.0; vdi[tid] = 1.0; vz[tid] = 0.0; vs[tid] = 0.0; vrz[tid] = -vh[tid]; }
     }
-    restart_first = 0;
+    have_hist = false;
     __syncthreads();
     // ---------------- right-hand side of the reduced system: hz = G Q^-1 rx + rs / d - rz   (rs = z)
     {
@@ -582,7 +577,7 @@ __global__ void __launch_bounds__(128, 4) k_res_chunk(const KArgs<double> a, con
     }
     __syncthreads();
     // ---------------- T = R + diag(1/d) = L D L^T with hz riding as the bordered row
-    const bool ok = res_factor<MPAD, PANEL>(C, tm, vdi, vhz, Up, pinv, Pb, m, tid, [&](int J) {
+    const bool ok = res_factor<MPAD, MC>(Ca, Cb, vdi, vhz, Up, pinv, Pb, m, tid, [&](int J) {
       if (warp == 1 && J == 0 && !init) {
         // residual norms and mu by an otherwise idle warp (batch.py:103-108)
         double s0 = 0.0, s1 = 0.0, s2 = 0.0;
@@ -603,7 +598,7 @@ __global__ void __launch_bounds__(128, 4) k_res_chunk(const KArgs<double> a, con
       }
     });
     // the tiles of the next iteration travel while one warp runs the sweeps
-    res_prefetch<MPAD>(Rf, lane, warp, C);
+    res_prefetch<MPAD>(Rf, lane, warp, Ca, Cb);
     if (!ok) {
       // non-positive / NaN pivot: this problem can never improve again (qp_common.cuh header); its ratios count
       // as NaN from this iteration on
@@ -611,7 +606,6 @@ __global__ void __launch_bounds__(128, 4) k_res_chunk(const KArgs<double> a, con
         ps[1] = it + 2;
         atomicMax(&a.ctl->kev_inv, (unsigned)(kKevBase - (it < 0 ? 0 : it)));
       }
-      poison = it + 2;
       alive = false;
       break;
     }
@@ -624,7 +618,7 @@ __global__ void __launch_bounds__(128, 4) k_res_chunk(const KArgs<double> a, con
         zr[s] = i < m ? vz[i] : 1.0; sr[s] = i < m ? vs[i] : 1.0; dr[s] = i < m ? vd[i] : 1.0;
         qa[s] = i < m ? Up[urow(i, mm) + m] : 0.0;  // D^-1 L^-1 hz: the bordered row of the factor
       }
-      res_bwd<RPL, SWEEP>(Up, m, mm, qa, lane);
+      res_bwd<RPL, MC>(Up, m, qa, lane);
       if (init) {
         // x, s, z of the initial point; shift s and z so that their minima are >= 1 (batch.py:76-86)
         double mn_s = t_inf<double>(), mn_z = t_inf<double>();
@@ -633,7 +627,7 @@ __global__ void __launch_bounds__(128, 4) k_res_chunk(const KArgs<double> a, con
           if (s * 32 + lane < m) { mn_s = nanmin(mn_s, qa[s]); mn_z = nanmin(mn_z, -qa[s]); }
         }
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) { mn_s = nanmin(mn_s, shfl_x(mn_s, o)); mn_z = nanmin(mn_z, shfl_x(mn_z, o)); }
+        for (int o2 = 16; o2 > 0; o2 >>= 1) { mn_s = nanmin(mn_s, shfl_x(mn_s, o2)); mn_z = nanmin(mn_z, shfl_x(mn_z, o2)); }
 #pragma unroll
         for (int s = 0; s < RPL; s++) {
           const int i = s * 32 + lane;
@@ -651,7 +645,7 @@ __global__ void __launch_bounds__(128, 4) k_res_chunk(const KArgs<double> a, con
 #pragma unroll
         for (int s = 0; s < RPL; s++) { dza[s] = -qa[s]; dsa[s] = (-zr[s] - dza[s]) / dr[s]; }
         double pc[4]; int has;
-        res_pieces<RPL>(zr, dza, sr, dsa, m, lane, pc, has);
+        res_pieces<RPL, false>(zr, dza, sr, dsa, m, lane, pc, has);
         // the clamp at 1 makes alpha_aff independent of the batch-global fill (batch.py:161-163)
         const double stz = (has & 1) ? nanmin(pc[0], 1.0) : pc[0];
         const double sts = (has & 2) ? nanmin(pc[1], 1.0) : pc[1];
@@ -670,10 +664,10 @@ __global__ void __launch_bounds__(128, 4) k_res_chunk(const KArgs<double> a, con
           rsc[s] = (-mu * sig + dsa[s] * dza[s]) / sr[s];
           qc[s] = (s * 32 + lane < m) ? rsc[s] / dr[s] : 0.0;
         }
-        res_fwd<RPL, SWEEP>(Up, m, mm, qc, lane);
+        res_fwd<RPL, MC>(Up, m, qc, lane);
 #pragma unroll
         for (int s = 0; s < RPL; s++) { const int i = s * 32 + lane; if (i < m) qc[s] *= pinv[i]; }
-        res_bwd<RPL, SWEEP>(Up, m, mm, qc, lane);
+        res_bwd<RPL, MC>(Up, m, qc, lane);
         double dz[RPL], ds[RPL];
 #pragma unroll
         for (int s = 0; s < RPL; s++) {
@@ -681,7 +675,7 @@ __global__ void __launch_bounds__(128, 4) k_res_chunk(const KArgs<double> a, con
           const double dsc = (-rsc[s] - dzc) / dr[s];
           dz[s] = dza[s] + dzc; ds[s] = dsa[s] + dsc;
         }
-        res_pieces<RPL>(zr, dz, sr, ds, m, lane, pc, has);
+        res_pieces<RPL, true>(zr, dz, sr, ds, m, lane, pc, has);
         const bool nz_ = is_nan(pc[2]), ns_ = is_nan(pc[3]);
         if (nz_ || ns_) {
           if (lane == 0) atomicMax(&a.ctl->kev_inv, (unsigned)(kKevBase - it));
@@ -697,7 +691,7 @@ __global__ void __launch_bounds__(128, 4) k_res_chunk(const KArgs<double> a, con
         }
         const bool F = it >= Kdyn;
         // F = 0: fill = max(1, a.max()) >= every unfilled ratio -> the unfilled minimum (+inf when fill-only:
-        //        0.999 * fill >= 1 is validated by k_res_finish);  F = 1: fill = 1.0 exactly
+        //        0.999 * fill >= 1 is validated by k_res_reduce);  F = 1: fill = 1.0 exactly
         const double a0_ = nanmin(0.999 * nanmin(pc[0], pc[1]), 1.0);
         const double z1 = (has & 1) ? nanmin(pc[0], 1.0) : pc[0], s1 = (has & 2) ? nanmin(pc[1], 1.0) : pc[1];
         const double a1_ = nanmin(0.999 * nanmin(z1, s1), 1.0);
@@ -716,7 +710,7 @@ __global__ void __launch_bounds__(128, 4) k_res_chunk(const KArgs<double> a, con
     }
     __syncthreads();
     // ---------------- dx = Q^-1 (-rx - G^T dz);  x += alpha dx   (initial point: x = dx)
-    res_mvt(sG, ldn, m, n, vdz, part, lane, warp);
+    res_mvt<MC>(sG, ldn, m, n, vdz, part, lane, warp);
     __syncthreads();
     if (tid < n) vt[tid] = -vrx[tid] - ((part[tid] + part[32 + tid]) + (part[64 + tid] + part[96 + tid]));
     __syncthreads();
@@ -729,9 +723,9 @@ __global__ void __launch_bounds__(128, 4) k_res_chunk(const KArgs<double> a, con
   }
   // ---- hand the state to the next launch
   if (alive) {
-    double* hh = ra.hist + ((size_t)prob * (a.max_iter + 1) + it) * ra.hs;
+    double* hh = hist + (size_t)it * hs;
     if (tid < n) hh[tid] = vx[tid];
-    if (tid < m) { hh[round4(n) + tid] = vs[tid]; hh[round4(n) + round4(m) + tid] = vz[tid]; }
+    if (tid < m) { hh[n4 + tid] = vs[tid]; hh[n4 + m4 + tid] = vz[tid]; }
   }
   // the masks live in warp 0's registers (every lane holds the same values)
   if (tid == 0) {

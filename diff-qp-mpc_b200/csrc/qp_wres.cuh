@@ -1,0 +1,655 @@
+// qp_wres.cuh -- ONE WARP PER QP on the resident route (fp64, neq == 0, nineq < 64, nz <= 32: the headline shape).
+//
+// Same algorithm, same launch protocol and same per-problem records as k_res_chunk (qp_resident.cuh; reference:
+// qpth/solvers/pdipm/batch.py:46-214 forward / get_step, :351-374 solve_kkt, :434-469 factor_kkt), different
+// machine mapping.  ncu on the 128-thread-CTA kernels showed ~25 k executed warp instructions per
+// problem-iteration (for 117 kflop), 4 problems in flight per SM and 40 % of the stall samples on CTA barriers
+// behind one-warp phases.  Here a problem never leaves its warp:
+//   * T = R + diag(s/z) lives in REGISTERS as the 36 lower 8x8 DMMA accumulator tiles of the 64-padded matrix
+//     (2 doubles per lane per tile).  Right-looking LDL^T by 8-column panels: the diagonal tile is factored with
+//     quad shuffles and carries W = L_JJ^-1 along; the tiles below are X_IJ = C_IJ W^T by two DMMAs each (the
+//     accumulator registers ARE the A operand when the contraction index is split into even / odd columns, and W
+//     in accumulator layout IS the B operand); the trailing update C_IK -= X_IJ D^-1 X_KJ^T is two DMMAs per tile
+//     with the accumulator registers of X_IJ as A and the scaled accumulator registers of X_KJ as B.  No layout
+//     conversion, no shared-memory round trip, no barrier.
+//   * the predictor's right-hand side rides through the factorisation as the bordered row m (as in qp_dmma.cuh);
+//   * the triangular sweeps are tile mat-vecs straight from the factor registers (forward: quad reductions,
+//     backward: reductions across quads), 8x8 diagonal blocks by their explicit inverse W;
+//   * G sits in shared memory (leading dimension 34: conflict-free 16-byte loads by row and by column pair), Q and
+//     Q^-1 are streamed from L2 as quad-per-row fragments, vectors live in registers in two layouts
+//     (compact: elements lane, lane + 32; pair: elements 2l, 2l + 1 in lane l < 16) and in 5 KB of shared memory
+//     wherever a mat-vec or a sweep needs a broadcast.
+// 8 problems per SM in flight (register bound), ~5 k executed instructions per problem-iteration.
+#pragma once
+#include "qp_resident.cuh"
+
+namespace b200qp {
+
+constexpr int kWLd = 34;  // leading dimension of G in shared memory (doubles)
+
+struct WOff { int G, x, rx, t, qx, z, dz, dinv, hz, u, q, r, rinv, total; };
+__host__ __device__ constexpr WOff wres_off(int m) {
+  WOff o{};
+  int p = 0;
+  o.G = p; p += ((m + 1) & ~1) * kWLd;
+  o.x = p; p += 32; o.rx = p; p += 32; o.t = p; p += 32; o.qx = p; p += 32;
+  o.z = p; p += 64; o.dz = p; p += 64; o.dinv = p; p += 64; o.hz = p; p += 64;
+  o.u = p; p += 64; o.q = p; p += 64; o.r = p; p += 64; o.rinv = p; p += 64;
+  o.total = p;
+  return o;
+}
+
+__device__ __forceinline__ void w_dmma(double& c0, double& c1, double a, double b) {
+  asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
+// 64-bit shuffles as two 32-bit ones, low word first (the toolkit's double overloads go through volatile asm moves and
+// shuffle the high word first, which costs a register-pair fix-up per shuffle under register pressure)
+__device__ __forceinline__ double wshfl(double v, int src) {
+  int lo = __double2loint(v), hi = __double2hiint(v);
+  lo = __shfl_sync(0xffffffffu, lo, src);
+  hi = __shfl_sync(0xffffffffu, hi, src);
+  return __hiloint2double(hi, lo);
+}
+__device__ __forceinline__ double wshfl_x(double v, int mask) {
+  int lo = __double2loint(v), hi = __double2hiint(v);
+  lo = __shfl_xor_sync(0xffffffffu, lo, mask);
+  hi = __shfl_xor_sync(0xffffffffu, hi, mask);
+  return __hiloint2double(hi, lo);
+}
+__device__ __forceinline__ double quad_sum(double v) { v += wshfl_x(v, 1); v += wshfl_x(v, 2); return v; }
+__device__ __forceinline__ double oct_sum(double v) { v += wshfl_x(v, 4); v += wshfl_x(v, 8); v += wshfl_x(v, 16); return v; }
+__device__ __forceinline__ double wsum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += wshfl_x(v, o);
+  return v;
+}
+
+static __device__ __noinline__ double w_rcp_slow(double dk) { return (dk > 0.0) ? 1.0 / dk : t_nan<double>(); }
+// 1 / dk: MUFU seed + two Newton steps; denormal / huge / non-positive / NaN pivots take the slow path (NaN poisons)
+__device__ __forceinline__ double w_rcp(double dk) {
+  double r;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(dk));
+  double e = fma(-dk, r, 1.0);
+  r = fma(r, e, r);
+  e = fma(-dk, r, 1.0);
+  r = fma(r, e, r);
+  // dk is the same in every lane (a broadcast pivot); the vote tells the compiler so: no divergence bookkeeping
+  if (__any_sync(0xffffffffu, !(dk > 1e-290 && dk < 1e290))) r = w_rcp_slow(dk);
+  return r;
+}
+
+__host__ __device__ constexpr int w_tile(int I, int K) { return I * (I + 1) / 2 + K; }
+
+// ------------------------------------------------------------------------------------------------------------
+// Quad-per-row fragment of an (n x n), n <= 32, row-major matrix in global memory: lane (g, q) holds
+// e[8 j + c] = M[8 j + g][8 q + c].  Loaded early (the latency hides behind whatever follows), applied later.
+struct WMat { double e[32]; };
+__device__ __forceinline__ void w_gload(WMat& M, const double* __restrict__ src, int ld, int n, int g, int q) {
+#pragma unroll
+  for (int j = 0; j < 4; j++) {
+    const int r = 8 * j + g;
+#pragma unroll
+    for (int c = 0; c < 8; c++) {
+      const int col = 8 * q + c;
+      M.e[8 * j + c] = (r < n && col < n) ? __ldg(src + (size_t)r * ld + col) : 0.0;
+    }
+  }
+}
+// out[r] = sum_c M[r][c] v[c] for r < 32 (rows >= n give 0); v, out in shared memory (32 entries, zero padded)
+__device__ __forceinline__ void w_gapply(const WMat& M, const double* v, double* out, int g, int q) {
+  double vv[8];
+#pragma unroll
+  for (int c = 0; c < 4; c++) {
+    const double2 t = *reinterpret_cast<const double2*>(v + 8 * q + 2 * c);
+    vv[2 * c] = t.x; vv[2 * c + 1] = t.y;
+  }
+#pragma unroll
+  for (int j = 0; j < 4; j++) {
+    double a0 = 0.0, a1 = 0.0;
+#pragma unroll
+    for (int c = 0; c < 8; c += 2) {
+      a0 = fma(M.e[8 * j + c], vv[c], a0);
+      a1 = fma(M.e[8 * j + c + 1], vv[c + 1], a1);
+    }
+    const double s = quad_sum(a0 + a1);
+    if (q == (j & 3)) out[8 * j + g] = s;
+  }
+}
+
+// y[r] = sum_c G[r][c] v[c] for the rows r = lane and lane + 32 (compact layout); G, v in shared memory
+template <int RPL>
+__device__ __forceinline__ void w_gv(const double* sG, const double* v, int n, int mr, int lane, double (&y)[RPL]) {
+  const int np = (n + 1) >> 1;
+#pragma unroll
+  for (int s = 0; s < RPL; s++) {
+    const int r = s * 32 + lane;
+    double a0 = 0.0, a1 = 0.0;
+    if (r < mr) {
+      const double* row = sG + r * kWLd;
+#pragma unroll
+      for (int c = 0; c < 16; c++) {
+        if (c < np) {
+          const double2 gv = *reinterpret_cast<const double2*>(row + 2 * c);
+          const double2 vv = *reinterpret_cast<const double2*>(v + 2 * c);
+          a0 = fma(gv.x, vv.x, a0);
+          a1 = fma(gv.y, vv.y, a1);
+        }
+      }
+    }
+    y[s] = a0 + a1;
+  }
+}
+// (o0, o1) = columns 2l, 2l + 1 (l = lane & 15, pair layout, both half-warps get the sum) of G^T u; G, u in shared memory
+__device__ __forceinline__ void w_gtu(const double* sG, const double* u, int mr, int lane, double& o0, double& o1) {
+  const int l = lane & 15, h = lane >> 4;
+  const double* gp = sG + h * kWLd + 2 * l;
+  const double* up = u + h;
+  double a0 = 0.0, a1 = 0.0, b0 = 0.0, b1 = 0.0;
+#pragma unroll
+  for (int j = 0; j < 32; j += 2) {
+    if (2 * j < mr) {
+      const double2 gv = *reinterpret_cast<const double2*>(gp + 2 * j * kWLd);
+      const double uu = up[2 * j];
+      a0 = fma(gv.x, uu, a0); a1 = fma(gv.y, uu, a1);
+    }
+    if (2 * j + 2 < mr) {
+      const double2 gv = *reinterpret_cast<const double2*>(gp + (2 * j + 2) * kWLd);
+      const double uu = up[2 * j + 2];
+      b0 = fma(gv.x, uu, b0); b1 = fma(gv.y, uu, b1);
+    }
+  }
+  o0 = a0 + b0; o1 = a1 + b1;
+  o0 += wshfl_x(o0, 16); o1 += wshfl_x(o1, 16);
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// LDL^T of one 8x8 diagonal tile in accumulator layout (lane (g, q): row g, columns 2q, 2q+1; lower triangle
+// valid), carrying W = L^-1 along.
+//   c0, c1 in/out: on exit column k < g of row g holds X[g][k] = L[g][k] D_k
+//   w0, w1 out   : W = L^-1 (unit lower triangular), accumulator layout
+//   rk out       : reciprocal pivots (uniform), 1 for bordered / padding columns (base + k >= m)
+// Returns false when a pivot of a real column is <= 0 or NaN.
+__device__ __forceinline__ bool w_diag(double& c0, double& c1, double& w0, double& w1, double (&rk)[8], int base, int m,
+                                       int lane, int g, int q) {
+  w0 = (g == 2 * q) ? 1.0 : 0.0;
+  w1 = (g == 2 * q + 1) ? 1.0 : 0.0;
+  const int lim0 = (2 * q <= g) ? 2 * q : 0, lim1 = (2 * q + 1 <= g) ? 2 * q + 1 : 0;  // slot s is updated at steps k < lim_s
+  bool ok = true;
+#pragma unroll
+  for (int k = 0; k < 8; k++) {
+    const int kq = k >> 1;
+    const double ck = (k & 1) ? c1 : c0;
+    const double dk = wshfl(ck, 4 * k + kq);            // C[k][k]
+    const double cik = wshfl(ck, (lane & ~3) | kq);     // C[g][k]
+    const double cj0 = wshfl(ck, 8 * q + kq);           // C[2q][k]
+    const double cj1 = wshfl(ck, 8 * q + 4 + kq);       // C[2q+1][k]
+    double r = w_rcp(dk);
+    if (base + k >= m) r = 1.0;
+    else if (is_nan(r)) ok = false;
+    rk[k] = r;
+    const double l = (g > k) ? cik * r : 0.0;
+    if (k < lim0) c0 = fma(-l, cj0, c0);
+    if (k < lim1) c1 = fma(-l, cj1, c1);
+    if (k < 7) {
+      const double wk0 = wshfl(w0, 4 * k + q), wk1 = wshfl(w1, 4 * k + q);  // row k of W (final after step k-1)
+      w0 = fma(-l, wk0, w0);
+      w1 = fma(-l, wk1, w1);
+    }
+  }
+  return ok;
+}
+
+// T = R + diag(dinv), bordered by the row hz at index m, padded by the identity: fix the tiles that are not interior
+template <int NTI, int MC>
+__device__ __forceinline__ void w_fix_tiles(double (&C)[NTI * (NTI + 1) / 2][2], const double* sdinv, const double* shz, int m_rt,
+                                            int g, int q) {
+  const int m = MC > 0 ? MC : m_rt;
+#pragma unroll
+  for (int I = 0; I < NTI; I++) {
+#pragma unroll
+    for (int K = 0; K <= I; K++) {
+      if (!(I != K && 8 * I + 8 <= m)) {  // uniform; folds for compile-time sizes
+        double& c0 = C[w_tile(I, K)][0];
+        double& c1 = C[w_tile(I, K)][1];
+        const int i = 8 * I + g, k = 8 * K + 2 * q;
+        double v0, v1;
+        if (i < m) {
+          v0 = (k <= i && k < m) ? c0 : 0.0;
+          v1 = (k + 1 <= i && k + 1 < m) ? c1 : 0.0;
+          if (I == K) {
+            const double di = sdinv[i];
+            if (k == i) v0 += di;
+            if (k + 1 == i) v1 += di;
+          }
+        } else if (i == m) {
+          const double2 hv = *reinterpret_cast<const double2*>(shz + k);  // zero beyond m
+          v0 = (k == m) ? 1.0 : hv.x;
+          v1 = (k + 1 == m) ? 1.0 : hv.y;
+        } else {
+          v0 = (k == i) ? 1.0 : 0.0;
+          v1 = (k + 1 == i) ? 1.0 : 0.0;
+        }
+        c0 = v0; c1 = v1;
+      }
+    }
+  }
+}
+
+// Blocked LDL^T of the register tiles (file header).  On exit: tiles (I, K < I) hold X = L D, diagonal tiles hold
+// W = L_II^-1, srinv[0..MPAD) the reciprocal pivots, su[k] = (D^-1 L^-1 hz)_k for k < m (0 beyond): the forward
+// substitution of the bordered right-hand side.  Returns false when a real pivot is <= 0 or NaN.
+template <int NTI, int MC>
+__device__ __forceinline__ bool w_factor(double (&C)[NTI * (NTI + 1) / 2][2], double* srinv, double* su, int m_rt, int lane, int g,
+                                         int q) {
+  const int m = MC > 0 ? MC : m_rt;
+  const int Ib = m >> 3, gb = m & 7;
+  bool ok = true;
+#pragma unroll
+  for (int J = 0; J < NTI; J++) {
+    if (J <= Ib) {  // uniform; tile rows beyond the bordered one are the identity
+      double w0, w1, rk[8];
+      double& d0 = C[w_tile(J, J)][0];
+      double& d1 = C[w_tile(J, J)][1];
+      ok &= w_diag(d0, d1, w0, w1, rk, 8 * J, m, lane, g, q);
+      const double sc0 = q == 0 ? rk[0] : (q == 1 ? rk[2] : (q == 2 ? rk[4] : rk[6]));
+      const double sc1 = q == 0 ? rk[1] : (q == 1 ? rk[3] : (q == 2 ? rk[5] : rk[7]));
+      if (lane < 4) *reinterpret_cast<double2*>(srinv + 8 * J + 2 * q) = make_double2(sc0, sc1);
+      if (J == Ib && g == gb)
+        *reinterpret_cast<double2*>(su + 8 * J + 2 * q) = make_double2(2 * q < gb ? d0 * sc0 : 0.0, 2 * q + 1 < gb ? d1 * sc1 : 0.0);
+      d0 = w0; d1 = w1;
+      double b0[NTI], b1[NTI];
+#pragma unroll
+      for (int I = J + 1; I < NTI; I++) {
+        if (I <= Ib) {
+          double x0 = 0.0, x1 = 0.0;
+          w_dmma(x0, x1, C[w_tile(I, J)][0], w0);
+          w_dmma(x0, x1, C[w_tile(I, J)][1], w1);
+          C[w_tile(I, J)][0] = x0; C[w_tile(I, J)][1] = x1;
+          if (I == Ib && g == gb) *reinterpret_cast<double2*>(su + 8 * J + 2 * q) = make_double2(x0 * sc0, x1 * sc1);
+          b0[I] = -sc0 * x0; b1[I] = -sc1 * x1;
+        }
+      }
+#pragma unroll
+      for (int I = J + 1; I < NTI; I++) {
+        if (I <= Ib) {
+#pragma unroll
+          for (int K = J + 1; K <= I; K++) {
+            w_dmma(C[w_tile(I, K)][0], C[w_tile(I, K)][1], C[w_tile(I, J)][0], b0[K]);
+            w_dmma(C[w_tile(I, K)][0], C[w_tile(I, K)][1], C[w_tile(I, J)][1], b1[K]);
+          }
+        }
+      }
+    }
+  }
+  return ok;
+}
+
+// su <- D^-1 L^-1 sr (natural order in shared memory; entries >= m come out 0)
+template <int NTI, int MC>
+__device__ __forceinline__ void w_fwd(const double (&C)[NTI * (NTI + 1) / 2][2], const double* sr, const double* srinv, double* su,
+                                      int m_rt, int lane, int g, int q) {
+  const int m = MC > 0 ? MC : m_rt;
+  const int Ib = m >> 3;
+#pragma unroll
+  for (int I = 0; I < NTI; I++) {
+    if (I <= Ib) {
+      double a0 = 0.0, a1 = 0.0;
+#pragma unroll
+      for (int K = 0; K < I; K++) {
+        const double2 uv = *reinterpret_cast<const double2*>(su + 8 * K + 2 * q);
+        a0 = fma(C[w_tile(I, K)][0], uv.x, a0);
+        a1 = fma(C[w_tile(I, K)][1], uv.y, a1);
+      }
+      const double v = sr[8 * I + g] - quad_sum(a0 + a1);  // row layout
+      const double v0 = wshfl(v, 8 * q), v1 = wshfl(v, 8 * q + 4);  // v[2q], v[2q+1]
+      const double y = quad_sum(fma(C[w_tile(I, I)][0], v0, C[w_tile(I, I)][1] * v1));
+      const double u = (8 * I + g < m) ? y * srinv[8 * I + g] : 0.0;
+      if (q == 0) su[8 * I + g] = u;
+      __syncwarp();
+    }
+  }
+}
+// sq <- L^-T su
+template <int NTI, int MC>
+__device__ __forceinline__ void w_bwd(const double (&C)[NTI * (NTI + 1) / 2][2], const double* su, const double* srinv, double* sq,
+                                      int m_rt, int lane, int g, int q) {
+  const int m = MC > 0 ? MC : m_rt;
+  const int Ib = m >> 3;
+#pragma unroll
+  for (int K = NTI - 1; K >= 0; K--) {
+    if (K <= Ib) {
+      double a0 = 0.0, a1 = 0.0;
+#pragma unroll
+      for (int I = K + 1; I < NTI; I++) {
+        if (I <= Ib) {
+          const double qi = sq[8 * I + g];
+          a0 = fma(C[w_tile(I, K)][0], qi, a0);
+          a1 = fma(C[w_tile(I, K)][1], qi, a1);
+        }
+      }
+      a0 = oct_sum(a0); a1 = oct_sum(a1);  // column layout, every lane
+      const double2 rv = *reinterpret_cast<const double2*>(srinv + 8 * K + 2 * q);
+      const double2 uv = *reinterpret_cast<const double2*>(su + 8 * K + 2 * q);
+      const double v0 = fma(-rv.x, a0, uv.x), v1 = fma(-rv.y, a1, uv.y);
+      const double s0 = wshfl(v0, g >> 1), s1 = wshfl(v1, g >> 1);
+      const double vg = (g & 1) ? s1 : s0;  // v[g]
+      const double p0 = oct_sum(C[w_tile(K, K)][0] * vg), p1 = oct_sum(C[w_tile(K, K)][1] * vg);
+      if (lane < 4) *reinterpret_cast<double2*>(sq + 8 * K + 2 * q) = make_double2(p0, p1);
+      __syncwarp();
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// One launch = the iterations [.., ra.it_end) of every problem, one warp (= one CTA) per problem.
+// NTI = tiles per dimension (8 NTI > nineq); <NC, MC> != 0: compile-time nz / nineq.
+template <int NTI, int NC, int MC>
+__global__ void __launch_bounds__(32, 8) k_wres_chunk(const KArgs<double> a, const RArgs ra) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  constexpr int NT = NTI * (NTI + 1) / 2, MPAD = 8 * NTI, RPL = (MPAD + 31) / 32;
+  const int prob = blockIdx.x, lane = threadIdx.x & 31, g = lane >> 2, q = lane & 3, l16 = lane & 15;
+  const int n = NC > 0 ? NC : a.n, m = MC > 0 ? MC : a.m;
+  const int n4 = res_r4(n), m4 = res_r4(m), hs = n4 + 2 * m4;
+  const int mr = (m + 1) & ~1;
+
+  // ---- where does this problem (re)start?  (protocol of qp_resident.cuh)
+  int* ps = ra.pst + (size_t)prob * kPst;
+  int stage = ps[0], poison = ps[1];
+  unsigned used = (unsigned)ps[2], sens = (unsigned)ps[3], fo = (unsigned)ps[4], azm = (unsigned)ps[5], asm_ = (unsigned)ps[6];
+  const unsigned kevi = *(volatile unsigned*)&a.ctl->kev_inv;
+  const int Kstart = kevi ? kKevBase - (int)kevi : INT_MAX;
+  int it = stage - 1;
+  if (stage > 1 && Kstart < it) {
+    const unsigned bad = sens & ~used & ~((1u << Kstart) - 1u) & ((1u << it) - 1u);
+    if (bad) {
+      it = __ffs(bad) - 1;
+      const unsigned keep = (1u << it) - 1u;
+      used &= keep; sens &= keep; fo &= keep; azm &= keep; asm_ &= keep;
+      poison = 0;
+    }
+  }
+  if (poison || it >= ra.it_end) return;  // uniform
+
+  double* sm = reinterpret_cast<double*>(smem_raw);
+  const WOff o = wres_off(m);
+  double* sG = sm + o.G;
+  double* sx = sm + o.x; double* srx = sm + o.rx; double* st = sm + o.t; double* sqx = sm + o.qx;
+  double* sz = sm + o.z; double* sdz = sm + o.dz; double* sdinv = sm + o.dinv; double* shz = sm + o.hz;
+  double* su = sm + o.u; double* sq = sm + o.q; double* sr = sm + o.r; double* srinv = sm + o.rinv;
+  double* hist = ra.hist + (size_t)prob * (a.max_iter + 1) * hs;
+
+  // ---- stage G (zero padded to 32 columns / an even number of rows), zero the vectors
+  {
+    const double* Gg = a.G + (size_t)prob * a.sG;
+    for (int r = 0; r < mr; r++) {
+      if (r < m && lane < n) cp_async8(sG + r * kWLd + lane, Gg + (size_t)r * n + lane);
+      else sG[r * kWLd + lane] = 0.0;
+    }
+    cp_async_commit();
+    for (int i = lane; i < o.total - o.x; i += 32) sm[o.x + i] = 0.0;
+  }
+  const double* Qg = a.Q + (size_t)prob * a.sQ;
+  const double* Qig = a.Qi + (size_t)prob * a.sQi;
+  const double* Rf = a.R + (size_t)prob * a.sR;
+  const int ldqi = a.ldn;
+  // p (pair layout), h and the iterate (compact layout)
+  double pp0 = 0.0, pp1 = 0.0, xp0 = 0.0, xp1 = 0.0;
+  double hr[RPL], zr[RPL], sr_[RPL];
+  {
+    const double* pg = a.pv + (size_t)prob * a.sp;
+    const double* hg = a.h + (size_t)prob * a.sh;
+    const double* hh = hist + (size_t)(it < 0 ? 0 : it) * hs;
+    const int c = 2 * l16;
+    if (c < n) { pp0 = pg[c]; if (it >= 0) xp0 = hh[c]; }
+    if (c + 1 < n) { pp1 = pg[c + 1]; if (it >= 0) xp1 = hh[c + 1]; }
+#pragma unroll
+    for (int s = 0; s < RPL; s++) {
+      const int i = s * 32 + lane;
+      hr[s] = i < m ? hg[i] : 0.0;
+      zr[s] = (i < m && it >= 0) ? hh[n4 + m4 + i] : 0.0;
+      sr_[s] = (i < m && it >= 0) ? hh[n4 + i] : 0.0;
+    }
+  }
+  __syncwarp();
+  if (lane < 16) *reinterpret_cast<double2*>(sx + 2 * lane) = make_double2(xp0, xp1);
+  cp_async_wait_all();
+  __syncwarp();
+
+  bool alive = true;
+  bool have_hist = true;  // the history entry of the first iteration of this launch already exists
+  double C[NT][2];
+#pragma unroll 1
+  for (; it < ra.it_end; ++it) {
+    const bool init = it < 0;
+    double dr[RPL], rz[RPL], rx0, rx1, mu = 0.0, t4 = 0.0;
+    if (!init) {
+      if (!have_hist) {
+        double* hh = hist + (size_t)it * hs;
+        const int c = 2 * lane;
+        if (lane < 16) { if (c < n) hh[c] = xp0; if (c + 1 < n) hh[c + 1] = xp1; }
+#pragma unroll
+        for (int s = 0; s < RPL; s++) {
+          const int i = s * 32 + lane;
+          if (i < m) { hh[n4 + i] = sr_[s]; hh[n4 + m4 + i] = zr[s]; }
+        }
+      }
+      // ---------------- residuals (batch.py:93-108)
+      WMat MQ;
+      w_gload(MQ, Qg, n, n, g, q);
+#pragma unroll
+      for (int s = 0; s < RPL; s++) {
+        const int i = s * 32 + lane;
+        dr[s] = zr[s] / sr_[s];
+        if (i < m) { sz[i] = zr[s]; sdinv[i] = 1.0 / dr[s]; } else dr[s] = 1.0;
+      }
+      __syncwarp();
+      double gx[RPL];
+      w_gv<RPL>(sG, sx, n, mr, lane, gx);
+#pragma unroll
+      for (int s = 0; s < RPL; s++) rz[s] = gx[s] + sr_[s] - hr[s];
+      double gz0, gz1;
+      w_gtu(sG, sz, mr, lane, gz0, gz1);
+      w_gapply(MQ, sx, sqx, g, q);
+      __syncwarp();
+      {
+        const double2 qx = *reinterpret_cast<const double2*>(sqx + 2 * l16);
+        rx0 = gz0 + (qx.x + pp0);
+        rx1 = gz1 + (qx.y + pp1);
+      }
+      // residual norms and mu (batch.py:103-108)
+      {
+        double s0 = 0.0, s1 = 0.0, s2 = 0.0;
+        if (lane < 16) s0 = fma(rx0, rx0, rx1 * rx1);
+#pragma unroll
+        for (int s = 0; s < RPL; s++) {
+          if (s * 32 + lane < m) { s1 = fma(rz[s], rz[s], s1); s2 = fma(sr_[s], zr[s], s2); }
+        }
+        s0 = wsum(s0); s1 = wsum(s1); s2 = wsum(s2);
+        mu = fabs(s2 / (double)m);
+        t4 = s2;
+        const double resid = sqrt(s1) + sqrt(s0) + (double)m * mu;
+        if (lane == 0) {
+          double* rc = ra.rec + ((size_t)prob * a.max_iter + it) * 2;
+          rc[0] = resid; rc[1] = mu;
+        }
+      }
+    } else {
+      // initial point (batch.py:60-66): d = 1, (rx, rs, rz) = (p, 0, -h)
+      rx0 = pp0; rx1 = pp1;
+#pragma unroll
+      for (int s = 0; s < RPL; s++) {
+        const int i = s * 32 + lane;
+        dr[s] = 1.0; zr[s] = 0.0; sr_[s] = 0.0; rz[s] = -hr[s];
+        if (i < m) sdinv[i] = 1.0;
+      }
+    }
+    have_hist = false;
+    // ---------------- right-hand side of the reduced system: hz = G Q^-1 rx + rs / d - rz   (rs = z)
+    if (lane < 16) *reinterpret_cast<double2*>(srx + 2 * lane) = make_double2(rx0, rx1);
+    {
+      WMat MQi;
+      w_gload(MQi, Qig, ldqi, n, g, q);
+      __syncwarp();
+      w_gapply(MQi, srx, st, g, q);
+    }
+    // the tiles of T travel while the right-hand side is formed
+#pragma unroll
+    for (int t = 0; t < NT; t++) {
+      const double2 v = __ldg(reinterpret_cast<const double2*>(Rf + (size_t)t * 64 + lane * 2));
+      C[t][0] = v.x; C[t][1] = v.y;
+    }
+    __syncwarp();
+    {
+      double gt[RPL];
+      w_gv<RPL>(sG, st, n, mr, lane, gt);
+#pragma unroll
+      for (int s = 0; s < RPL; s++) {
+        const int i = s * 32 + lane;
+        if (i < m) shz[i] = zr[s] / dr[s] + (gt[s] - rz[s]);
+      }
+    }
+    __syncwarp();
+    // ---------------- T = R + diag(1/d) = L D L^T with hz riding as the bordered row
+    w_fix_tiles<NTI, MC>(C, sdinv, shz, m, g, q);
+    const bool ok = w_factor<NTI, MC>(C, srinv, su, m, lane, g, q);
+    if (!ok) {
+      // non-positive / NaN pivot: this problem can never improve again; its ratios count as NaN from here on
+      if (lane == 0) {
+        ps[1] = it + 2;
+        atomicMax(&a.ctl->kev_inv, (unsigned)(kKevBase - (it < 0 ? 0 : it)));
+      }
+      alive = false;
+      break;
+    }
+    __syncwarp();
+    // ---------------- predictor: qa = T^-1 hz
+    w_bwd<NTI, MC>(C, su, srinv, sq, m, lane, g, q);
+    double qa[RPL];
+#pragma unroll
+    for (int s = 0; s < RPL; s++) { const int i = s * 32 + lane; qa[s] = i < m ? sq[i] : 0.0; }
+    double alpha = 1.0;
+    if (init) {
+      // x, s, z of the initial point; shift s and z so that their minima are >= 1 (batch.py:76-86)
+      double mn_s = t_inf<double>(), mn_z = t_inf<double>();
+#pragma unroll
+      for (int s = 0; s < RPL; s++) {
+        if (s * 32 + lane < m) { mn_s = nanmin(mn_s, qa[s]); mn_z = nanmin(mn_z, -qa[s]); }
+      }
+#pragma unroll
+      for (int o2 = 16; o2 > 0; o2 >>= 1) { mn_s = nanmin(mn_s, wshfl_x(mn_s, o2)); mn_z = nanmin(mn_z, wshfl_x(mn_z, o2)); }
+#pragma unroll
+      for (int s = 0; s < RPL; s++) {
+        const int i = s * 32 + lane;
+        double sv = qa[s], zv = -qa[s];
+        if (mn_s < 0.0) sv -= mn_s - 1.0;
+        if (mn_z < 0.0) zv -= mn_z - 1.0;
+        if (i < m) { sdz[i] = -qa[s]; sr_[s] = sv; zr[s] = zv; }
+      }
+    } else {
+      double dza[RPL], dsa[RPL];
+#pragma unroll
+      for (int s = 0; s < RPL; s++) { dza[s] = -qa[s]; dsa[s] = (-zr[s] - dza[s]) / dr[s]; }
+      double pc[4]; int has;
+      double zq[RPL], sq_[RPL];
+#pragma unroll
+      for (int s = 0; s < RPL; s++) { const bool v = s * 32 + lane < m; zq[s] = v ? zr[s] : 1.0; sq_[s] = v ? sr_[s] : 1.0; }
+      res_pieces<RPL, false>(zq, dza, sq_, dsa, m, lane, pc, has);
+      // the clamp at 1 makes alpha_aff independent of the batch-global fill (batch.py:161-163)
+      const double stz = (has & 1) ? nanmin(pc[0], 1.0) : pc[0];
+      const double sts = (has & 2) ? nanmin(pc[1], 1.0) : pc[1];
+      const double alpha_aff = nanmin(nanmin(stz, sts), 1.0);
+      double t3 = 0.0;
+#pragma unroll
+      for (int s = 0; s < RPL; s++)
+        if (s * 32 + lane < m) t3 += (sr_[s] + alpha_aff * dsa[s]) * (zr[s] + alpha_aff * dza[s]);
+      t3 = wsum(t3);
+      const double ratio = t3 / t4;
+      const double sig = ratio * ratio * ratio;
+      double rsc[RPL];
+#pragma unroll
+      for (int s = 0; s < RPL; s++) {
+        const int i = s * 32 + lane;
+        rsc[s] = (-mu * sig + dsa[s] * dza[s]) / sq_[s];
+        if (i < m) sr[i] = rsc[s] / dr[s];
+      }
+      __syncwarp();
+      // ---------------- corrector: qc = T^-1 (rsc / d)
+      w_fwd<NTI, MC>(C, sr, srinv, su, m, lane, g, q);
+      w_bwd<NTI, MC>(C, su, srinv, sq, m, lane, g, q);
+      double dz[RPL], ds[RPL];
+#pragma unroll
+      for (int s = 0; s < RPL; s++) {
+        const int i = s * 32 + lane;
+        const double qc = i < m ? sq[i] : 0.0;
+        const double dzc = -qc;
+        const double dsc = (-rsc[s] - dzc) / dr[s];
+        dz[s] = dza[s] + dzc; ds[s] = dsa[s] + dsc;
+      }
+      res_pieces<RPL, true>(zq, dz, sq_, ds, m, lane, pc, has);
+      const bool nz_ = is_nan(pc[2]), ns_ = is_nan(pc[3]);
+      if (nz_ || ns_) {
+        if (lane == 0) atomicMax(&a.ctl->kev_inv, (unsigned)(kKevBase - it));
+        if (nz_) azm |= 1u << it;
+        if (ns_) asm_ |= 1u << it;
+      }
+      // fill regime of this iteration: exact when it >= Kstart, else the freshest published event
+      int Kdyn = Kstart;
+      {
+        const unsigned kv = *(volatile unsigned*)&a.ctl->kev_inv;
+        const int Kn = kv ? kKevBase - (int)kv : INT_MAX;
+        Kdyn = Kn < Kdyn ? Kn : Kdyn;
+      }
+      Kdyn = __shfl_sync(0xffffffffu, Kdyn, 0);  // one view per warp
+      const bool F = it >= Kdyn;
+      const double a0_ = nanmin(0.999 * nanmin(pc[0], pc[1]), 1.0);
+      const double z1 = (has & 1) ? nanmin(pc[0], 1.0) : pc[0], s1 = (has & 2) ? nanmin(pc[1], 1.0) : pc[1];
+      const double a1_ = nanmin(0.999 * nanmin(z1, s1), 1.0);
+      const bool same = (a0_ == a1_) || (is_nan(a0_) && is_nan(a1_));
+      if (!same) sens |= 1u << it;
+      if (F) used |= 1u << it;
+      else if (((has & 1) && pc[0] == t_inf<double>()) || ((has & 2) && pc[1] == t_inf<double>())) fo |= 1u << it;
+      alpha = F ? a1_ : a0_;
+#pragma unroll
+      for (int s = 0; s < RPL; s++) {
+        const int i = s * 32 + lane;
+        if (i < m) { sdz[i] = dz[s]; sr_[s] = sr_[s] + alpha * ds[s]; zr[s] = zr[s] + alpha * dz[s]; }
+      }
+    }
+    __syncwarp();
+    // ---------------- dx = Q^-1 (-rx - G^T dz);  x += alpha dx   (initial point: x = dx)
+    {
+      WMat MQi;
+      w_gload(MQi, Qig, ldqi, n, g, q);
+      double gd0, gd1;
+      w_gtu(sG, sdz, mr, lane, gd0, gd1);
+      if (lane < 16) *reinterpret_cast<double2*>(st + 2 * lane) = make_double2(-rx0 - gd0, -rx1 - gd1);
+      __syncwarp();
+      w_gapply(MQi, st, sqx, g, q);
+      __syncwarp();
+      const double2 dx = *reinterpret_cast<const double2*>(sqx + 2 * l16);
+      xp0 = init ? dx.x : xp0 + alpha * dx.x;
+      xp1 = init ? dx.y : xp1 + alpha * dx.y;
+      __syncwarp();
+      if (lane < 16) *reinterpret_cast<double2*>(sx + 2 * lane) = make_double2(xp0, xp1);
+      __syncwarp();
+    }
+  }
+  // ---- hand the state to the next launch
+  if (alive) {
+    double* hh = hist + (size_t)it * hs;
+    const int c = 2 * lane;
+    if (lane < 16) { if (c < n) hh[c] = xp0; if (c + 1 < n) hh[c + 1] = xp1; }
+#pragma unroll
+    for (int s = 0; s < RPL; s++) {
+      const int i = s * 32 + lane;
+      if (i < m) { hh[n4 + i] = sr_[s]; hh[n4 + m4 + i] = zr[s]; }
+    }
+  }
+  if (lane == 0) {
+    ps[0] = (alive ? it : it + 1) + 1;
+    if (alive) ps[1] = 0;
+    ps[2] = (int)used; ps[3] = (int)sens; ps[4] = (int)fo; ps[5] = (int)azm; ps[6] = (int)asm_;
+  }
+}
+
+}  // namespace b200qp

@@ -168,7 +168,7 @@ int b200qp_profile_read(float* ms, int* kind, int cap);
 
 /* Process-wide tuning knobs (defaults come from the environment variables of the same upper-case name with the
  * prefix B200QP_, read once): "res" (1) take the resident route when eligible, "res_ch" (4) its iterations per
- * launch, "res_panel" (1) / "res_sweep" (1) its factorisation-panel / triangular-sweep variants; the routing overrides
+ * launch, "res_spec" (1) its compile-time-size specialisation of the nz = 30 / nineq = 60 shape; the routing overrides
  * "mid_fast" (B200QP_MID=fast), "blk_nt" (256), "factor_tile" (B200QP_FACTOR=tile), "force_generic".  Returns 0, or
  * B200QP_EINVAL for an unknown name.  Not to be changed between the forward and the backward of one problem. */
 int b200qp_set_option(const char* name, int value);

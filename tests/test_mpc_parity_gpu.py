@@ -321,7 +321,7 @@ def test_myenvs_dynamics_golden(name, cuda_device):
     assert rel(xn.cpu(), pxn) < 1e-13 and rel(A.cpu(), pA) < 1e-12 and rel(B.cpu(), pB) < 1e-12
 
 
-@pytest.mark.parametrize("case", ("cartpole1l_B8_T10", "cartpole2l_B4_T8", "pendulum1l_B8_T6"))
+@pytest.mark.parametrize("case", ("cartpole1l_B8_T10", "cartpole2l_B4_T8", "pendulum1l_B8_T6", "cartpole1l_B8_T20"))
 def test_al_mpc_myenvs_golden(case, cuda_device):
     """AL-MPC on the my_envs dynamics (the production configuration: CartpoleEnv + Tracking_MPC's al_mpc.MPC)
     against the real reference run on its generated code: cold call, warm-started call, state and backward."""

@@ -19,7 +19,7 @@ pytestmark = pytest.mark.gpu
 def opts():
     from b200qp import _lib
     yield _lib.set_option
-    for k, v in (("res", 1), ("res_ch", 4), ("res_panel", 1), ("res_sweep", 1)):
+    for k, v in (("res", 1), ("res_ch", 4), ("res_spec", 1)):
         _lib.set_option(k, v)
 
 
@@ -47,9 +47,9 @@ def rand_inputs(nb, nz, m, seed, wc=False):
 def test_chunk_invariance_bitwise(shape, cuda_device, opts):
     nb, nz, m, seed, wc = shape
     inp = rand_inputs(nb, nz, m, seed, wc)
-    for panel, sweep in ((1, 1), (0, 0), (1, 0), (0, 1)):
-        opts("res_panel", panel); opts("res_sweep", sweep)
-        ref = None
+    ref = None  # the compile-time-size specialisation does the same arithmetic in the same order as the generic kernel
+    for spec in (1, 0):
+        opts("res_spec", spec)
         for ch in (1, 3, 4, 20):
             opts("res_ch", ch)
             out, info = solve(inp, cuda_device)
@@ -61,7 +61,7 @@ def test_chunk_invariance_bitwise(shape, cuda_device, opts):
             for k in ("zhat", "lams", "slacks", "dp", "dG"):
                 a, b = out[k], ref[0][k]
                 same = (a == b) | (torch.isnan(a) & torch.isnan(b))
-                assert bool(same.all()), f"panel {panel} sweep {sweep} chunk {ch}: {k} differs from chunk 1 in {int((~same).sum())} entries"
+                assert bool(same.all()), f"spec {spec} chunk {ch}: {k} differs from (spec 1, chunk 1) in {int((~same).sum())} entries"
 
 
 @pytest.mark.parametrize("shape", [(256, 30, 60, 11, False), (128, 30, 60, 0, False), (64, 30, 60, 3, True), (96, 10, 10, 5, False), (50, 20, 31, 6, False)])
@@ -78,12 +78,12 @@ def test_resident_vs_per_iteration_route_and_oracle(shape, cuda_device, opts):
     if det:
         assert ex_info["n_iter"] == fwd["n_iter"]
     opts("res", 1)
-    for panel, sweep in ((1, 1), (0, 0)):
-        opts("res_panel", panel); opts("res_sweep", sweep)
+    for spec in (1, 0):
+        opts("res_spec", spec)
         out, info = solve(inp, cuda_device)
-        print(f"  resident route panel={panel} sweep={sweep}: {info['n_iter']} iterations, NaN onset {info['nan_onset']}")
+        print(f"  resident route spec={spec}: {info['n_iter']} iterations, NaN onset {info['nan_onset']}")
         if det:
-            assert info["n_iter"] == fwd["n_iter"], (panel, sweep, info["n_iter"], fwd["n_iter"])
+            assert info["n_iter"] == fwd["n_iter"], (spec, info["n_iter"], fwd["n_iter"])
         for k in ("zhat", "lams", "slacks"):
             gate(out[k], fwd[k], 1e-6, f"{k} vs oracle")
             gate(out[k], ex[k], 1e-7, f"{k} vs per-iteration route")
@@ -96,12 +96,12 @@ def test_resident_goldens_all_variants(case, cuda_device, opts):
     from tests.qp_cases import load_golden
     inp = make_inputs(case)
     g = load_golden(case)
-    for panel, sweep, ch in ((1, 1, 4), (0, 0, 4), (1, 1, 7), (1, 0, 20), (0, 1, 1)):
-        opts("res_panel", panel); opts("res_sweep", sweep); opts("res_ch", ch)
+    for spec, ch in ((1, 4), (0, 4), (1, 7), (0, 20), (1, 1)):
+        opts("res_spec", spec); opts("res_ch", ch)
         from tests.test_qp_parity_gpu import run_ours
         out, info = run_ours(inp, cuda_device)
         compare_with_golden(case, out, rtol=1e-6)
-        assert info["n_iter"] == int(g["n_iter"]), (panel, sweep, ch, info["n_iter"], int(g["n_iter"]))  # all three are deterministic
+        assert info["n_iter"] == int(g["n_iter"]), (spec, ch, info["n_iter"], int(g["n_iter"]))
 
 
 def test_fill_only_problems_fall_back_to_exact_route(cuda_device, opts):
