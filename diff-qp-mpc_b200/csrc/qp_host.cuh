@@ -136,7 +136,7 @@ inline int make_layout(const b200qp_problem_t* pr, Layout& L) {
           !(pr->flags & (B200QP_FLAG_DENSE | B200QP_FLAG_EXACT));
   L.res_chunk = opt.res_chunk < 1 ? 1 : opt.res_chunk;
   L.res_spec = opt.res_spec ? 1 : 0;
-  L.res_warp = opt.res_warp ? 1 : 0;
+  L.res_warp = opt.res_warp;  // 0: 128-thread CTAs per QP; 1 / 4 / 8: one warp per QP, that many QPs per CTA
   L.res_smem = (size_t)res_off(L.n, L.m, L.mpad).total * sizeof(double);
   L.ohist = L.orec = L.opst = 0;
   if (L.res) {

@@ -33,24 +33,25 @@ static int res_launch(const KArgs<double>& a, const RArgs& ra, const Layout& L, 
   CK(cudaGetLastError());
   return B200QP_OK;
 }
-template <int NTI, int NC, int MC>
+template <int NTI, int NC, int MC, int WPC>
 static int wres_launch(const KArgs<double>& a, const RArgs& ra, const Layout& L, cudaStream_t st) {
-  auto k = k_wres_chunk<NTI, NC, MC>;
-  const size_t smem = (size_t)wres_off(L.m).total * sizeof(double);
+  auto k = k_wres_chunk<NTI, NC, MC, WPC>;
+  const size_t smem = (size_t)wres_off(L.m).total * sizeof(double) * WPC;
   static bool once = false;  // per instantiation
   if (!once) {
     CK(cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     once = true;
   }
   CK(ensure_smem(k, smem));
-  k<<<(unsigned)a.nb, 32, smem, st>>>(a, ra);
+  k<<<(unsigned)((a.nb + WPC - 1) / WPC), 32 * WPC, smem, st>>>(a, ra);
   CK(cudaGetLastError());
   return B200QP_OK;
 }
 int res_chunk(const KArgs<double>& a, const RArgs& ra, const Layout& L, cudaStream_t st) {
   if (L.res_warp) {  // one warp per QP (qp_wres.cuh)
-    if (L.res_spec && L.n == 30 && L.m == 60) return wres_launch<8, 30, 60>(a, ra, L, st);
-    return L.m < 32 ? wres_launch<4, 0, 0>(a, ra, L, st) : wres_launch<8, 0, 0>(a, ra, L, st);
+    if (L.res_spec && L.n == 30 && L.m == 60)
+      return L.res_warp == 8 ? wres_launch<8, 30, 60, 8>(a, ra, L, st) : (L.res_warp == 4 ? wres_launch<8, 30, 60, 4>(a, ra, L, st) : wres_launch<8, 30, 60, 1>(a, ra, L, st));
+    return L.m < 32 ? wres_launch<4, 0, 0, 1>(a, ra, L, st) : wres_launch<8, 0, 0, 1>(a, ra, L, st);
   }
   if (L.res_spec && L.n == 30 && L.m == 60) return res_launch<64, 30, 60>(a, ra, L, st);
   return L.mpad == 32 ? res_launch<32, 0, 0>(a, ra, L, st) : res_launch<64, 0, 0>(a, ra, L, st);

@@ -64,20 +64,6 @@ __device__ __forceinline__ double wsum(double v) {
   return v;
 }
 
-static __device__ __noinline__ double w_rcp_slow(double dk) { return (dk > 0.0) ? 1.0 / dk : t_nan<double>(); }
-// 1 / dk: MUFU seed + two Newton steps; denormal / huge / non-positive / NaN pivots take the slow path (NaN poisons)
-__device__ __forceinline__ double w_rcp(double dk) {
-  double r;
-  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(dk));
-  double e = fma(-dk, r, 1.0);
-  r = fma(r, e, r);
-  e = fma(-dk, r, 1.0);
-  r = fma(r, e, r);
-  // dk is the same in every lane (a broadcast pivot); the vote tells the compiler so: no divergence bookkeeping
-  if (__any_sync(0xffffffffu, !(dk > 1e-290 && dk < 1e290))) r = w_rcp_slow(dk);
-  return r;
-}
-
 __host__ __device__ constexpr int w_tile(int I, int K) { return I * (I + 1) / 2 + K; }
 
 // ------------------------------------------------------------------------------------------------------------
@@ -163,40 +149,75 @@ __device__ __forceinline__ void w_gtu(const double* sG, const double* u, int mr,
 }
 
 // ------------------------------------------------------------------------------------------------------------
+// Lane coordinates, computed once and made opaque to the compiler (which otherwise re-derives them from
+// SR_TID.X -- a ~20-cycle special-register read -- at every use under register pressure).
+struct WLane {
+  int lane, g, q, q8, lim0, lim1;
+  __device__ __forceinline__ void init() {
+    lane = threadIdx.x & 31;
+    asm volatile("" : "+r"(lane));
+    g = lane >> 2; q = lane & 3; q8 = 8 * q;
+    lim0 = (2 * q <= g) ? 2 * q : 0;          // slot s of a diagonal tile is updated at steps k < lim_s
+    lim1 = (2 * q + 1 <= g) ? 2 * q + 1 : 0;
+    asm volatile("" : "+r"(g), "+r"(q), "+r"(q8), "+r"(lim0), "+r"(lim1));
+  }
+};
+// c += a * b where k < lim holds (one compare + one predicated DFMA instead of DFMA + two selects)
+__device__ __forceinline__ void pfma_lt(double& c, double a, double b, int k, int lim) {
+  asm("{\n .reg .pred pp;\n setp.lt.s32 pp, %3, %4;\n @pp fma.rn.f64 %0, %1, %2, %0;\n}" : "+d"(c) : "d"(a), "d"(b), "r"(k), "r"(lim));
+}
+// quad broadcast: the value of lane (lane & ~3) + src, src an immediate
+__device__ __forceinline__ double wshfl_quad(double v, int src) {
+  int lo = __double2loint(v), hi = __double2hiint(v);
+  lo = __shfl_sync(0xffffffffu, lo, src, 4);
+  hi = __shfl_sync(0xffffffffu, hi, src, 4);
+  return __hiloint2double(hi, lo);
+}
+
 // LDL^T of one 8x8 diagonal tile in accumulator layout (lane (g, q): row g, columns 2q, 2q+1; lower triangle
-// valid), carrying W = L^-1 along.
+// valid), carrying W = L^-1 along.  Branch-free: every pivot is broadcast, so all flags are warp-uniform.
 //   c0, c1 in/out: on exit column k < g of row g holds X[g][k] = L[g][k] D_k
 //   w0, w1 out   : W = L^-1 (unit lower triangular), accumulator layout
-//   rk out       : reciprocal pivots (uniform), 1 for bordered / padding columns (base + k >= m)
-// Returns false when a pivot of a real column is <= 0 or NaN.
-__device__ __forceinline__ bool w_diag(double& c0, double& c1, double& w0, double& w1, double (&rk)[8], int base, int m,
-                                       int lane, int g, int q) {
-  w0 = (g == 2 * q) ? 1.0 : 0.0;
-  w1 = (g == 2 * q + 1) ? 1.0 : 0.0;
-  const int lim0 = (2 * q <= g) ? 2 * q : 0, lim1 = (2 * q + 1 <= g) ? 2 * q + 1 : 0;  // slot s is updated at steps k < lim_s
-  bool ok = true;
+//   rinv out     : shared memory, the 8 reciprocal pivots (1 for bordered / padding columns, base + k >= m)
+//   bad          : set when a pivot of a real column is not a positive normal number in (2^-962, 2^962): the
+//                  factorisation failed (<= 0, NaN: the reference's poisoned iterate) -- or `oob` when it is positive
+//                  but outside the range the Newton reciprocal covers (never seen; the caller asks for the exact route)
+template <int MC>
+__device__ __forceinline__ void w_diag(double& c0, double& c1, double& w0, double& w1, double* rinv, int base, int m_rt,
+                                       const WLane& L, bool& bad, bool& oob) {
+  const int m = MC > 0 ? MC : m_rt;
+  w0 = (L.g == 2 * L.q) ? 1.0 : 0.0;
+  w1 = (L.g == 2 * L.q + 1) ? 1.0 : 0.0;
 #pragma unroll
   for (int k = 0; k < 8; k++) {
     const int kq = k >> 1;
     const double ck = (k & 1) ? c1 : c0;
-    const double dk = wshfl(ck, 4 * k + kq);            // C[k][k]
-    const double cik = wshfl(ck, (lane & ~3) | kq);     // C[g][k]
-    const double cj0 = wshfl(ck, 8 * q + kq);           // C[2q][k]
-    const double cj1 = wshfl(ck, 8 * q + 4 + kq);       // C[2q+1][k]
-    double r = w_rcp(dk);
-    if (base + k >= m) r = 1.0;
-    else if (is_nan(r)) ok = false;
-    rk[k] = r;
-    const double l = (g > k) ? cik * r : 0.0;
-    if (k < lim0) c0 = fma(-l, cj0, c0);
-    if (k < lim1) c1 = fma(-l, cj1, c1);
+    const double dk = wshfl(ck, 4 * k + kq);         // C[k][k]
+    const double cik = wshfl_quad(ck, kq);           // C[g][k]
+    const double cj0 = wshfl(ck, L.q8 + kq);         // C[2q][k]
+    const double cj1 = wshfl(ck, L.q8 + 4 + kq);     // C[2q+1][k]
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(dk));
+    double e = fma(-dk, r, 1.0);
+    r = fma(r, e, r);
+    e = fma(-dk, r, 1.0);
+    r = fma(r, e, r);
+    if (base + k < m) {  // folds for compile-time sizes
+      const bool inr = (unsigned)(__double2hiint(dk) - 0x03d00000) < 0x78400000u;  // positive, exponent in range
+      if (!inr) { r = t_nan<double>(); bad = true; if (dk > 0.0) oob = true; }
+    } else {
+      r = 1.0;
+    }
+    if (L.lane == 0) rinv[k] = r;
+    const double nl = -(cik * r);
+    pfma_lt(c0, nl, cj0, k, L.lim0);
+    pfma_lt(c1, nl, cj1, k, L.lim1);
     if (k < 7) {
-      const double wk0 = wshfl(w0, 4 * k + q), wk1 = wshfl(w1, 4 * k + q);  // row k of W (final after step k-1)
-      w0 = fma(-l, wk0, w0);
-      w1 = fma(-l, wk1, w1);
+      const double wk0 = wshfl(w0, L.q + 4 * k), wk1 = wshfl(w1, L.q + 4 * k);  // row k of W (final after step k-1)
+      pfma_lt(w0, nl, wk0, k, L.g);
+      pfma_lt(w1, nl, wk1, k, L.g);
     }
   }
-  return ok;
 }
 
 // T = R + diag(dinv), bordered by the row hz at index m, padded by the identity: fix the tiles that are not interior
@@ -237,25 +258,24 @@ __device__ __forceinline__ void w_fix_tiles(double (&C)[NTI * (NTI + 1) / 2][2],
 
 // Blocked LDL^T of the register tiles (file header).  On exit: tiles (I, K < I) hold X = L D, diagonal tiles hold
 // W = L_II^-1, srinv[0..MPAD) the reciprocal pivots, su[k] = (D^-1 L^-1 hz)_k for k < m (0 beyond): the forward
-// substitution of the bordered right-hand side.  Returns false when a real pivot is <= 0 or NaN.
+// substitution of the bordered right-hand side.  bad / oob as in w_diag.
 template <int NTI, int MC>
-__device__ __forceinline__ bool w_factor(double (&C)[NTI * (NTI + 1) / 2][2], double* srinv, double* su, int m_rt, int lane, int g,
-                                         int q) {
+__device__ __forceinline__ void w_factor(double (&C)[NTI * (NTI + 1) / 2][2], double* srinv, double* su, int m_rt, const WLane& L,
+                                         bool& bad, bool& oob) {
   const int m = MC > 0 ? MC : m_rt;
   const int Ib = m >> 3, gb = m & 7;
-  bool ok = true;
+  const int q = L.q;
 #pragma unroll
   for (int J = 0; J < NTI; J++) {
     if (J <= Ib) {  // uniform; tile rows beyond the bordered one are the identity
-      double w0, w1, rk[8];
+      double w0, w1;
       double& d0 = C[w_tile(J, J)][0];
       double& d1 = C[w_tile(J, J)][1];
-      ok &= w_diag(d0, d1, w0, w1, rk, 8 * J, m, lane, g, q);
-      const double sc0 = q == 0 ? rk[0] : (q == 1 ? rk[2] : (q == 2 ? rk[4] : rk[6]));
-      const double sc1 = q == 0 ? rk[1] : (q == 1 ? rk[3] : (q == 2 ? rk[5] : rk[7]));
-      if (lane < 4) *reinterpret_cast<double2*>(srinv + 8 * J + 2 * q) = make_double2(sc0, sc1);
-      if (J == Ib && g == gb)
-        *reinterpret_cast<double2*>(su + 8 * J + 2 * q) = make_double2(2 * q < gb ? d0 * sc0 : 0.0, 2 * q + 1 < gb ? d1 * sc1 : 0.0);
+      w_diag<MC>(d0, d1, w0, w1, srinv + 8 * J, 8 * J, m, L, bad, oob);
+      __syncwarp();
+      const double2 sc = *reinterpret_cast<const double2*>(srinv + 8 * J + 2 * q);
+      if (J == Ib && L.g == gb)
+        *reinterpret_cast<double2*>(su + 8 * J + 2 * q) = make_double2(2 * q < gb ? d0 * sc.x : 0.0, 2 * q + 1 < gb ? d1 * sc.y : 0.0);
       d0 = w0; d1 = w1;
       double b0[NTI], b1[NTI];
 #pragma unroll
@@ -265,8 +285,8 @@ __device__ __forceinline__ bool w_factor(double (&C)[NTI * (NTI + 1) / 2][2], do
           w_dmma(x0, x1, C[w_tile(I, J)][0], w0);
           w_dmma(x0, x1, C[w_tile(I, J)][1], w1);
           C[w_tile(I, J)][0] = x0; C[w_tile(I, J)][1] = x1;
-          if (I == Ib && g == gb) *reinterpret_cast<double2*>(su + 8 * J + 2 * q) = make_double2(x0 * sc0, x1 * sc1);
-          b0[I] = -sc0 * x0; b1[I] = -sc1 * x1;
+          if (I == Ib && L.g == gb) *reinterpret_cast<double2*>(su + 8 * J + 2 * q) = make_double2(x0 * sc.x, x1 * sc.y);
+          b0[I] = -sc.x * x0; b1[I] = -sc.y * x1;
         }
       }
 #pragma unroll
@@ -281,7 +301,6 @@ __device__ __forceinline__ bool w_factor(double (&C)[NTI * (NTI + 1) / 2][2], do
       }
     }
   }
-  return ok;
 }
 
 // su <- D^-1 L^-1 sr (natural order in shared memory; entries >= m come out 0)
@@ -341,13 +360,19 @@ __device__ __forceinline__ void w_bwd(const double (&C)[NTI * (NTI + 1) / 2][2],
 }
 
 // ------------------------------------------------------------------------------------------------------------
-// One launch = the iterations [.., ra.it_end) of every problem, one warp (= one CTA) per problem.
+// One launch = the iterations [.., ra.it_end) of every problem, one warp per problem, WPC independent warps
+// (problems) per CTA.  With WPC > 1 the warps of a CTA re-align at the top of every iteration (one CTA barrier):
+// they execute the same ~100 KB of straight-line code, and in step they share its instruction-cache lines.
 // NTI = tiles per dimension (8 NTI > nineq); <NC, MC> != 0: compile-time nz / nineq.
-template <int NTI, int NC, int MC>
-__global__ void __launch_bounds__(32, 8) k_wres_chunk(const KArgs<double> a, const RArgs ra) {
+template <int NTI, int NC, int MC, int WPC>
+__global__ void __launch_bounds__(32 * WPC, 8 / WPC) k_wres_chunk(const KArgs<double> a, const RArgs ra) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   constexpr int NT = NTI * (NTI + 1) / 2, MPAD = 8 * NTI, RPL = (MPAD + 31) / 32;
-  const int prob = blockIdx.x, lane = threadIdx.x & 31, g = lane >> 2, q = lane & 3, l16 = lane & 15;
+  WLane L;
+  L.init();
+  const int lane = L.lane, g = L.g, q = L.q, l16 = lane & 15;
+  const int prob = blockIdx.x * WPC + (WPC > 1 ? (int)(threadIdx.x >> 5) : 0);
+  if (prob >= a.nb) return;
   const int n = NC > 0 ? NC : a.n, m = MC > 0 ? MC : a.m;
   const int n4 = res_r4(n), m4 = res_r4(m), hs = n4 + 2 * m4;
   const int mr = (m + 1) & ~1;
@@ -370,8 +395,8 @@ __global__ void __launch_bounds__(32, 8) k_wres_chunk(const KArgs<double> a, con
   }
   if (poison || it >= ra.it_end) return;  // uniform
 
-  double* sm = reinterpret_cast<double*>(smem_raw);
   const WOff o = wres_off(m);
+  double* sm = reinterpret_cast<double*>(smem_raw) + (WPC > 1 ? (threadIdx.x >> 5) * o.total : 0);
   double* sG = sm + o.G;
   double* sx = sm + o.x; double* srx = sm + o.rx; double* st = sm + o.t; double* sqx = sm + o.qx;
   double* sz = sm + o.z; double* sdz = sm + o.dz; double* sdinv = sm + o.dinv; double* shz = sm + o.hz;
@@ -420,6 +445,7 @@ __global__ void __launch_bounds__(32, 8) k_wres_chunk(const KArgs<double> a, con
   double C[NT][2];
 #pragma unroll 1
   for (; it < ra.it_end; ++it) {
+    if (WPC > 1) __syncthreads();  // exited warps do not take part
     const bool init = it < 0;
     double dr[RPL], rz[RPL], rx0, rx1, mu = 0.0, t4 = 0.0;
     if (!init) {
@@ -511,8 +537,10 @@ __global__ void __launch_bounds__(32, 8) k_wres_chunk(const KArgs<double> a, con
     __syncwarp();
     // ---------------- T = R + diag(1/d) = L D L^T with hz riding as the bordered row
     w_fix_tiles<NTI, MC>(C, sdinv, shz, m, g, q);
-    const bool ok = w_factor<NTI, MC>(C, srinv, su, m, lane, g, q);
-    if (!ok) {
+    bool bad = false, oob = false;
+    w_factor<NTI, MC>(C, srinv, su, m, L, bad, oob);
+    if (oob && lane == 0) a.ctl->need_exact = 1;  // a positive pivot outside the range of the fast reciprocal
+    if (bad) {
       // non-positive / NaN pivot: this problem can never improve again; its ratios count as NaN from here on
       if (lane == 0) {
         ps[1] = it + 2;
