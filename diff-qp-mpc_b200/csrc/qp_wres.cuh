@@ -27,14 +27,14 @@ namespace b200qp {
 
 constexpr int kWLd = 34;  // leading dimension of G in shared memory (doubles)
 
-struct WOff { int G, x, rx, t, qx, z, dz, dinv, hz, u, q, r, rinv, total; };
+struct WOff { int G, x, rx, t, qx, p, z, dz, dinv, hz, u, q, r, rinv, h, total; };
 __host__ __device__ constexpr WOff wres_off(int m) {
   WOff o{};
   int p = 0;
   o.G = p; p += ((m + 1) & ~1) * kWLd;
-  o.x = p; p += 32; o.rx = p; p += 32; o.t = p; p += 32; o.qx = p; p += 32;
+  o.x = p; p += 32; o.rx = p; p += 32; o.t = p; p += 32; o.qx = p; p += 32; o.p = p; p += 32;
   o.z = p; p += 64; o.dz = p; p += 64; o.dinv = p; p += 64; o.hz = p; p += 64;
-  o.u = p; p += 64; o.q = p; p += 64; o.r = p; p += 64; o.rinv = p; p += 64;
+  o.u = p; p += 64; o.q = p; p += 64; o.r = p; p += 64; o.rinv = p; p += 64; o.h = p; p += 64;
   o.total = p;
   return o;
 }
@@ -175,16 +175,18 @@ __device__ __forceinline__ double wshfl_quad(double v, int src) {
 }
 
 // LDL^T of one 8x8 diagonal tile in accumulator layout (lane (g, q): row g, columns 2q, 2q+1; lower triangle
-// valid), carrying W = L^-1 along.  Branch-free: every pivot is broadcast, so all flags are warp-uniform.
+// valid, the rest finite), carrying W = L^-1 along.  Straight-line code, ~30 instructions per column:
+//   * column k is broadcast with the rows <= k masked to zero, so the multiplier of an eliminated row and the
+//     "pivot-row" entry of an eliminated column are exact zeros and every update is unconditional;
+//   * 1 / d_k = MUFU seed + one cubically convergent step r0 (1 + e + e^2), e = 1 - d r0 (>= 20 -> 60 bits).  A
+//     pivot <= 0, NaN, denormal or >= 2^1022 gives r <= 0, NaN, inf or 0: the caller checks the eight stored
+//     reciprocals once per tile (such a T is the reference's poisoned iterate).
 //   c0, c1 in/out: on exit column k < g of row g holds X[g][k] = L[g][k] D_k
 //   w0, w1 out   : W = L^-1 (unit lower triangular), accumulator layout
 //   rinv out     : shared memory, the 8 reciprocal pivots (1 for bordered / padding columns, base + k >= m)
-//   bad          : set when a pivot of a real column is not a positive normal number in (2^-962, 2^962): the
-//                  factorisation failed (<= 0, NaN: the reference's poisoned iterate) -- or `oob` when it is positive
-//                  but outside the range the Newton reciprocal covers (never seen; the caller asks for the exact route)
 template <int MC>
 __device__ __forceinline__ void w_diag(double& c0, double& c1, double& w0, double& w1, double* rinv, int base, int m_rt,
-                                       const WLane& L, bool& bad, bool& oob) {
+                                       const WLane& L) {
   const int m = MC > 0 ? MC : m_rt;
   w0 = (L.g == 2 * L.q) ? 1.0 : 0.0;
   w1 = (L.g == 2 * L.q + 1) ? 1.0 : 0.0;
@@ -193,29 +195,24 @@ __device__ __forceinline__ void w_diag(double& c0, double& c1, double& w0, doubl
     const int kq = k >> 1;
     const double ck = (k & 1) ? c1 : c0;
     const double dk = wshfl(ck, 4 * k + kq);         // C[k][k]
-    const double cik = wshfl_quad(ck, kq);           // C[g][k]
-    const double cj0 = wshfl(ck, L.q8 + kq);         // C[2q][k]
-    const double cj1 = wshfl(ck, L.q8 + 4 + kq);     // C[2q+1][k]
+    const double ckm = (L.g > k) ? ck : 0.0;         // rows that are still being eliminated
+    const double cik = wshfl_quad(ckm, kq);          // C[g][k]     (0 for g <= k)
+    const double cj0 = wshfl(ckm, L.q8 + kq);        // C[2q][k]    (0 for 2q <= k)
+    const double cj1 = wshfl(ckm, L.q8 + 4 + kq);    // C[2q+1][k]
     double r;
     asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(dk));
-    double e = fma(-dk, r, 1.0);
-    r = fma(r, e, r);
-    e = fma(-dk, r, 1.0);
-    r = fma(r, e, r);
-    if (base + k < m) {  // folds for compile-time sizes
-      const bool inr = (unsigned)(__double2hiint(dk) - 0x03d00000) < 0x78400000u;  // positive, exponent in range
-      if (!inr) { r = t_nan<double>(); bad = true; if (dk > 0.0) oob = true; }
-    } else {
-      r = 1.0;
-    }
+    const double e = fma(-dk, r, 1.0);
+    const double t = fma(e, e, e);
+    r = fma(r, t, r);
+    if (base + k >= m) r = 1.0;  // folds for compile-time sizes
     if (L.lane == 0) rinv[k] = r;
     const double nl = -(cik * r);
-    pfma_lt(c0, nl, cj0, k, L.lim0);
-    pfma_lt(c1, nl, cj1, k, L.lim1);
+    c0 = fma(nl, cj0, c0);   // entries (g, j) with j > g are never read unmasked
+    c1 = fma(nl, cj1, c1);
     if (k < 7) {
       const double wk0 = wshfl(w0, L.q + 4 * k), wk1 = wshfl(w1, L.q + 4 * k);  // row k of W (final after step k-1)
-      pfma_lt(w0, nl, wk0, k, L.g);
-      pfma_lt(w1, nl, wk1, k, L.g);
+      w0 = fma(nl, wk0, w0);
+      w1 = fma(nl, wk1, w1);
     }
   }
 }
@@ -256,12 +253,40 @@ __device__ __forceinline__ void w_fix_tiles(double (&C)[NTI * (NTI + 1) / 2][2],
   }
 }
 
+// Same for tiles written by the tensor-core path of k_prefactor (qp_kernels.cuh; fp64, no equalities, all
+// (m + 7) / 8 == NTI tile rows present): padding entries are exact zeros and the strict upper triangle of a diagonal
+// tile holds the mirrored values, which the factorisation never reads.  Left to do: the diagonal (1/d, or 1 for the
+// bordered / padding rows) and the bordered row.
+template <int NTI, int MC>
+__device__ __forceinline__ void w_fix_tiles_clean(double (&C)[NTI * (NTI + 1) / 2][2], const double* sdinv, const double* shz,
+                                                  int g, int q) {
+  static_assert(MC > 0 && (MC + 8) / 8 == NTI, "compile-time nineq filling all tile rows");
+  constexpr int Ib = MC >> 3, gb = MC & 7;
+#pragma unroll
+  for (int I = 0; I < NTI; I++) {
+    const int i = 8 * I + g;
+    const double di = (i < MC) ? sdinv[i] : 1.0;
+    if (2 * q == g) C[w_tile(I, I)][0] += di;
+    if (2 * q + 1 == g) C[w_tile(I, I)][1] += di;
+  }
+#pragma unroll
+  for (int K = 0; K <= Ib; K++) {
+    const double2 hv = *reinterpret_cast<const double2*>(shz + 8 * K + 2 * q);  // zero beyond m
+    if (g == gb) {
+      const int k = 8 * K + 2 * q;
+      C[w_tile(Ib, K)][0] = (k == MC) ? 1.0 : hv.x;
+      C[w_tile(Ib, K)][1] = (k + 1 == MC) ? 1.0 : hv.y;
+    }
+  }
+}
+
 // Blocked LDL^T of the register tiles (file header).  On exit: tiles (I, K < I) hold X = L D, diagonal tiles hold
 // W = L_II^-1, srinv[0..MPAD) the reciprocal pivots, su[k] = (D^-1 L^-1 hz)_k for k < m (0 beyond): the forward
-// substitution of the bordered right-hand side.  bad / oob as in w_diag.
+// substitution of the bordered right-hand side.  Returns false when some pivot was not a positive normal number
+// below 2^1022 (see w_diag).
 template <int NTI, int MC>
-__device__ __forceinline__ void w_factor(double (&C)[NTI * (NTI + 1) / 2][2], double* srinv, double* su, int m_rt, const WLane& L,
-                                         bool& bad, bool& oob) {
+__device__ __forceinline__ bool w_factor(double (&C)[NTI * (NTI + 1) / 2][2], double* srinv, double* su, int m_rt, const WLane& L) {
+  bool good = true;
   const int m = MC > 0 ? MC : m_rt;
   const int Ib = m >> 3, gb = m & 7;
   const int q = L.q;
@@ -271,9 +296,10 @@ __device__ __forceinline__ void w_factor(double (&C)[NTI * (NTI + 1) / 2][2], do
       double w0, w1;
       double& d0 = C[w_tile(J, J)][0];
       double& d1 = C[w_tile(J, J)][1];
-      w_diag<MC>(d0, d1, w0, w1, srinv + 8 * J, 8 * J, m, L, bad, oob);
+      w_diag<MC>(d0, d1, w0, w1, srinv + 8 * J, 8 * J, m, L);
       __syncwarp();
       const double2 sc = *reinterpret_cast<const double2*>(srinv + 8 * J + 2 * q);
+      good = good && (sc.x > 0.0) && (sc.x < t_inf<double>()) && (sc.y > 0.0) && (sc.y < t_inf<double>());
       if (J == Ib && L.g == gb)
         *reinterpret_cast<double2*>(su + 8 * J + 2 * q) = make_double2(2 * q < gb ? d0 * sc.x : 0.0, 2 * q + 1 < gb ? d1 * sc.y : 0.0);
       d0 = w0; d1 = w1;
@@ -301,6 +327,7 @@ __device__ __forceinline__ void w_factor(double (&C)[NTI * (NTI + 1) / 2][2], do
       }
     }
   }
+  return __all_sync(0xffffffffu, good);
 }
 
 // su <- D^-1 L^-1 sr (natural order in shared memory; entries >= m come out 0)
@@ -359,6 +386,38 @@ __device__ __forceinline__ void w_bwd(const double (&C)[NTI * (NTI + 1) / 2][2],
   }
 }
 
+// get_step pieces (batch.py:211-214) of (z, dz) and (s, ds) in the compact layout: the NaN-propagating minimum of
+// a = -v / dv over the entries the fill does not overwrite (dv > 0 is overwritten; +inf if none is left), whether some
+// entry is overwritten (has bit 0 / 1), and whether a holds a NaN anywhere (nanz / nans: the batch maximum that defines
+// the fill is then NaN).  NaNs are tracked as flags and combined by votes: the reductions are plain minima.
+template <int RPL>
+__device__ __forceinline__ void w_pieces(const double (&z)[RPL], const double (&dz)[RPL], const double (&s)[RPL],
+                                         const double (&ds)[RPL], int m, int lane, double& rz, double& rs, int& has, bool& nanz,
+                                         bool& nans) {
+  double mz = t_inf<double>(), ms = t_inf<double>();
+  bool hz = false, hs = false, nrz = false, nrs = false, naz = false, nas = false;
+#pragma unroll
+  for (int q = 0; q < RPL; q++) {
+    if (q * 32 + lane < m) {
+      const double a1 = -z[q] / dz[q], a2 = -s[q] / ds[q];
+      const bool n1 = is_nan(a1), n2 = is_nan(a2);
+      naz |= n1; nas |= n2;
+      if (dz[q] > 0.0) hz = true; else { nrz |= n1; mz = fmin(mz, a1); }
+      if (ds[q] > 0.0) hs = true; else { nrs |= n2; ms = fmin(ms, a2); }
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    mz = fmin(mz, wshfl_x(mz, o));
+    ms = fmin(ms, wshfl_x(ms, o));
+  }
+  has = (__any_sync(0xffffffffu, hz) ? 1 : 0) | (__any_sync(0xffffffffu, hs) ? 2 : 0);
+  rz = __any_sync(0xffffffffu, nrz) ? t_nan<double>() : mz;
+  rs = __any_sync(0xffffffffu, nrs) ? t_nan<double>() : ms;
+  nanz = __any_sync(0xffffffffu, naz);
+  nans = __any_sync(0xffffffffu, nas);
+}
+
 // ------------------------------------------------------------------------------------------------------------
 // One launch = the iterations [.., ra.it_end) of every problem, one warp per problem, WPC independent warps
 // (problems) per CTA.  With WPC > 1 the warps of a CTA re-align at the top of every iteration (one CTA barrier):
@@ -401,6 +460,7 @@ __global__ void __launch_bounds__(32 * WPC, 8 / WPC) k_wres_chunk(const KArgs<do
   double* sx = sm + o.x; double* srx = sm + o.rx; double* st = sm + o.t; double* sqx = sm + o.qx;
   double* sz = sm + o.z; double* sdz = sm + o.dz; double* sdinv = sm + o.dinv; double* shz = sm + o.hz;
   double* su = sm + o.u; double* sq = sm + o.q; double* sr = sm + o.r; double* srinv = sm + o.rinv;
+  double* sp = sm + o.p; double* sh = sm + o.h;
   double* hist = ra.hist + (size_t)prob * (a.max_iter + 1) * hs;
 
   // ---- stage G (zero padded to 32 columns / an even number of rows), zero the vectors
@@ -417,42 +477,47 @@ __global__ void __launch_bounds__(32 * WPC, 8 / WPC) k_wres_chunk(const KArgs<do
   const double* Qig = a.Qi + (size_t)prob * a.sQi;
   const double* Rf = a.R + (size_t)prob * a.sR;
   const int ldqi = a.ldn;
-  // p (pair layout), h and the iterate (compact layout)
-  double pp0 = 0.0, pp1 = 0.0, xp0 = 0.0, xp1 = 0.0;
-  double hr[RPL], zr[RPL], sr_[RPL];
+  // p, h and x live in shared memory (they are constants or rarely touched: registers are the scarce resource), the
+  // iterate s, z in registers (compact layout)
+  double zr[RPL], sr_[RPL];
   {
     const double* pg = a.pv + (size_t)prob * a.sp;
     const double* hg = a.h + (size_t)prob * a.sh;
     const double* hh = hist + (size_t)(it < 0 ? 0 : it) * hs;
-    const int c = 2 * l16;
-    if (c < n) { pp0 = pg[c]; if (it >= 0) xp0 = hh[c]; }
-    if (c + 1 < n) { pp1 = pg[c + 1]; if (it >= 0) xp1 = hh[c + 1]; }
+    __syncwarp();
+    if (lane < n) { sp[lane] = pg[lane]; if (it >= 0) sx[lane] = hh[lane]; }
 #pragma unroll
     for (int s = 0; s < RPL; s++) {
       const int i = s * 32 + lane;
-      hr[s] = i < m ? hg[i] : 0.0;
+      if (i < m) sh[i] = hg[i];
       zr[s] = (i < m && it >= 0) ? hh[n4 + m4 + i] : 0.0;
       sr_[s] = (i < m && it >= 0) ? hh[n4 + i] : 0.0;
     }
   }
-  __syncwarp();
-  if (lane < 16) *reinterpret_cast<double2*>(sx + 2 * lane) = make_double2(xp0, xp1);
   cp_async_wait_all();
   __syncwarp();
 
   bool alive = true;
   bool have_hist = true;  // the history entry of the first iteration of this launch already exists
   double C[NT][2];
+  // Register-heavy loads (Q, Q^-1 as quad-per-row fragments: 64 registers each; the 36 tiles of R: 144) are issued one
+  // phase ahead of their use, at points where the registers they land in are dead:
+  //   Q^-1 #1 (for t = Q^-1 rx)  with Q at the top of the iteration          (the tiles are not loaded yet)
+  //   R tiles                    after the Q product                        (Q's registers are free)
+  //   Q^-1 #2 (for dx)           after the last sweep                       (the factor is dead)
 #pragma unroll 1
   for (; it < ra.it_end; ++it) {
     if (WPC > 1) __syncthreads();  // exited warps do not take part
     const bool init = it < 0;
-    double dr[RPL], rz[RPL], rx0, rx1, mu = 0.0, t4 = 0.0;
+    double dr[RPL], rz[RPL], mu = 0.0, t4 = 0.0;
+    WMat MQi;
+    w_gload(MQi, Qig, ldqi, n, g, q);
     if (!init) {
+      WMat MQ;
+      w_gload(MQ, Qg, n, n, g, q);
       if (!have_hist) {
         double* hh = hist + (size_t)it * hs;
-        const int c = 2 * lane;
-        if (lane < 16) { if (c < n) hh[c] = xp0; if (c + 1 < n) hh[c + 1] = xp1; }
+        if (lane < n) hh[lane] = sx[lane];
 #pragma unroll
         for (int s = 0; s < RPL; s++) {
           const int i = s * 32 + lane;
@@ -460,8 +525,6 @@ __global__ void __launch_bounds__(32 * WPC, 8 / WPC) k_wres_chunk(const KArgs<do
         }
       }
       // ---------------- residuals (batch.py:93-108)
-      WMat MQ;
-      w_gload(MQ, Qg, n, n, g, q);
 #pragma unroll
       for (int s = 0; s < RPL; s++) {
         const int i = s * 32 + lane;
@@ -472,16 +535,35 @@ __global__ void __launch_bounds__(32 * WPC, 8 / WPC) k_wres_chunk(const KArgs<do
       double gx[RPL];
       w_gv<RPL>(sG, sx, n, mr, lane, gx);
 #pragma unroll
-      for (int s = 0; s < RPL; s++) rz[s] = gx[s] + sr_[s] - hr[s];
+      for (int s = 0; s < RPL; s++) { const int i = s * 32 + lane; rz[s] = gx[s] + sr_[s] - (i < m ? sh[i] : 0.0); }
+      w_gapply(MQ, sx, sqx, g, q);
+    } else {
+      // initial point (batch.py:60-66): d = 1, (rx, rs, rz) = (p, 0, -h)
+#pragma unroll
+      for (int s = 0; s < RPL; s++) {
+        const int i = s * 32 + lane;
+        dr[s] = 1.0; zr[s] = 0.0; sr_[s] = 0.0; rz[s] = i < m ? -sh[i] : 0.0;
+        if (i < m) sdinv[i] = 1.0;
+      }
+    }
+    // the tiles of T travel while the right-hand side is formed
+#pragma unroll
+    for (int t = 0; t < NT; t++) {
+      const double2 v = __ldg(reinterpret_cast<const double2*>(Rf + (size_t)t * 64 + lane * 2));
+      C[t][0] = v.x; C[t][1] = v.y;
+    }
+    if (!init) {
       double gz0, gz1;
       w_gtu(sG, sz, mr, lane, gz0, gz1);
-      w_gapply(MQ, sx, sqx, g, q);
       __syncwarp();
+      double rx0, rx1;
       {
         const double2 qx = *reinterpret_cast<const double2*>(sqx + 2 * l16);
-        rx0 = gz0 + (qx.x + pp0);
-        rx1 = gz1 + (qx.y + pp1);
+        const double2 pv = *reinterpret_cast<const double2*>(sp + 2 * l16);
+        rx0 = gz0 + (qx.x + pv.x);
+        rx1 = gz1 + (qx.y + pv.y);
       }
+      if (lane < 16) *reinterpret_cast<double2*>(srx + 2 * lane) = make_double2(rx0, rx1);
       // residual norms and mu (batch.py:103-108)
       {
         double s0 = 0.0, s1 = 0.0, s2 = 0.0;
@@ -500,30 +582,12 @@ __global__ void __launch_bounds__(32 * WPC, 8 / WPC) k_wres_chunk(const KArgs<do
         }
       }
     } else {
-      // initial point (batch.py:60-66): d = 1, (rx, rs, rz) = (p, 0, -h)
-      rx0 = pp0; rx1 = pp1;
-#pragma unroll
-      for (int s = 0; s < RPL; s++) {
-        const int i = s * 32 + lane;
-        dr[s] = 1.0; zr[s] = 0.0; sr_[s] = 0.0; rz[s] = -hr[s];
-        if (i < m) sdinv[i] = 1.0;
-      }
+      if (lane < 16) *reinterpret_cast<double2*>(srx + 2 * lane) = *reinterpret_cast<const double2*>(sp + 2 * lane);
     }
     have_hist = false;
     // ---------------- right-hand side of the reduced system: hz = G Q^-1 rx + rs / d - rz   (rs = z)
-    if (lane < 16) *reinterpret_cast<double2*>(srx + 2 * lane) = make_double2(rx0, rx1);
-    {
-      WMat MQi;
-      w_gload(MQi, Qig, ldqi, n, g, q);
-      __syncwarp();
-      w_gapply(MQi, srx, st, g, q);
-    }
-    // the tiles of T travel while the right-hand side is formed
-#pragma unroll
-    for (int t = 0; t < NT; t++) {
-      const double2 v = __ldg(reinterpret_cast<const double2*>(Rf + (size_t)t * 64 + lane * 2));
-      C[t][0] = v.x; C[t][1] = v.y;
-    }
+    __syncwarp();
+    w_gapply(MQi, srx, st, g, q);
     __syncwarp();
     {
       double gt[RPL];
@@ -536,10 +600,9 @@ __global__ void __launch_bounds__(32 * WPC, 8 / WPC) k_wres_chunk(const KArgs<do
     }
     __syncwarp();
     // ---------------- T = R + diag(1/d) = L D L^T with hz riding as the bordered row
-    w_fix_tiles<NTI, MC>(C, sdinv, shz, m, g, q);
-    bool bad = false, oob = false;
-    w_factor<NTI, MC>(C, srinv, su, m, L, bad, oob);
-    if (oob && lane == 0) a.ctl->need_exact = 1;  // a positive pivot outside the range of the fast reciprocal
+    if constexpr (MC > 0 && (MC + 8) / 8 == NTI) w_fix_tiles_clean<NTI, MC>(C, sdinv, shz, g, q);
+    else w_fix_tiles<NTI, MC>(C, sdinv, shz, m, g, q);
+    const bool bad = !w_factor<NTI, MC>(C, srinv, su, m, L);
     if (bad) {
       // non-positive / NaN pivot: this problem can never improve again; its ratios count as NaN from here on
       if (lane == 0) {
@@ -557,6 +620,7 @@ __global__ void __launch_bounds__(32 * WPC, 8 / WPC) k_wres_chunk(const KArgs<do
     for (int s = 0; s < RPL; s++) { const int i = s * 32 + lane; qa[s] = i < m ? sq[i] : 0.0; }
     double alpha = 1.0;
     if (init) {
+      w_gload(MQi, Qig, ldqi, n, g, q);
       // x, s, z of the initial point; shift s and z so that their minima are >= 1 (batch.py:76-86)
       double mn_s = t_inf<double>(), mn_z = t_inf<double>();
 #pragma unroll
@@ -577,14 +641,14 @@ __global__ void __launch_bounds__(32 * WPC, 8 / WPC) k_wres_chunk(const KArgs<do
       double dza[RPL], dsa[RPL];
 #pragma unroll
       for (int s = 0; s < RPL; s++) { dza[s] = -qa[s]; dsa[s] = (-zr[s] - dza[s]) / dr[s]; }
-      double pc[4]; int has;
+      double pz, psl; int has; bool nz_, ns_;
       double zq[RPL], sq_[RPL];
 #pragma unroll
       for (int s = 0; s < RPL; s++) { const bool v = s * 32 + lane < m; zq[s] = v ? zr[s] : 1.0; sq_[s] = v ? sr_[s] : 1.0; }
-      res_pieces<RPL, false>(zq, dza, sq_, dsa, m, lane, pc, has);
+      w_pieces<RPL>(zq, dza, sq_, dsa, m, lane, pz, psl, has, nz_, ns_);
       // the clamp at 1 makes alpha_aff independent of the batch-global fill (batch.py:161-163)
-      const double stz = (has & 1) ? nanmin(pc[0], 1.0) : pc[0];
-      const double sts = (has & 2) ? nanmin(pc[1], 1.0) : pc[1];
+      const double stz = (has & 1) ? nanmin(pz, 1.0) : pz;
+      const double sts = (has & 2) ? nanmin(psl, 1.0) : psl;
       const double alpha_aff = nanmin(nanmin(stz, sts), 1.0);
       double t3 = 0.0;
 #pragma unroll
@@ -604,6 +668,7 @@ __global__ void __launch_bounds__(32 * WPC, 8 / WPC) k_wres_chunk(const KArgs<do
       // ---------------- corrector: qc = T^-1 (rsc / d)
       w_fwd<NTI, MC>(C, sr, srinv, su, m, lane, g, q);
       w_bwd<NTI, MC>(C, su, srinv, sq, m, lane, g, q);
+      w_gload(MQi, Qig, ldqi, n, g, q);  // the factor is dead: Q^-1 for dx travels behind the step-length logic
       double dz[RPL], ds[RPL];
 #pragma unroll
       for (int s = 0; s < RPL; s++) {
@@ -613,8 +678,7 @@ __global__ void __launch_bounds__(32 * WPC, 8 / WPC) k_wres_chunk(const KArgs<do
         const double dsc = (-rsc[s] - dzc) / dr[s];
         dz[s] = dza[s] + dzc; ds[s] = dsa[s] + dsc;
       }
-      res_pieces<RPL, true>(zq, dz, sq_, ds, m, lane, pc, has);
-      const bool nz_ = is_nan(pc[2]), ns_ = is_nan(pc[3]);
+      w_pieces<RPL>(zq, dz, sq_, ds, m, lane, pz, psl, has, nz_, ns_);
       if (nz_ || ns_) {
         if (lane == 0) atomicMax(&a.ctl->kev_inv, (unsigned)(kKevBase - it));
         if (nz_) azm |= 1u << it;
@@ -629,13 +693,15 @@ __global__ void __launch_bounds__(32 * WPC, 8 / WPC) k_wres_chunk(const KArgs<do
       }
       Kdyn = __shfl_sync(0xffffffffu, Kdyn, 0);  // one view per warp
       const bool F = it >= Kdyn;
-      const double a0_ = nanmin(0.999 * nanmin(pc[0], pc[1]), 1.0);
-      const double z1 = (has & 1) ? nanmin(pc[0], 1.0) : pc[0], s1 = (has & 2) ? nanmin(pc[1], 1.0) : pc[1];
+      // F = 0: fill = max(1, a.max()) >= every unfilled ratio -> the unfilled minimum (+inf when fill-only:
+      //        0.999 * fill >= 1 is validated by k_res_reduce);  F = 1: fill = 1.0 exactly
+      const double a0_ = nanmin(0.999 * nanmin(pz, psl), 1.0);
+      const double z1 = (has & 1) ? nanmin(pz, 1.0) : pz, s1 = (has & 2) ? nanmin(psl, 1.0) : psl;
       const double a1_ = nanmin(0.999 * nanmin(z1, s1), 1.0);
       const bool same = (a0_ == a1_) || (is_nan(a0_) && is_nan(a1_));
       if (!same) sens |= 1u << it;
       if (F) used |= 1u << it;
-      else if (((has & 1) && pc[0] == t_inf<double>()) || ((has & 2) && pc[1] == t_inf<double>())) fo |= 1u << it;
+      else if (((has & 1) && pz == t_inf<double>()) || ((has & 2) && psl == t_inf<double>())) fo |= 1u << it;
       alpha = F ? a1_ : a0_;
 #pragma unroll
       for (int s = 0; s < RPL; s++) {
@@ -646,27 +712,29 @@ __global__ void __launch_bounds__(32 * WPC, 8 / WPC) k_wres_chunk(const KArgs<do
     __syncwarp();
     // ---------------- dx = Q^-1 (-rx - G^T dz);  x += alpha dx   (initial point: x = dx)
     {
-      WMat MQi;
-      w_gload(MQi, Qig, ldqi, n, g, q);
       double gd0, gd1;
       w_gtu(sG, sdz, mr, lane, gd0, gd1);
-      if (lane < 16) *reinterpret_cast<double2*>(st + 2 * lane) = make_double2(-rx0 - gd0, -rx1 - gd1);
+      if (lane < 16) {
+        const double2 rx = *reinterpret_cast<const double2*>(srx + 2 * lane);
+        *reinterpret_cast<double2*>(st + 2 * lane) = make_double2(-rx.x - gd0, -rx.y - gd1);
+      }
       __syncwarp();
       w_gapply(MQi, st, sqx, g, q);
       __syncwarp();
-      const double2 dx = *reinterpret_cast<const double2*>(sqx + 2 * l16);
-      xp0 = init ? dx.x : xp0 + alpha * dx.x;
-      xp1 = init ? dx.y : xp1 + alpha * dx.y;
-      __syncwarp();
-      if (lane < 16) *reinterpret_cast<double2*>(sx + 2 * lane) = make_double2(xp0, xp1);
+      if (lane < 16) {
+        const double2 dx = *reinterpret_cast<const double2*>(sqx + 2 * lane);
+        double2 xv = *reinterpret_cast<const double2*>(sx + 2 * lane);
+        xv.x = init ? dx.x : xv.x + alpha * dx.x;
+        xv.y = init ? dx.y : xv.y + alpha * dx.y;
+        *reinterpret_cast<double2*>(sx + 2 * lane) = xv;
+      }
       __syncwarp();
     }
   }
   // ---- hand the state to the next launch
   if (alive) {
     double* hh = hist + (size_t)it * hs;
-    const int c = 2 * lane;
-    if (lane < 16) { if (c < n) hh[c] = xp0; if (c + 1 < n) hh[c + 1] = xp1; }
+    if (lane < n) hh[lane] = sx[lane];
 #pragma unroll
     for (int s = 0; s < RPL; s++) {
       const int i = s * 32 + lane;
