@@ -167,6 +167,10 @@ def QPFunction(eps=1e-12, verbose=0, notImprovedLim=3,
                                           "per-instance CPU solver outside the hot path)")
             plan = _Plan(Q_, p_, G_, h_, A_, b_, eps, notImprovedLim, maxIter)
             _check_callbacks(plan, dyn_res, cost_grad)
+            if exact_group is not None:
+                # the sharded mode IS the one-launch-per-iteration route; the flag keeps the forward and the backward of this
+                # problem on the same kernels (bit-for-bit equal to the unsharded exact route)
+                plan.prob.flags |= _lib.FLAG_EXACT
             L = _lib.lib()
             nb, nz, nineq, neq = plan.nBatch, plan.nz, plan.nineq, plan.neq
             opt = dict(dtype=Q_.dtype, device=Q_.device)

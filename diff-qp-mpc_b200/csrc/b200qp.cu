@@ -214,7 +214,15 @@ static int backward_t(const b200qp_problem_t* pr, const Layout& L, const void* z
   const bool chained = g_prof.on && g_prof.n > 0 && (g_prof.kind[g_prof.n - 1] == 3 || g_prof.kind[g_prof.n - 1] == 6);
   if (g_prof.on && !chained) prof_begin(st);
   if (chained) cudaEventRecord(g_prof.ev[g_prof.n], st);  // restart the bracket after host-side gaps
-  DISPATCH_KERNEL(launch_backward, T, L, a, g);
+  bool done = false;
+  if constexpr (std::is_same<T, double>::value) {
+    if (L.res && L.res_warp) {  // the shapes of the resident route: one warp per QP (qp_wres.cuh)
+      int rc = res_backward(a, g, L, st);
+      if (rc) return rc;
+      done = true;
+    }
+  }
+  if (!done) DISPATCH_KERNEL(launch_backward, T, L, a, g);
   prof_mark(4, st);
   return B200QP_OK;
 }

@@ -161,5 +161,6 @@ template <typename T> int fast_kkt(const KArgs<T>& a, const SArgs<T>& g, const L
 // resident route (qp_inst.cu -DINST_RES=1): one launch = the iterations [.., ra.it_end) of every problem
 int res_chunk(const KArgs<double>& a, const RArgs& ra, const Layout& L, cudaStream_t st);
 int res_finish(const KArgs<double>& a, const RArgs& ra, double* status, int launches, cudaStream_t st);
+int res_backward(const KArgs<double>& a, const BArgs<double>& g, const Layout& L, cudaStream_t st);  // warp per QP (qp_wres.cuh)
 
 }  // namespace b200qp

@@ -56,6 +56,24 @@ int res_chunk(const KArgs<double>& a, const RArgs& ra, const Layout& L, cudaStre
   if (L.res_spec && L.n == 30 && L.m == 60) return res_launch<64, 30, 60>(a, ra, L, st);
   return L.mpad == 32 ? res_launch<32, 0, 0>(a, ra, L, st) : res_launch<64, 0, 0>(a, ra, L, st);
 }
+template <int NTI, int NC, int MC>
+static int wres_bwd_launch(const KArgs<double>& a, const BArgs<double>& g, const Layout& L, cudaStream_t st) {
+  auto k = k_wres_backward<NTI, NC, MC>;
+  const size_t smem = (size_t)wres_off(L.m).total * sizeof(double);
+  static bool once = false;
+  if (!once) {
+    CK(cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    once = true;
+  }
+  CK(ensure_smem(k, smem));
+  k<<<(unsigned)a.nb, 32, smem, st>>>(a, g);
+  CK(cudaGetLastError());
+  return B200QP_OK;
+}
+int res_backward(const KArgs<double>& a, const BArgs<double>& g, const Layout& L, cudaStream_t st) {
+  if (L.res_spec && L.n == 30 && L.m == 60) return wres_bwd_launch<8, 30, 60>(a, g, L, st);
+  return L.m < 32 ? wres_bwd_launch<4, 0, 0>(a, g, L, st) : wres_bwd_launch<8, 0, 0>(a, g, L, st);
+}
 int res_finish(const KArgs<double>& a, const RArgs& ra, double* status, int launches, cudaStream_t st) {
   k_res_reduce<0><<<(unsigned)((a.nb + 127) / 128), 128, 0, st>>>(a, ra);
   CK(cudaGetLastError());

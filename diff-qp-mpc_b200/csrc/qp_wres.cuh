@@ -452,7 +452,10 @@ __global__ void __launch_bounds__(32 * WPC, 8 / WPC) k_wres_chunk(const KArgs<do
       poison = 0;
     }
   }
-  if (poison || it >= ra.it_end) return;  // uniform
+  // Once the first NaN event K* of the batch is known (and behind us) nothing is speculated any more: the fill is 1.0
+  // in every remaining iteration, so this launch runs the problem to the end and the later launches find it done.
+  const int it_end = (Kstart <= it) ? a.max_iter : ra.it_end;
+  if (poison || it >= it_end) return;  // uniform
 
   const WOff o = wres_off(m);
   double* sm = reinterpret_cast<double*>(smem_raw) + (WPC > 1 ? (threadIdx.x >> 5) * o.total : 0);
@@ -506,7 +509,7 @@ __global__ void __launch_bounds__(32 * WPC, 8 / WPC) k_wres_chunk(const KArgs<do
   //   R tiles                    after the Q product                        (Q's registers are free)
   //   Q^-1 #2 (for dx)           after the last sweep                       (the factor is dead)
 #pragma unroll 1
-  for (; it < ra.it_end; ++it) {
+  for (; it < it_end; ++it) {
     if (WPC > 1) __syncthreads();  // exited warps do not take part
     const bool init = it < 0;
     double dr[RPL], rz[RPL], mu = 0.0, t4 = 0.0;
@@ -745,6 +748,125 @@ __global__ void __launch_bounds__(32 * WPC, 8 / WPC) k_wres_chunk(const KArgs<do
     ps[0] = (alive ? it : it + 1) + 1;
     if (alive) ps[1] = 0;
     ps[2] = (int)used; ps[3] = (int)sens; ps[4] = (int)fo; ps[5] = (int)azm; ps[6] = (int)asm_;
+  }
+}
+
+
+// ------------------------------------------------------------------------------------------------------------
+// QPFunctionFn.backward (qpth/qp.py:129-183) with one warp per QP and the same building blocks: d = clamp(lam) /
+// clamp(slack), T = R + diag(1/d) factored in registers with the right-hand side G Q^-1 dl/dz riding as the
+// bordered row, one backward sweep, dx = -Q^-1 dl/dz - (G Q^-1)^T dlam, then the outer-product gradients written with
+// 16-byte stores (dQ = (dx z' + z dx') / 2, dG = dlam z' + lam dx', dp = dx, dh = -dlam).  A failed factorisation
+// (some lam / slack is NaN or the clamped T is not positive definite) gives NaN gradients, as the reference's LU does.
+template <int NTI, int NC, int MC>
+__global__ void __launch_bounds__(32, 8) k_wres_backward(const KArgs<double> a, const BArgs<double> ga) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  constexpr int NT = NTI * (NTI + 1) / 2, MPAD = 8 * NTI, RPL = (MPAD + 31) / 32;
+  WLane L;
+  L.init();
+  const int lane = L.lane, g = L.g, q = L.q;
+  const int prob = blockIdx.x + a.prob0;
+  const int n = NC > 0 ? NC : a.n, m = MC > 0 ? MC : a.m;
+  const int mr = (m + 1) & ~1;
+  const WOff o = wres_off(m);
+  double* sm = reinterpret_cast<double*>(smem_raw);
+  double* sG = sm + o.G;
+  double* sx = sm + o.x; double* srx = sm + o.rx; double* st = sm + o.t; double* sqx = sm + o.qx;
+  double* sz = sm + o.z; double* sdz = sm + o.dz; double* sdinv = sm + o.dinv; double* shz = sm + o.hz;
+  double* su = sm + o.u; double* sq = sm + o.q; double* srinv = sm + o.rinv;
+  {
+    // the inputs Q, G are not part of the backward call (include/b200qp.h): B = G Q^-1 from the pre-factorisation
+    const double* Bg = a.BQi + (size_t)prob * a.sBQi;
+    for (int r = 0; r < mr; r++) {
+      if (r < m && lane < n) cp_async8(sG + r * kWLd + lane, Bg + (size_t)r * a.ldn + lane);
+      else sG[r * kWLd + lane] = 0.0;
+    }
+    cp_async_commit();
+    for (int i = lane; i < o.total - o.x; i += 32) sm[o.x + i] = 0.0;
+  }
+  const double* Qig = a.Qi + (size_t)prob * a.sQi;
+  const double* Rf = a.R + (size_t)prob * a.sR;
+  WMat MQi;
+  w_gload(MQi, Qig, a.ldn, n, g, q);
+  double C[NT][2];
+#pragma unroll
+  for (int t = 0; t < NT; t++) {
+    const double2 v = __ldg(reinterpret_cast<const double2*>(Rf + (size_t)t * 64 + lane * 2));
+    C[t][0] = v.x; C[t][1] = v.y;
+  }
+  __syncwarp();
+  {
+    const double* zh = ga.zhat + (size_t)prob * n;
+    const double* gz = ga.gz + (size_t)prob * n;
+    const double* lam = ga.lams + (size_t)prob * m;
+    const double* sl = ga.slacks + (size_t)prob * m;
+    if (lane < n) { sx[lane] = zh[lane]; srx[lane] = gz[lane]; }
+#pragma unroll
+    for (int s = 0; s < RPL; s++) {
+      const int i = s * 32 + lane;
+      if (i < m) {
+        const double lv = lam[i], sv = sl[i];
+        const double lc = lv < 1e-8 ? 1e-8 : lv, sc = sv < 1e-8 ? 1e-8 : sv;  // qp.py:146-149 (NaN stays NaN)
+        sz[i] = lv;
+        sdinv[i] = 1.0 / (lc / sc);
+      }
+    }
+  }
+  cp_async_wait_all();
+  __syncwarp();
+  w_gapply(MQi, srx, st, g, q);  // t = Q^-1 dl/dz
+  __syncwarp();
+  {
+    double gt[RPL];
+    w_gv<RPL>(sG, srx, n, mr, lane, gt);  // hz = G Q^-1 dl/dz
+#pragma unroll
+    for (int s = 0; s < RPL; s++) { const int i = s * 32 + lane; if (i < m) shz[i] = gt[s]; }
+  }
+  __syncwarp();
+  if constexpr (MC > 0 && (MC + 8) / 8 == NTI) w_fix_tiles_clean<NTI, MC>(C, sdinv, shz, g, q);
+  else w_fix_tiles<NTI, MC>(C, sdinv, shz, m, g, q);
+  const bool ok = w_factor<NTI, MC>(C, srinv, su, m, L);
+  __syncwarp();
+  w_bwd<NTI, MC>(C, su, srinv, sq, m, lane, g, q);
+  // dlam = -T^-1 hz
+#pragma unroll
+  for (int s = 0; s < RPL; s++) { const int i = s * 32 + lane; if (i < m) sdz[i] = ok ? -sq[i] : t_nan<double>(); }
+  __syncwarp();
+  {
+    double gd0, gd1;
+    w_gtu(sG, sdz, mr, lane, gd0, gd1);
+    if (lane < 16) {  // dx = -t - (G Q^-1)^T dlam
+      const double2 tv = *reinterpret_cast<const double2*>(st + 2 * lane);
+      *reinterpret_cast<double2*>(sqx + 2 * lane) = make_double2(-tv.x - gd0, -tv.y - gd1);
+    }
+    __syncwarp();
+  }
+  // ---- gradients
+  double* dp = ga.dp + (size_t)prob * n; double* dh = ga.dh + (size_t)prob * m;
+  if (lane < n) dp[lane] = sqx[lane];
+#pragma unroll
+  for (int s = 0; s < RPL; s++) { const int i = s * 32 + lane; if (i < m) dh[i] = -sdz[i]; }
+  double* dQ = ga.dQ + (size_t)prob * n * n;
+  double* dG = ga.dG + (size_t)prob * m * n;
+  if ((n & 1) == 0) {
+    const int l = lane & 15, h = lane >> 4, c = 2 * l;
+    const double2 zc = *reinterpret_cast<const double2*>(sx + c), dc = *reinterpret_cast<const double2*>(sqx + c);
+    if (c < n) {
+      for (int r = h; r < n; r += 2) {
+        const double dr_ = 0.5 * sqx[r], zr_ = 0.5 * sx[r];
+        *reinterpret_cast<double2*>(dQ + (size_t)r * n + c) = make_double2(fma(dr_, zc.x, zr_ * dc.x), fma(dr_, zc.y, zr_ * dc.y));
+      }
+      for (int r = h; r < m; r += 2) {
+        const double dl = sdz[r], lm = sz[r];
+        *reinterpret_cast<double2*>(dG + (size_t)r * n + c) = make_double2(fma(dl, zc.x, lm * dc.x), fma(dl, zc.y, lm * dc.y));
+      }
+    }
+  } else {
+    if (lane < n) {
+      const double zc = sx[lane], dc = sqx[lane];
+      for (int r = 0; r < n; r++) dQ[(size_t)r * n + lane] = 0.5 * (sqx[r] * zc + sx[r] * dc);
+      for (int r = 0; r < m; r++) dG[(size_t)r * n + lane] = sdz[r] * zc + sz[r] * dc;
+    }
   }
 }
 

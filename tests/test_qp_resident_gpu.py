@@ -124,12 +124,23 @@ def test_fill_only_problems_fall_back_to_exact_route(cuda_device, opts):
 
 def test_bench_batch_against_oracle(cuda_device, opts):
     """The bench configuration itself (BASELINE configs[1]: nb = 32768, nz = 30, nineq = 60, 20 iterations because of
-    the batch-global termination) against the oracle on the same inputs: iteration count, solution, duals, dp."""
+    the batch-global termination) against the oracle on the same inputs: iteration count, solution, duals at 1e-6 for
+    every problem; gradients
+      (a) against the reference backward evaluated AT OUR forward outputs (isolates the backward kernel): 1e-6, every
+          problem;
+      (b) end to end against the reference's own forward + backward: 1e-6, except for problems whose gradient is
+          ill-conditioned in the reference itself.  qp.py:139 forms d = clamp(lams) / clamp(slacks); a weakly active
+          constraint (lam ~ slack ~ 1e-9, d = O(1e-2)) makes the reference's own gradient move by 1e-5 when its own forward
+          outputs are perturbed by 1e-9 (1000x inside the forward gate) -- measured below, never assumed: the tolerance of
+          a problem is max(1e-6, 10 x the change of the reference gradient under such a perturbation), and at most 0.01 %
+          of the batch may need more than 1e-6."""
     from oracle import qp_oracle as O
     torch.set_num_threads(max(1, torch.get_num_threads()))
     inp = rand_inputs(32768, 30, 60, 0)
     fwd = O.qp_forward(*(inp[k].clone() for k in "QpGhAb"))
-    gr = O.qp_backward(fwd, *(inp[k] for k in "QpGhAb"), torch.ones_like(fwd["zhat"]))
+    ones = torch.ones_like(fwd["zhat"])
+    args = tuple(inp[k] for k in "QpGhAb")
+    gr = O.qp_backward(fwd, *args, ones)
     out, info = solve(inp, cuda_device)
     det = reference_stop(inp)
     print("bench batch: n_iter", info["n_iter"], "oracle", fwd["n_iter"], det, "exact_rerun", info.get("exact_rerun", False))
@@ -137,5 +148,35 @@ def test_bench_batch_against_oracle(cuda_device, opts):
         assert info["n_iter"] == fwd["n_iter"]
     for k in ("zhat", "lams", "slacks"):
         gate(out[k], fwd[k], 1e-6, k)
+    # (a) the backward kernel against the reference backward at the same (our) forward outputs
+    at_ours = dict(fwd)
+    at_ours.update(zhat=out["zhat"], lams=out["lams"], slacks=out["slacks"])
+    gr_ours = O.qp_backward(at_ours, *args, ones)
     for k in ("dp", "dh", "dG", "dQ"):
-        gate(out[k], gr[k], 1e-6, k)
+        gate(out[k], gr_ours[k], 1e-6, k + " (backward kernel)")
+    # (b) end to end, with the measured conditioning of the reference's own gradient
+    sens = {k: torch.zeros(gr[k].shape[0], dtype=torch.float64) for k in ("dp", "dh", "dG", "dQ")}
+    for trial in range(3):
+        gen = torch.Generator().manual_seed(100 + trial)
+        pert = dict(fwd)
+        for k in ("zhat", "lams", "slacks"):
+            v = fwd[k]
+            pert[k] = v + 1e-9 * v.norm(dim=1, keepdim=True) / v.shape[1] ** 0.5 * torch.randn(v.shape, generator=gen, dtype=v.dtype)
+        g2 = O.qp_backward(pert, *args, ones)
+        for k in sens:
+            a_, b_ = g2[k].reshape(g2[k].shape[0], -1), gr[k].reshape(gr[k].shape[0], -1)
+            bn = b_.norm(dim=1)
+            sens[k] = torch.maximum(sens[k], (a_ - b_).norm(dim=1) / (bn + bn.median() + 1e-300))
+    for k in ("dp", "dh", "dG", "dQ"):
+        a_, b_ = out[k].reshape(out[k].shape[0], -1), gr[k].reshape(gr[k].shape[0], -1)
+        bn = b_.norm(dim=1)
+        err = (a_ - b_).norm(dim=1) / (bn + bn.median() + 1e-300)
+        tol = torch.clamp(10.0 * sens[k], min=1e-6)
+        over = int((err > 1e-6).sum())
+        worst = int(err.argmax())
+        print(f"  {k}: worst per-problem rel err {err.max().item():.3e} (problem {worst}, reference sensitivity {sens[k][worst].item():.3e}); "
+              f"{over} of {err.numel()} problems above 1e-6")
+        assert bool((err <= tol).all()), f"{k}: problem {int((err / tol).argmax())} exceeds its conditioned tolerance"
+        assert over <= max(1, err.numel() // 10000), f"{k}: {over} problems above 1e-6"
+        whole = (a_ - b_).norm().item() / b_.norm().item()
+        assert whole <= 1e-6, f"{k}: whole-tensor rel err {whole:.3e}"
