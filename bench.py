@@ -139,10 +139,21 @@ class ClockSampler:
         return out
 
 
+def _fp64_peak():
+    try:
+        return json.load(open(os.path.join(ROOT, "profiles", "fp64_peaks_r01.json"))).get("dfma_tflops_sustained", 34.0)
+    except Exception:
+        return 34.0
+
+
+FP64_PEAK_TFLOPS = _fp64_peak()
+
+
 def cpu_oracle_rate(nb, repeats, threads):
     """The reference's algorithm (oracle port, bit-identical to qpth on CPU) on the host cores."""
     from oracle import qp_oracle as O
-    torch.set_num_threads(threads)
+    # torch's intra-op pool already spans the host cores; calling torch.set_num_threads here was found to corrupt
+    # MKL's threaded LU of larger matrices later in the same process (oneMKL DLASWP parameter errors, then a hang)
     Q, p, G, h, A, b = gen_batch(nb, torch.device("cpu"), seed=0)
     times = []
     n_iter = None
@@ -264,7 +275,7 @@ def bench_mpc_shapes(dev):
     g = torch.Generator(device="cpu").manual_seed(0)
     r = lambda *sh: torch.rand(*sh, generator=g, dtype=torch.float64)
 
-    def run(name, dx, dxj, nx, nu, T, B, x0, u0, qd, lo, hi, reps):
+    def run(name, dx, dxj, nx, nu, T, B, x0, u0, qd, lo, hi, reps, fdyn):
         Cd = torch.tensor(qd, dtype=torch.float64, device=dev).repeat(B, T, 1)
         ctrl = MPC(nx, nu, T, u_lower=lo, u_upper=hi, n_batch=B, u_init=u0, eps=1e-5, dtype=torch.float64)
         Cfull = torch.diag_embed(Cd).requires_grad_(True)
@@ -287,28 +298,52 @@ def bench_mpc_shapes(dev):
         e1.record()
         torch.cuda.synchronize()
         ms = e0.elapsed_time(e1) / reps
-        out[name] = {"B": B, "T": T, "nx": nx, "nu": nu, "ms_per_call": ms, "rollouts_per_s": B / (ms * 1e-3)}
+        # forward alone (the fused AL solve k_al_solve<Dyn> + a handful of tiny torch kernels) for the roofline
+        fms = []
+        for _ in range(max(2, reps // 2)):
+            ctrl.reinitialize(x0, None)
+            ctrl.u_init = u0
+            torch.cuda.synchronize()
+            e0.record()
+            with torch.no_grad():
+                ctrl(x0, QuadCost(Cfull.detach(), c.detach()), dx, dxj)
+            e1.record()
+            torch.cuda.synchronize()
+            fms.append(e0.elapsed_time(e1))
+        fwd_ms = min(fms)
+        nt = nx + nu
+        f_dyn = fdyn  # flops of one dynamics step (estimate, stated in DESIGN.md section 4)
+        f_jac = 2.0 * nt * f_dyn  # forward-mode duals: nt directions, ~2 flops per primal flop and direction
+        flops = 8.0 * T * ((7.0 / 3.0) * nt ** 3 + nx * nt ** 2 + 6 * nt ** 2 + f_jac + 21 * f_dyn)
+        tf = flops * B / (fwd_ms * 1e-3) / 1e12
+        out[name] = {"B": B, "T": T, "nx": nx, "nu": nu, "ms_per_call": ms, "rollouts_per_s": B / (ms * 1e-3),
+                     "forward_ms": fwd_ms,
+                     "roofline": {"kernel": "k_al_solve<Dyn,double> (whole AL solve, one warp per problem)", "bound": "fp64",
+                                  "flops_per_solve": flops, "achieved": tf, "peak": FP64_PEAK_TFLOPS, "unit": "TFLOP/s",
+                                  "frac": tf / FP64_PEAK_TFLOPS,
+                                  "formula": "8 T [(7/3) nt^3 + nx nt^2 + 6 nt^2 + F_jac + 21 F_dyn] (SURVEY.md 8d), "
+                                             f"F_dyn ~ {f_dyn:.0f}, F_jac ~ 2 nt F_dyn"}}
 
     B, T = 4096, 20
     th = r(B) * 0.6 - 0.3
     x0 = torch.stack((r(B) - 0.5, torch.zeros(B, dtype=torch.float64), torch.cos(th), torch.sin(th),
                       torch.zeros(B, dtype=torch.float64)), 1).to(dev)
     run("cartpole_env_dx_T20_B4096", envs.CartpoleDx(), envs.CartpoleDx_jac(), 5, 1, T, B, x0,
-        (0.1 * (r(B, T, 1) - 0.5)).to(dev), [0.1, 0.1, 1., 1., 0.1, 0.001], one(-100., 1), one(100., 1), 5)
+        (0.1 * (r(B, T, 1) - 0.5)).to(dev), [0.1, 0.1, 1., 1., 0.1, 0.001], one(-100., 1), one(100., 1), 5, 60.)
     # configs[2] with the dynamics deqmpc actually trains on: my_envs CartpoleEnv(nx=4, dt=0.05), u in +-100,
     # Qlqr = 1, Rlqr = 1e-8 (deqmpc/my_envs/cartpole.py:43-84, train.py:102); and the two-link variant (train.py:105)
     from b200qp import my_envs
     kw = dict(dtype=torch.float64, device=dev)
-    for nm, nx, dt_, um in (("cartpole1l_myenvs_T20_B4096", 4, 0.05, 100.), ("cartpole2l_myenvs_T20_B4096", 6, 0.03, 250.)):
+    for nm, nx, dt_, um, fd in (("cartpole1l_myenvs_T20_B4096", 4, 0.05, 100., 240.), ("cartpole2l_myenvs_T20_B4096", 6, 0.03, 250., 600.)):
         d = my_envs.CartpoleDynamics(nx=nx, dt=dt_, kwargs=kw)
         x0 = torch.cat((r(B, nx // 2) * 0.6 - 0.3, r(B, nx // 2) * 0.2 - 0.1), 1).to(dev)
         run(nm, d, d.dynamics_derivatives, nx, 1, T, B, x0, (0.1 * (r(B, T, 1) - 0.5)).to(dev), [1.] * nx + [1e-8],
-            one(-um, 1), one(um, 1), 5)
+            one(-um, 1), one(um, 1), 5, fd)
     B, T = 1024, 40
     x0 = torch.cat((r(B, 3) * 2 - 1, r(B, 3) * 0.2 - 0.1, r(B, 6) * 0.2 - 0.1), 1).to(dev)
     run("rex_quadrotor_T40_B1024", envs.RexQuadrotor_dynamics(), envs.RexQuadrotor_dynamics_jac(), 12, 4, T, B, x0,
         (14.9 + 0.1 * (r(B, T, 4) - 0.5)).to(dev), [10.] * 3 + [0.01] * 3 + [1.] * 3 + [0.01] * 3 + [1e-4] * 4,
-        one(11.5, 4), one(18.3, 4), 2)
+        one(11.5, 4), one(18.3, 4), 2, 1600.)
     return out
 
 
@@ -357,7 +392,6 @@ def bench_qp_sizes(dev):
 def cpu_mpc_rate(B=256, T=5, threads=1):
     """The reference's AL-MPC algorithm (oracle port) on the host cores, bounded sample."""
     from oracle import mpc_oracle as MO
-    torch.set_num_threads(threads)
     x0, u0, Cd = mpc_problem(B, T, torch.device("cpu"))
     dyn = MO.Pendulum()
     ub = 3.0 * torch.ones(1, dtype=torch.float64)
@@ -377,9 +411,8 @@ def cpu_mpc_rate(B=256, T=5, threads=1):
 def run_reference(args, rank):
     if rank != 0:
         return
-    threads = os.cpu_count() or 1
+    threads = torch.get_num_threads()
     from oracle import qp_oracle as O
-    torch.set_num_threads(threads)
     nb = args.ref_nb
     Q, p, G, h, A, b = gen_batch(nb, torch.device("cpu"), seed=0)
 
@@ -558,13 +591,14 @@ def main():
         # after the first), the iterate history written once per iteration
         ch_bytes = 8 * (n_l * (NZ * NZ + NINEQ * NZ + NZ * (NZ | 1)) + (n_iter + 1) * (36 * 64 + NZ + 2 * NINEQ + 2)) * nb
         bytes_per_launch = ch_bytes / n_l
-        kname = "k_res_chunk<MPAD=64> (several PDIPM iterations of one QP per CTA and launch, matrices resident in shared memory)"
+        kname = ("k_wres_chunk<NTI=8,NC=30,MC=60,WPC=1> (ten PDIPM iterations of one QP per launch, one warp per QP, the factor "
+                 "in registers as DMMA accumulator tiles; csrc/qp_wres.cuh)")
         try:
             tj = json.load(open(os.path.join(ROOT, "profiles", "r02", "ncu_traffic.json")))
             traffic = tj["dram_bytes_per_problem_per_launch"] * nb
-            traffic_src = "profiles/r02/ncu_traffic.json: dram__bytes_read+write of one k_res_chunk launch, per problem, x this batch"
+            traffic_src = "profiles/r02/ncu_traffic.json: dram__bytes_read+write of the first k_wres_chunk launch of a call (initial point + 10 iterations), per problem, x this batch"
         except Exception:
-            traffic, traffic_src = None, "no ncu capture of k_res_chunk committed yet"
+            traffic, traffic_src = None, "no ncu capture of k_wres_chunk committed yet"
     else:
         flops_per_launch = fl["iter"] * nb
         bytes_per_launch = iter_kernel_bytes(NZ, NINEQ) * nb
@@ -601,16 +635,17 @@ def main():
         gz = torch.ones(nb, NZ, dtype=torch.float64).pin_memory()
         shapes = dict(zhat=(nb, NZ), lams=(nb, NINEQ), slacks=(nb, NINEQ), dQ=(nb, NZ, NZ), dp=(nb, NZ),
                       dG=(nb, NINEQ, NZ), dh=(nb, NINEQ))
-        outs = [{k: torch.empty(sh, dtype=torch.float64).pin_memory() for k, sh in shapes.items()} for _ in range(2)]
-        sts = [torch.zeros(8, dtype=torch.float64).pin_memory() for _ in range(2)]
+        NS = 3  # jobs in flight: one per pipeline stage (H2D, kernels, D2H)
+        outs = [{k: torch.empty(sh, dtype=torch.float64).pin_memory() for k, sh in shapes.items()} for _ in range(NS)]
+        sts = [torch.zeros(8, dtype=torch.float64).pin_memory() for _ in range(NS)]
         out = outs[0]
         prob = _lib.Problem(nb, NZ, NINEQ, 0, _lib.F64, 20, 3, 0, 1e-12, NZ * NZ, NZ, NINEQ * NZ, NINEQ, 0, 0)
         P = lambda t: ctypes.c_void_p(t.data_ptr())
         NULL = ctypes.c_void_p(0)
 
-        def submit(slot):
+        def submit(slot, pr=prob):
             o = outs[slot]
-            rc = L.b200qp_solve_host_submit(slot, ctypes.byref(prob), P(host["Q"]), P(host["p"]), P(host["G"]), P(host["h"]),
+            rc = L.b200qp_solve_host_submit(slot, ctypes.byref(pr), P(host["Q"]), P(host["p"]), P(host["G"]), P(host["h"]),
                                             NULL, NULL, P(gz), P(o["zhat"]), P(o["lams"]), NULL, P(o["slacks"]), P(o["dQ"]),
                                             P(o["dp"]), P(o["dG"]), P(o["dh"]), NULL, NULL, P(sts[slot]))
             _lib.check(rc, "b200qp_solve_host_submit")
@@ -618,37 +653,53 @@ def main():
         def wait(slot):
             _lib.check(L.b200qp_solve_host_wait(slot), "b200qp_solve_host_wait")
 
-        # serving loop: every step copies its inputs from pinned host memory and returns its results
-        # to host memory; step k+1 is submitted before step k is awaited (two arenas, three streams)
-        for i in range(2):
-            submit(i % 2)
-        wait(0); wait(1)
-        barrier()
-        t0 = time.perf_counter()
-        for i in range(args.steps):
-            submit(i % 2)
-            if i > 0:
-                wait((i - 1) % 2)
-        wait((args.steps - 1) % 2)
-        torch.cuda.synchronize()
-        dt = time.perf_counter() - t0
-        tm = torch.tensor([dt], device=dev, dtype=torch.float64)
-        if world > 1:
-            dist.all_reduce(tm, op=dist.ReduceOp.MAX)
-        dt = tm.item()
+        def serve(pr):
+            """serving loop: every step copies its inputs from pinned host memory and returns its results to host
+            memory; steps k+1 and k+2 are submitted before step k is awaited (three arenas, three streams)"""
+            for i in range(NS):
+                submit(i, pr)
+            for i in range(NS):
+                wait(i)
+            barrier()
+            t0 = time.perf_counter()
+            for i in range(args.steps):
+                submit(i % NS, pr)
+                if i >= NS - 1:
+                    wait((i - (NS - 1)) % NS)
+            for i in range(max(0, args.steps - (NS - 1)), args.steps):
+                wait(i % NS)
+            torch.cuda.synchronize()
+            dt = time.perf_counter() - t0
+            tm = torch.tensor([dt], device=dev, dtype=torch.float64)
+            if world > 1:
+                dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+            return tm.item()
+
+        dt = serve(prob)
         # the synchronous single-call form, for the record
         t1 = time.perf_counter()
         for i in range(max(2, args.steps // 3)):
             submit(0); wait(0)
         dt_sync = (time.perf_counter() - t1) / max(2, args.steps // 3)
+        # opt-in factored gradients (B200QP_FLAG_FACTORED_GRAD): dQ, dG stay on the device as their four factors
+        prob_f = _lib.Problem(nb, NZ, NINEQ, 0, _lib.F64, 20, 3, 4, 1e-12, NZ * NZ, NZ, NINEQ * NZ, NINEQ, 0, 0)
+        dt_f = serve(prob_f)
         h2d = es * nb * (NZ * NZ + NZ + NINEQ * NZ + NINEQ + NZ)
         d2h = es * nb * (NZ + 2 * NINEQ + NZ * NZ + NZ + NINEQ * NZ + NINEQ) + 64
+        d2h_f = es * nb * (NZ + 2 * NINEQ + NZ + NINEQ) + 64
         e2e = {"value": nb * world * args.steps / dt, "unit": UNIT, "h2d_bytes_per_step": h2d,
                "d2h_bytes_per_step": d2h, "ms_per_step": 1e3 * dt / args.steps,
                "api": "b200qp_solve_host_submit/_wait (C ABI, pinned host buffers; every step copies its inputs in "
-                      "and its results out inside the timed region; two slots so that the copies of adjacent steps "
+                      "and its results out inside the timed region; three slots so that the copies of adjacent steps "
                       "overlap the kernels)",
-               "single_call_ms_per_step": 1e3 * dt_sync, "single_call_value": nb * world / dt_sync}
+               "pcie_gb_s_per_direction": 1e-9 * max(h2d, d2h) / (dt / args.steps),
+               "single_call_ms_per_step": 1e3 * dt_sync, "single_call_value": nb * world / dt_sync,
+               "factored_grad": {"value": nb * world * args.steps / dt_f, "unit": UNIT, "ms_per_step": 1e3 * dt_f / args.steps,
+                                 "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h_f,
+                                 "note": "opt-in B200QP_FLAG_FACTORED_GRAD: dQ, dG returned as their factors (dp, dh, zhat, "
+                                         "lams; qpth/qp.py:158-174), not part of the headline"}}
+        for i in range(NS):  # leave dense results in the host buffers for the check below
+            submit(i); wait(i)
         # keep the device path honest: same answer from both entry points
         zz = step().detach().cpu()
         assert torch.allclose(zz, out["zhat"], rtol=0, atol=0), "host-buffer path and device path disagree"
@@ -692,22 +743,47 @@ def main():
         except Exception as ex:  # pragma: no cover
             sizes = {"error": repr(ex)}
 
+    # MPC rollouts/s (BASELINE's second metric): every rank runs the same batch on its own GPU (weak scaling, problems are
+    # independent, no collective); the aggregate uses the slowest rank's time
     mpc = None
-    if rank == 0 and not args.quick:
+    if not args.quick:
         try:
+            barrier()
             mpc = bench_mpc(dev)
-            mpc["other_shapes"] = bench_mpc_shapes(dev)
-            if world == 1 and not args.no_cpu:
-                threads = os.cpu_count() or 1
+            shapes_ = bench_mpc_shapes(dev)
+            if world > 1:
+                names = sorted(shapes_)
+                t = torch.tensor([mpc["ms_per_call"], mpc["cuda_graph_ms_per_call"] if isinstance(mpc["cuda_graph_ms_per_call"], float) else 0.0]
+                                 + [shapes_[k]["ms_per_call"] for k in names], device=dev, dtype=torch.float64)
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                t = t.tolist()
+                mpc["ms_per_call"] = t[0]
+                if t[1] > 0:
+                    mpc["cuda_graph_ms_per_call"] = t[1]
+                for i, k in enumerate(names):
+                    shapes_[k]["ms_per_call"] = t[2 + i]
+            B0 = 1024
+            mpc["n_gpus"] = world
+            mpc["rollouts_per_s"] = B0 * world / (mpc["ms_per_call"] * 1e-3)
+            if isinstance(mpc["cuda_graph_ms_per_call"], float):
+                mpc["cuda_graph_rollouts_per_s"] = B0 * world / (mpc["cuda_graph_ms_per_call"] * 1e-3)
+            for k, v in shapes_.items():
+                v["rollouts_per_s"] = v["B"] * world / (v["ms_per_call"] * 1e-3)
+                v["n_gpus"] = world
+            mpc["other_shapes"] = shapes_
+            if rank == 0 and world == 1 and not args.no_cpu:
+                threads = torch.get_num_threads()
                 rate, sec = cpu_mpc_rate(256, 5, threads)
                 mpc["cpu_baseline"] = {"value": rate, "unit": "rollouts/s", "cores": threads, "kind": "port",
                                        "sample": f"oracle/mpc_oracle.py (dense restatement of qpth AL_mpc) B=256 T=5, median of 2 ({sec:.2f} s each)"}
         except Exception as ex:  # pragma: no cover
             mpc = {"error": repr(ex)}
+            if world > 1:
+                raise
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
-        threads = os.cpu_count() or 1
+        threads = torch.get_num_threads()
         rate, it_cpu, sec = cpu_oracle_rate(args.cpu_nb, 2, threads)
         cpu = {"value": rate, "unit": UNIT, "cores": threads, "kind": "port",
                "sample": f"oracle/qp_oracle.py (bit-identical restatement of qpth on torch CPU), nb={args.cpu_nb} of the same "

@@ -25,6 +25,7 @@ Options& options() {
     x.res_chunk = env_int("B200QP_RES_CH", x.res_chunk);
     x.res_spec = env_int("B200QP_RES_SPEC", x.res_spec);
     x.res_warp = env_int("B200QP_RES_WARP", x.res_warp);
+    x.res_pre = env_int("B200QP_RES_PRE", x.res_pre);
     const char* mid = getenv("B200QP_MID");
     x.mid_fast = (mid && mid[0] == 'f') ? 1 : 0;
     x.blk_nt = env_int("B200QP_BLK_NT", 0);
@@ -112,7 +113,12 @@ static void prof_mark(int kind, cudaStream_t st) {
 }
 
 template <typename T>
-static int run_prefactor(KArgs<T>& a, const Layout& L, cudaStream_t st) { return launch_prefactor<T>(a, L, st); }
+static int run_prefactor(KArgs<T>& a, const Layout& L, cudaStream_t st) {
+  if constexpr (std::is_same<T, double>::value) {
+    if (L.wpre) return res_prefactor(a, L, st);
+  }
+  return launch_prefactor<T>(a, L, st);
+}
 
 #define DISPATCH_KERNEL(FN, T, L, ...)                                   \
   do {                                                                   \
@@ -124,9 +130,10 @@ template <typename T>
 static int forward_t(const b200qp_problem_t* pr, const Layout& L, const void* Q, const void* p, const void* G,
                      const void* h, const void* A, const void* b, void* zhat, void* lams, void* nus, void* slacks,
                      void* ws, double* status, cudaStream_t st, bool prefactored = false,
-                     int phase = B200QP_PHASE_ALL) {
+                     int phase = B200QP_PHASE_ALL, const void* cb_cg = nullptr, const void* cb_ry = nullptr) {
   KArgs<T> a;
   fill_args(a, pr, L, ws);
+  a.cb_cg = (const T*)cb_cg; a.cb_ry = (const T*)cb_ry;
   a.Q = (const T*)Q; a.pv = (const T*)p; a.G = (const T*)G; a.h = (const T*)h;
   a.A = (const T*)(A ? A : G); a.b = (const T*)(b ? b : h);
   a.bx = (T*)zhat; a.bz = (T*)lams; a.bs = (T*)slacks; a.by = (T*)nus;
@@ -282,10 +289,23 @@ static int prefactor_range_t(const b200qp_problem_t* pr, const Layout& L, const 
   return run_prefactor(a, L, st);
 }
 
+template <typename T>
+static int cb_step_t(const b200qp_problem_t* pr, const Layout& L, int it, void* x_out, void* ws, cudaStream_t st) {
+  KArgs<T> a;
+  fill_args(a, pr, L, ws);
+  a.iter = it;
+  k_cb_step<T><<<(unsigned)L.nb, 128, 0, st>>>(a, (T*)x_out);
+  CK(cudaGetLastError());
+  return B200QP_OK;
+}
+
 // ---------------------------------------------------------------------------- host-buffer path
-// Two device arenas so that consecutive host-buffer solves overlap: the inputs of solve k+1 cross
-// the PCIe bus (stream g_cin) and the gradients of solve k go back (stream g_cout) while the kernels
-// of either run (stream g_st).  b200qp_solve_host uses slot 0 synchronously.
+// B200QP_HOST_SLOTS device arenas so that consecutive host-buffer solves overlap: the inputs of solve k+1
+// cross the PCIe bus (stream g_cin) and the gradients of solve k-1 go back (stream g_cout) while the kernels
+// of solve k run (stream g_st).  A job is three stages (H2D, kernels, D2H) of similar length at the headline
+// shape, so the steady state needs THREE jobs in flight: with two slots the period is (H2D + kernels + D2H) / 2
+// (measured 22.9 ms against 16.5 ms of kernels), with three it is the longest stage.  b200qp_solve_host uses
+// slot 0 synchronously.
 struct Arena {
   char* base = nullptr;
   size_t cap = 0;
@@ -299,7 +319,7 @@ struct Arena {
   void* job_out[10];
   double* job_status = nullptr;
 };
-static Arena g_arenas[2];
+static Arena g_arenas[B200QP_HOST_SLOTS];
 static cudaStream_t g_st = nullptr, g_cin = nullptr, g_cout = nullptr;
 static std::mutex g_host_mu;
 
@@ -364,6 +384,35 @@ int b200qp_forward_phase(const b200qp_problem_t* prob, int phase, const void* Q,
   return forward_t<float>(prob, L, Q, p, G, h, A, b, zhat, lams, nus, slacks, workspace, status, st, false, phase);
 }
 
+int b200qp_forward_phase_cb(const b200qp_problem_t* prob, int phase, const void* Q, const void* p, const void* G,
+                            const void* h, const void* A, const void* b, void* zhat, void* lams, void* nus, void* slacks,
+                            void* workspace, double* status, const void* cost_grad_x, const void* dyn_res_x,
+                            b200qp_stream_t stream) {
+  Layout L;
+  int rc = make_layout(prob, L);
+  if (rc) return rc;
+  if (!Q || !p || !G || !h || !zhat || !lams || !slacks || !workspace || !status) return B200QP_EINVAL;
+  if (prob->neq > 0 && (!A || !b || !nus)) return B200QP_EINVAL;
+  if (phase < 0 || phase >= prob->max_iter) return B200QP_EINVAL;  // callbacks only enter the iterations proper
+  L.res = false;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (prob->dtype == B200QP_F64)
+    return forward_t<double>(prob, L, Q, p, G, h, A, b, zhat, lams, nus, slacks, workspace, status, st, false, phase,
+                             cost_grad_x, dyn_res_x);
+  return forward_t<float>(prob, L, Q, p, G, h, A, b, zhat, lams, nus, slacks, workspace, status, st, false, phase,
+                          cost_grad_x, dyn_res_x);
+}
+
+int b200qp_forward_cb_step(const b200qp_problem_t* prob, int it, void* x_out, void* workspace, b200qp_stream_t stream) {
+  Layout L;
+  int rc = make_layout(prob, L);
+  if (rc) return rc;
+  if (!x_out || !workspace || it < 0 || it >= prob->max_iter) return B200QP_EINVAL;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (prob->dtype == B200QP_F64) return cb_step_t<double>(prob, L, it, x_out, workspace, st);
+  return cb_step_t<float>(prob, L, it, x_out, workspace, st);
+}
+
 int b200qp_forward(const b200qp_problem_t* prob, const void* Q, const void* p, const void* G, const void* h,
                    const void* A, const void* b, void* zhat, void* lams, void* nus, void* slacks, void* workspace,
                    double* status, b200qp_stream_t stream) {
@@ -419,7 +468,7 @@ int b200qp_kkt_solve(const b200qp_problem_t* prob, int prefactor, const void* Q,
 }
 
 int b200qp_solve_host_wait(int slot) {
-  if (slot < 0 || slot > 1) return B200QP_EINVAL;
+  if (slot < 0 || slot >= B200QP_HOST_SLOTS) return B200QP_EINVAL;
   Arena& AR = g_arenas[slot];
   {
     std::lock_guard<std::mutex> lock(g_host_mu);
@@ -449,7 +498,7 @@ int b200qp_solve_host_submit(int slot, const b200qp_problem_t* prob, const void*
                              const void* h, const void* A, const void* b, const void* dl_dzhat, void* zhat, void* lams,
                              void* nus, void* slacks, void* dQ, void* dp, void* dG, void* dh, void* dA, void* db,
                              double* status) {
-  if (slot < 0 || slot > 1) return B200QP_EINVAL;
+  if (slot < 0 || slot >= B200QP_HOST_SLOTS) return B200QP_EINVAL;
   Layout L;
   int rc = make_layout(prob, L);
   if (rc) return rc;
@@ -457,7 +506,8 @@ int b200qp_solve_host_submit(int slot, const b200qp_problem_t* prob, const void*
   const size_t es = L.es, nb = (size_t)L.nb, n = (size_t)L.n, m = (size_t)L.m, pe = (size_t)L.p;
   if (pe > 0 && (!A || !b || !nus)) return B200QP_EINVAL;
   const bool bwd = dl_dzhat != nullptr;
-  if (bwd && (!dQ || !dp || !dG || !dh || (pe > 0 && (!dA || !db)))) return B200QP_EINVAL;
+  const bool factored = (prob->flags & B200QP_FLAG_FACTORED_GRAD) != 0;
+  if (bwd && ((!factored && (!dQ || !dG)) || !dp || !dh || (pe > 0 && (!dA || !db)))) return B200QP_EINVAL;
   Arena& AR = g_arenas[slot];
   {
     int rcw = b200qp_solve_host_wait(slot);  // the previous job of this slot still owns the arena (and its output buffers)
@@ -551,19 +601,22 @@ int b200qp_solve_host_submit(int slot, const b200qp_problem_t* prob, const void*
       return cudaMemcpyAsync((char*)dst + (size_t)lo * per * es, d + off + (size_t)lo * per * es, (size_t)cnt * per * es,
                              cudaMemcpyDeviceToHost, co);
     };
+    // factored gradients: the warp-per-QP backward kernel skips the outer products altogether; the other backward
+    // kernels still write them to the arena, they are just not copied
+    const bool skipQG = factored && prob->dtype == B200QP_F64 && L.res && L.res_warp;
     for (int c = 0; c < nch; c++) {
       const int lo = lo_of(c), cnt = lo_of(c + 1) - lo;
       rc = prob->dtype == B200QP_F64
-               ? backward_t<double>(prob, L, d + oz, d + ol, d + on, d + os, d + ogz, d + odQ, d + odp, d + odG, d + odh,
-                                    d + odA, d + odb, d + ows, st, lo, cnt)
+               ? backward_t<double>(prob, L, d + oz, d + ol, d + on, d + os, d + ogz, skipQG ? nullptr : d + odQ, d + odp,
+                                    skipQG ? nullptr : d + odG, d + odh, d + odA, d + odb, d + ows, st, lo, cnt)
                : backward_t<float>(prob, L, d + oz, d + ol, d + on, d + os, d + ogz, d + odQ, d + odp, d + odG, d + odh,
                                    d + odA, d + odb, d + ows, st, lo, cnt);
       if (rc) return rc;
       CK(cudaEventRecord(AR.ev_out[c], st));
       CK(cudaStreamWaitEvent(co, AR.ev_out[c], 0));
-      CK(slice_d2h(dQ, odQ, n * n, lo, cnt));
+      if (!factored) CK(slice_d2h(dQ, odQ, n * n, lo, cnt));
       CK(slice_d2h(dp, odp, n, lo, cnt));
-      CK(slice_d2h(dG, odG, m * n, lo, cnt));
+      if (!factored) CK(slice_d2h(dG, odG, m * n, lo, cnt));
       CK(slice_d2h(dh, odh, m, lo, cnt));
       if (pe > 0) { CK(slice_d2h(dA, odA, pe * n, lo, cnt)); CK(slice_d2h(db, odb, pe, lo, cnt)); }
     }
@@ -604,6 +657,7 @@ int b200qp_set_option(const char* name, int value) {
   else if (!strcmp(name, "res_ch")) o.res_chunk = value;
   else if (!strcmp(name, "res_spec")) o.res_spec = value;
   else if (!strcmp(name, "res_warp")) o.res_warp = value;
+  else if (!strcmp(name, "res_pre")) o.res_pre = value;
   else if (!strcmp(name, "mid_fast")) o.mid_fast = value;
   else if (!strcmp(name, "blk_nt")) o.blk_nt = value;
   else if (!strcmp(name, "factor_tile")) o.factor_tile = value;

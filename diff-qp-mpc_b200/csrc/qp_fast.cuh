@@ -630,7 +630,7 @@ __global__ void __launch_bounds__(NT, (NT == 128 ? (FK == 1 ? FAST_DMMA_MIN_CTAS
     if (p > 0) gemv_cols_nt<T, NT>(Ag, n, p, n, S.y, S.scrn, S.part, tid);  // A^T y
     T acc[4] = {T(0), T(0), T(0), T(0)};
     for (int c = tid; c < n; c += NT) {
-      T v = S.rx[c] + pg[c] + S.t[c];
+      T v = (a.cb_cg ? a.cb_cg[(size_t)prob * n + c] : S.rx[c] + pg[c]) + S.t[c];
       if (p > 0) v += S.scrn[c];
       S.rx[c] = v;
       acc[0] += v * v;
@@ -646,7 +646,7 @@ __global__ void __launch_bounds__(NT, (NT == 128 ? (FK == 1 ? FAST_DMMA_MIN_CTAS
       S.scr[i] = T(1) / dv + (T)a.reg;
     }
     for (int j = tid; j < p; j += NT) {
-      const T v = S.ry[j] - bg[j];
+      const T v = a.cb_ry ? a.cb_ry[(size_t)prob * p + j] : S.ry[j] - bg[j];
       S.ry[j] = v;
       acc[2] += v * v;
     }

@@ -32,6 +32,7 @@ struct Layout {
   // resident route (qp_resident.cuh): several iterations per launch, history + records per problem
   bool res;
   int res_chunk, res_spec, res_warp;
+  bool wpre;  // pre-factorisation by k_wres_prefactor (one warp per QP, qp_wres.cuh)
   size_t res_smem, ohist, orec, opst;
 };
 
@@ -40,9 +41,10 @@ struct Layout {
 // descriptor always agree on it.
 struct Options {
   int res = 1;        // B200QP_RES       0: never take the resident route
-  int res_chunk = 4;  // B200QP_RES_CH    iterations per launch of the resident route
+  int res_chunk = 10; // B200QP_RES_CH    iterations per launch of the resident route
   int res_spec = 1;   // B200QP_RES_SPEC  1: use the compile-time-size specialisation where one exists (nz=30, nineq=60)
   int res_warp = 1;   // B200QP_RES_WARP  1: one warp per QP with the factor in registers (qp_wres.cuh), 0: 128-thread CTAs
+  int res_pre = 1;    // B200QP_RES_PRE   1: warp-per-QP pre-factorisation on the shapes of the resident route
   int mid_fast = 0;   // B200QP_MID=fast  64 < nineq <= 128 on the register-tile route
   int blk_nt = 0;     // B200QP_BLK_NT    256 forces the wide CTAs of the blocked route
   int factor_tile = 0;// B200QP_FACTOR=tile
@@ -139,6 +141,8 @@ inline int make_layout(const b200qp_problem_t* pr, Layout& L) {
   L.res_warp = opt.res_warp;  // 0: 128-thread CTAs per QP; 1 / 4 / 8: one warp per QP, that many QPs per CTA
   L.res_smem = (size_t)res_off(L.n, L.m, L.mpad).total * sizeof(double);
   L.ohist = L.orec = L.opst = 0;
+  // same shapes, but independent of the EXACT flag: the exact re-run of a call starts from the same pre-factorisation
+  L.wpre = opt.res_pre && opt.res_warp && L.fast && L.fk && L.p == 0 && L.n <= 32 && !(pr->flags & B200QP_FLAG_DENSE);
   if (L.res) {
     L.ohist = put(nb * (size_t)(pr->max_iter + 1) * res_hs(L.n, L.m), sizeof(double));
     L.orec = put(nb * (size_t)pr->max_iter * 2, sizeof(double));
@@ -162,5 +166,6 @@ template <typename T> int fast_kkt(const KArgs<T>& a, const SArgs<T>& g, const L
 int res_chunk(const KArgs<double>& a, const RArgs& ra, const Layout& L, cudaStream_t st);
 int res_finish(const KArgs<double>& a, const RArgs& ra, double* status, int launches, cudaStream_t st);
 int res_backward(const KArgs<double>& a, const BArgs<double>& g, const Layout& L, cudaStream_t st);  // warp per QP (qp_wres.cuh)
+int res_prefactor(const KArgs<double>& a, const Layout& L, cudaStream_t st);                        // warp per QP (qp_wres.cuh)
 
 }  // namespace b200qp

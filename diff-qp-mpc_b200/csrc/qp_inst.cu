@@ -74,6 +74,16 @@ int res_backward(const KArgs<double>& a, const BArgs<double>& g, const Layout& L
   if (L.res_spec && L.n == 30 && L.m == 60) return wres_bwd_launch<8, 30, 60>(a, g, L, st);
   return L.m < 32 ? wres_bwd_launch<4, 0, 0>(a, g, L, st) : wres_bwd_launch<8, 0, 0>(a, g, L, st);
 }
+template <int NTI, int NC, int MC>
+static int wres_pre_launch(const KArgs<double>& a, cudaStream_t st) {
+  k_wres_prefactor<NTI, NC, MC><<<(unsigned)a.nb, 32, 0, st>>>(a);
+  CK(cudaGetLastError());
+  return B200QP_OK;
+}
+int res_prefactor(const KArgs<double>& a, const Layout& L, cudaStream_t st) {
+  if (L.res_spec && L.n == 30 && L.m == 60) return wres_pre_launch<8, 30, 60>(a, st);
+  return L.m <= 32 ? wres_pre_launch<4, 0, 0>(a, st) : wres_pre_launch<8, 0, 0>(a, st);
+}
 int res_finish(const KArgs<double>& a, const RArgs& ra, double* status, int launches, cudaStream_t st) {
   k_res_reduce<0><<<(unsigned)((a.nb + 127) / 128), 128, 0, st>>>(a, ra);
   CK(cudaGetLastError());

@@ -110,6 +110,9 @@ struct KArgs {
   int pre_blocked;           // prefactor: byte offset (+1) of the panel buffer in dynamic shared memory when the
                              // blocked tensor-core route is taken (fp64, large nz; qp_blocked.cuh), else 0
   int rtile_mpad, rtile_nt;  // != 0: R is stored in register-tile order (qp_fast.cuh); nt = -1: DMMA fragment order
+  // caller-evaluated residual callbacks of this fork (qpth/solvers/pdipm/batch.py:93-102): when non-null, cb_cg[nb][n]
+  // = cost_grad(x) replaces Q x + p in rx and cb_ry[nb][p] = dyn_res(x) replaces A x - b (b200qp_forward_phase_cb)
+  const T *cb_cg, *cb_ry;
 };
 
 // ------------------------------------------------------------------------------------------
@@ -461,7 +464,7 @@ __global__ void __launch_bounds__(NT, (!SMEM && sizeof(T) == 8) ? (NT == 256 ? 3
   if (p > 0) gemv_cols(Ag, n, p, n, S.y, S.dxc, S.part, tid, NT);
   T acc[4] = {T(0), T(0), T(0), T(0)};  // |rx|^2, |rz|^2, |ry|^2, s.z
   for (int c = tid; c < n; c += NT) {
-    T v = S.rx[c] + pg[c] + S.t[c];
+    T v = (a.cb_cg ? a.cb_cg[(size_t)prob * n + c] : S.rx[c] + pg[c]) + S.t[c];
     if (p > 0) v += S.dxc[c];
     S.rx[c] = v;
     acc[0] += v * v;
@@ -475,7 +478,7 @@ __global__ void __launch_bounds__(NT, (!SMEM && sizeof(T) == 8) ? (NT == 256 ? 3
     S.d[i] = zv / sv;
   }
   for (int j = tid; j < p; j += NT) {
-    const T v = S.ry[j] - bg[j];
+    const T v = a.cb_ry ? a.cb_ry[(size_t)prob * p + j] : S.ry[j] - bg[j];
     S.ry[j] = v;
     acc[2] += v * v;
   }
@@ -572,6 +575,50 @@ __global__ void __launch_bounds__(NT, (!SMEM && sizeof(T) == 8) ? (NT == 256 ? 3
       if (ds_ != ds_) slot->as_nan = 1; else atomic_max_key(&slot->amax_s, ord_key(ds_));
     }
   }
+}
+
+// ------------------------------------------------------------------------------------------
+// Caller-evaluated residual callbacks (this fork's dyn_res / cost_grad, batch.py:93-102): the callbacks need the
+// iterate AFTER the step of iteration it-1, which the iteration kernels apply at their own start.  This kernel applies
+// that step on its own (same termination test, same fill, same alpha as the head of k_pdipm_iter / k_fast_iter), zeroes
+// the stored direction -- the iteration kernel that follows then adds alpha * 0 -- and hands x to the caller.
+template <typename T>
+__global__ void __launch_bounds__(128) k_cb_step(const KArgs<T> a, T* x_out) {
+  __shared__ int s_term;
+  const int prob = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, NT = 128;
+  const int n = a.n, m = a.m, p = a.p, it = a.iter;
+  const int pp = p > 0 ? p : 1;
+  T* gx = a.x + (size_t)prob * round4(n);
+  if (tid == 0) s_term = -1;
+  __syncthreads();
+  if (it > 0 && warp == 0) {
+    const int term = eval_termination(a.slots, it, a.lim, a.eps, lane);
+    if (lane == 0) s_term = term;
+  }
+  __syncthreads();
+  const int flags = a.flags[prob];
+  if (it > 0 && s_term < 0 && !(flags & FLAG_POISON)) {
+    const Slot* sl = a.slots + (it - 1);
+    const double gz = sl->az_nan ? 0.0 : ord_unkey(sl->amax_z);
+    const double gs = sl->as_nan ? 0.0 : ord_unkey(sl->amax_s);
+    const T fill_z = gz > 1.0 ? (T)gz : T(1), fill_s = gs > 1.0 ? (T)gs : T(1);
+    const T rz_ = a.rmu[(size_t)prob * 2], rs_ = a.rmu[(size_t)prob * 2 + 1];
+    const T stz = (flags & FLAG_FILL_Z) ? nanmin(rz_, fill_z) : rz_;
+    const T sts = (flags & FLAG_FILL_S) ? nanmin(rs_, fill_s) : rs_;
+    const T alpha = nanmin(T(0.999) * nanmin(stz, sts), T(1));
+    T* gs_ = a.s + (size_t)prob * round4(m);
+    T* gz_ = a.z + (size_t)prob * round4(m);
+    T* gy = a.y + (size_t)prob * round4(pp);
+    T* gdx = a.dx + (size_t)prob * round4(n);
+    T* gds = a.ds + (size_t)prob * round4(m);
+    T* gdz = a.dz + (size_t)prob * round4(m);
+    T* gdy = a.dy + (size_t)prob * round4(pp);
+    for (int c = tid; c < n; c += NT) { gx[c] += alpha * gdx[c]; gdx[c] = T(0); }
+    for (int i = tid; i < m; i += NT) { gs_[i] += alpha * gds[i]; gz_[i] += alpha * gdz[i]; gds[i] = T(0); gdz[i] = T(0); }
+    for (int j = tid; j < p; j += NT) { gy[j] += alpha * gdy[j]; gdy[j] = T(0); }
+  }
+  __syncthreads();
+  for (int c = tid; c < n; c += NT) x_out[(size_t)prob * n + c] = gx[c];
 }
 
 // ------------------------------------------------------------------------------------------

@@ -753,6 +753,163 @@ __global__ void __launch_bounds__(32 * WPC, 8 / WPC) k_wres_chunk(const KArgs<do
 
 
 // ------------------------------------------------------------------------------------------------------------
+// pre_factor_kkt (qpth/solvers/pdipm/batch.py:377-428) with one warp per QP, everything on the FP64 tensor cores and
+// in registers (fp64, neq == 0, nz <= 32, nineq < 64).  The 128-thread-CTA k_prefactor spends 3.2 ms on 32768
+// problems of the headline shape in ~90 CTA barriers (column-by-column LDL^T of Q and two triangular sweeps over the
+// identity); its arithmetic is 0.25 ms of the FP64 pipe.  Here:
+//   * Q (10 lower 8x8 tiles, accumulator layout) -> w_factor: X = L D below the diagonal, W = L_JJ^-1 on it;
+//   * U = L^-T by block back-substitution written so that every tile product has the form A B^T, the one a DMMA
+//     computes from two accumulator-layout operands without any data movement (w_factor's trick):
+//         U_JJ = W_J^T,   U_JI = -(sum_{J <= K < I} U_JK L_IK^T) W_I^T   (J < I)
+//   * Q^-1 = U D^-1 U^T:   Qi_IJ = sum_{K >= I} (U_IK D_K^-1) U_JK^T  (I >= J), the upper tiles by transposition;
+//   * per tile row I of G (loaded from global memory straight into accumulator layout):
+//         (G Q^-1)_IJ = sum_K G_IK Qi_JK^T,    R_IK = sum_J (G Q^-1)_IJ G_KJ^T   (K <= I)
+//     R leaves the accumulators in fragment order (one 16-byte store per lane and tile).
+// 648 DMMAs per problem at the headline shape, no shared-memory traffic beyond the 64 reciprocal pivots, no barrier.
+__device__ __forceinline__ void w_transpose(double c0, double c1, double& t0, double& t1, const WLane& L) {
+  const int s0 = L.q8 + (L.g >> 1);
+  const double a0 = wshfl(c0, s0), a1 = wshfl(c1, s0), b0 = wshfl(c0, s0 + 4), b1 = wshfl(c1, s0 + 4);
+  t0 = (L.g & 1) ? a1 : a0;
+  t1 = (L.g & 1) ? b1 : b0;
+}
+// C = A B^T for accumulator-layout tiles (a0, a1), (b0, b1), accumulated into (c0, c1)
+__device__ __forceinline__ void w_abt(double& c0, double& c1, double a0, double a1, double b0, double b1) {
+  w_dmma(c0, c1, a0, b0);
+  w_dmma(c0, c1, a1, b1);
+}
+
+template <int NTI, int NC, int MC>
+__global__ void __launch_bounds__(32, 8) k_wres_prefactor(const KArgs<double> a) {
+  __shared__ __align__(16) double s_rinv[32];
+  __shared__ __align__(16) double s_u[32];
+  WLane L;
+  L.init();
+  const int lane = L.lane, g = L.g, q = L.q;
+  const int prob = blockIdx.x + a.prob0;
+  const int n = NC > 0 ? NC : a.n, m = MC > 0 ? MC : a.m;
+  const int MT = (m + 7) >> 3;  // tile rows of G / R
+  const double* Qg = a.Q + (size_t)prob * a.sQ;
+  const double* Gg = a.G + (size_t)prob * a.sG;
+  const bool vec = ((n & 1) == 0) && ((a.sQ & 1) == 0) && ((a.sG & 1) == 0) && ((((size_t)a.Q | (size_t)a.G) & 15) == 0);
+  // one accumulator-layout tile of a row-major matrix with `rows` x n valid entries; `diag1`: identity padding
+  auto load_tile = [&](const double* M, int rows, int I, int K, bool diag1, double& c0, double& c1) {
+    const int i = 8 * I + g, k = 8 * K + 2 * q;
+    c0 = (diag1 && i == k && i >= n) ? 1.0 : 0.0;
+    c1 = (diag1 && i == k + 1 && i >= n) ? 1.0 : 0.0;
+    if (i < rows) {
+      if (vec) {
+        if (k < n) { const double2 v = __ldg(reinterpret_cast<const double2*>(M + (size_t)i * n + k)); c0 = v.x; c1 = v.y; }
+      } else {
+        if (k < n) c0 = __ldg(M + (size_t)i * n + k);
+        if (k + 1 < n) c1 = __ldg(M + (size_t)i * n + k + 1);
+      }
+    }
+  };
+  // ---- G travels first (64 registers); Q is needed at once
+  double Gt[NTI][4][2];
+#pragma unroll
+  for (int I = 0; I < NTI; I++)
+#pragma unroll
+    for (int K = 0; K < 4; K++) {
+      Gt[I][K][0] = 0.0; Gt[I][K][1] = 0.0;
+      if (I < MT) load_tile(Gg, m, I, K, false, Gt[I][K][0], Gt[I][K][1]);
+    }
+  double C[10][2];
+#pragma unroll
+  for (int I = 0; I < 4; I++)
+#pragma unroll
+    for (int K = 0; K <= I; K++) {
+      load_tile(Qg, n, I, K, true, C[w_tile(I, K)][0], C[w_tile(I, K)][1]);
+      if (I == K && a.reg != 0.0) {
+        const int i = 8 * I + g;
+        if (i < n && i == 8 * K + 2 * q) C[w_tile(I, K)][0] += a.reg;
+        if (i < n && i == 8 * K + 2 * q + 1) C[w_tile(I, K)][1] += a.reg;
+      }
+    }
+  // ---- Q = L D L^T  (the "bordered row" of w_factor is row n of the identity padding here, or absent when n == 32)
+  s_rinv[lane] = 1.0;  // tile rows that are all padding are skipped by w_factor
+  __syncwarp();
+  const bool okQ = w_factor<4, NC>(C, s_rinv, s_u, n, L);
+  if (!okQ && lane == 0) atomicAdd(&a.ctl->q_fail, 1u);
+  __syncwarp();
+  double rv[4][2];  // reciprocal pivots of this lane's columns
+#pragma unroll
+  for (int K = 0; K < 4; K++) {
+    const double2 r = *reinterpret_cast<const double2*>(s_rinv + 8 * K + 2 * q);
+    rv[K][0] = r.x; rv[K][1] = r.y;
+  }
+  // ---- U = L^-T (upper tiles U[J][I], J <= I, stored at w_tile(I, J))
+  double U[10][2];
+#pragma unroll
+  for (int J = 0; J < 4; J++) w_transpose(C[w_tile(J, J)][0], C[w_tile(J, J)][1], U[w_tile(J, J)][0], U[w_tile(J, J)][1], L);
+#pragma unroll
+  for (int I = 1; I < 4; I++) {
+#pragma unroll
+    for (int J = 0; J < I; J++) {
+      double s0 = 0.0, s1 = 0.0;
+#pragma unroll
+      for (int K = J; K < I; K++)  // L_IK = X_IK D_K^-1
+        w_abt(s0, s1, U[w_tile(K, J)][0], U[w_tile(K, J)][1], C[w_tile(I, K)][0] * rv[K][0], C[w_tile(I, K)][1] * rv[K][1]);
+      double t0 = 0.0, t1 = 0.0;
+      w_abt(t0, t1, s0, s1, C[w_tile(I, I)][0], C[w_tile(I, I)][1]);
+      U[w_tile(I, J)][0] = -t0; U[w_tile(I, J)][1] = -t1;
+    }
+  }
+  // ---- Q^-1 = U D^-1 U^T: full 4 x 4 tiles (Qi[I][J], I >= J computed, I < J transposed)
+  double Qi[4][4][2];
+#pragma unroll
+  for (int I = 0; I < 4; I++)
+#pragma unroll
+    for (int J = 0; J <= I; J++) {
+      double c0 = 0.0, c1 = 0.0;
+#pragma unroll
+      for (int K = I; K < 4; K++)
+        w_abt(c0, c1, U[w_tile(K, I)][0] * rv[K][0], U[w_tile(K, I)][1] * rv[K][1], U[w_tile(K, J)][0], U[w_tile(K, J)][1]);
+      Qi[I][J][0] = c0; Qi[I][J][1] = c1;
+      if (J < I) w_transpose(c0, c1, Qi[J][I][0], Qi[J][I][1], L);
+    }
+  {
+    double* Qo = a.Qi + (size_t)prob * a.sQi;
+    const int ld = a.ldn;
+#pragma unroll
+    for (int I = 0; I < 4; I++)
+#pragma unroll
+      for (int J = 0; J < 4; J++) {
+        const int i = 8 * I + g, k = 8 * J + 2 * q;
+        if (i < n && k < n) Qo[(size_t)i * ld + k] = Qi[I][J][0];
+        if (i < n && k + 1 < n) Qo[(size_t)i * ld + k + 1] = Qi[I][J][1];
+      }
+  }
+  // ---- G Q^-1 and R = G Q^-1 G^T, one tile row at a time
+  double* Bo = a.BQi + (size_t)prob * a.sBQi;
+  double* Rf = a.R + (size_t)prob * a.sR;
+  const int ld = a.ldn;
+#pragma unroll
+  for (int I = 0; I < NTI; I++) {
+    if (I < MT) {  // uniform
+      double B[4][2];
+#pragma unroll
+      for (int J = 0; J < 4; J++) {
+        double c0 = 0.0, c1 = 0.0;
+#pragma unroll
+        for (int K = 0; K < 4; K++) w_abt(c0, c1, Gt[I][K][0], Gt[I][K][1], Qi[J][K][0], Qi[J][K][1]);
+        B[J][0] = c0; B[J][1] = c1;
+        const int i = 8 * I + g, k = 8 * J + 2 * q;
+        if (i < m && k < n) Bo[(size_t)i * ld + k] = c0;
+        if (i < m && k + 1 < n) Bo[(size_t)i * ld + k + 1] = c1;
+      }
+#pragma unroll
+      for (int K = 0; K <= I; K++) {
+        double c0 = 0.0, c1 = 0.0;
+#pragma unroll
+        for (int J = 0; J < 4; J++) w_abt(c0, c1, B[J][0], B[J][1], Gt[K][J][0], Gt[K][J][1]);
+        *reinterpret_cast<double2*>(Rf + (size_t)w_tile(I, K) * 64 + lane * 2) = make_double2(c0, c1);
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------
 // QPFunctionFn.backward (qpth/qp.py:129-183) with one warp per QP and the same building blocks: d = clamp(lam) /
 // clamp(slack), T = R + diag(1/d) factored in registers with the right-hand side G Q^-1 dl/dz riding as the
 // bordered row, one backward sweep, dx = -Q^-1 dl/dz - (G Q^-1)^T dlam, then the outer-product gradients written with
@@ -846,6 +1003,7 @@ __global__ void __launch_bounds__(32, 8) k_wres_backward(const KArgs<double> a, 
   if (lane < n) dp[lane] = sqx[lane];
 #pragma unroll
   for (int s = 0; s < RPL; s++) { const int i = s * 32 + lane; if (i < m) dh[i] = -sdz[i]; }
+  if (ga.dQ == nullptr) return;  // factored gradients (B200QP_FLAG_FACTORED_GRAD): dp, dh, zhat, lams are the factors
   double* dQ = ga.dQ + (size_t)prob * n * n;
   double* dG = ga.dG + (size_t)prob * m * n;
   if ((n & 1) == 0) {

@@ -51,6 +51,13 @@ extern "C" {
  * NaN at different iterations): forward then sets status[B200QP_ST_SPEC_FAIL] != 0, the outputs are NOT valid,
  * and the caller repeats the call with this flag (b200qp_solve_host* and the Python layer do so themselves). */
 #define B200QP_FLAG_EXACT 2
+/* Host-buffer entry points only (b200qp_solve_host*): return the gradients w.r.t. Q and G in FACTORED form.  The
+ * reference forms them as outer products of four vectors (qpth/qp.py:158-174): dQ = (dx z^T + z dx^T) / 2,
+ * dG = dlam z^T + lam dx^T with dx = dp, dlam = -dh, z = zhat, lam = lams -- all of which the call returns anyway.
+ * With this flag dQ and dG are neither written nor copied to the host (they may be NULL): the device->host
+ * traffic of a step drops from 23.5 KB to 2.2 KB per problem at nz = 30, nineq = 60, which is what bounds the
+ * pipelined host path (PCIe duplex).  The dense form stays the default contract. */
+#define B200QP_FLAG_FACTORED_GRAD 4
 
 #define B200QP_MAX_ITER_CAP 64
 #define B200QP_STATUS_DOUBLES 8
@@ -100,6 +107,27 @@ int b200qp_forward(const b200qp_problem_t* prob,
 #define B200QP_PHASE_BEGIN (-1001) /* zero the slots, pre-factorise, initial point              */
 #define B200QP_PHASE_END (-1002)   /* iteration count / worst residual -> status                */
 size_t b200qp_slot_offset(const b200qp_problem_t* prob);
+
+/* Caller-evaluated residual callbacks.  This fork of qpth evaluates cost_grad(x) (in place of Q x + p) and dyn_res(x)
+ * (in place of A x - b) at the top of every PDIPM iteration (qpth/solvers/pdipm/batch.py:93-102; its MPC callers pass
+ * the NON-linear dynamics residual, qpth/qp_wrapper.py:303-316, sl1qp_mpc.py:312-320).  Protocol, one launch per
+ * iteration like the phased mode above:
+ *   b200qp_forward_phase(BEGIN)
+ *   for it in 0..max_iter-1:
+ *     b200qp_forward_cb_step(it, x)        applies the step of iteration it-1 (nothing once the loop has terminated)
+ *                                          and writes the iterate x[nb][nz] the reference would hand to the callbacks
+ *     caller evaluates cg = cost_grad(x) [nb][nz] and / or ry = dyn_res(x) [nb][neq] on the same stream
+ *     b200qp_forward_phase_cb(it, ..., cg or NULL, ry or NULL)
+ *   b200qp_forward_phase(END)
+ * A NULL vector keeps the kernel's own Q x + p / A x - b.  The KKT solves, step rule, termination and backward are
+ * those of the plain call (the reference's are, too). */
+int b200qp_forward_cb_step(const b200qp_problem_t* prob, int it, void* x_out, void* workspace, b200qp_stream_t stream);
+int b200qp_forward_phase_cb(const b200qp_problem_t* prob, int phase,
+                            const void* Q, const void* p, const void* G, const void* h,
+                            const void* A, const void* b,
+                            void* zhat, void* lams, void* nus, void* slacks,
+                            void* workspace, double* status,
+                            const void* cost_grad_x, const void* dyn_res_x, b200qp_stream_t stream);
 int b200qp_forward_phase(const b200qp_problem_t* prob, int phase,
                          const void* Q, const void* p, const void* G, const void* h,
                          const void* A, const void* b,
@@ -142,13 +170,15 @@ int b200qp_solve_host(const b200qp_problem_t* prob,
                       void* dQ, void* dp, void* dG, void* dh, void* dA, void* db,
                       double* status);
 
-/* Pipelined form of b200qp_solve_host for back-to-back batches (serving): two slots, each with its
- * own device arena.  submit(slot, ...) enqueues H2D copies, the solve and the D2H copies and
- * returns; wait(slot) blocks until that job's results are in the caller's host buffers.  Inputs
- * of job k+1 travel while job k computes and job k's gradients travel back while job k+1
- * computes (three streams, PCIe full duplex).  A slot's host buffers must stay untouched between
- * submit and wait; submitting to a busy slot waits for it first.  Host buffers should be pinned
- * (pageable memory makes the copies synchronous). */
+/* Pipelined form of b200qp_solve_host for back-to-back batches (serving): B200QP_HOST_SLOTS slots
+ * (0 .. B200QP_HOST_SLOTS-1), each with its own device arena.  submit(slot, ...) enqueues H2D copies,
+ * the solve and the D2H copies and returns; wait(slot) blocks until that job's results are in the
+ * caller's host buffers.  Inputs of job k+1 travel while job k computes and job k-1's gradients travel
+ * back (three streams, PCIe full duplex): a job has three stages, so rotate over THREE slots to keep
+ * every stage busy (two slots leave the bus idle a third of the time).  A slot's host buffers must stay
+ * untouched between submit and wait; submitting to a busy slot waits for it first.  Host buffers should
+ * be pinned (pageable memory makes the copies synchronous). */
+#define B200QP_HOST_SLOTS 4
 int b200qp_solve_host_submit(int slot, const b200qp_problem_t* prob,
                              const void* Q, const void* p, const void* G, const void* h,
                              const void* A, const void* b, const void* dl_dzhat,

@@ -54,7 +54,6 @@ def test_al_mpc_matches_reference_golden(case, cuda_device):
             assert errs[key] <= RTOL64, (key, errs)
 
 
-@pytest.mark.parametrize("env", ["pendulum", "integrator", "pendulum_dx", "cartpole_dx"])
 @pytest.mark.parametrize("name", ["pendulum", "cartpole"])
 def test_envdx_against_reference_modules(name, cuda_device):
     """PendulumDx / CartpoleDx kernels against goldens produced by the reference's OWN modules
@@ -74,6 +73,7 @@ def test_envdx_against_reference_modules(name, cuda_device):
     assert bool((B.cpu()[clamped] == 0).all())
 
 
+@pytest.mark.parametrize("env", ["pendulum", "integrator", "pendulum_dx", "cartpole_dx"])
 def test_dynamics_step_and_jacobian(env, cuda_device):
     """b200dyn_step / b200dyn_jac against a torch restatement + autograd Jacobians on the CPU."""
     from b200qp import envs

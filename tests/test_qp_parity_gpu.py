@@ -206,7 +206,7 @@ def test_host_buffer_entry_point_matches_device_path(nb, cuda_device):
 
 
 def test_pipelined_host_entry_points(cuda_device):
-    """b200qp_solve_host_submit / _wait: two jobs in flight in the two slots return what the
+    """b200qp_solve_host_submit / _wait: three jobs in flight in three slots return what the
     synchronous call returns (different inputs per slot, pinned buffers)."""
     import ctypes
     from b200qp import _lib
@@ -217,7 +217,7 @@ def test_pipelined_host_entry_points(cuda_device):
     P = lambda t: ctypes.c_void_p(t.data_ptr())
     N0 = ctypes.c_void_p(0)
     jobs = []
-    for seed in (5, 6):
+    for seed in (5, 6, 7):
         Q, p, G, h, A, b = O.random_qp(nb, nz, m, 0, seed=seed)
         inp = {k: v.pin_memory() for k, v in dict(Q=Q, p=p, G=G, h=h).items()}
         out = {k: torch.empty(s, dtype=torch.float64).pin_memory() for k, s in dict(
@@ -233,7 +233,8 @@ def test_pipelined_host_entry_points(cuda_device):
 
     for slot, job in enumerate(jobs):
         assert call(L.b200qp_solve_host_submit, slot)(*job) == 0
-    assert L.b200qp_solve_host_wait(0) == 0 and L.b200qp_solve_host_wait(1) == 0
+    assert L.b200qp_solve_host_wait(0) == 0 and L.b200qp_solve_host_wait(1) == 0 and L.b200qp_solve_host_wait(2) == 0
+    assert L.b200qp_solve_host_wait(4) != 0  # B200QP_HOST_SLOTS = 4
     got = [{k: v.clone() for k, v in job[1].items()} for job in jobs]
     iters = [int(job[2][0]) for job in jobs]
     for i, job in enumerate(jobs):
@@ -243,6 +244,21 @@ def test_pipelined_host_entry_points(cuda_device):
         assert int(job[2][0]) == iters[i]
         for k in got[i]:
             assert torch.equal(got[i][k], job[1][k]), (i, k)
+    # B200QP_FLAG_FACTORED_GRAD: dQ / dG are not written; the four factors reproduce them (qpth/qp.py:158-174)
+    inp, out, st = jobs[0]
+    for v in out.values():
+        v.fill_(7.0)
+    prob.flags = 4
+    assert call(L.b200qp_solve_host)(inp, out, st) == 0
+    prob.flags = 0
+    assert bool((out["dQ"] == 7.0).all()) and bool((out["dG"] == 7.0).all())
+    for k in ("zhat", "lams", "slacks", "dp", "dh"):
+        assert torch.equal(out[k], got[0][k]), k
+    dx, dlam, z, lam = out["dp"], -out["dh"], out["zhat"], out["lams"]
+    dQ = 0.5 * (dx.unsqueeze(2) * z.unsqueeze(1) + z.unsqueeze(2) * dx.unsqueeze(1))
+    dG = dlam.unsqueeze(2) * z.unsqueeze(1) + lam.unsqueeze(2) * dx.unsqueeze(1)
+    assert (dQ - got[0]["dQ"]).abs().max() <= 1e-12 * got[0]["dQ"].abs().max()
+    assert (dG - got[0]["dG"]).abs().max() <= 1e-12 * got[0]["dG"].abs().max()
 
 
 @pytest.mark.parametrize("case", ["dense_nb16_nz10_m12_p4", "dense_nb32_nz30_m60_p0", "dense_nb8_nz15_m10_p10"])

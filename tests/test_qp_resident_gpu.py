@@ -135,7 +135,6 @@ def test_bench_batch_against_oracle(cuda_device, opts):
           a problem is max(1e-6, 10 x the change of the reference gradient under such a perturbation), and at most 0.01 %
           of the batch may need more than 1e-6."""
     from oracle import qp_oracle as O
-    torch.set_num_threads(max(1, torch.get_num_threads()))
     inp = rand_inputs(32768, 30, 60, 0)
     fwd = O.qp_forward(*(inp[k].clone() for k in "QpGhAb"))
     ones = torch.ones_like(fwd["zhat"])
