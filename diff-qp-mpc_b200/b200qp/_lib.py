@@ -18,10 +18,12 @@ ST_NITER, ST_BEST_MAX, ST_Q_FAIL, ST_AQA_FAIL, ST_LAUNCHES, ST_SPEC_FAIL, ST_NAN
 MAX_ITER_CAP = 64
 FLAG_DENSE = 1
 FLAG_EXACT = 2
+FLAG_FACTORED_GRAD = 4
+HOST_SLOTS = 4
 PHASE_ALL, PHASE_BEGIN, PHASE_END = -1000, -1001, -1002
 
 EXPORTS = (
-    "b200qp_workspace_bytes", "b200qp_prefactor", "b200qp_forward", "b200qp_forward_phase", "b200qp_slot_offset", "b200qp_backward", "b200qp_kkt_solve",
+    "b200qp_workspace_bytes", "b200qp_prefactor", "b200qp_forward", "b200qp_forward_phase", "b200qp_forward_phase_cb", "b200qp_forward_cb_step", "b200qp_slot_offset", "b200qp_backward", "b200qp_kkt_solve",
     "b200qp_solve_host", "b200qp_solve_host_submit", "b200qp_solve_host_wait", "b200qp_last_cuda_error", "b200qp_version", "b200qp_profile_enable",
     "b200qp_profile_read", "b200qp_set_option",
     "b200mpc_env_dims", "b200mpc_factor_elems", "b200mpc_scratch_bytes", "b200mpc_al_solve", "b200mpc_al_backward",
@@ -82,6 +84,10 @@ def lib():
     L.b200qp_forward.argtypes = [pp] + [vp] * 13
     L.b200qp_forward_phase.restype = ctypes.c_int
     L.b200qp_forward_phase.argtypes = [pp, ctypes.c_int] + [vp] * 13
+    L.b200qp_forward_phase_cb.restype = ctypes.c_int
+    L.b200qp_forward_phase_cb.argtypes = [pp, ctypes.c_int] + [vp] * 15
+    L.b200qp_forward_cb_step.restype = ctypes.c_int
+    L.b200qp_forward_cb_step.argtypes = [pp, ctypes.c_int] + [vp] * 3
     L.b200qp_slot_offset.restype = ctypes.c_size_t
     L.b200qp_slot_offset.argtypes = [pp]
     L.b200qp_backward.restype = ctypes.c_int

@@ -166,7 +166,12 @@ def QPFunction(eps=1e-12, verbose=0, notImprovedLim=3,
                 raise NotImplementedError("b200qp: only QPSolvers.PDIPM_BATCHED is implemented (CVXPY is a "
                                           "per-instance CPU solver outside the hot path)")
             plan = _Plan(Q_, p_, G_, h_, A_, b_, eps, notImprovedLim, maxIter)
-            _check_callbacks(plan, dyn_res, cost_grad)
+            cb_cg, cb_ry = _classify_callbacks(plan, dyn_res, cost_grad)
+            with_cb = cb_cg is not None or cb_ry is not None
+            if with_cb and exact_group is not None:
+                raise NotImplementedError("b200qp: non-canonical dyn_res / cost_grad callbacks together with process_group")
+            if with_cb:
+                plan.prob.flags |= _lib.FLAG_EXACT  # one launch per iteration, forward and backward on the same kernels
             if exact_group is not None:
                 # the sharded mode IS the one-launch-per-iteration route; the flag keeps the forward and the backward of this
                 # problem on the same kernels (bit-for-bit equal to the unsharded exact route)
@@ -182,6 +187,9 @@ def QPFunction(eps=1e-12, verbose=0, notImprovedLim=3,
             with torch.cuda.device(Q_.device):
                 if exact_group is not None:
                     _forward_exact_sharded(L, plan, (zhats, lams, nus, slacks), status, Q_.device, exact_group)
+                    rc = 0
+                elif with_cb:
+                    _forward_callbacks(L, plan, (zhats, lams, nus, slacks), status, Q_.device, cb_cg, cb_ry)
                     rc = 0
                 else:
                     rc = L.b200qp_forward(ctypes.byref(plan.prob), _ptr(plan.Q), _ptr(plan.p), _ptr(plan.G), _ptr(plan.h),
@@ -277,8 +285,9 @@ def DenseQPFunction(bsz=1, eps=1e-12, verbose=0, notImprovedLim=3, maxIter=20):
     of its get_step, backward with the best iterate's K without clamping -- but the 2 x LU of the
     (nz + 2 nineq + neq)^2 matrix per solve is replaced by the same Schur-complement kernels as
     QPFunction (b200qp_forward with B200QP_FLAG_DENSE), which solve the identical regularised system.
-    All six parameters are batched (as in the reference).  `dyn_res` / `cost_grad` must be the
-    canonical Ax - b / Qx + p (checked on a probe point)."""
+    All six parameters are batched (as in the reference).  `dyn_res` / `cost_grad` that are the canonical
+    Ax - b / Qx + p (checked on a probe point) stay inside the fused kernels; any other callback -- the reference's
+    MPC callers pass the non-linear dynamics residual -- is evaluated between launches (`_forward_callbacks`)."""
     info = {}
 
     class Solver(Function):
@@ -287,7 +296,7 @@ def DenseQPFunction(bsz=1, eps=1e-12, verbose=0, notImprovedLim=3, maxIter=20):
             if Q.dim() != 3 or G.dim() != 3 or A.dim() != 3:
                 raise RuntimeError("b200qp.DenseQPFunction: batched (3-D) Q, G, A are required, as in the reference")
             plan = _Plan(Q, p, G, h, A, b, eps, notImprovedLim, maxIter, flags=_lib.FLAG_DENSE, kkt_reg=DENSE_KKT_EPS)
-            _check_callbacks(plan, dyn_res, cost_grad)
+            cb_cg, cb_ry = _classify_callbacks(plan, dyn_res, cost_grad)
             L = _lib.lib()
             nb, nz, nineq, neq = plan.nBatch, plan.nz, plan.nineq, plan.neq
             opt = dict(dtype=Q.dtype, device=Q.device)
@@ -295,9 +304,13 @@ def DenseQPFunction(bsz=1, eps=1e-12, verbose=0, notImprovedLim=3, maxIter=20):
             nus = torch.empty(nb, neq, **opt)
             status = torch.empty(_lib.STATUS_DOUBLES, dtype=torch.float64, device=Q.device)
             with torch.cuda.device(Q.device):
-                rc = L.b200qp_forward(ctypes.byref(plan.prob), _ptr(plan.Q), _ptr(plan.p), _ptr(plan.G), _ptr(plan.h),
-                                      _ptr(plan.A), _ptr(plan.b), _ptr(zhats), _ptr(lams), _ptr(nus), _ptr(slacks),
-                                      _ptr(plan.workspace), _ptr(status), _stream(Q.device))
+                if cb_cg is not None or cb_ry is not None:
+                    _forward_callbacks(L, plan, (zhats, lams, nus, slacks), status, Q.device, cb_cg, cb_ry)
+                    rc = 0
+                else:
+                    rc = L.b200qp_forward(ctypes.byref(plan.prob), _ptr(plan.Q), _ptr(plan.p), _ptr(plan.G), _ptr(plan.h),
+                                          _ptr(plan.A), _ptr(plan.b), _ptr(zhats), _ptr(lams), _ptr(nus), _ptr(slacks),
+                                          _ptr(plan.workspace), _ptr(status), _stream(Q.device))
             if rc == -3:
                 raise NotImplementedError("b200qp.DenseQPFunction: this problem size is outside the fused kernels "
                                           "(nineq <= 128 and nz, neq + nineq <= 128)")
@@ -348,31 +361,56 @@ def DenseQPFunction(bsz=1, eps=1e-12, verbose=0, notImprovedLim=3, maxIter=20):
     return apply
 
 
-def _check_callbacks(plan, dyn_res, cost_grad):
-    """This fork evaluates `cost_grad(x)` in place of Qx+p and `dyn_res(x)` in place of Ax-b inside
-    the loop (qpth/solvers/pdipm/batch.py:93-102).  The fused kernels implement the canonical
-    linear forms, so a callback is accepted iff it IS that form (checked on a probe point)."""
+def _classify_callbacks(plan, dyn_res, cost_grad):
+    """This fork evaluates `cost_grad(x)` in place of Qx+p and `dyn_res(x)` in place of Ax-b at the top of every
+    iteration (qpth/solvers/pdipm/batch.py:93-102, batch_LU.py:88-97); its MPC callers pass the NON-linear dynamics
+    residual (qpth/qp_wrapper.py:303-316, sl1qp_mpc.py:312-320).  A callback that IS the canonical linear form
+    (checked on a probe point) stays inside the fused kernels -- including the resident several-iterations-per-launch
+    route; any other callback is evaluated by the caller between launches (`_forward_callbacks`).
+    Returns (cost_grad or None, dyn_res or None): the callbacks that must really be called."""
     if dyn_res is None and cost_grad is None:
-        return
+        return None, None
     nb, nz = plan.nBatch, plan.nz
     g = torch.Generator(device="cpu").manual_seed(1234)
     x = torch.randn(nb, nz, generator=g, dtype=torch.float64).to(device=plan.Q.device, dtype=plan.Q.dtype)
     tol = 1e-9 if plan.Q.dtype == torch.float64 else 1e-4
 
     def close(a, b):
-        return torch.allclose(a, b, rtol=tol, atol=tol * (1 + float(b.abs().max()) if b.numel() else 1.0))
+        return a.shape == b.shape and torch.allclose(a, b, rtol=tol, atol=tol * (1 + float(b.abs().max()) if b.numel() else 1.0))
 
-    if cost_grad is not None:
-        Q = plan.Q if not plan.Q_e else plan.Q.unsqueeze(0).expand(nb, nz, nz)
-        p = plan.p if not plan.p_e else plan.p.unsqueeze(0).expand(nb, nz)
-        want = torch.bmm(Q, x.unsqueeze(2)).squeeze(2) + p
-        if not close(cost_grad(x), want):
-            raise NotImplementedError("b200qp: cost_grad callbacks other than x -> Qx+p are not supported by the "
-                                      "fused kernels")
-    if dyn_res is not None and plan.neq > 0:
-        A = plan.A if not plan.A_e else plan.A.unsqueeze(0).expand(nb, plan.neq, nz)
-        b = plan.b if not plan.b_e else plan.b.unsqueeze(0).expand(nb, plan.neq)
-        want = torch.bmm(A, x.unsqueeze(2)).squeeze(2) - b
-        if not close(dyn_res(x), want):
-            raise NotImplementedError("b200qp: dyn_res callbacks other than x -> Ax-b are not supported by the "
-                                      "fused kernels")
+    keep_cg, keep_ry = None, None
+    with torch.no_grad():
+        if cost_grad is not None:
+            Q = plan.Q if not plan.Q_e else plan.Q.unsqueeze(0).expand(nb, nz, nz)
+            p = plan.p if not plan.p_e else plan.p.unsqueeze(0).expand(nb, nz)
+            want = torch.bmm(Q, x.unsqueeze(2)).squeeze(2) + p
+            if not close(cost_grad(x), want):
+                keep_cg = cost_grad
+        if dyn_res is not None and plan.neq > 0:
+            A = plan.A if not plan.A_e else plan.A.unsqueeze(0).expand(nb, plan.neq, nz)
+            b = plan.b if not plan.b_e else plan.b.unsqueeze(0).expand(nb, plan.neq)
+            want = torch.bmm(A, x.unsqueeze(2)).squeeze(2) - b
+            if not close(dyn_res(x), want):
+                keep_ry = dyn_res
+    return keep_cg, keep_ry
+
+
+def _forward_callbacks(L, plan, bufs, status, device, cost_grad, dyn_res):
+    """The forward with caller-evaluated residual callbacks (include/b200qp.h, b200qp_forward_cb_step /
+    b200qp_forward_phase_cb): one launch per iteration; between the step of iteration it-1 and the body of iteration it
+    the iterate x is handed to `cost_grad` / `dyn_res` on the current stream, exactly where the reference calls them."""
+    base = [_ptr(plan.Q), _ptr(plan.p), _ptr(plan.G), _ptr(plan.h), _ptr(plan.A), _ptr(plan.b)] + [_ptr(t) for t in bufs] + \
+           [_ptr(plan.workspace), _ptr(status)]
+    st = _stream(device)
+    pr = ctypes.byref(plan.prob)
+    _lib.check(L.b200qp_forward_phase(pr, _lib.PHASE_BEGIN, *base, st), "b200qp_forward_phase(begin)")
+    nb, nz, neq = plan.nBatch, plan.nz, plan.neq
+    dt = plan.Q.dtype
+    x = torch.empty(nb, nz, dtype=dt, device=device)
+    for it in range(plan.prob.max_iter):
+        _lib.check(L.b200qp_forward_cb_step(pr, it, _ptr(x), _ptr(plan.workspace), st), "b200qp_forward_cb_step")
+        with torch.no_grad():
+            cg = cost_grad(x).to(dt).reshape(nb, nz).contiguous() if cost_grad is not None else None
+            ry = dyn_res(x).to(dt).reshape(nb, neq).contiguous() if dyn_res is not None else None
+        _lib.check(L.b200qp_forward_phase_cb(pr, it, *base, _ptr(cg), _ptr(ry), st), "b200qp_forward_phase_cb")
+    _lib.check(L.b200qp_forward_phase(pr, _lib.PHASE_END, *base, st), "b200qp_forward_phase(end)")

@@ -392,9 +392,9 @@ def _dense_step(v, dv):
     return a.min(1)[0].squeeze()
 
 
-def dense_forward(Q, p, G, h, A, b, eps=1e-12, notImprovedLim=3, maxIter=20):
-    """DenseQPFunction forward with the canonical residual callbacks (dyn_res = Ax - b,
-    cost_grad = None): batch_LU.forward (batch_LU.py:29-201).  Returns best iterates and the best K."""
+def dense_forward(Q, p, G, h, A, b, eps=1e-12, notImprovedLim=3, maxIter=20, cost_grad=None, dyn_res=None):
+    """DenseQPFunction forward: batch_LU.forward (batch_LU.py:29-201).  `dyn_res` / `cost_grad` are this fork's
+    residual callbacks (batch_LU.py:88-97); None = the canonical Ax - b / Qx + p.  Returns best iterates and the best K."""
     nb, m, n = G.shape
     neq = A.shape[1]
     K = dense_kkt_matrix(Q, G, A)
@@ -419,11 +419,15 @@ def dense_forward(Q, p, G, h, A, b, eps=1e-12, notImprovedLim=3, maxIter=20):
     GT, AT = G.transpose(1, 2), A.transpose(1, 2)
     for i in range(maxIter):
         n_iter = i + 1
-        rx = ((AT.bmm(y.unsqueeze(-1)).squeeze(-1) if neq > 0 else 0.) + GT.bmm(z.unsqueeze(-1)).squeeze(-1)
-              + Q.bmm(x.unsqueeze(-1)).squeeze(-1) + p)
+        if cost_grad is None:
+            rx = ((AT.bmm(y.unsqueeze(-1)).squeeze(-1) if neq > 0 else 0.) + GT.bmm(z.unsqueeze(-1)).squeeze(-1)
+                  + Q.bmm(x.unsqueeze(-1)).squeeze(-1) + p)
+        else:
+            rx = ((AT.bmm(y.unsqueeze(-1)).squeeze(-1) if neq > 0 else 0.) + GT.bmm(z.unsqueeze(-1)).squeeze(-1)
+                  + cost_grad(x))
         rs = s * z
         rz = G.bmm(x.unsqueeze(-1)).squeeze(-1) + s - h
-        ry = A.bmm(x.unsqueeze(-1)).squeeze(-1) - b
+        ry = dyn_res(x) if dyn_res is not None else A.bmm(x.unsqueeze(-1)).squeeze(-1) - b
         mu = torch.abs((s * z).sum(1).squeeze() / m)
         z_resid = torch.norm(rz, 2, 1).squeeze()
         y_resid = torch.norm(ry, 2, 1).squeeze() if neq > 0 else 0

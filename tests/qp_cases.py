@@ -119,3 +119,29 @@ def compare_with_golden(case, out, rtol):
         else:
             worst[k] = gate(v, head, rtol, f"{case}:{k}")
     return worst
+
+
+# ---- this fork's residual callbacks (qpth/solvers/pdipm/batch.py:93-102) with NON-linear functions ----------------
+# name -> (nb, nz, nineq, neq, seed, dense)
+CB_CASES = {
+    "cb_qp_nb16_nz12_m10_p4": (16, 12, 10, 4, 21, False),
+    "cb_qp_nb32_nz30_m60_p6": (32, 30, 60, 6, 22, False),      # fast-path kernels (nineq <= 64)
+    "cb_qp_nb8_nz40_m96_p8": (8, 40, 96, 8, 23, False),        # generic / blocked kernels (nineq > 64)
+    "cb_dense_nb16_nz15_m10_p10": (16, 15, 10, 10, 24, True),  # the shape of qp_wrapper.MPC's pendulum QP (T = 5)
+    "cb_dense_nb8_nz30_m24_p8": (8, 30, 24, 8, 25, True),
+}
+
+
+def nonlinear_callbacks(Q, p, A, b):
+    """cost_grad(x) = Qx + p + 0.05 tanh(x)  (the gradient of a non-quadratic convex cost);
+    dyn_res(x) = Ax - b + 0.1 sin(x[:, :neq])  (a non-linear equality residual, like the dynamics residual the
+    reference's MPC callers pass).  Same expressions on whatever device / dtype the tensors live on."""
+    neq = A.shape[-2]
+
+    def cost_grad(x):
+        return torch.bmm(Q, x.unsqueeze(-1)).squeeze(-1) + p + 0.05 * torch.tanh(x)
+
+    def dyn_res(x):
+        return torch.bmm(A, x.unsqueeze(-1)).squeeze(-1) - b + 0.1 * torch.sin(x[:, :neq])
+
+    return cost_grad, dyn_res

@@ -84,3 +84,29 @@ def test_dense_oracle_matches_reference_golden(case):
     gate(fwd["zhat"], g["zhat"], 1e-9, "zhat")
     for k in ("dQ", "dp", "dG", "dh", "dA", "db"):
         gate(gr[k], g[k], 1e-9, k)
+
+
+def test_oracle_reproduces_callback_goldens():
+    """The oracle with this fork's NON-linear residual callbacks against the goldens of the real reference
+    (oracle/gen_golden_callbacks.py): forward solution and all gradients."""
+    import os
+    import numpy as np
+    import torch
+    from oracle import qp_oracle as O
+    from tests.qp_cases import CB_CASES, GOLDEN_DIR, nonlinear_callbacks
+    for case in ("cb_qp_nb16_nz12_m10_p4", "cb_dense_nb16_nz15_m10_p10"):
+        nb, nz, m, p, seed, dense = CB_CASES[case]
+        Q, pp, G, h, A, b = O.random_qp(nb, nz, m, p, seed=seed, well_conditioned=True)
+        g = dict(np.load(os.path.join(GOLDEN_DIR, f"{case}.npz")))
+        cost_grad, dyn_res = nonlinear_callbacks(Q, pp, A, b)
+        ones = torch.ones(nb, nz, dtype=torch.float64)
+        if dense:
+            fwd = O.dense_forward(Q.clone(), pp.clone(), G.clone(), h.clone(), A.clone(), b.clone(), dyn_res=dyn_res)
+            gr = O.dense_backward(fwd, ones)
+        else:
+            fwd = O.qp_forward(Q.clone(), pp.clone(), G.clone(), h.clone(), A.clone(), b.clone(), cost_grad=cost_grad, dyn_res=dyn_res)
+            gr = O.qp_backward(fwd, Q, pp, G, h, A, b, ones)
+        assert fwd["n_iter"] == int(g["n_iter"])
+        assert torch.equal(fwd["zhat"], torch.tensor(g["zhat"]))
+        for k in ("dQ", "dp", "dG", "dh", "dA", "db"):
+            assert (gr[k] - torch.tensor(g[k])).abs().max() <= 1e-12 * max(1.0, float(np.abs(g[k]).max())), k

@@ -375,3 +375,48 @@ def test_alternative_kernel_routes_golden(opt, case, cuda_device):
     worst = compare_with_golden(case, out, rtol=1e-6)
     print(opt, case, "n_iter", info["n_iter"], "ref", int(g["n_iter"]), {k: f"{v:.1e}" for k, v in worst.items()})
     check_iterations(case, info["n_iter"], int(g["n_iter"]), route=opt)
+
+
+@pytest.mark.parametrize("case", list(__import__("tests.qp_cases", fromlist=["CB_CASES"]).CB_CASES))
+def test_nonlinear_callbacks_golden(case, cuda_device):
+    """This fork's residual callbacks with NON-linear functions (qpth/solvers/pdipm/batch.py:93-102, batch_LU.py:88-97):
+    QPFunction (8-argument form) and DenseQPFunction against goldens of the real reference run with the same callbacks
+    (oracle/gen_golden_callbacks.py).  The callbacks are evaluated between the launches of b200qp_forward_cb_step /
+    b200qp_forward_phase_cb, on the device."""
+    from oracle import qp_oracle as O
+    from tests.qp_cases import CB_CASES, GOLDEN_DIR, nonlinear_callbacks
+    from b200qp.qp import DenseQPFunction, QPFunction
+    import os
+    nb, nz, m, p, seed, dense = CB_CASES[case]
+    Q, pp, G, h, A, b = O.random_qp(nb, nz, m, p, seed=seed, well_conditioned=True)
+    g = dict(np.load(os.path.join(GOLDEN_DIR, f"{case}.npz")))
+    t = [v.to(cuda_device).requires_grad_(True) for v in (Q, pp, G, h, A, b)]
+    cost_grad, dyn_res = nonlinear_callbacks(t[0].detach(), t[1].detach(), t[4].detach(), t[5].detach())
+    calls = {"cg": 0, "ry": 0}
+
+    def cg(x):
+        calls["cg"] += 1
+        return cost_grad(x)
+
+    def ry(x):
+        calls["ry"] += 1
+        return dyn_res(x)
+
+    if dense:
+        fn = DenseQPFunction(verbose=-1)
+        z = fn(*t, ry)
+    else:
+        fn = QPFunction(verbose=-1, check_Q_spd=False)
+        z = fn(*t, ry, cg)
+    z.backward(torch.ones_like(z))
+    assert calls["ry"] >= int(g["n_iter"]) and (dense or calls["cg"] >= int(g["n_iter"]))
+    print(case, "n_iter", fn.info["n_iter"], "reference", int(g["n_iter"]))
+    gate(z.detach().cpu(), torch.tensor(g["zhat"]), 1e-6, "zhat")
+    for k, ten in zip(("dQ", "dp", "dG", "dh", "dA", "db"), t):
+        gate(ten.grad.cpu(), torch.tensor(g[k]), 1e-6, k)
+    assert fn.info["n_iter"] == int(g["n_iter"])
+    # a callback that IS the canonical form stays inside the fused kernels (no call per iteration)
+    calls["ry"] = 0
+    lin = lambda x: (calls.__setitem__("ry", calls["ry"] + 1), torch.bmm(t[4].detach(), x.unsqueeze(-1)).squeeze(-1) - t[5].detach())[1]
+    z2 = (DenseQPFunction(verbose=-1) if dense else QPFunction(verbose=-1, check_Q_spd=False))(*[v.detach() for v in t], lin)
+    assert calls["ry"] == 1 and torch.isfinite(z2).all()
