@@ -5,10 +5,11 @@ fused AL-MPC kernels.  Same constructor (`args`, `env`) and call surface:
     mpc.reinitialize(x, mask)
     x_nom, u_nom = mpc(x0, xu_ref, x_ref, u_ref)       # (bsz,T,nx) (bsz,T,nu) float32
 
-Only `args.solver_type == "al"` is implemented (the reference's "ip" branch goes through
-qp_wrapper / DenseQPFunction).  `env.dynamics` / `env.dynamics_derivatives` may
-be the reference's own (jit-scripted) modules or b200qp.envs classes; they select the fused
-dynamics by class name.
+`args.solver_type == "al"` -> b200qp.AL_mpc.MPC (fused augmented-Lagrangian kernels); anything else ("ip") ->
+b200qp.qp_wrapper.MPC (SQP on DenseQPFunction, deqmpc/policies.py:622-639).  `env.dynamics` /
+`env.dynamics_derivatives` may be the reference's own (jit-scripted) modules or b200qp.envs / b200qp.my_envs
+classes; they select the fused dynamics by class name.  (The reference's own "ip" branch raises in
+qp_wrapper.py:487 -- `.view` on the transposed `u_init` it passes; here the tensor is made contiguous.)
 """
 from __future__ import annotations
 
@@ -16,6 +17,7 @@ import torch
 
 from . import AL_mpc as al_mpc
 from . import al_utils
+from . import qp_wrapper as ip_mpc
 
 
 class Tracking_MPC(torch.nn.Module):
@@ -41,21 +43,33 @@ class Tracking_MPC(torch.nn.Module):
         self.u_init = torch.randn(self.bsz, self.T, self.nu, dtype=self.dtype, device=self.device)
         self.x_init = None
         self.single_qp_solve = self.qp_iter == 1
-        if args.solver_type != "al":
-            raise NotImplementedError("b200qp Tracking_MPC: only solver_type='al' is implemented")
-        self.ctrl = al_mpc.MPC(self.nx, self.nu, self.T, u_lower=self.u_lower, u_upper=self.u_upper,
-                               exit_unconverged=False, eps=1e-5, n_batch=self.bsz, backprop=False, verbose=0,
-                               u_init=self.u_init, solver_type="dense", dtype=self.dtype)
+        if args.solver_type == "al":
+            self.ctrl = al_mpc.MPC(self.nx, self.nu, self.T, u_lower=self.u_lower, u_upper=self.u_upper,
+                                   exit_unconverged=False, eps=1e-5, n_batch=self.bsz, backprop=False, verbose=0,
+                                   u_init=self.u_init, solver_type="dense", dtype=self.dtype)
+        else:  # deqmpc/policies.py:622-639
+            self.ctrl = ip_mpc.MPC(self.nx, self.nu, self.T, u_lower=self.u_lower.to(self.dtype), u_upper=self.u_upper.to(self.dtype),
+                                   qp_iter=self.qp_iter, exit_unconverged=False, eps=1e-5, n_batch=self.bsz, backprop=False,
+                                   verbose=0, u_init=self.u_init.transpose(0, 1).contiguous(),
+                                   grad_method=ip_mpc.GradMethods.ANALYTIC, solver_type="dense",
+                                   single_qp_solve=self.single_qp_solve)
 
     def forward(self, x0, xu_ref, x_ref, u_ref):
         """deqmpc/policies.py:641-664"""
-        xu_ref = torch.cat([x_ref, u_ref], dim=-1)
-        if self.x_init is None:
-            self.x_init = self.ctrl.x_init = x_ref
-            self.u_init = self.ctrl.u_init = u_ref
-        self.compute_p(xu_ref)
-        cost = al_utils.QuadCost(self.Q, self.p)
-        nominal_states, nominal_actions = self.ctrl(x0, cost, self.dyn, self.dyn_jac)
+        if self.args.solver_type == "al":
+            xu_ref = torch.cat([x_ref, u_ref], dim=-1)
+            if self.x_init is None:
+                self.x_init = self.ctrl.x_init = x_ref
+                self.u_init = self.ctrl.u_init = u_ref
+            self.compute_p(xu_ref)
+            cost = al_utils.QuadCost(self.Q, self.p)
+            nominal_states, nominal_actions = self.ctrl(x0, cost, self.dyn, self.dyn_jac)
+        else:
+            self.compute_p(xu_ref)
+            cost = ip_mpc.QuadCost(self.Q.transpose(0, 1), self.p.transpose(0, 1))
+            self.ctrl.u_init = self.u_init.transpose(0, 1).contiguous()
+            nominal_states, nominal_actions = self.ctrl(x0, cost, self.dyn, self.dyn_jac)
+            nominal_states, nominal_actions = nominal_states.transpose(0, 1), nominal_actions.transpose(0, 1)
         self.u_init = nominal_actions.clone().detach()
         return nominal_states, nominal_actions
 
@@ -68,4 +82,5 @@ class Tracking_MPC(torch.nn.Module):
         """deqmpc/policies.py:681-686"""
         self.u_init = torch.randn(self.bsz, self.T, self.nu, dtype=x.dtype, device=x.device)
         self.x_init = None
-        self.ctrl.reinitialize(x, mask)
+        if hasattr(self.ctrl, "reinitialize"):  # qp_wrapper.MPC keeps no solver state (the reference calls it regardless and raises)
+            self.ctrl.reinitialize(x, mask)

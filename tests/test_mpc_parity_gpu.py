@@ -351,3 +351,76 @@ def test_al_mpc_myenvs_golden(case, cuda_device):
         assert errs["x"] <= RTOL32 and errs["u"] <= RTOL32, errs
         for key in ("lam", "rho", "dC", "dc"):
             assert errs[key] <= RTOL64, (key, errs)
+
+
+@pytest.mark.parametrize("case", ["ipmpc_pendulum1l_B8_T5_single", "ipmpc_pendulum1l_B8_T5_sqp3",
+                                  "ipmpc_cartpole1l_B4_T10_single", "ipmpc_cartpole1l_B4_T10_sqp3"])
+def test_ip_mpc_matches_reference_golden(case, cuda_device):
+    """b200qp.qp_wrapper.MPC (the interior-point MPC: SQP loop, DenseQPFunction with the NON-linear dynamics residual as
+    its dyn_res callback, line search) against goldens of the real qpth.qp_wrapper.MPC on the reference's my_envs
+    dynamics (oracle/gen_golden_ipmpc.py): nominal states / controls and the gradients w.r.t. the cost."""
+    from b200qp import qp_wrapper as ip_mpc
+    g = dict(np.load(os.path.join(GOLDEN, f"{case}.npz")))
+    name = case.split("_")[1]
+    d = _my_dynamics(name, float(g["dt"]), cuda_device)
+    T, B, nu = g["u_init"].shape
+    nx = g["x0"].shape[1]
+    qp_iter = 1 if case.endswith("single") else 3
+    um = float(g["umax"])
+    dev = cuda_device
+    ctrl = ip_mpc.MPC(nx, nu, T, u_lower=-um * torch.ones(nu, dtype=torch.float64, device=dev),
+                      u_upper=um * torch.ones(nu, dtype=torch.float64, device=dev), qp_iter=qp_iter, exit_unconverged=False,
+                      eps=1e-5, n_batch=B, backprop=False, verbose=0, u_init=torch.tensor(g["u_init"]).to(dev),
+                      grad_method=ip_mpc.GradMethods.ANALYTIC, solver_type="dense", single_qp_solve=(qp_iter == 1))
+    C = torch.diag(torch.tensor(g["Cd"])).repeat(T, B, 1, 1).to(dev).requires_grad_(True)
+    c = torch.tensor(g["c"]).to(dev).requires_grad_(True)
+    xs, us = ctrl(torch.tensor(g["x0"]).to(dev), ip_mpc.QuadCost(C, c), d, d.dynamics_derivatives)
+    (xs.sum() + 2 * us.sum()).backward()
+    errs = {k: rel(a.detach().cpu(), torch.tensor(g[n])) for k, a, n in (("x", xs, "out_x"), ("u", us, "out_u"))}
+    # Gradients.  The outputs are x + alpha (x_hat - x) with alpha the step of the LAST line search (qp_wrapper.py:399-401),
+    # so every gradient is alpha_j times the adjoint of the last QP.  In SQP mode that line search runs at a converged
+    # point where `cost_new < cost` is rounding noise, and alpha_j is an arbitrary power of linesearch_decay in the
+    # reference as here (oracle/gen_golden_ipmpc.py records it): compare gradient / alpha, per problem.
+    a_ref, a_ours = torch.tensor(g["alpha"]), ctrl.info["alpha"].cpu()
+    if qp_iter == 1:
+        assert torch.equal(a_ref, a_ours), "single-QP mode: the line search starts far from convergence, alpha must agree"
+    for k, a, n in (("dC", C.grad, "dC"), ("dc", c.grad, "dc")):
+        ours = a.detach().cpu().transpose(0, 1).reshape(B, -1) / a_ours[:, None]
+        ref = torch.tensor(g[n]).transpose(0, 1).reshape(B, -1) / a_ref[:, None]
+        errs[k] = float(((ours - ref).norm(dim=1) / (ref.norm(dim=1) + ref.norm(dim=1).median())).max())
+    print(case, "QP iterations", ctrl.info["qp_iters"], {k: f"{v:.1e}" for k, v in errs.items()}, "alpha ours", a_ours.tolist(),
+          "reference", a_ref.tolist())
+    for k, v in errs.items():
+        assert v <= RTOL64, (k, errs)
+
+
+def test_tracking_mpc_ip_branch(cuda_device):
+    """Tracking_MPC(solver_type='ip') (deqmpc/policies.py:622-639, 649-663) drives b200qp.qp_wrapper.MPC.  The reference's
+    own 'ip' branch raises before it reaches the solver (qp_wrapper.py:487, `.view` on the transposed u_init), so there is
+    no golden: the shim is checked against a direct qp_wrapper.MPC call with the cost the reference would build
+    (p = -Q x_ref), which is itself golden-tested above."""
+    import types
+    from b200qp import my_envs, policies, qp_wrapper as ip_mpc
+    dev = cuda_device
+    kw = dict(dtype=torch.float64, device=dev)
+    env = my_envs.PendulumEnv(nx=2, dt=0.05, kwargs=kw)
+    B, T = 8, 5
+    args = types.SimpleNamespace(T=T, bsz=B, Q=torch.tensor([1.0, 1.0], dtype=torch.float64), R=torch.tensor([1e-2], dtype=torch.float64), dtype="double", solver_type="ip",
+                                 qp_iter=1, eps=1e-2, warm_start=True, device=dev)
+    torch.manual_seed(0)
+    mpc = policies.Tracking_MPC(args, env)
+    u_init = mpc.u_init.clone()
+    x0 = torch.rand(B, 2, **kw) - 0.5
+    x_ref, u_ref = (0.3 * torch.randn(B, T, 2, **kw)).requires_grad_(True), (0.3 * torch.randn(B, T, 1, **kw)).requires_grad_(True)
+    xs, us = mpc(x0, torch.cat([x_ref, u_ref], -1), x_ref, u_ref)
+    assert xs.shape == (B, T, 2) and us.shape == (B, T, 1)
+    (xs.sum() + us.sum()).backward()
+    assert torch.isfinite(x_ref.grad).all() and x_ref.grad.abs().sum() > 0
+    ctrl = ip_mpc.MPC(2, 1, T, u_lower=mpc.u_lower.double(), u_upper=mpc.u_upper.double(), qp_iter=1, exit_unconverged=False, eps=1e-5,
+                      n_batch=B, backprop=False, verbose=0, u_init=u_init.transpose(0, 1).contiguous(),
+                      grad_method=ip_mpc.GradMethods.ANALYTIC, solver_type="dense", single_qp_solve=True)
+    Q = torch.diag(torch.tensor([1.0, 1.0, 1e-2], **kw)).repeat(T, B, 1, 1)
+    p = -(torch.tensor([1.0, 1.0, 1e-2], **kw) * torch.cat([x_ref, u_ref], -1).detach()).transpose(0, 1)
+    xd, ud = ctrl(x0, ip_mpc.QuadCost(Q, p), env.dynamics, env.dynamics_derivatives)
+    assert torch.equal(xd.transpose(0, 1), xs.detach()) and torch.equal(ud.transpose(0, 1), us.detach())
+    assert torch.equal(mpc.u_init, us.detach())
