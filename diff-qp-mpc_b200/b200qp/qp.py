@@ -166,6 +166,16 @@ def QPFunction(eps=1e-12, verbose=0, notImprovedLim=3,
                 raise NotImplementedError("b200qp: only QPSolvers.PDIPM_BATCHED is implemented (CVXPY is a "
                                           "per-instance CPU solver outside the hot path)")
             plan = _Plan(Q_, p_, G_, h_, A_, b_, eps, notImprovedLim, maxIter)
+            if check_Q_spd:
+                # qpth/qp.py:82-86 raises when some eigenvalue of Q has a non-positive real part.  For a symmetric Q that
+                # is exactly "the LDL^T of the pre-factorisation meets a non-positive pivot" (checked below from the
+                # status block, no extra work).  A NON-symmetric Q can have positive pivots and still fail the
+                # reference's test, so it gets the reference's own criterion (batched eigvals on the device).
+                Qc = plan.Q
+                if not torch.equal(Qc, Qc.transpose(-1, -2)):
+                    ev = torch.linalg.eigvals(Qc)
+                    if not bool(torch.all(ev.real > 0)):
+                        raise RuntimeError('Q is not SPD.')
             cb_cg, cb_ry = _classify_callbacks(plan, dyn_res, cost_grad)
             with_cb = cb_cg is not None or cb_ry is not None
             if with_cb and exact_group is not None:

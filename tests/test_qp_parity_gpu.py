@@ -420,3 +420,30 @@ def test_nonlinear_callbacks_golden(case, cuda_device):
     lin = lambda x: (calls.__setitem__("ry", calls["ry"] + 1), torch.bmm(t[4].detach(), x.unsqueeze(-1)).squeeze(-1) - t[5].detach())[1]
     z2 = (DenseQPFunction(verbose=-1) if dense else QPFunction(verbose=-1, check_Q_spd=False))(*[v.detach() for v in t], lin)
     assert calls["ry"] == 1 and torch.isfinite(z2).all()
+
+
+def test_check_Q_spd_matches_reference_criterion(cuda_device):
+    """qpth/qp.py:82-86: `check_Q_spd=True` raises 'Q is not SPD.' when some eigenvalue of Q has a non-positive real part.
+    Symmetric indefinite Q: caught by the pivots of the pre-factorisation.  NON-symmetric Q whose leading pivots are all
+    positive but which has a negative eigenvalue: caught by the reference's own criterion (eigvals); a non-symmetric Q
+    with eigenvalues in the right half plane passes, as in the reference."""
+    from oracle import qp_oracle as O
+    from b200qp.qp import QPFunction
+    Q, p, G, h, A, b = O.random_qp(4, 6, 5, 0, seed=3)
+    t = [v.to(cuda_device) for v in (Q, p, G, h, A, b)]
+    QPFunction(verbose=-1, check_Q_spd=True)(*t)                     # SPD: fine
+    Qi = t[0].clone(); Qi[1] = -Qi[1]                                  # symmetric, negative definite
+    with pytest.raises(RuntimeError, match="Q is not SPD"):
+        QPFunction(verbose=-1, check_Q_spd=True)(Qi, *t[1:])
+    # [[1, 4], [1, 1]] block: pivots 1, -3?  use [[1, -4], [-1, 1]]... pivots 1 and 1 - 4 = -3; instead a matrix with positive
+    # LU pivots and a negative eigenvalue: [[1, 3], [3, 10]] is SPD, so take the non-symmetric [[1, -3], [3, -8.9]]:
+    # pivots 1 and -8.9 + 9 = 0.1 > 0, eigenvalues approx -0.01 and -7.9
+    Qn = torch.eye(6, dtype=torch.float64, device=cuda_device).repeat(4, 1, 1)
+    Qn[:, 0, 0], Qn[:, 0, 1], Qn[:, 1, 0], Qn[:, 1, 1] = 1.0, -3.0, 3.0, -8.9
+    assert bool((torch.linalg.eigvals(Qn[0]).real <= 0).any())
+    with pytest.raises(RuntimeError, match="Q is not SPD"):
+        QPFunction(verbose=-1, check_Q_spd=True)(Qn, *t[1:])
+    Qr = torch.eye(6, dtype=torch.float64, device=cuda_device).repeat(4, 1, 1)
+    Qr[:, 0, 1], Qr[:, 1, 0] = 0.5, -0.5                              # non-symmetric, eigenvalues 1 +- 0.5i
+    z = QPFunction(verbose=-1, check_Q_spd=True)(Qr, *t[1:])
+    assert torch.isfinite(z).all()
