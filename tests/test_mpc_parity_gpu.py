@@ -424,3 +424,95 @@ def test_tracking_mpc_ip_branch(cuda_device):
     xd, ud = ctrl(x0, ip_mpc.QuadCost(Q, p), env.dynamics, env.dynamics_derivatives)
     assert torch.equal(xd.transpose(0, 1), xs.detach()) and torch.equal(ud.transpose(0, 1), us.detach())
     assert torch.equal(mpc.u_init, us.detach())
+
+
+def _policy_setup(dev, B=8, T=5):
+    import types
+    from b200qp import envs, policies
+
+    class _Spaces:
+        def __init__(self, low, high):
+            self.low, self.high = low, high
+
+    class IntegratorEnv:  # deqmpc/envs.py:246-268
+        def __init__(self):
+            self.dynamics, self.dynamics_derivatives = envs.IntegratorDynamics(), envs.IntegratorDynamics_jac()
+            self.nx, self.nu, self.nq, self.dt = 2, 1, 1, 0.1
+            self.action_space = _Spaces(-np.full(1, 2.0), np.full(1, 2.0))
+            self.Qlqr, self.Rlqr = torch.Tensor([10.0, 1.00]), torch.Tensor([0.01])
+
+    env = IntegratorEnv()
+    args = types.SimpleNamespace(T=T, bsz=B, dtype="double", solver_type="al", nq=1, hdim=128, layer_type="mlp", deq_out_type=1,
+                                 policy_out_type=1, kernel_width=3, pooling="mean", deq_iter=6, qp_iter=1, eps=1e-2, warm_start=True,
+                                 device=dev, deq=True, en_qp_solve=True, Q=env.Qlqr, R=env.Rlqr)
+    return policies, env, args
+
+
+def test_deqmpc_policy_matches_reference_golden(cuda_device):
+    """DEQMPCPolicy (deqmpc/policies.py:426-529: six rounds of DEQLayer -> Tracking_MPC, the run.sh configuration on the
+    integrator) with the reference's own weights against the reference's trajectories of every DEQ iteration, its loss
+    (policies.py:800-808) and the gradients of all network parameters (oracle/gen_golden_policy.py).
+
+    The chain is chaotic at float32 noise level IN THE REFERENCE (measured by the generator: 1e-7 on the input moves DEQ
+    iteration 2 by 1e-2 -- the AL solve's discrete 20-way line search, fed back six times), so the golden and this test run
+    the network in float64 (two dtype casts, nothing else changed); the native float32 policy is compared on iterations 0-1,
+    before the amplification sets in."""
+    policies, env, args = _policy_setup(cuda_device)
+    g = dict(np.load(os.path.join(GOLDEN, "policy_integrator_B8_T5.npz")))
+    sd = {k[2:]: torch.tensor(v) for k, v in g.items() if k.startswith("w_")}
+    t = lambda k, dt: torch.tensor(g[k]).to(device=cuda_device, dtype=dt)
+
+    def run(dt):
+        policy = policies.DEQMPCPolicy(args, env)
+        policy.model.load_state_dict(sd)
+        if dt == torch.float64:
+            policy.model.double()
+            policy.model.init_z = lambda bsz: torch.zeros(bsz, args.hdim, dtype=torch.float64, device=cuda_device)
+            fwd = policy.tracking_mpc.forward
+            policy.tracking_mpc.forward = lambda *a: tuple(o.double() for o in fwd(*a))
+        x, gs, ga, gm = t("x", dt), t("gt_states", dt), t("gt_actions", dt), t("mask", dt)
+        trajs, dyn_res = policy(x, gs, ga, gm, qp_solve=True)
+        loss, _ = policies.compute_loss(policy, gs, ga, gm, trajs, args)
+        loss.backward()
+        errs = [[rel(ten.detach().cpu().double(), torch.tensor(g[f"{nm}{k}"]).double()) for nm, ten in (("net", a), ("xs", b), ("us", c))]
+                for k, (a, b, c) in enumerate(trajs)]
+        gw = max(rel(p.grad.cpu().double(), torch.tensor(g["g_" + n]).double()) for n, p in policy.model.named_parameters())
+        return errs, gw, float(loss.detach()), dyn_res
+
+    errs, gw, loss, dyn_res = run(torch.float64)
+    worst = max(max(e) for e in errs)
+    print(f"policy (float64 network): worst trajectory rel err {worst:.2e} per iteration {[f'{max(e):.1e}' for e in errs]}, loss {loss:.9f} "
+          f"(reference {float(g['loss']):.9f}), dyn_res {dyn_res:.9f} ({float(g['dyn_res']):.9f}), worst parameter-gradient rel err {gw:.2e}")
+    # the MPC hands float32 values back (AL_mpc.py:319-320): one of them rounding the other way (our fp64 solve differs from
+    # the reference's by ~1e-12) is a 6e-8 perturbation that the remaining iterations amplify (reference: 1e-12 -> 5e-7 over
+    # six iterations).  Hence: early iterations to rounding, the whole chain at 1e-5, the parameter gradients at 1e-4.
+    assert max(max(e) for e in errs[:3]) <= 1e-9 and worst <= 1e-5 and gw <= 1e-4
+    assert abs(loss - float(g["loss"])) <= 1e-6 * abs(float(g["loss"]))
+    assert abs(dyn_res - float(g["dyn_res"])) <= 1e-6 * abs(float(g["dyn_res"]))
+    errs32, _, loss32, _ = run(torch.float32)
+    print(f"policy (native float32 network): per iteration {[f'{max(e):.1e}' for e in errs32]}, loss {loss32:.6f}")
+    assert max(errs32[0]) <= 1e-4 and max(errs32[1]) <= 1e-4
+
+
+def test_graphed_train_step_equals_eager(cuda_device):
+    """GraphedTrainStep: the policy forward + loss + backward captured once in a CUDA graph gives the same loss and the
+    same parameter gradients as the eager step, step after step (Adam updates included)."""
+    policies, env, args = _policy_setup(cuda_device, B=16)
+    torch.manual_seed(1)
+    pol_a = policies.DEQMPCPolicy(args, env)
+    pol_b = policies.DEQMPCPolicy(args, env)
+    pol_b.model.load_state_dict(pol_a.model.state_dict())
+    kw = dict(device=cuda_device)
+    batches = [(torch.rand(16, 2, **kw) * 2 - 1, 0.5 * torch.randn(16, 5, 2, **kw), 0.5 * torch.randn(16, 5, 1, **kw), torch.ones(16, 5, **kw))
+               for _ in range(3)]
+    opt_a = torch.optim.Adam(pol_a.model.parameters(), lr=1e-3)
+    opt_b = torch.optim.Adam(pol_b.model.parameters(), lr=1e-3)
+    eager = policies.GraphedTrainStep(pol_a, opt_a, args, batches[0], use_graph=False)
+    sd0 = {k: v.clone() for k, v in pol_b.model.state_dict().items()}
+    graphed = policies.GraphedTrainStep(pol_b, opt_b, args, batches[0], use_graph=True)
+    pol_b.model.load_state_dict(sd0)   # the warm-up passes of the capture do not step the optimizer, but be explicit
+    for bt in batches:
+        la, lb = eager(*bt), graphed(*bt)
+        assert abs(float(la) - float(lb)) <= 1e-5 * abs(float(la)), (float(la), float(lb))
+    for (n, pa), (_, pb) in zip(pol_a.model.named_parameters(), pol_b.model.named_parameters()):
+        assert rel(pb.detach().cpu().double(), pa.detach().cpu().double()) <= 1e-4, n
