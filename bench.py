@@ -347,6 +347,74 @@ def bench_mpc_shapes(dev):
     return out
 
 
+def bench_policy(dev, world, B=256, T=5, reps=20):
+    """deqmpc training step on the run.sh configuration (integrator, T=5, bsz=256, deq_iter=6, hdim=128): DEQMPCPolicy
+    forward (6 x DEQLayer + Tracking_MPC AL solve), loss, backward through the implicit MPC adjoints, one flat-bucket
+    all-reduce of the DEQLayer gradients over the ranks (NCCL), Adam step.  Eager and captured in one CUDA graph."""
+    import types
+    import numpy as np
+    import torch.distributed as dist
+    from b200qp import envs, policies
+
+    class _Sp:
+        def __init__(self, low, high):
+            self.low, self.high = low, high
+
+    class IntegratorEnv:  # deqmpc/envs.py:246-268
+        def __init__(self):
+            self.dynamics, self.dynamics_derivatives = envs.IntegratorDynamics(), envs.IntegratorDynamics_jac()
+            self.nx, self.nu, self.nq, self.dt = 2, 1, 1, 0.1
+            self.action_space = _Sp(-np.full(1, 2.0), np.full(1, 2.0))
+            self.Qlqr, self.Rlqr = torch.Tensor([10.0, 1.00]), torch.Tensor([0.01])
+
+    env = IntegratorEnv()
+    args = types.SimpleNamespace(T=T, bsz=B, dtype="double", solver_type="al", nq=1, hdim=128, layer_type="mlp", deq_out_type=1,
+                                 policy_out_type=1, kernel_width=3, pooling="mean", deq_iter=6, qp_iter=1, eps=1e-2, warm_start=True,
+                                 device=dev, deq=True, en_qp_solve=True, Q=env.Qlqr, R=env.Rlqr)
+    torch.manual_seed(0)
+    group = dist.group.WORLD if world > 1 else None
+    out = {"workload": f"deqmpc/run.sh shape: integrator, T={T}, bsz={B} per GPU, deq_iter=6, hdim=128, solver_type=al; "
+                       "policy forward + loss + backward + gradient all-reduce + Adam", "n_gpus": world}
+    kw = dict(device=dev)
+    batch = (torch.rand(B, 2, **kw) * 2 - 1, 0.5 * torch.randn(B, T, 2, **kw), 0.5 * torch.randn(B, T, 1, **kw), torch.ones(B, T, **kw))
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    for name, use_graph in (("eager", False), ("cuda_graph", True)):
+        policy = policies.DEQMPCPolicy(args, env)
+        opt = torch.optim.Adam(policy.model.parameters(), lr=1e-3)
+        step = policies.GraphedTrainStep(policy, opt, args, batch, process_group=group, use_graph=use_graph)
+        for _ in range(3):
+            step(*batch)
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        e0.record()
+        for _ in range(reps):
+            step(*batch)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = torch.tensor([e0.elapsed_time(e1) / reps], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        ms = ms.item()
+        out[name] = {"ms_per_step": ms, "train_steps_per_s": 1e3 / ms, "policy_forwards_per_s": B * world * 1e3 / ms,
+                     "mpc_solves_per_s": 6 * B * world * 1e3 / ms}
+        # forward only (rollout / evaluation)
+        with torch.no_grad():
+            for _ in range(2):
+                policy(*batch, qp_solve=True)
+            torch.cuda.synchronize()
+            e0.record()
+            for _ in range(reps):
+                policy(*batch, qp_solve=True)
+            e1.record()
+            torch.cuda.synchronize()
+        if not use_graph:
+            out["forward_only_eager_ms"] = e0.elapsed_time(e1) / reps
+    out["gradient_allreduce"] = ("one flat-bucket NCCL all-reduce of %d DEQLayer parameters per step" % sum(p.numel() for p in policy.model.parameters())
+                                 if world > 1 else "n/a at 1 GPU")
+    return out
+
+
 def bench_qp_sizes(dev):
     """BASELINE configs[4], the larger sizes of the sweep (device-resident, fp64, forward+backward): the
     nineq x nineq system no longer fits in shared memory and the blocked tensor-core kernels of
@@ -781,6 +849,16 @@ def main():
             if world > 1:
                 raise
 
+    pol = None
+    if not args.quick:
+        try:
+            barrier()
+            pol = bench_policy(dev, world)
+        except Exception as ex:  # pragma: no cover
+            pol = {"error": repr(ex)[:300]}
+            if world > 1:
+                raise
+
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
         threads = torch.get_num_threads()
@@ -801,7 +879,7 @@ def main():
                        "nan_onset_iteration": fn.info.get("nan_onset"), "parallelism": f"batch-sharded x{world}, no data-path collective",
                        "l2": "inputs+workspace per step exceed the 126 MB L2 (no flush needed)"},
             "clocks": clocks, "e2e": e2e, "gpu_launches": launches_per_step * args.steps,
-            "roofline": roofline, "cpu_baseline": cpu, "cfg1_nb128": small, "cfg4_sizes": sizes, "mpc": mpc,
+            "roofline": roofline, "cpu_baseline": cpu, "cfg1_nb128": small, "cfg4_sizes": sizes, "mpc": mpc, "policy": pol,
         }
         emit(line)
     if world > 1:

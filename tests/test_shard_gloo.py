@@ -43,6 +43,13 @@ def _worker(rank, world, port, nb, q):
         gr = O.qp_backward(fwd, *mine, torch.ones_like(fwd["zhat"]))
         dG_global = D.allreduce_shared_grad(gr["dG"], sl.stop - sl.start)
         zhat = D.gather_batch(fwd["zhat"])
+        # data-parallel policy training (deqmpc/train.py:165-175): one flat-bucket all-reduce averages the gradients
+        lin = torch.nn.Sequential(torch.nn.Linear(3, 4), torch.nn.LayerNorm(4))
+        for i, prm in enumerate(lin.parameters()):
+            prm.grad = torch.full_like(prm, float(rank + 1) * (i + 1))
+        D.allreduce_gradients(list(lin.parameters()))
+        for i, prm in enumerate(lin.parameters()):
+            assert torch.allclose(prm.grad, torch.full_like(prm, 1.5 * (i + 1))), "allreduce_gradients"
         if rank == 0:
             # the same thing computed by one process, shard by shard
             zs, num = [], 0
