@@ -27,11 +27,12 @@ EXPORTS = (
     "b200qp_solve_host", "b200qp_solve_host_submit", "b200qp_solve_host_wait", "b200qp_last_cuda_error", "b200qp_version", "b200qp_profile_enable",
     "b200qp_profile_read", "b200qp_set_option",
     "b200mpc_env_dims", "b200mpc_factor_elems", "b200mpc_scratch_bytes", "b200mpc_al_solve", "b200mpc_al_backward",
-    "b200dyn_step", "b200dyn_jac", "b200dyn_rollout",
+    "b200dyn_step", "b200dyn_jac", "b200dyn_rollout", "b200data_sample_windows",
 )
 
 ENV_PENDULUM, ENV_INTEGRATOR, ENV_PENDULUM_DX, ENV_CARTPOLE_DX, ENV_REX_QUADROTOR = 0, 1, 2, 3, 4
 ENV_PENDULUM1L, ENV_CARTPOLE1L, ENV_CARTPOLE2L = 5, 6, 7
+ENV_CARTPOLE1L_V1, ENV_CARTPOLE2L_V1 = 8, 9
 MPC_MAX_PARAMS = 64
 
 
@@ -102,6 +103,9 @@ def lib():
     L.b200qp_solve_host_submit.argtypes = [ctypes.c_int, pp] + [vp] * 18
     L.b200qp_solve_host_wait.restype = ctypes.c_int
     L.b200qp_solve_host_wait.argtypes = [ctypes.c_int]
+    L.b200data_sample_windows.restype = ctypes.c_int
+    L.b200data_sample_windows.argtypes = [vp, vp, vp, ctypes.c_longlong, ctypes.c_int, ctypes.c_int, vp, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                          ctypes.c_int, vp, vp, vp, vp, vp, vp]
     L.b200qp_profile_enable.restype = None
     L.b200qp_profile_enable.argtypes = [ctypes.c_int]
     L.b200qp_profile_read.restype = ctypes.c_int

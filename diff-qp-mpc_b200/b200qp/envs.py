@@ -51,6 +51,10 @@ def dyn_spec(dx):
         polemass_length = masspole * length
         return (_lib.ENV_CARTPOLE_DX, [float(dx.dt), float(gravity), float(masscart), float(masspole), float(length),
                                        float(total_mass), float(polemass_length), float(dx.force_mag)], 5, 1)
+    if base == "OneLinkCartpoleDynamics":   # deqmpc/envs_v1.py:28-82
+        return _lib.ENV_CARTPOLE1L_V1, [float(dx.dt), float(dx.M), float(dx.m), float(dx.l), float(dx.g)], 4, 1
+    if base == "TwoLinkCartpoleDynamics":   # deqmpc/envs_v1.py:226-310 (numeric constants are part of the formulas)
+        return _lib.ENV_CARTPOLE2L_V1, [float(dx.dt)], 6, 1
     if base == "RexQuadrotor_dynamics":
         f32 = lambda t: [float(v) for v in torch.as_tensor(t).detach().to(dtype=torch.float32, device="cpu").reshape(-1)]
         mg = torch.as_tensor(dx.g).detach().to(dtype=torch.float32, device="cpu") * float(dx.m)  # float32, as self.m * self.g
@@ -61,7 +65,8 @@ def dyn_spec(dx):
         return _lib.ENV_REX_QUADROTOR, params, 12, 4
     raise NotImplementedError(f"b200qp: no fused kernel for dynamics {name!r}; supported: PendulumDynamics, "
                               "IntegratorDynamics, PendulumDx, CartpoleDx, RexQuadrotor_dynamics (and their *_jac "
-                              "variants), and the deqmpc/my_envs CartpoleDynamics / PendulumDynamics")
+                              "variants), the deqmpc/my_envs CartpoleDynamics / PendulumDynamics and the deqmpc/envs_v1 "
+                              "OneLinkCartpoleDynamics / TwoLinkCartpoleDynamics")
 
 
 def _run(spec, x, u, want_jac):
@@ -259,3 +264,53 @@ class RexQuadrotor_dynamics(_Dynamics):
 
 class RexQuadrotor_dynamics_jac(_DynamicsJac, RexQuadrotor_dynamics):
     """deqmpc/rex_quadrotor.py:130-146"""
+
+
+def _angle_normalize_2pi(x):
+    """deqmpc/envs_v1.py angle_normalize_2pi"""
+    return ((x) % (2 * torch.pi))
+
+
+class OneLinkCartpoleDynamics(_Dynamics):
+    """deqmpc/envs_v1.py:28-94: cart + one pole, closed-form accelerations, classical RK4 (dt = 0.01)"""
+
+    def __init__(self):
+        super().__init__()
+        self.dt, self.max_force, self.g, self.M, self.m, self.l = 0.01, 500.0, -9.81, 0.5, 0.2, 0.5
+        self.n = 1
+        self.nx, self.nu = 2 * self.n + 2, 1
+        self.np = self.nx // 2
+
+    def action_clip(self, action):
+        return torch.clamp(action, -self.max_force, self.max_force)
+
+    def state_clip(self, state):
+        state[..., 1:self.np] = _angle_normalize_2pi(state[..., 1:self.np])
+        return state
+
+
+class OneLinkCartpoleDynamics_jac(_DynamicsJac, OneLinkCartpoleDynamics):
+    """Jacobian companion (forward-mode duals in the kernel); the reference has none for envs_v1 (its users are the RL /
+    data-generation scripts), the return convention is that of deqmpc/envs.py:74-82."""
+
+
+class TwoLinkCartpoleDynamics(_Dynamics):
+    """deqmpc/envs_v1.py:226-321: the OpenOCL double cart-pole (M = 5, m1 = m2 = l1 = l2 = 1), classical RK4 (dt = 0.05)"""
+
+    def __init__(self):
+        super().__init__()
+        self.dt, self.max_force, self.g, self.M, self.m1, self.m2, self.l1, self.l2 = 0.05, 5.0, 9.81, 5., 1., 1., 1., 1.
+        self.n = 2
+        self.nx, self.nu = 2 * self.n + 2, 1
+        self.np = self.nx // 2
+
+    def action_clip(self, action):
+        return torch.clamp(action, -self.max_force, self.max_force)
+
+    def state_clip(self, state):
+        state[..., 1:self.np] = _angle_normalize_2pi(state[..., 1:self.np])
+        return state
+
+
+class TwoLinkCartpoleDynamics_jac(_DynamicsJac, TwoLinkCartpoleDynamics):
+    """Jacobian companion (see OneLinkCartpoleDynamics_jac)."""

@@ -29,6 +29,8 @@ static bool env_dims(int env, int& nx, int& nu) {
     case ENV_PENDULUM1L: nx = Pendulum1L::NX; nu = Pendulum1L::NU; return true;
     case ENV_CARTPOLE1L: nx = Cartpole1L::NX; nu = Cartpole1L::NU; return true;
     case ENV_CARTPOLE2L: nx = Cartpole2L::NX; nu = Cartpole2L::NU; return true;
+    case ENV_CARTPOLE1L_V1: nx = Cartpole1LV1::NX; nu = Cartpole1LV1::NU; return true;
+    case ENV_CARTPOLE2L_V1: nx = Cartpole2LV1::NX; nu = Cartpole2LV1::NU; return true;
   }
   return false;
 }
@@ -116,14 +118,105 @@ static int rollout_t(const double* params, const void* x0, const void* u, void* 
     case ENV_PENDULUM1L: EXPR_MACRO(Pendulum1L);              \
     case ENV_CARTPOLE1L: EXPR_MACRO(Cartpole1L);              \
     case ENV_CARTPOLE2L: EXPR_MACRO(Cartpole2L);              \
+    case ENV_CARTPOLE1L_V1: EXPR_MACRO(Cartpole1LV1);         \
+    case ENV_CARTPOLE2L_V1: EXPR_MACRO(Cartpole2LV1);         \
   }                                                           \
   return B200QP_EINVAL
+
+
+// ---------------------------------------------------------------------------------------------------------------
+// Expert-data sampling on the device (deqmpc/datagen.py:358-408 sample_trajectory, deqmpc/utils.py:256-288
+// unnormalize_states_*): the reference assembles every training batch with a Python loop over bsz windows, a torch.cat per
+// window and a sequential un-normalisation over T on the host.  Here the concatenated expert data stays in HBM, the
+// candidate start indices (drawn by the caller with the reference's own RNG call) are filtered and compacted by one CTA,
+// and one thread per window gathers (state, action, mask), forms the running mask product and un-wraps the angles.
+__global__ void __launch_bounds__(1024) k_data_select(const float* __restrict__ mask, const long long* __restrict__ idxs, int n_idx,
+                                                      int bsz, long long* __restrict__ sel, int* __restrict__ status) {
+  __shared__ int s_warp[32];
+  __shared__ int s_base;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid == 0) s_base = 0;
+  __syncthreads();
+  for (int start = 0; start < n_idx; start += 1024) {
+    const int i = start + tid;
+    const long long ix = i < n_idx ? idxs[i] : 0;
+    const int v = (i < n_idx && mask[ix] != 0.0f) ? 1 : 0;   // datagen.py:374: windows may not start on an end-of-trajectory row
+    const unsigned bal = __ballot_sync(0xffffffffu, v);
+    const int wpre = __popc(bal & ((1u << lane) - 1u));
+    if (lane == 0) s_warp[warp] = __popc(bal);
+    __syncthreads();
+    int off = s_base;
+    for (int w = 0; w < warp; w++) off += s_warp[w];
+    const int rank = off + wpre;
+    if (v && rank < bsz) sel[rank] = ix;
+    __syncthreads();
+    if (tid == 0) { int t = 0; for (int w = 0; w < 32; w++) t += s_warp[w]; s_base += t; }
+    __syncthreads();
+  }
+  if (tid == 0) status[0] = s_base;
+}
+
+__global__ void __launch_bounds__(128) k_data_gather(const float* __restrict__ state, const float* __restrict__ action,
+                                                     const float* __restrict__ mask, long long N, int nx, int nu,
+                                                     const long long* __restrict__ sel, int bsz, int T, int unnorm,
+                                                     float* __restrict__ os, float* __restrict__ oa, float* __restrict__ om) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= bsz) return;
+  const long long i0 = sel[j];
+  float* s = os + (size_t)j * T * nx;
+  float* a = oa + (size_t)j * T * nu;
+  float* m = om + (size_t)j * T;
+  float run = 1.0f;
+  for (int t = 0; t < T; t++) {
+    const long long r = i0 + t;
+    const bool in = r < N;                                   // datagen.py:381-399: zero padding past the end of the data
+    for (int c = 0; c < nx; c++) s[t * nx + c] = in ? state[r * nx + c] : 0.0f;
+    for (int c = 0; c < nu; c++) a[t * nu + c] = in ? action[r * nu + c] : 0.0f;
+    run *= in ? mask[r] : 0.0f;                              // datagen.py:404-405: running product of the masks
+    m[t] = run;
+  }
+  const float kHalfPi = 1.57079637050628662f, kTwoPi = 6.28318548202514648f;  // float32(pi / 2), 2 * float32(pi)
+  if (unnorm == 1) {                                         // utils.py:256-270 (pendulum): sign of the ANGLE, column 0
+    float prev = s[0];
+    for (int t = 0; t < T; t++) {
+      const float cur = s[t * nx];
+      if (fabsf(cur - prev) > kHalfPi) s[t * nx] = cur - (cur > 0.0f ? 1.0f : (cur < 0.0f ? -1.0f : 0.0f)) * kTwoPi;
+      prev = s[t * nx];
+    }
+  } else if (unnorm == 2) {                                  // utils.py:273-288 (n-link cart-pole): sign of the JUMP, columns
+    const int nq = nx / 2 + 1;                               // 1 .. nx/2 (the reference's own column range, kept as is)
+    for (int c = 1; c < nq; c++) {
+      float prev = s[c];
+      for (int t = 0; t < T; t++) {
+        const float cur = s[t * nx + c];
+        const float d = cur - prev;
+        if (fabsf(d) > kHalfPi) s[t * nx + c] = cur - (d > 0.0f ? 1.0f : (d < 0.0f ? -1.0f : 0.0f)) * kTwoPi;
+        prev = s[t * nx + c];
+      }
+    }
+  }
+}
 
 }  // namespace b200mpc
 
 using namespace b200mpc;
 
 extern "C" {
+
+int b200data_sample_windows(const float* state, const float* action, const float* mask, long long N, int nx, int nu,
+                            const long long* idxs, int n_idx, int bsz, int T, int unnormalize, long long* sel,
+                            float* out_state, float* out_action, float* out_mask, int* status, b200qp_stream_t stream) {
+  if (!state || !action || !mask || !idxs || !sel || !out_state || !out_action || !out_mask || !status) return B200QP_EINVAL;
+  if (N < 1 || nx < 1 || nu < 1 || n_idx < 1 || bsz < 1 || T < 1 || unnormalize < 0 || unnormalize > 2) return B200QP_EINVAL;
+  cudaStream_t st = (cudaStream_t)stream;
+  CKM(cudaMemsetAsync(sel, 0, sizeof(long long) * (size_t)bsz, st));
+  k_data_select<<<1, 1024, 0, st>>>(mask, idxs, n_idx, bsz, sel, status);
+  CKM(cudaGetLastError());
+  k_data_gather<<<(unsigned)((bsz + 127) / 128), 128, 0, st>>>(state, action, mask, N, nx, nu, sel, bsz, T, unnormalize,
+                                                              out_state, out_action, out_mask);
+  CKM(cudaGetLastError());
+  return B200QP_OK;
+}
 
 int b200mpc_env_dims(int env, int* nx, int* nu) {
   int a, b;

@@ -120,6 +120,7 @@ template <typename R, int N> struct real_of<Dual<R, N>> { typedef R type; };
 // ---------------------------------------------------------------------------- environments
 constexpr int ENV_PENDULUM = 0, ENV_INTEGRATOR = 1, ENV_PENDULUM_DX = 2, ENV_CARTPOLE_DX = 3, ENV_REX_QUADROTOR = 4;
 constexpr int ENV_PENDULUM1L = 5, ENV_CARTPOLE1L = 6, ENV_CARTPOLE2L = 7;
+constexpr int ENV_CARTPOLE1L_V1 = 8, ENV_CARTPOLE2L_V1 = 9;  // deqmpc/envs_v1.py RK4 cart-poles
 constexpr int MAX_PARAMS = 64;
 
 struct DynParams { double v[MAX_PARAMS]; };
@@ -399,7 +400,57 @@ struct Cartpole2LModel {
   }
 };
 
+// ---- deqmpc/envs_v1.py: closed-form cart-pole accelerations under the same classical RK4
+// OneLinkCartpoleDynamics (envs_v1.py:28-82): params dt, M, m, l, g (the reference sets g = -9.81); state (x, th, xd, thd)
+struct Cartpole1LV1Model {
+  static constexpr int NQ = 2;
+  template <typename S>
+  __device__ static __forceinline__ void accel(const DynParams& P, const S* q, const S* qd, const S& u, S* a) {
+    typedef typename real_of<S>::type R;
+    const R M = (R)P.v[1], m = (R)P.v[2], l = (R)P.v[3], g = (R)P.v[4];
+    const S s = m_sin(q[1]), c = m_cos(q[1]);
+    const S w2 = qd[1] * qd[1];
+    const S den = M + m * (s * s);
+    a[0] = (u + (m * l) * w2 * s - (m * g) * s * c) / den;
+    a[1] = (-(u * c) - (m * l) * w2 * s * c + ((M + m) * g) * s) / (l * den);
+  }
+};
+// TwoLinkCartpoleDynamics (envs_v1.py:226-310): the OpenOCL double cart-pole with its numeric constants
+// (M = 5, m1 = m2 = l1 = l2 = 1, g = 9.81) folded into the formulas, f = -u; params dt only
+struct Cartpole2LV1Model {
+  static constexpr int NQ = 3;
+  template <typename S>
+  __device__ static __forceinline__ void accel(const DynParams& P, const S* q, const S* qd, const S& u, S* a) {
+    typedef typename real_of<S>::type R;
+    const S f = -u;
+    const S q1 = q[1], q2 = q[2], w1 = qd[1], w2 = qd[2];
+    const S w11 = w1 * w1, w12 = w1 * w2, w22 = w2 * w2;
+    const S c1 = m_cos(q1), s1 = m_sin(q1), c2 = m_cos(q2), s2 = m_sin(q2);
+    const S c_1m2 = m_cos(q1 - q2), s_1m2 = m_sin(q1 - q2);
+    const S c_1p2 = m_cos(q1 + q2), s_1p2 = m_sin(q1 + q2);
+    const S c_1p22 = m_cos(q1 + R(2) * q2), s_1p22 = m_sin(q1 + R(2) * q2);
+    const S c_21 = m_cos(R(2) * q1), s_21 = m_sin(R(2) * q1);
+    const S c_22 = m_cos(R(2) * q2), s_22 = m_sin(R(2) * q2);
+    const S c_21p2 = m_cos(R(2) * q1 + q2), s_21p2 = m_sin(R(2) * q1 + q2);
+    const S c_21p22 = m_cos(R(2) * q1 + R(2) * q2), s_21p22 = m_sin(R(2) * q1 + R(2) * q2);
+    const S den = R(3) * c_21 - R(22) * c_22 - c_21p22 + R(34);
+    a[0] = (R(4) * f * c_22 - R(6) * f + R(4) * w11 * c1 + w11 * c_1m2 - w11 * c_1p22 + R(2) * w12 * c_1m2 + w22 * c_1m2
+            - R(29.43) * s_21 + R(9.81) * s_21p22) / den;
+    a[1] = (-(R(8) * f * s1) + R(4) * f * s_1p22 + R(3) * w11 * s_21 + R(23) * w11 * s2 + R(22) * w11 * s_22 + w11 * s_21p2
+            + R(46) * w12 * s2 + R(2) * w12 * s_21p2 + R(23) * w22 * s2 + w22 * s_21p2 - R(490.5) * c1 + R(215.82) * c_1p22) / den;
+    const S t = R(3) * s1 + s_1p2;
+    a[2] = -((R(100) * w11 * s2 + R(981) * c_1p2) * (-(t * t) + R(28) * c2 + R(42))
+             + R(0.5) * (R(200) * w12 * s2 + R(100) * w22 * s2 - R(2943) * c1 - R(981) * c_1p2)
+                   * (R(25) * c2 + R(3) * c_21p2 + c_21p22 + R(13))
+             + R(50) * (R(2) * s1 + R(3) * s_1m2 - R(2) * s_1p2 - s_1p22)
+                   * (-(R(2) * f) + R(3) * w11 * c1 + w11 * c_1p2 + R(2) * w12 * c_1p2 + w22 * c_1p2))
+           / (R(75) * c_21 - R(550) * c_22 - R(25) * c_21p22 + R(850));
+  }
+};
+
 typedef SecondOrderRK4<Pendulum1LModel> Pendulum1L;
+typedef SecondOrderRK4<Cartpole1LV1Model> Cartpole1LV1;
+typedef SecondOrderRK4<Cartpole2LV1Model> Cartpole2LV1;
 typedef SecondOrderRK4<Cartpole1LModel> Cartpole1L;
 typedef SecondOrderRK4<Cartpole2LModel> Cartpole2L;
 

@@ -43,6 +43,8 @@ extern "C" {
 #define B200MPC_ENV_PENDULUM1L 5    /* pendulum1l (nx=2): params dt, 1/I, mgl/I                          */
 #define B200MPC_ENV_CARTPOLE1L 6    /* cartpole1l, cartpole1l_v2 (nx=4): params dt, mt, ml, I, g         */
 #define B200MPC_ENV_CARTPOLE2L 7    /* cartpole2l (nx=6): params dt, mt, h1, h2, J1, J2, k, g            */
+#define B200MPC_ENV_CARTPOLE1L_V1 8 /* deqmpc/envs_v1.py:28-82 OneLinkCartpoleDynamics (nx=4): params dt, M, m, l, g */
+#define B200MPC_ENV_CARTPOLE2L_V1 9 /* deqmpc/envs_v1.py:226-310 TwoLinkCartpoleDynamics (nx=6): params dt        */
 #define B200MPC_MAX_PARAMS 64
 
 typedef struct {
@@ -99,6 +101,18 @@ int b200dyn_jac(int env, int dtype, const double* params, const void* x, const v
 /* open-loop rollout xs (B,T,nx): xs[:,0] = x0, xs[:,t+1] = f(xs[:,t], u[:,t])  (qpth/AL_mpc.py:398-411) */
 int b200dyn_rollout(int env, int dtype, const double* params, const void* x0, const void* u, void* xs, int64_t B,
                     int32_t T, b200qp_stream_t stream);
+
+/* Expert-data sampling on the device: deqmpc/datagen.py:358-408 `sample_trajectory` (bsz windows of T consecutive rows of
+ * the concatenated expert data, windows may not START on an end-of-trajectory row (mask == 0), rows past the end of the
+ * data are zero, the returned mask is the running product of the row masks) followed by deqmpc/utils.py:256-288
+ * `unnormalize_states_pendulum` (unnormalize = 1) / `unnormalize_states_cartpole_nlink` (= 2) or nothing (= 0).
+ * state [N][nx], action [N][nu], mask [N]: float32 device arrays (the reference keeps them in float32).  idxs [n_idx]: the
+ * candidate start rows, drawn by the caller exactly as the reference draws them (np.random.randint(0, N, 2 bsz)); they are
+ * consumed in order, skipping masked rows.  sel [bsz] receives the chosen start rows; status[0] the number of admissible
+ * candidates (the reference raises IndexError when it is < bsz: outputs are then incomplete). */
+int b200data_sample_windows(const float* state, const float* action, const float* mask, long long N, int nx, int nu,
+                            const long long* idxs, int n_idx, int bsz, int T, int unnormalize, long long* sel,
+                            float* out_state, float* out_action, float* out_mask, int* status, b200qp_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -516,3 +516,19 @@ def test_graphed_train_step_equals_eager(cuda_device):
         assert abs(float(la) - float(lb)) <= 1e-5 * abs(float(la)), (float(la), float(lb))
     for (n, pa), (_, pb) in zip(pol_a.model.named_parameters(), pol_b.model.named_parameters()):
         assert rel(pb.detach().cpu().double(), pa.detach().cpu().double()) <= 1e-4, n
+
+
+@pytest.mark.parametrize("name", ["cartpole1l", "cartpole2l"])
+def test_envs_v1_against_reference_modules(name, cuda_device):
+    """deqmpc/envs_v1.py OneLinkCartpoleDynamics / TwoLinkCartpoleDynamics (closed-form accelerations, classical RK4) against
+    goldens of the reference's own modules (oracle/gen_golden_envs_v1.py): next state and both Jacobians."""
+    from b200qp import envs
+    g = dict(np.load(os.path.join(GOLDEN, f"dyn_envsv1_{name}.npz")))
+    mod = envs.OneLinkCartpoleDynamics_jac() if name == "cartpole1l" else envs.TwoLinkCartpoleDynamics_jac()
+    fwd = envs.OneLinkCartpoleDynamics() if name == "cartpole1l" else envs.TwoLinkCartpoleDynamics()
+    x, u = torch.tensor(g["x"]).to(cuda_device), torch.tensor(g["u"]).to(cuda_device)
+    xn, (A, B) = mod(x, u)
+    assert rel(xn.cpu(), torch.tensor(g["xn"])) < 1e-13
+    assert rel(fwd(x, u).cpu(), torch.tensor(g["xn"])) < 1e-13
+    assert rel(A.cpu(), torch.tensor(g["A"])) < 1e-11
+    assert rel(B.cpu(), torch.tensor(g["B"])) < 1e-11
