@@ -136,6 +136,10 @@ def _forward_exact_sharded(L, plan, bufs, status, device, group):
         keys.copy_(red[:4] ^ _I64_MIN)
         flags.copy_(red[4:].to(torch.int32))
     _lib.check(L.b200qp_forward_phase(pr, _lib.PHASE_END, *args), "b200qp_forward_phase(end)")
+    # factorisation-failure counts of ALL ranks: every rank must raise (or not) together, otherwise the ranks that carry
+    # on hang in the next collective (the shared-parameter mean of backward)
+    fails = status[_lib.ST_Q_FAIL:_lib.ST_AQA_FAIL + 1]
+    dist.all_reduce(fails, op=dist.ReduceOp.SUM, group=group)
 
 
 def _global_mean(local_mean, local_nb, group):

@@ -63,7 +63,8 @@ static int solve_t(const b200mpc_problem_t* p, const b200mpc_buffers_t* b, cudaS
   a.use_smem = smem <= kSmemLimit;
   if (!a.use_smem && !a.scratch) return B200QP_EINVAL;
   auto k = k_al_solve<Dyn, R>;
-  const size_t dyn_smem = a.use_smem ? smem : 0;
+  // global-scratch mode: 5 KB per warp to stage the block being factored (block_cholesky_staged)
+  const size_t dyn_smem = a.use_smem ? smem : (size_t)kWarpsPerCta * al_stage_elems<Dyn::NX, Dyn::NU>() * sizeof(R);
   if (dyn_smem > 48 * 1024) CKM(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn_smem));
   const int grid = (p->B + kWarpsPerCta - 1) / kWarpsPerCta;
   k<<<grid, 32 * kWarpsPerCta, dyn_smem, st>>>(a);

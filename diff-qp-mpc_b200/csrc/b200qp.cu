@@ -323,7 +323,15 @@ static Arena g_arenas[B200QP_HOST_SLOTS];
 static cudaStream_t g_st = nullptr, g_cin = nullptr, g_cout = nullptr;
 static std::mutex g_host_mu;
 
+static int g_host_device = -1;  // the host-buffer pipeline (streams, arenas) belongs to the device of its first use
 static int arena_reserve(Arena& A, size_t bytes) {
+  int dev = -1;
+  CK(cudaGetDevice(&dev));
+  if (g_host_device < 0) g_host_device = dev;
+  if (dev != g_host_device) {  // one process per GPU: refuse to mix devices instead of corrupting them
+    snprintf(g_err, sizeof(g_err), "b200qp_solve_host*: first used on device %d, now called with device %d current", g_host_device, dev);
+    return B200QP_EINVAL;
+  }
   if (!g_st) CK(cudaStreamCreateWithFlags(&g_st, cudaStreamNonBlocking));
   if (!g_cin) CK(cudaStreamCreateWithFlags(&g_cin, cudaStreamNonBlocking));
   if (!g_cout) CK(cudaStreamCreateWithFlags(&g_cout, cudaStreamNonBlocking));

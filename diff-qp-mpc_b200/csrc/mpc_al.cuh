@@ -253,6 +253,73 @@ __device__ __forceinline__ void block_cholesky(R* D, R* E, int T, int lane) {
   }
 }
 
+// The same factorisation for problems whose state lives in the GLOBAL scratch slab (rex quadrotor, T = 40: 175 KB per
+// problem): the block being factored is staged in shared memory (5 KB per warp: D_t, the factored E_{t-1} and E_t, leading
+// dimension NT + 1 so that row and column walks are bank-conflict free).  In the slab every step of the column loop was a
+// dependent global-memory round trip (~10^3 cycles x 16 columns x T blocks x 8 Newton steps: ~20 of the 21 ms of a rex
+// solve); the arithmetic and its order are unchanged.
+template <int NX, int NU>
+__host__ __device__ constexpr int al_stage_elems() { return ((NX + NU) * (NX + NU + 1) + 2 * NX * (NX + NU + 1) + 3) & ~3; }
+
+template <int NX, int NU, typename R>
+__device__ __forceinline__ void block_cholesky_staged(R* D, R* E, int T, int lane, R* wk) {
+  constexpr int NT = NX + NU, LD = NT + 1;
+  R* sD = wk;
+  R* sEp = wk + NT * LD;
+  R* sEn = sEp + NX * LD;
+  for (int t = 0; t < T; t++) {
+    R* Dt = D + t * NT * NT;
+    for (int idx = lane; idx < NT * NT; idx += 32) sD[(idx / NT) * LD + (idx % NT)] = Dt[idx];
+    if (t < T - 1) {
+      const R* Eg = E + t * NX * NT;
+      for (int idx = lane; idx < NX * NT; idx += 32) sEn[(idx / NT) * LD + (idx % NT)] = Eg[idx];
+    }
+    __syncwarp();
+    if (t > 0) {
+      for (int idx = lane; idx < NX * NX; idx += 32) {
+        const int i = idx / NX, k = idx - i * NX;
+        if (k <= i) {
+          R acc = R(0);
+#pragma unroll
+          for (int j = 0; j < NT; j++) acc += sEp[i * LD + j] * sEp[k * LD + j];
+          sD[i * LD + k] -= acc;
+        }
+      }
+      __syncwarp();
+    }
+#pragma unroll 1
+    for (int j = 0; j < NT; j++) {
+      const R djj = sD[j * LD + j];
+      const R ljj = djj > R(0) ? sqrt(djj) : r_nan<R>();
+      __syncwarp();
+      if (lane >= j && lane < NT) sD[lane * LD + j] = (lane == j) ? ljj : sD[lane * LD + j] / ljj;
+      __syncwarp();
+      for (int idx = lane; idx < NT * NT; idx += 32) {
+        const int i = idx / NT, k = idx - i * NT;
+        if (k > j && k <= i) sD[i * LD + k] -= sD[i * LD + j] * sD[k * LD + j];
+      }
+      __syncwarp();
+    }
+    if (t < T - 1) {
+      if (lane < NX) {
+        R* row = sEn + lane * LD;
+#pragma unroll 1
+        for (int j = 0; j < NT; j++) {
+          R v = row[j];
+          for (int k = 0; k < j; k++) v -= row[k] * sD[j * LD + k];
+          row[j] = v / sD[j * LD + j];
+        }
+      }
+      __syncwarp();
+      R* Eg = E + t * NX * NT;
+      for (int idx = lane; idx < NX * NT; idx += 32) Eg[idx] = sEn[(idx / NT) * LD + (idx % NT)];
+      R* tmp = sEp; sEp = sEn; sEn = tmp;
+    }
+    for (int idx = lane; idx < NT * NT; idx += 32) Dt[idx] = sD[(idx / NT) * LD + (idx % NT)];
+    __syncwarp();
+  }
+}
+
 // g <- H^-1 g with the block factor (two block-bidiagonal sweeps; in-block solves by shuffles).
 template <int NX, int NU, typename R>
 __device__ __forceinline__ void block_solve(const R* D, const R* E, R* g, int T, int lane) {
@@ -271,11 +338,19 @@ __device__ __forceinline__ void block_solve(const R* D, const R* E, R* g, int T,
         v -= acc;
       }
     }
+    // this lane's row of L_tt, loaded up front (independent loads: one latency instead of NT dependent ones when the
+    // factor lives in the global slab); the diagonal travels by shuffle
+    R rowv[NT];
+#pragma unroll
+    for (int j = 0; j < NT; j++) rowv[j] = (lane < NT && j <= lane) ? Dt[lane * NT + j] : R(0);
+    R dg = R(1);
+#pragma unroll
+    for (int j = 0; j < NT; j++) dg = (lane == j) ? rowv[j] : dg;
 #pragma unroll
     for (int j = 0; j < NT; j++) {
-      const R vj = __shfl_sync(0xffffffffu, v, j) / Dt[j * NT + j];
+      const R vj = __shfl_sync(0xffffffffu, v, j) / __shfl_sync(0xffffffffu, dg, j);
       if (lane == j) v = vj;
-      else if (lane > j && lane < NT) v -= Dt[lane * NT + j] * vj;
+      else if (lane > j && lane < NT) v -= rowv[j] * vj;
     }
     if (lane < NT) g[t * NT + lane] = v;
     __syncwarp();
@@ -293,11 +368,17 @@ __device__ __forceinline__ void block_solve(const R* D, const R* E, R* g, int T,
         v -= acc;
       }
     }
+    R colv[NT];  // column `lane` of L_tt (rows j >= lane), loaded up front
+#pragma unroll
+    for (int j = 0; j < NT; j++) colv[j] = (lane < NT && j >= lane) ? Dt[j * NT + lane] : R(0);
+    R dg = R(1);
+#pragma unroll
+    for (int j = 0; j < NT; j++) dg = (lane == j) ? colv[j] : dg;
 #pragma unroll
     for (int j = NT - 1; j >= 0; j--) {
-      const R vj = __shfl_sync(0xffffffffu, v, j) / Dt[j * NT + j];
+      const R vj = __shfl_sync(0xffffffffu, v, j) / __shfl_sync(0xffffffffu, dg, j);
       if (lane == j) v = vj;
-      else if (lane < j) v -= Dt[j * NT + lane] * vj;
+      else if (lane < j) v -= colv[j] * vj;
     }
     if (lane < NT) g[t * NT + lane] = v;
     __syncwarp();
@@ -308,7 +389,10 @@ template <class Dyn, typename R>
 // Occupancy: the cart-pole of deqmpc/my_envs (NX = 4, RK4 under 4-wide duals) compiles to 252 registers = 2 CTAs/SM;
 // capped at 128 (4 CTAs/SM, ~0.8 KB of spills) it runs 45 % faster (5.04 -> 3.48 ms at T=20, B=4096).  The two-link
 // model (NX = 6) loses 5-7 % under the same cap and the other environments already sit at <= 166 registers.
-__global__ void __launch_bounds__(128, (Dyn::NX == 4 ? 4 : 0)) k_al_solve(const ALArgs<R> a) {
+#ifndef B200MPC_REX_MINB
+#define B200MPC_REX_MINB 0
+#endif
+__global__ void __launch_bounds__(128, (Dyn::NX == 4 ? 4 : (Dyn::NX >= 12 ? B200MPC_REX_MINB : 0))) k_al_solve(const ALArgs<R> a) {
   constexpr int NX = Dyn::NX, NU = Dyn::NU, NT = NX + NU;
   extern __shared__ __align__(16) unsigned char al_smem[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -366,7 +450,8 @@ __global__ void __launch_bounds__(128, (Dyn::NX == 4 ? 4 : 0)) k_al_solve(const 
     R merit = merit_eval<Dyn, R>(S, a.P, T, rho, false, R(0), false);
     for (int ns = 0; ns < a.newton_steps; ns++) {
       assemble<Dyn, R>(S, a.P, T, rho, lane);
-      block_cholesky<NX, NU, R>(S.D, S.E, T, lane);
+      if (a.use_smem) block_cholesky<NX, NU, R>(S.D, S.E, T, lane);
+      else block_cholesky_staged<NX, NU, R>(S.D, S.E, T, lane, reinterpret_cast<R*>(al_smem) + (size_t)warp * al_stage_elems<NX, NU>());
       block_solve<NX, NU, R>(S.D, S.E, S.g, T, lane);
       for (int idx = lane; idx < T * NT; idx += 32) S.g[idx] = -S.g[idx];
       __syncwarp();

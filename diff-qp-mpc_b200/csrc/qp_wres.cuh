@@ -26,6 +26,9 @@
 namespace b200qp {
 
 constexpr int kWLd = 34;  // leading dimension of G in shared memory (doubles)
+#ifndef B200QP_WRES_MINB
+#define B200QP_WRES_MINB 8  // resident warps (= CTAs) per SM the chunk kernel is compiled for
+#endif
 
 struct WOff { int G, x, rx, t, qx, p, z, dz, dinv, hz, u, q, r, rinv, h, total; };
 __host__ __device__ constexpr WOff wres_off(int m) {
@@ -424,7 +427,7 @@ __device__ __forceinline__ void w_pieces(const double (&z)[RPL], const double (&
 // they execute the same ~100 KB of straight-line code, and in step they share its instruction-cache lines.
 // NTI = tiles per dimension (8 NTI > nineq); <NC, MC> != 0: compile-time nz / nineq.
 template <int NTI, int NC, int MC, int WPC>
-__global__ void __launch_bounds__(32 * WPC, 8 / WPC) k_wres_chunk(const KArgs<double> a, const RArgs ra) {
+__global__ void __launch_bounds__(32 * WPC, WPC == 1 ? B200QP_WRES_MINB : 8 / WPC) k_wres_chunk(const KArgs<double> a, const RArgs ra) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   constexpr int NT = NTI * (NTI + 1) / 2, MPAD = 8 * NTI, RPL = (MPAD + 31) / 32;
   WLane L;
