@@ -501,8 +501,12 @@ def run_reference(args, rank):
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"random-QP batch nz={NZ} nineq={NINEQ} neq=0 fp64 fwd+bwd (BASELINE configs[0]/[4])",
-                   "batch_per_step": nb},
+        "config": {"workload": f"random-QP batch (prof-linear.py:64-75 recipe, torch RNG) nz={NZ} nineq={NINEQ} neq=0 "
+                               f"fp64, QPFunction forward+backward; BASELINE configs[4] sweep point, {args.nb} QPs per GPU",
+                   "batch_per_step": nb,
+                   "sample": f"each step is a bounded sample of that workload: the first {nb} problems of the same generator "
+                             "(the reference's CPU time is linear in the batch: 20 iterations either way; the full batch was "
+                             "timed once, profiles/r02/bench_r02_reference_arm_nb32768.json)"},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -761,6 +765,10 @@ def main():
                       "and its results out inside the timed region; three slots so that the copies of adjacent steps "
                       "overlap the kernels)",
                "pcie_gb_s_per_direction": 1e-9 * max(h2d, d2h) / (dt / args.steps),
+               # all ranks together, both directions: on one box this saturates at ~130 GB/s (host side: PCIe root / DRAM),
+               # which is what bounds the end-to-end number at 4 and 8 GPUs (46 KB cross the bus per solve with dense gradients)
+               "host_aggregate_gb_s": 1e-9 * (h2d + d2h) * world / (dt / args.steps),
+               "bus_bytes_per_solve": (h2d + d2h) / nb,
                "single_call_ms_per_step": 1e3 * dt_sync, "single_call_value": nb * world / dt_sync,
                "factored_grad": {"value": nb * world * args.steps / dt_f, "unit": UNIT, "ms_per_step": 1e3 * dt_f / args.steps,
                                  "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h_f,
@@ -772,6 +780,36 @@ def main():
         zz = step().detach().cpu()
         assert torch.allclose(zz, out["zhat"], rtol=0, atol=0), "host-buffer path and device path disagree"
         del host, out, outs
+
+    # ---- exact global-batch mode (N > 1): the sharded batch solved as ONE reference batch -- the batch-global termination
+    # test and step fill are all-reduced once per iteration (96 bytes, NCCL MAX), one launch per iteration by construction
+    exact = None
+    if world > 1 and not args.quick:
+        try:
+            fx = QPFunction(verbose=-1, check_Q_spd=False, process_group=dist.group.WORLD)
+
+            def xstep():
+                for t in (Q, p, G, h):
+                    t.grad = None
+                fx(Q, p, G, h, A, b).backward(ones)
+
+            for _ in range(2):
+                xstep()
+            barrier()
+            x0_, x1_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            x0_.record()
+            for _ in range(3):
+                xstep()
+            x1_.record()
+            barrier()
+            xm = torch.tensor([x0_.elapsed_time(x1_) / 3], device=dev, dtype=torch.float64)
+            dist.all_reduce(xm, op=dist.ReduceOp.MAX)
+            exact = {"workload": f"the same {nb} QPs per GPU treated as one batch of {nb * world} (QPFunction(process_group=...)): "
+                                 "bit-identical to the unsharded reference batch", "ms_per_step": xm.item(),
+                     "value": nb * world / (xm.item() * 1e-3), "unit": UNIT, "n_iter": fx.info["n_iter"],
+                     "collectives_per_step": fx.info["n_iter"] + 1}
+        except Exception as ex:  # pragma: no cover
+            exact = {"error": repr(ex)[:300]}
 
     # ---- BASELINE configs[0] shape (nb=128) for reference: latency-bound -----------------------
     small = None
@@ -878,7 +916,7 @@ def main():
                        "eps": 1e-12, "maxIter": 20, "exact_rerun": bool(fn.info.get("exact_rerun", False)),
                        "nan_onset_iteration": fn.info.get("nan_onset"), "parallelism": f"batch-sharded x{world}, no data-path collective",
                        "l2": "inputs+workspace per step exceed the 126 MB L2 (no flush needed)"},
-            "clocks": clocks, "e2e": e2e, "gpu_launches": launches_per_step * args.steps,
+            "clocks": clocks, "e2e": e2e, "exact_global_batch": exact, "gpu_launches": launches_per_step * args.steps,
             "roofline": roofline, "cpu_baseline": cpu, "cfg1_nb128": small, "cfg4_sizes": sizes, "mpc": mpc, "policy": pol,
         }
         emit(line)

@@ -25,6 +25,9 @@ CASES = {
     "ipmpc_pendulum1l_B8_T5_sqp3": ("pendulum1l", 8, 5, 3),
     "ipmpc_cartpole1l_B4_T10_single": ("cartpole1l", 4, 10, 1),
     "ipmpc_cartpole1l_B4_T10_sqp3": ("cartpole1l", 4, 10, 3),
+    # BASELINE configs[2]'s horizon: the QP has nz = 100, neq = 80, nineq = 40 (KKT order 260); appended last so that the
+    # earlier cases keep their random inputs
+    "ipmpc_cartpole1l_B4_T20_single": ("cartpole1l", 4, 20, 1),
 }
 
 

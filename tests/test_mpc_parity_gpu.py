@@ -354,7 +354,8 @@ def test_al_mpc_myenvs_golden(case, cuda_device):
 
 
 @pytest.mark.parametrize("case", ["ipmpc_pendulum1l_B8_T5_single", "ipmpc_pendulum1l_B8_T5_sqp3",
-                                  "ipmpc_cartpole1l_B4_T10_single", "ipmpc_cartpole1l_B4_T10_sqp3"])
+                                  "ipmpc_cartpole1l_B4_T10_single", "ipmpc_cartpole1l_B4_T10_sqp3",
+                                  "ipmpc_cartpole1l_B4_T20_single"])
 def test_ip_mpc_matches_reference_golden(case, cuda_device):
     """b200qp.qp_wrapper.MPC (the interior-point MPC: SQP loop, DenseQPFunction with the NON-linear dynamics residual as
     its dyn_res callback, line search) against goldens of the real qpth.qp_wrapper.MPC on the reference's my_envs
