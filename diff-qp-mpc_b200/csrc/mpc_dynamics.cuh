@@ -75,21 +75,33 @@ template <typename R, int N> __device__ __forceinline__ Dual<R, N> operator*(R b
 template <typename R, int N> __device__ __forceinline__ Dual<R, N> operator/(const Dual<R, N>& a, R b) { return a * (R(1) / b); }
 template <typename R, int N> __device__ __forceinline__ Dual<R, N> operator/(R a, const Dual<R, N>& b) { return Dual<R, N>(a) / b; }
 
+__device__ __forceinline__ void m_sincos(double x, double& s, double& c) { sincos(x, &s, &c); }
+__device__ __forceinline__ void m_sincos(float x, float& s, float& c) { sincosf(x, &s, &c); }
 __device__ __forceinline__ double m_sin(double x) { return sin(x); }
 __device__ __forceinline__ float m_sin(float x) { return sinf(x); }
 __device__ __forceinline__ double m_cos(double x) { return cos(x); }
 __device__ __forceinline__ float m_cos(float x) { return cosf(x); }
 template <typename R, int N> __device__ __forceinline__ Dual<R, N> m_sin(const Dual<R, N>& a) {
-  Dual<R, N> r; r.v = m_sin(a.v); const R c = m_cos(a.v);
+  Dual<R, N> r; R c; m_sincos(a.v, r.v, c);
 #pragma unroll
   for (int i = 0; i < N; i++) r.d[i] = c * a.d[i];
   return r;
 }
 template <typename R, int N> __device__ __forceinline__ Dual<R, N> m_cos(const Dual<R, N>& a) {
-  Dual<R, N> r; r.v = m_cos(a.v); const R s = -m_sin(a.v);
+  Dual<R, N> r; R sp; m_sincos(a.v, sp, r.v); const R s = -sp;
 #pragma unroll
   for (int i = 0; i < N; i++) r.d[i] = s * a.d[i];
   return r;
+}
+// sine and cosine of the same angle in one call: one argument reduction instead of two (four under duals, where each of
+// m_sin / m_cos needs both).  ncu on k_al_solve<Cartpole1L>: 20 % of the samples were in sin / cos.
+template <typename R, int N> __device__ __forceinline__ void m_sincos(const Dual<R, N>& a, Dual<R, N>& s, Dual<R, N>& c) {
+  R sv, cv;
+  m_sincos(a.v, sv, cv);
+  s.v = sv; c.v = cv;
+  const R ns = -sv;
+#pragma unroll
+  for (int i = 0; i < N; i++) { s.d[i] = cv * a.d[i]; c.d[i] = ns * a.d[i]; }
 }
 __device__ __forceinline__ double m_atan2(double y, double x) { return atan2(y, x); }
 __device__ __forceinline__ float m_atan2(float y, float x) { return atan2f(y, x); }
@@ -164,8 +176,7 @@ struct PendulumDx {
     const S th = m_atan2(sth, cth);
     const S newdth = dth + dt * ((R(-3) * g / (R(2) * l)) * (-sth) + R(3) * uc / (m * l * l));
     const S newth = th + newdth * dt;
-    xn[0] = m_cos(newth);
-    xn[1] = m_sin(newth);
+    m_sincos(newth, xn[1], xn[0]);
     xn[2] = newdth;
   }
 };
@@ -189,8 +200,7 @@ struct CartpoleDx {
     const S nth = th + dt * dth;
     xn[0] = px + dt * dx;
     xn[1] = dx + dt * xacc;
-    xn[2] = m_cos(nth);
-    xn[3] = m_sin(nth);
+    m_sincos(nth, xn[3], xn[2]);
     xn[4] = dth + dt * th_acc;
   }
 };
@@ -362,7 +372,8 @@ struct Cartpole1LModel {
   __device__ static __forceinline__ void accel(const DynParams& P, const S* q, const S* qd, const S& u, S* a) {
     typedef typename real_of<S>::type R;
     const R mt = (R)P.v[1], ml = (R)P.v[2], I = (R)P.v[3], g = (R)P.v[4];
-    const S s = m_sin(q[1]), c = m_cos(q[1]);
+    S s, c;
+    m_sincos(q[1], s, c);
     const S mc = ml * c;
     const S r0 = u - ml * s * (qd[1] * qd[1]);
     const S r1 = (ml * g) * s;
@@ -381,7 +392,9 @@ struct Cartpole2LModel {
     typedef typename real_of<S>::type R;
     const R mt = (R)P.v[1], h1 = (R)P.v[2], h2 = (R)P.v[3], J1 = (R)P.v[4], J2 = (R)P.v[5], k = (R)P.v[6], g = (R)P.v[7];
     const S p2 = q[1] + q[2], w1 = qd[1], w2 = qd[1] + qd[2];
-    const S s1 = m_sin(q[1]), c1 = m_cos(q[1]), s2 = m_sin(p2), c2 = m_cos(p2);
+    S s1, c1, s2, c2;
+    m_sincos(q[1], s1, c1);
+    m_sincos(p2, s2, c2);
     const S s12 = s1 * c2 - c1 * s2, c12 = c1 * c2 + s1 * s2;
     const S m01 = -h1 * c1, m02 = -h2 * c2, m12 = k * c12;
     const S r0 = u - h1 * s1 * (w1 * w1) - h2 * s2 * (w2 * w2);
@@ -408,7 +421,8 @@ struct Cartpole1LV1Model {
   __device__ static __forceinline__ void accel(const DynParams& P, const S* q, const S* qd, const S& u, S* a) {
     typedef typename real_of<S>::type R;
     const R M = (R)P.v[1], m = (R)P.v[2], l = (R)P.v[3], g = (R)P.v[4];
-    const S s = m_sin(q[1]), c = m_cos(q[1]);
+    S s, c;
+    m_sincos(q[1], s, c);
     const S w2 = qd[1] * qd[1];
     const S den = M + m * (s * s);
     a[0] = (u + (m * l) * w2 * s - (m * g) * s * c) / den;
@@ -425,14 +439,16 @@ struct Cartpole2LV1Model {
     const S f = -u;
     const S q1 = q[1], q2 = q[2], w1 = qd[1], w2 = qd[2];
     const S w11 = w1 * w1, w12 = w1 * w2, w22 = w2 * w2;
-    const S c1 = m_cos(q1), s1 = m_sin(q1), c2 = m_cos(q2), s2 = m_sin(q2);
-    const S c_1m2 = m_cos(q1 - q2), s_1m2 = m_sin(q1 - q2);
-    const S c_1p2 = m_cos(q1 + q2), s_1p2 = m_sin(q1 + q2);
-    const S c_1p22 = m_cos(q1 + R(2) * q2), s_1p22 = m_sin(q1 + R(2) * q2);
-    const S c_21 = m_cos(R(2) * q1), s_21 = m_sin(R(2) * q1);
-    const S c_22 = m_cos(R(2) * q2), s_22 = m_sin(R(2) * q2);
-    const S c_21p2 = m_cos(R(2) * q1 + q2), s_21p2 = m_sin(R(2) * q1 + q2);
-    const S c_21p22 = m_cos(R(2) * q1 + R(2) * q2), s_21p22 = m_sin(R(2) * q1 + R(2) * q2);
+    S c1, s1, c2, s2, c_1m2, s_1m2, c_1p2, s_1p2, c_1p22, s_1p22, c_21, s_21, c_22, s_22, c_21p2, s_21p2, c_21p22, s_21p22;
+    m_sincos(q1, s1, c1);
+    m_sincos(q2, s2, c2);
+    m_sincos(q1 - q2, s_1m2, c_1m2);
+    m_sincos(q1 + q2, s_1p2, c_1p2);
+    m_sincos(q1 + R(2) * q2, s_1p22, c_1p22);
+    m_sincos(R(2) * q1, s_21, c_21);
+    m_sincos(R(2) * q2, s_22, c_22);
+    m_sincos(R(2) * q1 + q2, s_21p2, c_21p2);
+    m_sincos(R(2) * q1 + R(2) * q2, s_21p22, c_21p22);
     const S den = R(3) * c_21 - R(22) * c_22 - c_21p22 + R(34);
     a[0] = (R(4) * f * c_22 - R(6) * f + R(4) * w11 * c1 + w11 * c_1m2 - w11 * c_1p22 + R(2) * w12 * c_1m2 + w22 * c_1m2
             - R(29.43) * s_21 + R(9.81) * s_21p22) / den;
