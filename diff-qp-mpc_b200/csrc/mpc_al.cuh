@@ -123,7 +123,11 @@ __device__ __forceinline__ R merit_eval(const ALScratch<R, Dyn::NX, Dyn::NU>& S,
 
 // Gradient (into S.g) and block-tridiagonal Hessian (S.D lower blocks, S.E = H_{t+1,t} top rows)
 // of the AL merit at S.xu (al_utils.py:62-102).
-template <class Dyn, typename R>
+// TILE16 (NT = 16, fp64: block_cholesky_tiles16 follows): the Jacobian [A_t B_t] is ALSO written transposed into D_t's slot
+// (16 x 16, columns 12..15 zero); the Hessian blocks D_t = diag + rho J^T J are then formed as DMMA tile products inside the
+// factorisation (J^T J = JT JT^T is of the A B^T form), E is scaled by -rho as it is loaded there, and the two scalar
+// passes below are skipped.
+template <class Dyn, typename R, bool TILE16 = false>
 __device__ __forceinline__ void assemble(const ALScratch<R, Dyn::NX, Dyn::NU>& S, const DynParams& P, int T, R rho, int lane) {
   constexpr int NX = Dyn::NX, NU = Dyn::NU, NT = NX + NU;
   const int neq = T * NX;
@@ -149,8 +153,19 @@ __device__ __forceinline__ void assemble(const ALScratch<R, Dyn::NX, Dyn::NU>& S
         for (int i = 0; i < NX; i++) {
 #pragma unroll
           for (int q = 0; q < DW; q++)
-            if (c0 + q < NT) S.E[(t * NX + i) * NT + c0 + q] = f[i].d[q];
+            if (c0 + q < NT) {
+              S.E[(t * NX + i) * NT + c0 + q] = f[i].d[q];
+              if (TILE16) S.D[t * NT * NT + (c0 + q) * NT + i] = f[i].d[q];
+            }
           if (c0 == 0) S.w[t * NX + i] = S.lam[t * NX + i] + rho * (S.xu[(t + 1) * NT + i] - f[i].v);
+        }
+        if (TILE16) {
+#pragma unroll
+          for (int q = 0; q < DW; q++)
+            if (c0 + q < NT) {
+#pragma unroll
+              for (int i = NX; i < NT; i++) S.D[t * NT * NT + (c0 + q) * NT + i] = R(0);
+            }
         }
       }
     }
@@ -180,6 +195,7 @@ __device__ __forceinline__ void assemble(const ALScratch<R, Dyn::NX, Dyn::NU>& S
     }
     S.g[idx] = gv;
   }
+  if constexpr (!TILE16) {
   for (int idx = lane; idx < T * NT * NT; idx += 32) {
     const int t = idx / (NT * NT), rem = idx - t * NT * NT, j = rem / NT, k = rem - j * NT;
     if (k > j) continue;
@@ -201,6 +217,7 @@ __device__ __forceinline__ void assemble(const ALScratch<R, Dyn::NX, Dyn::NU>& S
   }
   __syncwarp();
   for (int idx = lane; idx < (T - 1) * NX * NT; idx += 32) S.E[idx] = -rho * S.E[idx];
+  }
   __syncwarp();
 }
 
@@ -316,6 +333,182 @@ __device__ __forceinline__ void block_cholesky_staged(R* D, R* E, int T, int lan
       R* tmp = sEp; sEp = sEn; sEn = tmp;
     }
     for (int idx = lane; idx < NT * NT; idx += 32) Dt[idx] = sD[(idx / NT) * LD + (idx % NT)];
+    __syncwarp();
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// The block factorisation for NT = nx + nu = 16 (rex quadrotor: nx = 12, nu = 4) on the FP64 TENSOR CORES, one warp per
+// problem, the blocks in registers as 8x8 DMMA accumulator tiles (lane (g, q) = (lane >> 2, lane & 3) holds row g, columns
+// 2q, 2q+1 of a tile) -- the tile algebra of qp_wres.cuh:
+//   * D_t (16x16) = [[A00, .], [A10, A11]] is factored as L Delta L^T: each 8x8 diagonal tile by quad shuffles, carrying
+//     W = L_JJ^-1 along (td_diag), X10 = A10 W0^T and A11 -= X10 Delta0^-1 X10^T as DMMAs;
+//   * E_t (12x16, two row tiles) becomes Y = E L^-T = [E0 W0^T, (E1 - Y0 L10^T) W1^T]: every product has the form A B^T,
+//     which mma.sync.m8n8k4.f64 computes from two accumulator-layout operands without moving data;
+//   * the Schur complement of the next block, D_{t+1}[0:12, 0:12] -= Y Delta^-1 Y^T, uses Y straight from registers.
+// 28 DMMAs and two 8-step pivot chains per knot; the results are written back in the CHOLESKY convention the block solves
+// and k_al_backward read (L_chol = L Delta^1/2, E_chol = Y Delta^-1/2), so nothing else changes.  A non-positive pivot
+// gives a NaN factor, as before.  (ncu before: 37 % of the samples of k_al_solve<RexQuadrotor> in the scalar block factor.)
+__device__ __forceinline__ void td_dmma(double& c0, double& c1, double a, double b) {
+  asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
+__device__ __forceinline__ void td_abt(double& c0, double& c1, double a0, double a1, double b0, double b1) {  // C += A B^T
+  td_dmma(c0, c1, a0, b0);
+  td_dmma(c0, c1, a1, b1);
+}
+__device__ __forceinline__ double td_shfl(double v, int src, int width = 32) {
+  int lo = __double2loint(v), hi = __double2hiint(v);
+  lo = __shfl_sync(0xffffffffu, lo, src, width);
+  hi = __shfl_sync(0xffffffffu, hi, src, width);
+  return __hiloint2double(hi, lo);
+}
+// LDL^T of one 8x8 diagonal tile (lower triangle valid): on exit column k < g of row g holds L[g][k] Delta_k, (w0, w1) = L^-1,
+// rinv[0..8) (shared memory) the reciprocal pivots
+__device__ __forceinline__ void td_diag(double& c0, double& c1, double& w0, double& w1, double* rinv, int lane) {
+  const int g = lane >> 2, q = lane & 3, q8 = 8 * q;
+  w0 = (g == 2 * q) ? 1.0 : 0.0;
+  w1 = (g == 2 * q + 1) ? 1.0 : 0.0;
+#pragma unroll
+  for (int k = 0; k < 8; k++) {
+    const int kq = k >> 1;
+    const double ck = (k & 1) ? c1 : c0;
+    const double dk = td_shfl(ck, 4 * k + kq);
+    const double ckm = (g > k) ? ck : 0.0;
+    const double cik = td_shfl(ckm, kq, 4);
+    const double cj0 = td_shfl(ckm, q8 + kq);
+    const double cj1 = td_shfl(ckm, q8 + 4 + kq);
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(dk));
+    const double e = fma(-dk, r, 1.0);
+    const double t = fma(e, e, e);
+    r = fma(r, t, r);
+    if (lane == 0) rinv[k] = r;
+    const double nl = -(cik * r);
+    c0 = fma(nl, cj0, c0);
+    c1 = fma(nl, cj1, c1);
+    if (k < 7) {
+      const double wk0 = td_shfl(w0, q + 4 * k), wk1 = td_shfl(w1, q + 4 * k);
+      w0 = fma(nl, wk0, w0);
+      w1 = fma(nl, wk1, w1);
+    }
+  }
+}
+
+// On entry (assemble<.., TILE16 = true>): D_t's slot holds J_t^T = [A_t B_t]^T (16 x 16, columns 12..15 zero; nothing for the
+// last knot, which has no dynamics), E_t the UNSCALED J_t (12 x 16).  Cd, xu (T x 16), uu, ul (T x 4): the diagonal terms of
+// al_utils.py:62-102.  rinv: 16 doubles of shared memory.
+__device__ __forceinline__ void block_cholesky_tiles16(double* D, double* E, int T, int lane, double* rinv, double rho,
+                                                       const double* Cd, const double* xu, const double* uu, const double* ul) {
+  constexpr int NT = 16, NX = 12, NU = 4;
+  const int g = lane >> 2, q = lane & 3, c = 2 * q;
+  double Y[2][2][2];  // Y of the previous knot: [row tile][column tile][slot]
+  double yr[2][2];    // its reciprocal pivots of this lane's columns, per column tile
+  for (int t = 0; t < T; t++) {
+    double* Dt = D + t * NT * NT;
+    // ---- D_t = diag(C_t) + rho (J^T J + E_x + active control bounds), J^T J = JT JT^T as tile products
+    double a00[2] = {0.0, 0.0}, a10[2] = {0.0, 0.0}, a11[2] = {0.0, 0.0};
+    double e[2][2][2];
+    if (t < T - 1) {
+      double jt[2][2][2];  // JT tiles: [row tile of tau][column tile of the next state]
+#pragma unroll
+      for (int r = 0; r < 2; r++)
+#pragma unroll
+        for (int k = 0; k < 2; k++) {
+          const double2 v = *reinterpret_cast<const double2*>(Dt + (8 * r + g) * NT + 8 * k + c);
+          jt[r][k][0] = v.x; jt[r][k][1] = v.y;
+        }
+#pragma unroll
+      for (int k = 0; k < 2; k++) {
+        td_abt(a00[0], a00[1], jt[0][k][0], jt[0][k][1], jt[0][k][0], jt[0][k][1]);
+        td_abt(a10[0], a10[1], jt[1][k][0], jt[1][k][1], jt[0][k][0], jt[0][k][1]);
+        td_abt(a11[0], a11[1], jt[1][k][0], jt[1][k][1], jt[1][k][0], jt[1][k][1]);
+      }
+      const double* Eg = E + t * NX * NT;
+      const double nr = -rho;
+#pragma unroll
+      for (int r = 0; r < 2; r++)
+#pragma unroll
+        for (int k = 0; k < 2; k++) {
+          double2 v = make_double2(0.0, 0.0);
+          if (8 * r + g < NX) v = *reinterpret_cast<const double2*>(Eg + (8 * r + g) * NT + 8 * k + c);
+          e[r][k][0] = nr * v.x; e[r][k][1] = nr * v.y;   // H_{t+1,t} = -rho [A_t B_t]
+        }
+    }
+    {
+      // diagonal terms, on the lanes that hold a diagonal entry (c == g or c + 1 == g)
+      const bool on0 = (c == g), on1 = (c + 1 == g);
+      double ex0 = 0.0, ex1 = 0.0, cd0 = 0.0, cd1 = 0.0;
+      if (on0 || on1) {
+        cd0 = Cd[t * NT + g]; cd1 = Cd[t * NT + 8 + g];
+        ex0 = 1.0;                                     // rows 0..7 are states
+        if (8 + g < NX) ex1 = 1.0;
+        else {
+          const int ju = 8 + g - NX;
+          const double u = xu[t * NT + 8 + g];
+          if (u - uu[t * NU + ju] > 0.0) ex1 += 1.0;
+          if (-u + ul[t * NU + ju] > 0.0) ex1 += 1.0;
+        }
+      }
+      a00[0] = rho * (a00[0] + (on0 ? ex0 : 0.0)) + (on0 ? cd0 : 0.0);
+      a00[1] = rho * (a00[1] + (on1 ? ex0 : 0.0)) + (on1 ? cd0 : 0.0);
+      a10[0] = rho * a10[0]; a10[1] = rho * a10[1];
+      a11[0] = rho * (a11[0] + (on0 ? ex1 : 0.0)) + (on0 ? cd1 : 0.0);
+      a11[1] = rho * (a11[1] + (on1 ? ex1 : 0.0)) + (on1 ? cd1 : 0.0);
+    }
+    // ---- Schur complement of the previous knot: D_t[0:12, 0:12] -= Y Delta^-1 Y^T (rows 12..15 of Y are zero)
+    if (t > 0) {
+#pragma unroll
+      for (int k = 0; k < 2; k++) {
+        const double s0 = -yr[k][0], s1 = -yr[k][1];
+        td_abt(a00[0], a00[1], Y[0][k][0] * s0, Y[0][k][1] * s1, Y[0][k][0], Y[0][k][1]);
+        td_abt(a10[0], a10[1], Y[1][k][0] * s0, Y[1][k][1] * s1, Y[0][k][0], Y[0][k][1]);
+        td_abt(a11[0], a11[1], Y[1][k][0] * s0, Y[1][k][1] * s1, Y[1][k][0], Y[1][k][1]);
+      }
+    }
+    // ---- L Delta L^T of the 16x16 block
+    double w0[2], w1[2];
+    td_diag(a00[0], a00[1], w0[0], w0[1], rinv, lane);
+    __syncwarp();
+    const double2 r0 = *reinterpret_cast<const double2*>(rinv + c);
+    double x10[2] = {0.0, 0.0};
+    td_abt(x10[0], x10[1], a10[0], a10[1], w0[0], w0[1]);                     // X10 = A10 W0^T = L10 Delta0
+    td_abt(a11[0], a11[1], x10[0] * -r0.x, x10[1] * -r0.y, x10[0], x10[1]);   // A11 -= X10 Delta0^-1 X10^T
+    td_diag(a11[0], a11[1], w1[0], w1[1], rinv + 8, lane);
+    __syncwarp();
+    const double2 r1 = *reinterpret_cast<const double2*>(rinv + 8 + c);
+    const double sr0x = sqrt(r0.x), sr0y = sqrt(r0.y), sr1x = sqrt(r1.x), sr1y = sqrt(r1.y);  // Delta^-1/2 of this lane's columns
+    // ---- Y = E L^-T, written back as E_chol = Y Delta^-1/2
+    if (t < T - 1) {
+      double* Eg = E + t * NX * NT;
+#pragma unroll
+      for (int r = 0; r < 2; r++) {
+        double y0[2] = {0.0, 0.0};
+        td_abt(y0[0], y0[1], e[r][0][0], e[r][0][1], w0[0], w0[1]);           // Y0 = E0 W0^T
+        double tt[2] = {0.0, 0.0};
+        td_abt(tt[0], tt[1], y0[0], y0[1], x10[0] * r0.x, x10[1] * r0.y);     // Y0 L10^T, L10 = X10 Delta0^-1
+        tt[0] = e[r][1][0] - tt[0]; tt[1] = e[r][1][1] - tt[1];
+        double y1[2] = {0.0, 0.0};
+        td_abt(y1[0], y1[1], tt[0], tt[1], w1[0], w1[1]);                     // Y1 = (E1 - Y0 L10^T) W1^T
+        Y[r][0][0] = y0[0]; Y[r][0][1] = y0[1]; Y[r][1][0] = y1[0]; Y[r][1][1] = y1[1];
+        if (8 * r + g < NX) {
+          *reinterpret_cast<double2*>(Eg + (8 * r + g) * NT + c) = make_double2(y0[0] * sr0x, y0[1] * sr0y);
+          *reinterpret_cast<double2*>(Eg + (8 * r + g) * NT + 8 + c) = make_double2(y1[0] * sr1x, y1[1] * sr1y);
+        }
+      }
+      yr[0][0] = r0.x; yr[0][1] = r0.y; yr[1][0] = r1.x; yr[1][1] = r1.y;
+    }
+    // ---- L_chol = L Delta^1/2 (lower triangle; the diagonal is Delta^1/2 = 1 / sqrt(rinv))
+    {
+      double2 o0, o1, o2;
+      o0.x = (c < g) ? a00[0] * sr0x : (c == g ? 1.0 / sr0x : 0.0);
+      o0.y = (c + 1 < g) ? a00[1] * sr0y : (c + 1 == g ? 1.0 / sr0y : 0.0);
+      o1.x = x10[0] * sr0x; o1.y = x10[1] * sr0y;
+      o2.x = (c < g) ? a11[0] * sr1x : (c == g ? 1.0 / sr1x : 0.0);
+      o2.y = (c + 1 < g) ? a11[1] * sr1y : (c + 1 == g ? 1.0 / sr1y : 0.0);
+      *reinterpret_cast<double2*>(Dt + g * NT + c) = o0;
+      *reinterpret_cast<double2*>(Dt + (8 + g) * NT + c) = o1;
+      *reinterpret_cast<double2*>(Dt + (8 + g) * NT + 8 + c) = o2;
+    }
     __syncwarp();
   }
 }
@@ -449,8 +642,15 @@ __global__ void __launch_bounds__(128, (Dyn::NX == 4 ? 4 : (Dyn::NX >= 12 ? B200
     // ---- NewtonAL.forward (al_utils.py:363-460)
     R merit = merit_eval<Dyn, R>(S, a.P, T, rho, false, R(0), false);
     for (int ns = 0; ns < a.newton_steps; ns++) {
-      assemble<Dyn, R>(S, a.P, T, rho, lane);
-      if (a.use_smem) block_cholesky<NX, NU, R>(S.D, S.E, T, lane);
+      constexpr bool kTile16 = NX == 12 && NU == 4 && sizeof(R) == 8;
+      assemble<Dyn, R, kTile16>(S, a.P, T, rho, lane);
+      if constexpr (kTile16) {
+        // 16x16 knot blocks as DMMA tiles in registers (a.use_smem or not: the blocks are read and written once per knot)
+        double* rinv = a.use_smem ? reinterpret_cast<double*>(S.mer) : reinterpret_cast<double*>(al_smem) + (size_t)warp * al_stage_elems<NX, NU>();
+        block_cholesky_tiles16(reinterpret_cast<double*>(S.D), reinterpret_cast<double*>(S.E), T, lane, rinv, (double)rho,
+                               reinterpret_cast<const double*>(S.C), reinterpret_cast<const double*>(S.xu),
+                               reinterpret_cast<const double*>(S.uu), reinterpret_cast<const double*>(S.ul));
+      } else if (a.use_smem) block_cholesky<NX, NU, R>(S.D, S.E, T, lane);
       else block_cholesky_staged<NX, NU, R>(S.D, S.E, T, lane, reinterpret_cast<R*>(al_smem) + (size_t)warp * al_stage_elems<NX, NU>());
       block_solve<NX, NU, R>(S.D, S.E, S.g, T, lane);
       for (int idx = lane; idx < T * NT; idx += 32) S.g[idx] = -S.g[idx];
