@@ -224,8 +224,9 @@ __device__ __forceinline__ void assemble(const ALScratch<R, Dyn::NX, Dyn::NU>& S
 // In-place block Cholesky: D_t <- L_tt (lower), E_t <- L_{t+1,t} top rows = S_t L_tt^-T.
 // A non-positive pivot poisons the factor with NaN (the reference's cholesky_ex would hand back
 // an unusable factor and fall back to a dense LU solve for the WHOLE batch, al_utils.py:419-427).
+// rd: NT reals of scratch (the reciprocal diagonal of the block being factored, for the row solves of E_t).
 template <int NX, int NU, typename R>
-__device__ __forceinline__ void block_cholesky(R* D, R* E, int T, int lane) {
+__device__ __forceinline__ void block_cholesky(R* D, R* E, int T, int lane, R* rd) {
   constexpr int NT = NX + NU;
   for (int t = 0; t < T; t++) {
     R* Dt = D + t * NT * NT;
@@ -246,8 +247,10 @@ __device__ __forceinline__ void block_cholesky(R* D, R* E, int T, int lane) {
     for (int j = 0; j < NT; j++) {
       const R djj = Dt[j * NT + j];
       const R ljj = djj > R(0) ? sqrt(djj) : r_nan<R>();
+      const R rjj = R(1) / ljj;   // one division per column; everything below multiplies
       __syncwarp();
-      if (lane >= j && lane < NT) Dt[lane * NT + j] = (lane == j) ? ljj : Dt[lane * NT + j] / ljj;
+      if (lane >= j && lane < NT) Dt[lane * NT + j] = (lane == j) ? ljj : Dt[lane * NT + j] * rjj;
+      if (lane == 0) rd[j] = rjj;
       __syncwarp();
       for (int idx = lane; idx < NT * NT; idx += 32) {
         const int i = idx / NT, k = idx - i * NT;
@@ -262,7 +265,7 @@ __device__ __forceinline__ void block_cholesky(R* D, R* E, int T, int lane) {
         for (int j = 0; j < NT; j++) {
           R v = row[j];
           for (int k = 0; k < j; k++) v -= row[k] * Dt[j * NT + k];
-          row[j] = v / Dt[j * NT + j];
+          row[j] = v * rd[j];
         }
       }
       __syncwarp();
@@ -652,7 +655,7 @@ __global__ void __launch_bounds__(128, (Dyn::NX == 4 ? 4 : (Dyn::NX >= 12 ? B200
         block_cholesky_tiles16(reinterpret_cast<double*>(S.D), reinterpret_cast<double*>(S.E), T, lane, rinv, (double)rho,
                                reinterpret_cast<const double*>(S.C), reinterpret_cast<const double*>(S.xu),
                                reinterpret_cast<const double*>(S.uu), reinterpret_cast<const double*>(S.ul));
-      } else if (a.use_smem) block_cholesky<NX, NU, R>(S.D, S.E, T, lane);
+      } else if (a.use_smem) block_cholesky<NX, NU, R>(S.D, S.E, T, lane, S.mer);
       else block_cholesky_staged<NX, NU, R>(S.D, S.E, T, lane, reinterpret_cast<R*>(al_smem) + (size_t)warp * al_stage_elems<NX, NU>());
       block_solve<NX, NU, R>(S.D, S.E, S.g, T, lane);
       for (int idx = lane; idx < T * NT; idx += 32) S.g[idx] = -S.g[idx];
