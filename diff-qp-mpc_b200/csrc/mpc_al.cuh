@@ -137,10 +137,13 @@ __device__ __forceinline__ void assemble(const ALScratch<R, Dyn::NX, Dyn::NU>& S
   constexpr int DWMAX = (NX == 4 || NX >= 12) ? 2 : 4;
   constexpr int DW = NT <= DWMAX ? NT : DWMAX;
   typedef Dual<R, DW> DR;
-  for (int t = lane; t < T; t += 32) {
-    if (t < T - 1) {
-#pragma unroll 1
-      for (int c0 = 0; c0 < NT; c0 += DW) {
+  // one task = one knot and one group of DW directions, tasks dealt round-robin to the lanes: with "lane = knot" a
+  // horizon of 40 knots kept 8 lanes busy for a second round of all NT / DW passes while 24 idled
+  constexpr int NPASS = (NT + DW - 1) / DW;
+  for (int task = lane; task < (T - 1) * NPASS; task += 32) {
+    const int t = task / NPASS, c0 = (task - t * NPASS) * DW;
+    {
+      {
         DR z[NT], f[NX];
 #pragma unroll
         for (int j = 0; j < NT; j++) {
@@ -169,11 +172,8 @@ __device__ __forceinline__ void assemble(const ALScratch<R, Dyn::NX, Dyn::NU>& S
         }
       }
     }
-    if (t == 0) {
-#pragma unroll
-      for (int i = 0; i < NX; i++) S.w[(T - 1) * NX + i] = S.lam[(T - 1) * NX + i] + rho * (S.xu[i] - S.x0[i]);
-    }
   }
+  if (lane < NX) S.w[(T - 1) * NX + lane] = S.lam[(T - 1) * NX + lane] + rho * (S.xu[lane] - S.x0[lane]);
   __syncwarp();
   for (int idx = lane; idx < T * NT; idx += 32) {
     const int t = idx / NT, j = idx - t * NT;
