@@ -600,6 +600,11 @@ __global__ void __launch_bounds__(128, (Dyn::NX == 4 ? 4 : (Dyn::NX >= 12 ? B200
   ALScratch<R, NX, NU> S;
   S.carve(a.use_smem ? reinterpret_cast<R*>(al_smem) + (size_t)warp * a.scratch_stride
                      : a.scratch + (size_t)prob * a.scratch_stride, T);
+  const int fe = al_factor_elems(T, NX, NU);
+  if (!a.use_smem) {  // global mode: factor straight into the output buffer of the call (no copy at the end)
+    S.D = a.factor + (size_t)prob * fe;
+    S.E = S.D + T * NT * NT;
+  }
   const size_t B = (size_t)a.B;
 
   // ---- load the problem
@@ -729,8 +734,8 @@ __global__ void __launch_bounds__(128, (Dyn::NX == 4 ? 4 : (Dyn::NX >= 12 ? B200
     if (j < NX) a.x_out[((size_t)prob * T + t) * NX + j] = (float)v;
     else a.u_out[((size_t)prob * T + t) * NU + (j - NX)] = (float)v;
   }
-  const int fe = al_factor_elems(T, NX, NU);
-  for (int idx = lane; idx < fe; idx += 32) a.factor[(size_t)prob * fe + idx] = S.D[idx];
+  if (a.use_smem)
+    for (int idx = lane; idx < fe; idx += 32) a.factor[(size_t)prob * fe + idx] = S.D[idx];
 }
 
 // NewtonAL.backward (al_utils.py:462-500): ig = -H^-1 grad ; dC = ig * x_est ; dc = ig.
