@@ -521,66 +521,112 @@ template <int NX, int NU, typename R>
 __device__ __forceinline__ void block_solve(const R* D, const R* E, R* g, int T, int lane) {
   constexpr int NT = NX + NU;
   static_assert(NT <= 32, "one lane per row of a knot block");
-  for (int t = 0; t < T; t++) {
-    const R* Dt = D + t * NT * NT;
-    R v = R(0);
-    if (lane < NT) {
-      v = g[t * NT + lane];
-      if (t > 0 && lane < NX) {
-        const R* row = E + ((t - 1) * NX + lane) * NT;
+  // Software-pipelined over the knots: the factor row / column, the E row / column and the right-hand side of knot t+1 are
+  // loaded while knot t is substituted, and the previous knot's solution is broadcast by shuffles instead of being
+  // re-read from memory -- with the state in the global slab every knot was a chain of dependent L2 round trips
+  // (ncu: 20 % of the samples of the rex solve).  Same operations in the same order.
+  const bool act = lane < NT;
+  // ---- forward: L y = g
+  {
+    R rowv[NT], erow[NT];
+#pragma unroll
+    for (int j = 0; j < NT; j++) { rowv[j] = (act && j <= lane) ? D[lane * NT + j] : R(0); erow[j] = R(0); }
+    R gv = act ? g[lane] : R(0);
+    R vprev = R(0);
+    for (int t = 0; t < T; t++) {
+      R rowv_n[NT], erow_n[NT], gv_n = R(0);
+      if (t + 1 < T) {
+        const R* Dn = D + (t + 1) * NT * NT;
+        const R* En = E + (t * NX + lane) * NT;
+#pragma unroll
+        for (int j = 0; j < NT; j++) {
+          rowv_n[j] = (act && j <= lane) ? Dn[lane * NT + j] : R(0);
+          erow_n[j] = (lane < NX) ? En[j] : R(0);
+        }
+        if (act) gv_n = g[(t + 1) * NT + lane];
+      } else {
+#pragma unroll
+        for (int j = 0; j < NT; j++) { rowv_n[j] = R(0); erow_n[j] = R(0); }
+      }
+      R v = gv;
+      if (t > 0) {
         R acc = R(0);
 #pragma unroll
-        for (int j = 0; j < NT; j++) acc += row[j] * g[(t - 1) * NT + j];
-        v -= acc;
+        for (int j = 0; j < NT; j++) acc += erow[j] * __shfl_sync(0xffffffffu, vprev, j);
+        if (lane < NX) v -= acc;
       }
+      R dg = R(1);
+#pragma unroll
+      for (int j = 0; j < NT; j++) dg = (lane == j) ? rowv[j] : dg;
+      dg = R(1) / dg;  // one division per lane and knot instead of NT (a double division is ~25 instructions)
+#pragma unroll
+      for (int j = 0; j < NT; j++) {
+        const R vj = __shfl_sync(0xffffffffu, v, j) * __shfl_sync(0xffffffffu, dg, j);
+        if (lane == j) v = vj;
+        else if (lane > j && act) v -= rowv[j] * vj;
+      }
+      if (act) g[t * NT + lane] = v;
+      vprev = v;
+      gv = gv_n;
+#pragma unroll
+      for (int j = 0; j < NT; j++) { rowv[j] = rowv_n[j]; erow[j] = erow_n[j]; }
     }
-    // this lane's row of L_tt, loaded up front (independent loads: one latency instead of NT dependent ones when the
-    // factor lives in the global slab); the diagonal travels by shuffle
-    R rowv[NT];
-#pragma unroll
-    for (int j = 0; j < NT; j++) rowv[j] = (lane < NT && j <= lane) ? Dt[lane * NT + j] : R(0);
-    R dg = R(1);
-#pragma unroll
-    for (int j = 0; j < NT; j++) dg = (lane == j) ? rowv[j] : dg;
-    dg = R(1) / dg;  // one division per lane and knot instead of NT (a double division is ~25 instructions)
-#pragma unroll
-    for (int j = 0; j < NT; j++) {
-      const R vj = __shfl_sync(0xffffffffu, v, j) * __shfl_sync(0xffffffffu, dg, j);
-      if (lane == j) v = vj;
-      else if (lane > j && lane < NT) v -= rowv[j] * vj;
-    }
-    if (lane < NT) g[t * NT + lane] = v;
-    __syncwarp();
   }
-  for (int t = T - 1; t >= 0; t--) {
-    const R* Dt = D + t * NT * NT;
-    R v = R(0);
-    if (lane < NT) {
-      v = g[t * NT + lane];
+  // ---- backward: L^T x = y
+  {
+    R colv[NT], ecol[NX];
+    {
+      const R* Dl = D + (T - 1) * NT * NT;
+#pragma unroll
+      for (int j = 0; j < NT; j++) colv[j] = (act && j >= lane) ? Dl[j * NT + lane] : R(0);
+#pragma unroll
+      for (int i = 0; i < NX; i++) ecol[i] = R(0);
+    }
+    R gv = act ? g[(T - 1) * NT + lane] : R(0);
+    R vnext = R(0);
+    for (int t = T - 1; t >= 0; t--) {
+      R colv_n[NT], ecol_n[NX], gv_n = R(0);
+      if (t > 0) {
+        const R* Dn = D + (t - 1) * NT * NT;
+        const R* En = E + (t - 1) * NX * NT;
+#pragma unroll
+        for (int j = 0; j < NT; j++) colv_n[j] = (act && j >= lane) ? Dn[j * NT + lane] : R(0);
+#pragma unroll
+        for (int i = 0; i < NX; i++) ecol_n[i] = act ? En[i * NT + lane] : R(0);
+        if (act) gv_n = g[(t - 1) * NT + lane];
+      } else {
+#pragma unroll
+        for (int j = 0; j < NT; j++) colv_n[j] = R(0);
+#pragma unroll
+        for (int i = 0; i < NX; i++) ecol_n[i] = R(0);
+      }
+      R v = gv;
       if (t < T - 1) {
-        const R* Et = E + t * NX * NT;
         R acc = R(0);
 #pragma unroll
-        for (int i = 0; i < NX; i++) acc += Et[i * NT + lane] * g[(t + 1) * NT + i];
-        v -= acc;
+        for (int i = 0; i < NX; i++) acc += ecol[i] * __shfl_sync(0xffffffffu, vnext, i);
+        if (act) v -= acc;
       }
+      R dg = R(1);
+#pragma unroll
+      for (int j = 0; j < NT; j++) dg = (lane == j) ? colv[j] : dg;
+      dg = R(1) / dg;
+#pragma unroll
+      for (int j = NT - 1; j >= 0; j--) {
+        const R vj = __shfl_sync(0xffffffffu, v, j) * __shfl_sync(0xffffffffu, dg, j);
+        if (lane == j) v = vj;
+        else if (lane < j) v -= colv[j] * vj;
+      }
+      if (act) g[t * NT + lane] = v;
+      vnext = v;
+      gv = gv_n;
+#pragma unroll
+      for (int j = 0; j < NT; j++) colv[j] = colv_n[j];
+#pragma unroll
+      for (int i = 0; i < NX; i++) ecol[i] = ecol_n[i];
     }
-    R colv[NT];  // column `lane` of L_tt (rows j >= lane), loaded up front
-#pragma unroll
-    for (int j = 0; j < NT; j++) colv[j] = (lane < NT && j >= lane) ? Dt[j * NT + lane] : R(0);
-    R dg = R(1);
-#pragma unroll
-    for (int j = 0; j < NT; j++) dg = (lane == j) ? colv[j] : dg;
-    dg = R(1) / dg;
-#pragma unroll
-    for (int j = NT - 1; j >= 0; j--) {
-      const R vj = __shfl_sync(0xffffffffu, v, j) * __shfl_sync(0xffffffffu, dg, j);
-      if (lane == j) v = vj;
-      else if (lane < j) v -= colv[j] * vj;
-    }
-    if (lane < NT) g[t * NT + lane] = v;
-    __syncwarp();
   }
+  __syncwarp();
 }
 
 template <class Dyn, typename R>
