@@ -59,6 +59,9 @@ template <typename R> __device__ __forceinline__ R r_inf();
 template <> __device__ __forceinline__ double r_inf<double>() { return __longlong_as_double(0x7ff0000000000000LL); }
 template <> __device__ __forceinline__ float r_inf<float>() { return __int_as_float(0x7f800000); }
 
+__device__ __forceinline__ double r_rsqrt(double x) { return rsqrt(x); }
+__device__ __forceinline__ float r_rsqrt(float x) { return rsqrtf(x); }
+
 template <typename R> __device__ __forceinline__ R warp_sum(R v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
@@ -246,8 +249,10 @@ __device__ __forceinline__ void block_cholesky(R* D, R* E, int T, int lane, R* r
 #pragma unroll 1
     for (int j = 0; j < NT; j++) {
       const R djj = Dt[j * NT + j];
-      const R ljj = djj > R(0) ? sqrt(djj) : r_nan<R>();
-      const R rjj = R(1) / ljj;   // one division per column; everything below multiplies
+      // 1 / sqrt(d) first (MUFU seed + Newton: ~12 instructions), then l = d * (1 / sqrt(d)): a double sqrt followed by a
+      // double division is ~55 instructions on the pivot chain.  d <= 0 gives NaN as before.
+      const R rjj = djj > R(0) ? r_rsqrt(djj) : r_nan<R>();
+      const R ljj = djj * rjj;
       __syncwarp();
       if (lane >= j && lane < NT) Dt[lane * NT + j] = (lane == j) ? ljj : Dt[lane * NT + j] * rjj;
       if (lane == 0) rd[j] = rjj;
