@@ -124,6 +124,87 @@ __device__ __forceinline__ R merit_eval(const ALScratch<R, Dyn::NX, Dyn::NU>& S,
   return cost + R(0.5) * rho * pen + lin;
 }
 
+// The same merit for problems whose vectors live in the GLOBAL slab (rex): executed by the WHOLE warp.  The per-knot data
+// (xu, g, C, c, the multipliers and bounds of the knot: 4 NT + NX + 4 NU reals) is fetched cooperatively -- three coalesced
+// loads per lane, issued one knot ahead -- into a double-buffered shared-memory stage and read from there by the candidate
+// lanes (`active`); with every candidate lane walking the slab on its own each knot cost a chain of L2 round trips
+// (ncu: 20 % of the samples of the rex solve, nearly all long-scoreboard).  Same operations in the same order.
+template <class Dyn, typename R>
+__device__ __forceinline__ R merit_eval_staged(const ALScratch<R, Dyn::NX, Dyn::NU>& S, const DynParams& P, int T, R rho,
+                                               bool use_upd, R s, bool force, bool active, int lane, R* stage) {
+  constexpr int NX = Dyn::NX, NU = Dyn::NU, NT = NX + NU;
+  constexpr int O_G = NT, O_C = 2 * NT, O_c = 3 * NT, O_LX = 4 * NT, O_LU = O_LX + NX, O_UU = O_LU + 2 * NU, O_UL = O_UU + NU,
+                CNT = O_UL + NU, STG = (CNT + 3) & ~3, NLD = (CNT + 31) / 32;
+  const int neq = T * NX;
+  auto fetch = [&](int t, R (&r)[NLD]) {
+#pragma unroll
+    for (int k = 0; k < NLD; k++) {
+      const int idx = lane + 32 * k;
+      R v = R(0);
+      if (idx < O_G) v = S.xu[t * NT + idx];
+      else if (idx < O_C) v = S.g[t * NT + idx - O_G];
+      else if (idx < O_c) v = S.C[t * NT + idx - O_C];
+      else if (idx < O_LX) v = S.c[t * NT + idx - O_c];
+      else if (idx < O_LU) v = S.lam[(t == 0 ? T - 1 : t - 1) * NX + idx - O_LX];
+      else if (idx < O_UU) v = S.lam[neq + t * 2 * NU + idx - O_LU];
+      else if (idx < O_UL) v = S.uu[t * NU + idx - O_UU];
+      else if (idx < CNT) v = S.ul[t * NU + idx - O_UL];
+      r[k] = v;
+    }
+  };
+  auto put = [&](R* buf, const R (&r)[NLD]) {
+#pragma unroll
+    for (int k = 0; k < NLD; k++) { const int idx = lane + 32 * k; if (idx < CNT) buf[idx] = r[k]; }
+  };
+  R x0v[NX];
+#pragma unroll
+  for (int j = 0; j < NX; j++) x0v[j] = S.x0[j];
+  R pre[NLD];
+  fetch(0, pre);
+  put(stage, pre);
+  __syncwarp();
+  R cost = R(0), pen = R(0), lin = R(0);
+  R fprev[NX];
+  for (int t = 0; t < T; t++) {
+    const R* b = stage + (t & 1) * STG;
+    if (t + 1 < T) fetch(t + 1, pre);
+    if (active) {
+      R z[NT];
+#pragma unroll
+      for (int j = 0; j < NT; j++) {
+        z[j] = b[j];
+        if (use_upd) z[j] += s * b[O_G + j];
+      }
+      if (force && t == 0) {
+#pragma unroll
+        for (int j = 0; j < NX; j++) z[j] = x0v[j];
+      }
+      R q1 = R(0), q2 = R(0);
+#pragma unroll
+      for (int j = 0; j < NT; j++) { q1 += z[j] * b[O_C + j] * z[j]; q2 += b[O_c + j] * z[j]; }
+      cost += R(0.5) * q1 + q2;
+#pragma unroll
+      for (int j = 0; j < NX; j++) {
+        const R r = (t == 0) ? z[j] - x0v[j] : z[j] - fprev[j];
+        const R l = b[O_LX + j];
+        pen += r * r;
+        lin += l * r;
+      }
+#pragma unroll
+      for (int j = 0; j < NU; j++) {
+        const R r1 = z[NX + j] - b[O_UU + j], r2 = -z[NX + j] + b[O_UL + j];
+        const R c1 = r1 > R(0) ? r1 : (r1 != r1 ? r1 : R(0)), c2 = r2 > R(0) ? r2 : (r2 != r2 ? r2 : R(0));
+        pen += c1 * c1 + c2 * c2;
+        lin += b[O_LU + j] * r1 + b[O_LU + NU + j] * r2;
+      }
+      if (t < T - 1) Dyn::template step<R>(P, z, z + NX, fprev);
+    }
+    if (t + 1 < T) put(stage + ((t + 1) & 1) * STG, pre);
+    __syncwarp();
+  }
+  return cost + R(0.5) * rho * pen + lin;
+}
+
 // Gradient (into S.g) and block-tridiagonal Hessian (S.D lower blocks, S.E = H_{t+1,t} top rows)
 // of the AL merit at S.xu (al_utils.py:62-102).
 // TILE16 (NT = 16, fp64: block_cholesky_tiles16 follows): the Jacobian [A_t B_t] is ALSO written transposed into D_t's slot
@@ -284,7 +365,12 @@ __device__ __forceinline__ void block_cholesky(R* D, R* E, int T, int lane, R* r
 // dependent global-memory round trip (~10^3 cycles x 16 columns x T blocks x 8 Newton steps: ~20 of the 21 ms of a rex
 // solve); the arithmetic and its order are unchanged.
 template <int NX, int NU>
-__host__ __device__ constexpr int al_stage_elems() { return ((NX + NU) * (NX + NU + 1) + 2 * NX * (NX + NU + 1) + 3) & ~3; }
+__host__ __device__ constexpr int al_stage_elems() {
+  // the larger of: the staged block factorisation (D_t, E_{t-1}, E_t) and 32 + the double-buffered merit stage
+  constexpr int a = ((NX + NU) * (NX + NU + 1) + 2 * NX * (NX + NU + 1) + 3) & ~3;
+  constexpr int b = 32 + 2 * ((4 * (NX + NU) + NX + 4 * NU + 3) & ~3);
+  return a > b ? a : b;
+}
 
 template <int NX, int NU, typename R>
 __device__ __forceinline__ void block_cholesky_staged(R* D, R* E, int T, int lane, R* wk) {
@@ -701,7 +787,9 @@ __global__ void __launch_bounds__(128, (Dyn::NX == 4 ? 4 : (Dyn::NX >= 12 ? B200
   R status = R(0);
   for (int ai = 0; ai < a.al_iter; ai++) {
     // ---- NewtonAL.forward (al_utils.py:363-460)
-    R merit = merit_eval<Dyn, R>(S, a.P, T, rho, false, R(0), false);
+    R* mstage = reinterpret_cast<R*>(al_smem) + (size_t)warp * al_stage_elems<NX, NU>() + 32;  // global mode only
+    R merit = a.use_smem ? merit_eval<Dyn, R>(S, a.P, T, rho, false, R(0), false)
+                         : merit_eval_staged<Dyn, R>(S, a.P, T, rho, false, R(0), false, true, lane, mstage);
     for (int ns = 0; ns < a.newton_steps; ns++) {
       constexpr bool kTile16 = NX == 12 && NU == 4 && sizeof(R) == 8;
       assemble<Dyn, R, kTile16>(S, a.P, T, rho, lane);
@@ -720,7 +808,12 @@ __global__ void __launch_bounds__(128, (Dyn::NX == 4 ? 4 : (Dyn::NX >= 12 ? B200
       R mv = r_inf<R>();
       R step = R(1);
       for (int k = 0; k < lane; k++) step *= R(0.5);
-      if (lane < a.n_ls) mv = merit_eval<Dyn, R>(S, a.P, T, rho, true, step, true);
+      if (a.use_smem) {
+        if (lane < a.n_ls) mv = merit_eval<Dyn, R>(S, a.P, T, rho, true, step, true);
+      } else {
+        const R mm = merit_eval_staged<Dyn, R>(S, a.P, T, rho, true, step, true, lane < a.n_ls, lane, mstage);
+        if (lane < a.n_ls) mv = mm;
+      }
       // argmin, first index on ties, NaN wins (torch.min propagates NaN)
       R bv = mv;
       int bi = lane;
