@@ -21,4 +21,12 @@ for _ in range(2):
     with torch.no_grad():
         x, u = ctrl(x0, QuadCost(torch.diag_embed(Cd), torch.zeros(B, T, 16, dtype=torch.float64, device=dev)), dx, dxj)
 torch.cuda.synchronize()
+e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+ctrl.reinitialize(x0, None); ctrl.u_init = u0
+e0.record()
+with torch.no_grad():
+    x, u = ctrl(x0, QuadCost(torch.diag_embed(Cd), torch.zeros(B, T, 16, dtype=torch.float64, device=dev)), dx, dxj)
+e1.record()
+torch.cuda.synchronize()
+print("B", B, "forward ms", e0.elapsed_time(e1), "rollouts/s", B / (e0.elapsed_time(e1) * 1e-3))
 print("finite", bool(torch.isfinite(x).all()), float(x.double().norm()))
