@@ -252,7 +252,8 @@ struct RexQuadrotor {
     const S* pm = x + 3; const S* v = x + 6; const S* w = x + 9;
     S q[4], qn[4];
     mrp2quat<S, R>(pm, R(1), q);
-    mrp2quat<S, R>(pm, R(-1), qn);
+    // the quaternion of -m is the conjugate: (2 * -1) m inv == -(2 m inv) exactly, so no second evaluation (one division)
+    qn[0] = q[0]; qn[1] = -q[1]; qn[2] = -q[2]; qn[3] = -q[3];
     // forces (rex_quadrotor.py:51-68)
     const R kff = (R)P.v[3];
     const S Fz = kff * us[0] + kff * us[1] + kff * us[2] + kff * us[3];
