@@ -533,3 +533,21 @@ def test_envs_v1_against_reference_modules(name, cuda_device):
     assert rel(fwd(x, u).cpu(), torch.tensor(g["xn"])) < 1e-13
     assert rel(A.cpu(), torch.tensor(g["A"])) < 1e-11
     assert rel(B.cpu(), torch.tensor(g["B"])) < 1e-11
+
+
+def test_global_slab_mode_matches_goldens(cuda_device):
+    """The code paths of problems whose state does not fit shared memory (global scratch slab: staged block Cholesky, staged
+    line search, factor built in the output buffer) driven with the small goldens: B200MPC_FORCE_GLOBAL=1 in a child process
+    (the switch is read once per process) must pass the same parity tests as the shared-memory mode."""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, B200MPC_FORCE_GLOBAL="1")
+    sel = ("test_al_mpc_matches_reference_golden or test_al_mpc_myenvs_golden or test_tracking_mpc_matches_reference_golden or "
+           "test_al_mpc_float32_solver_precision or test_al_mpc_vs_oracle_seeded_large_horizon")
+    r = subprocess.run([sys.executable, "-m", "pytest", os.path.join(root, "tests", "test_mpc_parity_gpu.py"), "-q", "-m", "gpu", "-x",
+                        "-k", sel, "-p", "no:cacheprovider"], cwd=root, env=env, capture_output=True, text=True, timeout=900)
+    tail = (r.stdout + r.stderr)[-1500:]
+    assert r.returncode == 0, tail
+    assert " passed" in r.stdout and "no tests ran" not in r.stdout, tail
+    print(r.stdout.strip().splitlines()[-1])
