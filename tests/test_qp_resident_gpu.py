@@ -64,7 +64,10 @@ def test_chunk_invariance_bitwise(shape, cuda_device, opts):
                 assert bool(same.all()), f"spec {spec} chunk {ch}: {k} differs from (spec 1, chunk 1) in {int((~same).sum())} entries"
 
 
-@pytest.mark.parametrize("shape", [(256, 30, 60, 11, False), (128, 30, 60, 0, False), (64, 30, 60, 3, True), (96, 10, 10, 5, False), (50, 20, 31, 6, False)])
+# the last three shapes: odd nz (scalar loads in k_wres_prefactor), nz = 32 (no padding row in Q's tiles), nineq = 32 (four tile rows
+# of G with a bordered fifth row of T)
+@pytest.mark.parametrize("shape", [(256, 30, 60, 11, False), (128, 30, 60, 0, False), (64, 30, 60, 3, True), (96, 10, 10, 5, False), (50, 20, 31, 6, False),
+                                   (40, 7, 9, 12, False), (33, 32, 40, 13, False), (48, 17, 32, 14, True)])
 def test_resident_vs_per_iteration_route_and_oracle(shape, cuda_device, opts):
     from oracle import qp_oracle as O
     nb, nz, m, seed, wc = shape
