@@ -658,8 +658,10 @@ def main():
     if resident:
         # resident route: the iteration work of a step is spread over the k_res_chunk launches (several iterations of every
         # problem per launch + one repair launch).  Algorithmic flops of those launches together: the initial point and
-        # n_iter iterations of EVERY problem, as the reference executes them; iterations the kernels skip for
-        # problems that are already NaN, and the repair launch, are not credited.
+        # n_iter iterations of EVERY problem, as the reference executes them (it keeps iterating NaN problems
+        # until the batch-global test stops the loop).  The kernels stop a problem once its iterate has turned NaN (nothing
+        # of it can be returned any more), so the executed flops are lower than the credited ones on batches with NaN
+        # problems; the repair launch is not credited.
         step_flops = (fl["init"] + n_iter * fl["iter"]) * nb
         n_l = statistics.mean(res_launches)
         avg_iter_ms = statistics.mean(res_ms) / n_l
@@ -688,6 +690,8 @@ def main():
         "achieved": ach_tf, "peak": fp64_peak, "unit": "TFLOP/s", "frac": ach_tf / fp64_peak,
         "peak_source": "profiles/fp64_peaks_r01.json (DFMA microbenchmark on this pool's B200; MEASURED_PEAKS.json has no FP64 figure)",
         "flops_per_launch": flops_per_launch, "avg_launch_ms": avg_iter_ms,
+        "flops_basis": "algorithmic = what the reference executes (init + n_iter iterations of every problem); problems whose "
+                       "iterate turned NaN are not iterated further by the kernels",
         "launches_timed": int(sum(res_launches)) if resident else len(iter_ms),
         "traffic": traffic,
         "traffic_source": traffic_src,
