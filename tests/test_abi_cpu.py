@@ -111,3 +111,21 @@ def test_my_envs_host_mirror_selects_the_fused_models():
         my_envs.package_spec("cartpole3l", 0.05)
     with pytest.raises(RuntimeError, match="CUDA"):
         env.dynamics(torch.zeros(2, 4, dtype=torch.float64), torch.zeros(2, 1, dtype=torch.float64))
+
+
+def test_new_entry_points_validate_before_any_launch():
+    """b200qp_forward_cb_step / _phase_cb (residual callbacks), b200qp_solve_host_* slots, b200data_sample_windows: argument
+    validation returns EINVAL (-1) without touching the device."""
+    from b200qp import _lib
+    L = _lib.lib()
+    pr = _lib.Problem(4, 5, 6, 0, _lib.F64, 20, 3, 0, 1e-12, 25, 5, 30, 6, 0, 0)
+    null = ctypes.c_void_p(0)
+    one = ctypes.c_void_p(16)   # never dereferenced: validation fails first
+    assert L.b200qp_forward_cb_step(ctypes.byref(pr), 0, null, one, null) == -1          # no x_out
+    assert L.b200qp_forward_cb_step(ctypes.byref(pr), 20, one, one, null) == -1          # iteration out of range
+    assert L.b200qp_forward_phase_cb(ctypes.byref(pr), -1001, *([one] * 12), null, null, null) == -1   # BEGIN is not a cb phase
+    assert L.b200qp_solve_host_wait(_lib.HOST_SLOTS) == -1 and L.b200qp_solve_host_wait(-1) == -1
+    assert L.b200qp_solve_host_wait(_lib.HOST_SLOTS - 1) == 0                            # idle slot: nothing to wait for
+    assert L.b200data_sample_windows(null, one, one, 10, 2, 1, one, 8, 4, 3, 0, one, one, one, one, one, null) == -1
+    assert L.b200data_sample_windows(one, one, one, 10, 2, 1, one, 8, 4, 3, 5, one, one, one, one, one, null) == -1   # bad mode
+    assert _lib.FLAG_FACTORED_GRAD == 4 and _lib.HOST_SLOTS == 4
