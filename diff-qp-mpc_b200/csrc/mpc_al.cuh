@@ -607,6 +607,51 @@ __device__ __forceinline__ void block_cholesky_tiles16(double* D, double* E, int
   }
 }
 
+// The same tile factorisation for SMALL knot blocks (NT = nx + nu <= 8: pendulum, integrator, the cart-poles), fp64: D_t
+// is ONE 8x8 accumulator tile padded by the identity, E_t (nx x NT) one tile padded by zeros.  Per knot: one Schur product,
+// one 8-step pivot chain, one product for Y = E W^T (6 DMMAs) instead of NT rounds of (sqrt, divide, warp barrier, rank-1
+// update, warp barrier) on shared memory -- ncu had 36 % of the samples of k_al_solve<Cartpole1L> in the scalar block factor.
+// D (assembled by `assemble`, lower triangle) and E (already scaled by -rho) are read and written in place, in the Cholesky
+// convention (L_chol = L Delta^1/2, E_chol = Y Delta^-1/2).
+template <int NX, int NU>
+__device__ __forceinline__ void block_cholesky_tiles8(double* D, double* E, int T, int lane, double* rinv) {
+  constexpr int NT = NX + NU;
+  static_assert(NT <= 8, "one tile per knot block");
+  const int g = lane >> 2, q = lane & 3, c = 2 * q;
+  double Y[2] = {0.0, 0.0}, yr[2] = {1.0, 1.0};
+  for (int t = 0; t < T; t++) {
+    double* Dt = D + t * NT * NT;
+    double a[2];
+    a[0] = (g < NT && c <= g) ? Dt[g * NT + c] : ((g >= NT && c == g) ? 1.0 : 0.0);
+    a[1] = (g < NT && c + 1 <= g) ? Dt[g * NT + c + 1] : ((g >= NT && c + 1 == g) ? 1.0 : 0.0);
+    double e[2] = {0.0, 0.0};
+    if (t < T - 1) {
+      const double* Eg = E + t * NX * NT;
+      if (g < NX && c < NT) e[0] = Eg[g * NT + c];
+      if (g < NX && c + 1 < NT) e[1] = Eg[g * NT + c + 1];
+    }
+    if (t > 0) td_abt(a[0], a[1], Y[0] * -yr[0], Y[1] * -yr[1], Y[0], Y[1]);   // D_t[0:nx, 0:nx] -= Y Delta^-1 Y^T
+    double w[2];
+    td_diag(a[0], a[1], w[0], w[1], rinv, lane);
+    __syncwarp();
+    const double2 r = *reinterpret_cast<const double2*>(rinv + c);
+    const double srx = sqrt(r.x), sry = sqrt(r.y);
+    if (t < T - 1) {
+      double y[2] = {0.0, 0.0};
+      td_abt(y[0], y[1], e[0], e[1], w[0], w[1]);                               // Y = E W^T
+      Y[0] = y[0]; Y[1] = y[1]; yr[0] = r.x; yr[1] = r.y;
+      double* Eg = E + t * NX * NT;
+      if (g < NX && c < NT) Eg[g * NT + c] = y[0] * srx;
+      if (g < NX && c + 1 < NT) Eg[g * NT + c + 1] = y[1] * sry;
+    }
+    if (g < NT) {
+      if (c <= g) Dt[g * NT + c] = (c < g) ? a[0] * srx : 1.0 / srx;
+      if (c + 1 <= g) Dt[g * NT + c + 1] = (c + 1 < g) ? a[1] * sry : 1.0 / sry;
+    }
+    __syncwarp();
+  }
+}
+
 // g <- H^-1 g with the block factor (two block-bidiagonal sweeps; in-block solves by shuffles).
 template <int NX, int NU, typename R>
 __device__ __forceinline__ void block_solve(const R* D, const R* E, R* g, int T, int lane) {
@@ -799,6 +844,10 @@ __global__ void __launch_bounds__(128, (Dyn::NX == 4 ? 4 : (Dyn::NX >= 12 ? B200
         block_cholesky_tiles16(reinterpret_cast<double*>(S.D), reinterpret_cast<double*>(S.E), T, lane, rinv, (double)rho,
                                reinterpret_cast<const double*>(S.C), reinterpret_cast<const double*>(S.xu),
                                reinterpret_cast<const double*>(S.uu), reinterpret_cast<const double*>(S.ul));
+      } else if constexpr (NT <= 8 && sizeof(R) == 8) {
+        // small knot blocks as one DMMA tile each (shared-memory or global-slab state alike)
+        double* rinv = a.use_smem ? reinterpret_cast<double*>(S.mer) : reinterpret_cast<double*>(al_smem) + (size_t)warp * al_stage_elems<NX, NU>();
+        block_cholesky_tiles8<NX, NU>(reinterpret_cast<double*>(S.D), reinterpret_cast<double*>(S.E), T, lane, rinv);
       } else if (a.use_smem) block_cholesky<NX, NU, R>(S.D, S.E, T, lane, S.mer);
       else block_cholesky_staged<NX, NU, R>(S.D, S.E, T, lane, reinterpret_cast<R*>(al_smem) + (size_t)warp * al_stage_elems<NX, NU>());
       block_solve<NX, NU, R>(S.D, S.E, S.g, T, lane);
