@@ -384,9 +384,10 @@ struct Cartpole1LModel {
     const S mc = ml * c;
     const S r0 = u - ml * s * (qd[1] * qd[1]);
     const S r1 = (ml * g) * s;
-    const S f = mc / mt;                 // eliminate the cart row
+    const R imt = R(1) / mt;             // loop-invariant: one division per step instead of two per stage
+    const S f = mc * imt;                // eliminate the cart row
     a[1] = (r1 + f * r0) / (I - f * mc);
-    a[0] = (r0 + mc * a[1]) / mt;
+    a[0] = (r0 + mc * a[1]) * imt;
   }
 };
 
@@ -408,13 +409,14 @@ struct Cartpole2LModel {
     const S r1 = (h1 * g) * s1 - k * s12 * (w2 * w2);
     const S r2 = (h2 * g) * s2 + k * s12 * (w1 * w1);
     // symmetric elimination, no pivoting (the mass matrix is SPD)
-    const S f1 = m01 / mt, f2 = m02 / mt;
+    const R imt = R(1) / mt;
+    const S f1 = m01 * imt, f2 = m02 * imt;
     const S b11 = J1 - f1 * m01, b12 = m12 - f1 * m02, b22 = J2 - f2 * m02;
     const S t1 = r1 - f1 * r0, t2 = r2 - f2 * r0;
     const S f3 = b12 / b11;
     const S ph2 = (t2 - f3 * t1) / (b22 - f3 * b12);
     const S ph1 = (t1 - b12 * ph2) / b11;
-    a[0] = (r0 - m01 * ph1 - m02 * ph2) / mt;
+    a[0] = (r0 - m01 * ph1 - m02 * ph2) * imt;
     a[1] = ph1;
     a[2] = ph2 - ph1;
   }
