@@ -194,9 +194,10 @@ struct CartpoleDx {
     const S uc = m_clamp(u[0], -fmag, fmag);
     const S px = x[0], dx = x[1], cth = x[2], sth = x[3], dth = x[4];
     const S th = m_atan2(sth, cth);
-    const S cart_in = (uc + pml * (dth * dth) * sth) / total_mass;
-    const S th_acc = (gravity * sth - cth * cart_in) / (length * (R(4.0 / 3.0) - masspole * (cth * cth) / total_mass));
-    const S xacc = cart_in - pml * th_acc * cth / total_mass;
+    const R itm = R(1) / total_mass;   // one division instead of three per step
+    const S cart_in = (uc + pml * (dth * dth) * sth) * itm;
+    const S th_acc = (gravity * sth - cth * cart_in) / (length * (R(4.0 / 3.0) - masspole * (cth * cth) * itm));
+    const S xacc = cart_in - pml * th_acc * cth * itm;
     const S nth = th + dt * dth;
     xn[0] = px + dt * dx;
     xn[1] = dx + dt * xacc;
