@@ -177,65 +177,59 @@ class MPC(Module):
         F = torch.cat((R.reshape(self.T - 1, B, self.n_state, self.n_state), S.reshape(self.T - 1, B, self.n_state, self.n_ctrl)), 3)
         return F, f
 
-    def dyn_res(self, x, dx, x0):
-        """qp_wrapper.py:328-349: the equality residual of the QP with the TRUE (non-linear) dynamics"""
+    def dyn_res(self, z, dx, x0):
+        """qp_wrapper.py:328-349: the equality residual of the QP evaluated with the TRUE (non-linear) dynamics, in the row
+        order of `compute_Ab_dense`: [x_{t+1} - f(x_t, u_t) for t < T-1 (sign: f - x_{t+1}), x_0 - x0, (x_{T-1} - x_goal)]"""
         B, T, nx, nu = self.n_batch, self.T, self.n_state, self.n_ctrl
-        x = x.reshape(B, T, nx + nu)
-        x, u = x[:, :, :nx], x[:, :, nx:]
+        tau = z.reshape(B, T, nx + nu)
+        xs, us = tau[..., :nx], tau[..., nx:]
         if isinstance(dx, LinDx):
-            x_next = (dx.F.permute(1, 0, 2, 3) * torch.cat((x, u), dim=2)[:, :-1, None, :]).sum(dim=-1) + dx.f.permute(1, 0, 2)
+            F = dx.F.permute(1, 0, 2, 3)                                   # (B, T-1, nx, n_tau)
+            pred = (F * tau[:, :-1, None, :]).sum(dim=-1) + dx.f.permute(1, 0, 2)
         else:
-            x_next = dx(x.reshape(-1, nx), u.reshape(-1, nu)).reshape(B, T, nx)[:, :-1]
-        res = (x_next - x[:, 1:, :]).reshape(B, -1)
-        res_init = (x[:, 0, :] - x0).reshape(B, -1)
+            pred = dx(xs.reshape(-1, nx), us.reshape(-1, nu)).reshape(B, T, nx)[:, :-1]
+        rows = [(pred - xs[:, 1:]).reshape(B, -1), (xs[:, 0] - x0).reshape(B, -1)]
         if self.add_goal_constraint:
-            res_goal = (x[:, -1, :] - self.x_goal).reshape(B, -1)
-            return torch.cat((res, res_init, res_goal), dim=1)
-        return torch.cat((res, res_init), dim=1)
+            rows.append((xs[:, -1] - self.x_goal).reshape(B, -1))
+        return torch.cat(rows, dim=1)
 
     # ---------------------------------------------------------------------------------------------- solve
+    def _time_batch(self, t, full_ndim, n_batch):
+        """broadcast a cost term given without its time and / or batch dimension to (T, B, ...) (qp_wrapper.py:236-254)"""
+        missing = full_ndim - t.ndimension()
+        if missing == 2:
+            t = t[None, None]
+        elif missing == 1:
+            t = t[:, None]
+        elif missing != 0:
+            raise RuntimeError('MPC Error: Unexpected QuadCost shape.')
+        return t.expand(self.T, n_batch, *t.shape[2:])
+
     def forward(self, x0, cost, dx, dx_jac, dx_true=None):
         self.dx_true = dx if dx_true is None else dx_true
-        assert isinstance(cost, tuple) and len(cost) == 2, "b200qp qp_wrapper.MPC: QuadCost(C, c) costs only"
-        if self.n_batch is not None:
-            n_batch = self.n_batch
-        elif cost[0].ndimension() == 4:
-            n_batch = self.n_batch = cost[0].size(1)
-        else:
-            raise RuntimeError('MPC Error: Could not infer batch size, pass in as n_batch')
+        if not (isinstance(cost, tuple) and len(cost) == 2):
+            raise NotImplementedError("b200qp qp_wrapper.MPC: QuadCost(C, c) costs only")
         C, c = cost
-        nt = self.n_state + self.n_ctrl
-        if C.ndimension() == 2:
-            C = C.unsqueeze(0).unsqueeze(0).expand(self.T, n_batch, nt, -1)
-        elif C.ndimension() == 3:
-            C = C.unsqueeze(1).expand(self.T, n_batch, nt, -1)
-        if c.ndimension() == 1:
-            c = c.unsqueeze(0).unsqueeze(0).expand(self.T, n_batch, -1)
-        elif c.ndimension() == 2:
-            c = c.unsqueeze(1).expand(self.T, n_batch, -1)
-        if C.ndimension() != 4 or c.ndimension() != 3:
-            raise RuntimeError('MPC Error: Unexpected QuadCost shape.')
-        cost = QuadCost(C, c)
-        assert x0.ndimension() == 2 and x0.size(0) == n_batch
-        if self.u_init is None:
-            u = torch.zeros(self.T, n_batch, self.n_ctrl, dtype=x0.dtype, device=x0.device)
-        else:
-            u = self.u_init
-            if u.ndimension() == 2:
-                u = u.unsqueeze(1).expand(self.T, n_batch, -1).clone()
-        u = u.to(x0).contiguous()
-        if self.x_init is None:
-            x = self.rollout(x0, u, dx)
-        else:
-            x = self.x_init
-            if x.ndimension() == 2:
-                x = x.unsqueeze(1).expand(self.T, n_batch, -1).clone()
-        x = x.to(x0)
+        if self.n_batch is None:
+            if C.ndimension() != 4:
+                raise RuntimeError('MPC Error: Could not infer batch size, pass in as n_batch')
+            self.n_batch = C.size(1)
+        B = self.n_batch
+        cost = QuadCost(self._time_batch(C, 4, B), self._time_batch(c, 3, B))
+        assert x0.ndimension() == 2 and x0.size(0) == B
+        opt = dict(dtype=x0.dtype, device=x0.device)
+        # initial controls (T, B, nu) and states (rolled out from them unless given)
+        u = torch.zeros(self.T, B, self.n_ctrl, **opt) if self.u_init is None else self.u_init
+        if u.ndimension() == 2:
+            u = u[:, None].expand(self.T, B, -1)
+        u = u.to(**opt).contiguous()
+        x = self.rollout(x0, u, dx) if self.x_init is None else self.x_init
+        if x.ndimension() == 2:
+            x = x[:, None].expand(self.T, B, -1)
+        x = x.to(**opt).contiguous()
         self.info = {"qp_iters": []}
-        if self.single_qp_solve:
-            x, u, _ = self.single_qp_ls(x, u, dx, dx_jac, x0, cost)
-        else:
-            x, u, _ = self.solve_nonlin(x, u, dx, dx_jac, x0, cost)
+        step = self.single_qp_ls if self.single_qp_solve else self.solve_nonlin
+        x, u, _ = step(x, u, dx, dx_jac, x0, cost)
         return (x, u)
 
     def single_qp(self, x, u, dx, dx_jac, x0, cost):
